@@ -1,0 +1,185 @@
+/*
+ * mmannot_b200 -- C ABI of the B200 read-annotation hot path.
+ *
+ * This is the drop-in boundary for the part of mzytnicki/mmannot that annotates
+ * alignment records ("hits") and counts element combinations.  The reference has
+ * no FFI of its own; the entry points below sit exactly where its hot loop calls
+ *
+ *     IntervalList::scan(Read&, regions, ids, position)      mmannot.cpp:1291-1332
+ *     Counter::addCount(name, regions, ids, nHits)           mmannot.cpp:1665-1739
+ *     Counter::read() end-of-file flush                      mmannot.cpp:1783-1800
+ *     Counter::getCounts() / TableCount::addCounter()        mmannot.cpp:1803, 1861-1876
+ *
+ * (called from Counter::read, mmannot.cpp:1772-1778, and main, mmannot.cpp:2109-2115).
+ * Everything before that loop (config, GTF -> typed intervals, SAM/BAM decode) and
+ * after it (table / statistics formatting) stays on the host.
+ *
+ * Conventions: plain pointers and sizes, no C++ types, no exceptions, no exit().
+ * Every function returns MMA_OK (0) or a negative MMA_ERR_* code; the message is
+ * available from mma_last_error().  Calls on one context must be serialised by the
+ * caller; different contexts (one per GPU) may be driven from different threads.
+ * There is no CPU fallback: without a usable CUDA device mma_create() fails.
+ */
+#ifndef MMANNOT_B200_H
+#define MMANNOT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MMA_OK 0
+#define MMA_ERR_INVALID (-1)   /* bad argument / unsorted features / unsupported size */
+#define MMA_ERR_CUDA (-2)      /* CUDA runtime error */
+#define MMA_ERR_STATE (-3)     /* wrong call sequence */
+#define MMA_ERR_CAPACITY (-4)  /* combination table or staging capacity exceeded */
+#define MMA_ERR_NO_DEVICE (-5) /* no CUDA device: the product path has no CPU fallback */
+
+/* -y (Strategy, mmannot.cpp:50, 2033-2045) */
+#define MMA_STRATEGY_DEFAULT 0
+#define MMA_STRATEGY_UNIQUE 1
+#define MMA_STRATEGY_RANDOM 2
+#define MMA_STRATEGY_RATIO 3
+
+/* element strand / feature strand (Strand, mmannot.cpp:49) */
+#define MMA_STRAND_ALL 0
+#define MMA_STRAND_F 1
+#define MMA_STRAND_R 2
+
+/* element kind used for the distance tie-break (Config::isUpstream/isDownstream, mmannot.cpp:463-470) */
+#define MMA_VICINITY_NONE 0
+#define MMA_VICINITY_UP 1
+#define MMA_VICINITY_DOWN 2
+
+/* hit meta word */
+#define MMA_HIT_CHR_MASK 0x00FFFFFFu   /* bits 0..23: annotation chromosome id */
+#define MMA_HIT_CHR_NONE 0x00FFFFFFu   /* chromosome unknown to the annotation (mmannot.cpp:1294-1302) */
+#define MMA_HIT_STRAND_BIT 0x80000000u /* bit 31: read strand after the -s mapping (mmannot.cpp:836-844, 884) */
+
+#define MMA_MAX_ELEMENTS 64
+
+typedef struct mma_ctx mma_ctx; /* one per GPU, opaque */
+
+typedef struct mma_params {
+  int32_t device;          /* CUDA device ordinal */
+  int32_t strategy;        /* MMA_STRATEGY_* */
+  float overlap;           /* -l as parsed by stof (Globals::overlap, mmannot.cpp:70, 1972-1977):
+                              <0 inclusion, <1 fraction of the read, else nucleotides */
+  float rescue_threshold;  /* -e/100 in fp32 (mmannot.cpp:2024); >=1 disables rescue */
+  int32_t read_stats;      /* -m: rescue only acts when read statistics are requested (mmannot.cpp:491) */
+  int32_t interval_stats;  /* -M */
+  uint32_t n_elements;     /* E = flattened length of the Order section, <= MMA_MAX_ELEMENTS */
+  const uint16_t *elem_line;    /* [E] Order line (priority rank) of each element */
+  const uint8_t *elem_strand;   /* [E] MMA_STRAND_* of the element (' +' / ' -' suffix) */
+  const uint8_t *elem_vicinity; /* [E] MMA_VICINITY_* */
+  uint32_t n_samples;      /* number of input files (table columns) */
+  uint32_t max_batch_hits; /* staging capacity: largest n of one mma_submit_hits call */
+  uint32_t table_log2;     /* log2(slots) of the per-sample combination table; 0 = 16 */
+  uint32_t bin_shift;      /* log2(bin width) of the position index; 0 = chosen from the annotation extent */
+  uint32_t rand_seed;      /* -y random: seed of the glibc rand() stream the reference draws from (1 = unseeded) */
+  uint32_t reserved;
+} mma_params;
+
+/* Typed intervals in REFERENCE ORDER (mmannot.cpp:1267: sorted by chromosome id then start,
+ * ties in the order the reference's std::sort leaves them).  1-based closed coordinates. */
+typedef struct mma_features {
+  uint32_t n;
+  uint32_t n_chr;          /* number of annotation chromosomes; chr[i] < n_chr */
+  const uint32_t *chr;
+  const uint32_t *start;
+  const uint32_t *end;
+  const uint8_t *type;     /* flattened Order element index */
+  const uint8_t *strand;   /* MMA_STRAND_F or MMA_STRAND_R */
+} mma_features;
+
+/* One batch of hits, struct-of-arrays, in file order.  start/end are the reference's
+ * Read interval (mmannot.cpp:852-886: end = start + sum(M,D,=,X) - 1). */
+typedef struct mma_hit_batch {
+  uint64_t n;
+  const uint32_t *start;
+  const uint32_t *end;
+  const uint32_t *meta;      /* MMA_HIT_* */
+  const uint32_t *nh;        /* NH of the record (XamRecord::nHits) */
+  const uint64_t *read_key;  /* 64-bit key of the read name (the reference keys by the name string) */
+} mma_hit_batch;
+
+typedef struct mma_sample_stats { /* Counter's counters, mmannot.cpp:1663, printed at 1807-1818 */
+  uint64_t n_hits, n_reads, n_unique, n_ambiguous, n_multiple, n_unassigned, n_rescued;
+} mma_sample_stats;
+
+/* One row per distinct element combination.  The value the reference keeps in
+ * regionCounts (a double, mmannot.cpp:1658) is  sum over rows with the same mask of
+ * count * (nh ? 1.0 / nh : 1.0);  nh is non-zero only under -y ratio. */
+typedef struct mma_sample_result {
+  mma_sample_stats stats;
+  uint64_t n_rows;
+  const uint64_t *row_mask;  /* bit i set <=> element i in the combination */
+  const uint32_t *row_nh;
+  const uint64_t *row_count;
+} mma_sample_result;
+
+/* Per-kernel device time since mma_timing_reset(), from CUDA events recorded on the
+ * context's own compute stream (timing must have been switched on). */
+typedef struct mma_timing {
+  double ms_index;    /* K1 feature index build */
+  double ms_annotate; /* K2 per-hit overlap + priority pick (+ single-hit counting) */
+  double ms_resolve;  /* K3 per-read resolution of multi-mapping reads */
+  double ms_merge;    /* K4 table merge / bookkeeping kernels */
+  double ms_finish;   /* deferred (name-sorted) resolution at mma_finish_sample */
+  uint64_t launches;  /* kernels launched by this library since the reset */
+  uint64_t hits;      /* hits submitted since the reset */
+} mma_timing;
+
+int mma_create(mma_ctx **out, const mma_params *params);
+void mma_destroy(mma_ctx *ctx);
+const char *mma_last_error(const mma_ctx *ctx); /* ctx may be NULL: error of the last failed mma_create */
+
+/* Uploads the feature buffer and builds the device index (chromosome offsets, running
+ * max-end, position bins).  Replaces the sort/bins of mmannot.cpp:1267-1284. */
+int mma_load_features(mma_ctx *ctx, const mma_features *features);
+
+/* Page-locked host memory for hit buffers (plain malloc'ed buffers also work, slower). */
+void *mma_alloc_pinned(size_t bytes);
+void mma_free_pinned(void *p);
+
+/* Asynchronous: copies the batch to the device on a side stream and enqueues the kernels.
+ * The caller's buffers must stay untouched until the NEXT mma_submit_hits /
+ * mma_finish_sample / mma_sync on this context returns (double-buffer on the host).
+ * Replaces scan() + addCount() for the hits of the batch (mmannot.cpp:1772-1778). */
+int mma_submit_hits(mma_ctx *ctx, uint32_t sample, const mma_hit_batch *batch);
+
+/* Same, but the arrays already live in device memory of ctx's GPU (no copy is made; they
+ * must stay valid until mma_sync / mma_finish_sample). */
+int mma_submit_hits_device(mma_ctx *ctx, uint32_t sample, const mma_hit_batch *device_batch);
+
+/* Synchronous: end-of-file flush of the sample (mmannot.cpp:1783-1792) and read-back of its
+ * counters and rows.  The arrays belong to the context and stay valid until the next
+ * mma_finish_sample / mma_reset_sample / mma_destroy. */
+int mma_finish_sample(mma_ctx *ctx, uint32_t sample, mma_sample_result *out);
+
+/* Forget everything counted for `sample` (Counter::clear, mmannot.cpp:1742-1747). */
+int mma_reset_sample(mma_ctx *ctx, uint32_t sample);
+
+/* Dense device vector for a cross-GPU sum: out_dev[i] = count of row (mask[i], nh[i]) of
+ * `sample`, 0 if absent.  out_dev is device memory (n x uint64); the collective itself is
+ * issued by whoever owns the communicator (torch.distributed / NCCL). */
+int mma_dense_counts(mma_ctx *ctx, uint32_t sample, const uint64_t *mask, const uint32_t *nh, uint64_t n, uint64_t *out_dev);
+
+int mma_sync(mma_ctx *ctx);
+void *mma_stream(mma_ctx *ctx); /* cudaStream_t of the compute stream */
+
+int mma_timing_enable(mma_ctx *ctx, int on);
+int mma_timing_reset(mma_ctx *ctx);
+int mma_timing_get(mma_ctx *ctx, mma_timing *out); /* synchronises */
+
+/* Size in bytes of the device index built by mma_load_features (0 before). */
+uint64_t mma_index_bytes(const mma_ctx *ctx);
+
+const char *mma_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MMANNOT_B200_H */

@@ -1,0 +1,87 @@
+// SAM / BAM decode -> packed struct-of-arrays hit batches (the buffers of mma_submit_hits()).
+// Hit semantics follow Reader / SamReader / BamReader / Read of the reference
+// (mmannot.cpp:846-903, 1339-1650) with XamRecord::setFlags repaired (mm:606: the FLAG
+// is honoured).  One hit = one record or one XA alternative (one iteration of mm:1772).
+#pragma once
+#include <zlib.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <fstream>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "annotation.hpp"
+
+namespace mmb {
+
+enum class ReadsFormat { UNKNOWN, SAM, BAM };
+enum class Strandedness { U, F, R };
+
+static const uint32_t HIT_CHR_MASK = 0x00FFFFFFu;  // meta bits 0..23: annotation chromosome id
+static const uint32_t HIT_CHR_NONE = 0x00FFFFFFu;  // chromosome without features / unmapped
+static const uint32_t HIT_STRAND_BIT = 0x80000000u;  // meta bit 31: read strand after -s mapping (mm:836-844)
+
+// Caller-owned struct-of-arrays destination (typically pinned memory).
+struct HitBuffers {
+  uint32_t *start = nullptr, *end = nullptr, *meta = nullptr, *nh = nullptr;
+  uint64_t *key = nullptr;
+  size_t capacity = 0;
+};
+
+class XamReader {
+ public:
+  XamReader(const std::string &fileName, ReadsFormat format, Strandedness strandedness, const FeatureTable &features);
+  ~XamReader();
+
+  // false + message when the file cannot be opened / is not what it claims to be
+  bool open(std::string &err);
+  bool isBam() const { return bam_; }
+
+  // Decodes hits into `dst` until it is full or the input ends.  A batch never ends in
+  // the middle of a run of records sharing a read name (unless one run fills the whole
+  // buffer).  Returns the number of hits written; 0 = end of input.
+  // If `names` is given, the name of every hit is appended (for -m).
+  size_t nextBatch(const HitBuffers &dst, std::vector<std::string> *names = nullptr);
+
+  uint64_t recordsRead() const { return nRecords_; }  // reference's "lines read" (= hits, mm:1772)
+  std::string takeWarnings();                         // unknown chromosomes, CIGAR problems, XA problems
+
+ private:
+  struct Hit { uint32_t start, end, meta, nh; uint64_t key; };
+  struct Alt { uint32_t chrMeta; bool strand; uint64_t start; std::vector<std::pair<char, int> > cigar; };
+
+  bool fillRaw(size_t need);  // make `need` bytes available at rawPos_ (BAM)
+  bool decodeBamRecord();
+  bool decodeSamRecord();
+  void pushRecordHits(const std::string &name, uint32_t chrMeta, uint64_t start, bool strand,
+                      const std::vector<std::pair<char, int> > &cigar, bool cigarIsStar, uint32_t nHits);
+  uint64_t cigarEnd(uint64_t start, uint64_t prevEnd, const std::vector<std::pair<char, int> > &cigar);
+  uint32_t chrMetaOf(const std::string &name);
+  void parseAlternatives(const std::string &xa);
+
+  std::string fileName_;
+  ReadsFormat format_;
+  Strandedness strandedness_;
+  const FeatureTable &features_;
+  std::unordered_map<std::string, uint32_t> chrByName_;
+  std::vector<std::string> unknownChr_;
+  bool bam_ = false, over_ = false;
+  gzFile gz_ = nullptr;
+  std::ifstream sam_;
+  std::vector<unsigned char> raw_;
+  size_t rawPos_ = 0, rawEnd_ = 0;
+  std::vector<uint32_t> bamChrMeta_;  // per BAM refID
+  std::vector<std::string> bamChrName_;
+  uint32_t nMismatches_ = 0;          // persists across records like XamRecord::nMismatches (mm:596)
+  std::vector<Alt> alts_;
+  std::vector<Hit> pending_;          // decoded but not yet handed out
+  std::vector<std::string> pendingNames_;
+  size_t pendingPos_ = 0;
+  bool keepNames_ = false;
+  uint64_t nRecords_ = 0;
+  std::string warnings_;
+};
+
+}  // namespace mmb

@@ -1,0 +1,191 @@
+"""ctypes view of the host front-end (libmmannot_host.so, include/mmannot_b200_host.h).
+
+Config / annotation / alignment decoding -- the producers of the packed buffers that
+cross the device boundary.  Mirrors Config (mmannot.cpp:219-471), the IntervalList
+constructor (mmannot.cpp:1094-1290) and the SAM/BAM readers (mmannot.cpp:1339-1650).
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "lib", "libmmannot_host.so")
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_LIB_PATH):
+            raise RuntimeError(f"{_LIB_PATH} is missing: run `make host` (or __graft_entry__.build())")
+        L = C.CDLL(_LIB_PATH)
+        L.mmh_last_error.restype = C.c_char_p
+        L.mmh_config_load.argtypes = [C.c_char_p, C.POINTER(C.c_void_p)]
+        L.mmh_config_free.argtypes = [C.c_void_p]
+        L.mmh_config_n_elements.argtypes = [C.c_void_p]
+        L.mmh_config_n_elements.restype = C.c_uint32
+        L.mmh_config_tables.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.mmh_config_name.argtypes = [C.c_void_p, C.c_uint32, C.c_char_p, C.c_size_t]
+        L.mmh_config_name.restype = C.c_size_t
+        L.mmh_config_order_echo.argtypes = [C.c_void_p, C.c_char_p, C.c_size_t]
+        L.mmh_config_order_echo.restype = C.c_size_t
+        L.mmh_annotation_build.argtypes = [C.c_void_p, C.c_char_p, C.c_uint64, C.c_uint64, C.POINTER(C.c_void_p)]
+        L.mmh_annotation_free.argtypes = [C.c_void_p]
+        for name, res in [("n", C.c_uint32), ("n_chr", C.c_uint32), ("n_genes", C.c_uint64), ("n_lines", C.c_uint64),
+                          ("chr", C.c_void_p), ("start", C.c_void_p), ("end", C.c_void_p), ("type", C.c_void_p),
+                          ("strand", C.c_void_p), ("warnings", C.c_char_p)]:
+            f = getattr(L, "mmh_annotation_" + name)
+            f.argtypes = [C.c_void_p]
+            f.restype = res
+        L.mmh_annotation_id.argtypes = [C.c_void_p, C.c_uint32]
+        L.mmh_annotation_id.restype = C.c_char_p
+        L.mmh_annotation_chr_name.argtypes = [C.c_void_p, C.c_uint32]
+        L.mmh_annotation_chr_name.restype = C.c_char_p
+        L.mmh_reader_open.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.c_char, C.POINTER(C.c_void_p)]
+        L.mmh_reader_close.argtypes = [C.c_void_p]
+        L.mmh_reader_next.argtypes = [C.c_void_p, C.c_uint64] + [C.c_void_p] * 5
+        L.mmh_reader_next.restype = C.c_uint64
+        L.mmh_reader_records.argtypes = [C.c_void_p]
+        L.mmh_reader_records.restype = C.c_uint64
+        L.mmh_reader_warnings.argtypes = [C.c_void_p, C.c_char_p, C.c_size_t]
+        L.mmh_reader_warnings.restype = C.c_size_t
+        L.mmh_name_key.argtypes = [C.c_char_p, C.c_size_t]
+        L.mmh_name_key.restype = C.c_uint64
+        _lib = L
+    return _lib
+
+
+class HostError(RuntimeError):
+    pass
+
+
+def _err():
+    return HostError(lib().mmh_last_error().decode("utf-8", "replace"))
+
+
+class Config:
+    """Parsed configuration file; element i = i-th item of the flattened Order section."""
+
+    def __init__(self, path):
+        self._h = C.c_void_p()
+        if lib().mmh_config_load(os.fsencode(path), C.byref(self._h)) != 0:
+            raise _err()
+        self.n_elements = lib().mmh_config_n_elements(self._h)
+        self.elem_line = np.zeros(self.n_elements, np.uint16)
+        self.elem_strand = np.zeros(self.n_elements, np.uint8)
+        self.elem_vicinity = np.zeros(self.n_elements, np.uint8)
+        lib().mmh_config_tables(self._h, self.elem_line.ctypes.data, self.elem_strand.ctypes.data, self.elem_vicinity.ctypes.data)
+        buf = C.create_string_buffer(4096)
+        self.names = []
+        for i in range(self.n_elements):
+            lib().mmh_config_name(self._h, i, buf, 4096)
+            self.names.append(buf.value.decode())
+
+    def order_echo(self):
+        buf = C.create_string_buffer(1 << 16)
+        lib().mmh_config_order_echo(self._h, buf, 1 << 16)
+        return buf.value.decode()
+
+    def row_name(self, mask):
+        """Table row label of an element set (TableCount::dump, mmannot.cpp:1889-1893)."""
+        return "--".join(self.names[i] for i in range(self.n_elements) if (int(mask) >> i) & 1)
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().mmh_config_free(self._h)
+            self._h = None
+
+
+def _view(ptr, n, dtype):
+    if n == 0:
+        return np.zeros(0, dtype)
+    ct = {np.uint32: C.c_uint32, np.uint8: C.c_uint8}[dtype]
+    return np.ctypeslib.as_array(C.cast(ptr, C.POINTER(ct)), shape=(n,)).copy()
+
+
+class Annotation:
+    """Typed intervals in reference order (the feature buffer of mma_load_features)."""
+
+    def __init__(self, config, gtf_path, upstream=1000, downstream=1000):
+        self.config = config
+        self._h = C.c_void_p()
+        if lib().mmh_annotation_build(config._h, os.fsencode(gtf_path), upstream, downstream, C.byref(self._h)) != 0:
+            raise _err()
+        L = lib()
+        self.n = L.mmh_annotation_n(self._h)
+        self.n_chr = L.mmh_annotation_n_chr(self._h)
+        self.n_genes = L.mmh_annotation_n_genes(self._h)
+        self.n_lines = L.mmh_annotation_n_lines(self._h)
+        self.chr = _view(L.mmh_annotation_chr(self._h), self.n, np.uint32)
+        self.start = _view(L.mmh_annotation_start(self._h), self.n, np.uint32)
+        self.end = _view(L.mmh_annotation_end(self._h), self.n, np.uint32)
+        self.type = _view(L.mmh_annotation_type(self._h), self.n, np.uint8)
+        self.strand = _view(L.mmh_annotation_strand(self._h), self.n, np.uint8)
+        self.warnings = L.mmh_annotation_warnings(self._h).decode("utf-8", "replace")
+
+    def ids(self):
+        return [lib().mmh_annotation_id(self._h, i).decode() for i in range(self.n)]
+
+    def chromosomes(self):
+        return [lib().mmh_annotation_chr_name(self._h, i).decode() for i in range(self.n_chr)]
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().mmh_annotation_free(self._h)
+            self._h = None
+
+
+class Hits:
+    """Struct-of-arrays hit batch (mma_hit_batch)."""
+
+    __slots__ = ("start", "end", "meta", "nh", "read_key")
+
+    def __init__(self, start, end, meta, nh, read_key):
+        self.start = np.ascontiguousarray(start, np.uint32)
+        self.end = np.ascontiguousarray(end, np.uint32)
+        self.meta = np.ascontiguousarray(meta, np.uint32)
+        self.nh = np.ascontiguousarray(nh, np.uint32)
+        self.read_key = np.ascontiguousarray(read_key, np.uint64)
+
+    @property
+    def n(self):
+        return int(self.start.shape[0])
+
+    def slice(self, a, b):
+        return Hits(self.start[a:b], self.end[a:b], self.meta[a:b], self.nh[a:b], self.read_key[a:b])
+
+    @staticmethod
+    def concat(parts):
+        return Hits(*[np.concatenate([getattr(p, k) for p in parts]) for k in Hits.__slots__])
+
+
+def read_hits(annotation, path, strandedness="F", fmt=0, batch=1 << 20):
+    """Decode a whole SAM/BAM file into one Hits object (plus the decoder's warnings)."""
+    L = lib()
+    h = C.c_void_p()
+    if L.mmh_reader_open(annotation._h, os.fsencode(path), fmt, strandedness.encode()[0:1], C.byref(h)) != 0:
+        raise _err()
+    parts = []
+    try:
+        while True:
+            arrs = [np.empty(batch, np.uint32) for _ in range(4)] + [np.empty(batch, np.uint64)]
+            n = L.mmh_reader_next(h, batch, *[a.ctypes.data for a in arrs])
+            if n == 0:
+                break
+            parts.append(Hits(*[a[:n] for a in arrs]))
+        buf = C.create_string_buffer(1 << 20)
+        L.mmh_reader_warnings(h, buf, 1 << 20)
+        warnings = buf.value.decode("utf-8", "replace")
+    finally:
+        L.mmh_reader_close(h)
+    if not parts:
+        z = np.zeros(0, np.uint32)
+        return Hits(z, z, z, z, np.zeros(0, np.uint64)), warnings
+    return Hits.concat(parts), warnings
+
+
+def name_key(name):
+    b = name.encode() if isinstance(name, str) else name
+    return int(lib().mmh_name_key(b, len(b)))
