@@ -1,0 +1,761 @@
+// C ABI of the device hot path (include/mmannot_b200.h): context, streams, staging, launches.
+// No CPU fallback lives here: every entry point either drives the sm_100a kernels of
+// mma_device.cuh or fails with an error code.
+#include "mmannot_b200.h"
+
+#include <cub/device/device_radix_sort.cuh>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "mma_device.cuh"
+
+using namespace mma;
+
+namespace {
+
+thread_local std::string g_createError;
+
+#define CK(call)                                                                                   \
+  do {                                                                                             \
+    cudaError_t _e = (call);                                                                       \
+    if (_e != cudaSuccess) return ctx->fail(MMA_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(_e)); \
+  } while (0)
+
+enum TimeCat { TC_INDEX = 0, TC_ANNOTATE, TC_RESOLVE, TC_MERGE, TC_FINISH, TC_N };
+
+struct DevBuf {
+  void *p = nullptr;
+  size_t bytes = 0;
+  cudaError_t ensure(size_t need) {
+    if (need <= bytes) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr; bytes = 0;
+    cudaError_t e = cudaMalloc(&p, need);
+    if (e == cudaSuccess) bytes = need;
+    return e;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; bytes = 0; }
+  template <typename T> T *as() const { return reinterpret_cast<T *>(p); }
+};
+
+struct Staging {  // one batch resident on the device
+  DevBuf start, end, meta, nh, key, mask;
+  cudaEvent_t copied = nullptr, done = nullptr;
+};
+
+struct Sample {
+  SampleCtl *ctl = nullptr;
+  DevBuf tableKeys, tableVals, deltaKeys, deltaVals;
+  DevBuf slowKey, slowOrd, slowMask, slowNh, openKeys;
+  u32 slowCap = 0, openCap = 0;
+  // host-side bound on the number of deferred records (see ensureDeferred)
+  u32 *countRing = nullptr;  // pinned, 4 entries
+  cudaEvent_t ringEv[4] = {nullptr, nullptr, nullptr, nullptr};
+  uint64_t ringCum[4] = {0, 0, 0, 0};
+  bool ringUsed[4] = {false, false, false, false};
+  uint64_t cumHits = 0, seq = 0;
+  uint64_t knownCount = 0, knownCum = 0;
+  bool touched = false;
+  // results
+  std::vector<uint64_t> rowMask, rowCount;
+  std::vector<uint32_t> rowNh;
+};
+
+}  // namespace
+
+struct mma_ctx {
+  mma_params params;
+  std::vector<uint16_t> elemLine;
+  std::vector<uint8_t> elemStrand, elemVic;
+  Rules rules;
+  bool wideMask = false;
+  int device = 0;
+  cudaStream_t sc = nullptr, sh = nullptr;
+  Staging stage[2];
+  uint64_t submitSeq = 0;
+  u32 tableCap = 0;
+  // index
+  bool haveIndex = false;
+  DevBuf feat, chrInfo, bins, spanIdx, dElemLine, dElemStrand, dElemVic;
+  IndexView index;
+  uint64_t indexBytes = 0;
+  std::vector<Sample> samples;
+  std::string error;
+  // timing
+  bool timing = false;
+  struct Span { int cat; cudaEvent_t a, b; };
+  std::vector<Span> spans;
+  std::vector<cudaEvent_t> eventPool;
+  double ms[TC_N] = {0, 0, 0, 0, 0};
+  uint64_t launches = 0, hitsSubmitted = 0;
+
+  int fail(int code, const std::string &msg) {
+    error = msg;
+    return code;
+  }
+  cudaEvent_t getEvent() {
+    if (!eventPool.empty()) { cudaEvent_t e = eventPool.back(); eventPool.pop_back(); return e; }
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    return e;
+  }
+  struct Timed {
+    mma_ctx *c; int cat; cudaEvent_t a = nullptr;
+    Timed(mma_ctx *ctx, int category) : c(ctx), cat(category) {
+      if (c->timing) { a = c->getEvent(); cudaEventRecord(a, c->sc); }
+    }
+    ~Timed() {
+      if (a) { cudaEvent_t b = c->getEvent(); cudaEventRecord(b, c->sc); c->spans.push_back(Span{cat, a, b}); }
+    }
+  };
+  void collectTiming() {
+    for (Span &s : spans) {
+      float t = 0;
+      if (cudaEventElapsedTime(&t, s.a, s.b) == cudaSuccess) ms[s.cat] += t;
+      eventPool.push_back(s.a); eventPool.push_back(s.b);
+    }
+    spans.clear();
+  }
+};
+
+namespace {
+
+inline u32 gridFor(uint64_t n, u32 threads) { return (u32)((n + threads - 1) / threads); }
+
+TableView tableView(const DevBuf &k, const DevBuf &v, u32 cap, SampleCtl *ctl) {
+  TableView t;
+  t.keys = k.as<u64>(); t.vals = v.as<u64>(); t.capMask = cap - 1; t.overflow = &ctl->overflow;
+  return t;
+}
+SlowView slowView(const Sample &s) {
+  SlowView v;
+  v.key = s.slowKey.as<u64>(); v.ord = s.slowOrd.as<u64>(); v.mask = s.slowMask.as<u64>(); v.nh = s.slowNh.as<u32>(); v.cap = s.slowCap;
+  return v;
+}
+KeySetView openView(const Sample &s) {
+  KeySetView v;
+  v.keys = s.openKeys.as<u64>(); v.capMask = s.openCap ? s.openCap - 1 : 0;
+  return v;
+}
+
+int initSample(mma_ctx *ctx, Sample &s) {
+  if (s.ctl) return MMA_OK;
+  CK(cudaMalloc(&s.ctl, sizeof(SampleCtl)));
+  CK(cudaMemsetAsync(s.ctl, 0, sizeof(SampleCtl), ctx->sc));
+  const size_t tb = (size_t)ctx->tableCap * sizeof(u64);
+  CK(s.tableKeys.ensure(tb)); CK(s.tableVals.ensure(tb)); CK(s.deltaKeys.ensure(tb)); CK(s.deltaVals.ensure(tb));
+  CK(cudaMemsetAsync(s.tableKeys.p, 0, tb, ctx->sc)); CK(cudaMemsetAsync(s.tableVals.p, 0, tb, ctx->sc));
+  CK(cudaMemsetAsync(s.deltaKeys.p, 0, tb, ctx->sc)); CK(cudaMemsetAsync(s.deltaVals.p, 0, tb, ctx->sc));
+  CK(cudaHostAlloc(&s.countRing, 4 * sizeof(u32), cudaHostAllocDefault));
+  for (int i = 0; i < 4; ++i) CK(cudaEventCreateWithFlags(&s.ringEv[i], cudaEventDisableTiming));
+  return MMA_OK;
+}
+
+__global__ void k_keyset_rehash(KeySetView from, KeySetView to, SampleCtl *ctl) {
+  const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i > from.capMask) return;
+  const u64 k = from.keys[i];
+  if (k == KEY_EMPTY) return;
+  u32 slot = (u32)mix64(k) & to.capMask;
+  for (;;) {
+    const u64 o = atomicCAS(&to.keys[slot], KEY_EMPTY, k);
+    if (o == KEY_EMPTY || o == k) return;
+    slot = (slot + 1) & to.capMask;
+  }
+}
+
+// Deferred list / open-key set sizing.  The device appends without asking; the host keeps an
+// upper bound on the list length (last count read back asynchronously + hits submitted since)
+// and only synchronises when that bound says the next batch might not fit.
+int ensureDeferred(mma_ctx *ctx, Sample &s, uint64_t n) {
+  const bool needs = (ctx->rules.strategy == MMA_STRATEGY_DEFAULT || ctx->rules.strategy == MMA_STRATEGY_RANDOM);
+  if (!needs) return MMA_OK;
+  // freshest completed read-back
+  for (int k = 0; k < 4; ++k) {
+    const int slot = (int)((s.seq + 3 - k) & 3);  // newest first
+    if (!s.ringUsed[slot]) continue;
+    if (cudaEventQuery(s.ringEv[slot]) == cudaSuccess) {
+      if (s.ringCum[slot] >= s.knownCum) { s.knownCount = s.countRing[slot]; s.knownCum = s.ringCum[slot]; }
+      break;
+    }
+  }
+  uint64_t upper = s.knownCount + (s.cumHits - s.knownCum);
+  if (s.slowCap != 0 && upper + n <= s.slowCap) return MMA_OK;
+  uint64_t actual = 0;
+  if (s.slowCap != 0) {
+    CK(cudaStreamSynchronize(ctx->sc));
+    u32 c = 0;
+    CK(cudaMemcpy(&c, &s.ctl->slowCount, sizeof(u32), cudaMemcpyDeviceToHost));
+    actual = c;
+    s.knownCount = actual; s.knownCum = s.cumHits;
+    if (actual + n <= s.slowCap) return MMA_OK;
+  }
+  uint64_t want = std::max<uint64_t>(std::max<uint64_t>(4ull * ctx->params.max_batch_hits, 1u << 16), 2 * (actual + n));
+  if (want > 0xFFFFFFF0ull) return ctx->fail(MMA_ERR_CAPACITY, "deferred read list would exceed 2^32 records");
+  u32 newCap = (u32)want;
+  DevBuf nk, no, nm, nn;
+  CK(nk.ensure((size_t)newCap * 8)); CK(no.ensure((size_t)newCap * 8)); CK(nm.ensure((size_t)newCap * 8)); CK(nn.ensure((size_t)newCap * 4));
+  if (actual) {
+    CK(cudaMemcpyAsync(nk.p, s.slowKey.p, actual * 8, cudaMemcpyDeviceToDevice, ctx->sc));
+    CK(cudaMemcpyAsync(no.p, s.slowOrd.p, actual * 8, cudaMemcpyDeviceToDevice, ctx->sc));
+    CK(cudaMemcpyAsync(nm.p, s.slowMask.p, actual * 8, cudaMemcpyDeviceToDevice, ctx->sc));
+    CK(cudaMemcpyAsync(nn.p, s.slowNh.p, actual * 4, cudaMemcpyDeviceToDevice, ctx->sc));
+  }
+  u32 newOpen = 1;
+  while (newOpen < 2ull * newCap && newOpen < 0x80000000u) newOpen <<= 1;
+  DevBuf nopen;
+  CK(nopen.ensure((size_t)newOpen * 8));
+  k_fill_u64<<<gridFor(newOpen, 256), 256, 0, ctx->sc>>>(nopen.as<u64>(), KEY_EMPTY, newOpen);
+  ctx->launches++;
+  if (s.openCap) {
+    KeySetView from = openView(s), to;
+    to.keys = nopen.as<u64>(); to.capMask = newOpen - 1;
+    k_keyset_rehash<<<gridFor(s.openCap, 256), 256, 0, ctx->sc>>>(from, to, s.ctl);
+    ctx->launches++;
+  }
+  CK(cudaStreamSynchronize(ctx->sc));
+  s.slowKey.release(); s.slowOrd.release(); s.slowMask.release(); s.slowNh.release(); s.openKeys.release();
+  s.slowKey = nk; s.slowOrd = no; s.slowMask = nm; s.slowNh = nn; s.openKeys = nopen;
+  s.slowCap = newCap; s.openCap = newOpen;
+  return MMA_OK;
+}
+
+template <typename MaskT>
+int launchBatch(mma_ctx *ctx, Sample &s, const HitView &h, MaskT *maskBuf) {
+  const Rules &r = ctx->rules;
+  TableView table = tableView(s.tableKeys, s.tableVals, ctx->tableCap, s.ctl);
+  TableView delta = tableView(s.deltaKeys, s.deltaVals, ctx->tableCap, s.ctl);
+  SlowView slow = slowView(s);
+  KeySetView open = openView(s);
+  const u32 gA = gridFor(h.n, ANNOTATE_THREADS);
+  {
+    mma_ctx::Timed t(ctx, TC_ANNOTATE);
+    if (r.mode == 0) k_annotate<0, MaskT><<<gA, ANNOTATE_THREADS, 0, ctx->sc>>>(ctx->index, h, r, maskBuf, table, s.ctl, slow);
+    else if (r.mode == 1) k_annotate<1, MaskT><<<gA, ANNOTATE_THREADS, 0, ctx->sc>>>(ctx->index, h, r, maskBuf, table, s.ctl, slow);
+    else k_annotate<2, MaskT><<<gA, ANNOTATE_THREADS, 0, ctx->sc>>>(ctx->index, h, r, maskBuf, table, s.ctl, slow);
+    ctx->launches++;
+  }
+  if (r.strategy == MMA_STRATEGY_DEFAULT) {
+    const u32 gR = gridFor(h.n, RESOLVE_THREADS);
+    const u32 gT = gridFor(ctx->tableCap, 256);
+    {
+      mma_ctx::Timed t(ctx, TC_RESOLVE);
+      k_resolve<MaskT><<<gR, RESOLVE_THREADS, 0, ctx->sc>>>(h, r, maskBuf, delta, s.ctl, slow, open, 0);
+      ctx->launches++;
+    }
+    {
+      mma_ctx::Timed t(ctx, TC_MERGE);
+      k_batch_mid<<<gT, 256, 0, ctx->sc>>>(delta, s.ctl);
+      ctx->launches++;
+    }
+    {
+      mma_ctx::Timed t(ctx, TC_RESOLVE);
+      k_resolve<MaskT><<<gR, RESOLVE_THREADS, 0, ctx->sc>>>(h, r, maskBuf, delta, s.ctl, slow, open, 1);
+      ctx->launches++;
+    }
+    {
+      mma_ctx::Timed t(ctx, TC_MERGE);
+      k_batch_merge<<<gT, 256, 0, ctx->sc>>>(delta, table, s.ctl, h.n);
+      ctx->launches++;
+    }
+  } else {
+    mma_ctx::Timed t(ctx, TC_MERGE);
+    k_batch_advance<<<1, 1, 0, ctx->sc>>>(s.ctl, h.n);
+    ctx->launches++;
+  }
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return ctx->fail(MMA_ERR_CUDA, std::string("kernel launch: ") + cudaGetErrorString(e));
+  return MMA_OK;
+}
+
+int afterBatch(mma_ctx *ctx, Sample &s, uint64_t n) {
+  s.cumHits += n;
+  s.touched = true;
+  ctx->hitsSubmitted += n;
+  const int slot = (int)(s.seq & 3);
+  CK(cudaMemcpyAsync(&s.countRing[slot], &s.ctl->slowCount, sizeof(u32), cudaMemcpyDeviceToHost, ctx->sc));
+  CK(cudaEventRecord(s.ringEv[slot], ctx->sc));
+  s.ringCum[slot] = s.cumHits;
+  s.ringUsed[slot] = true;
+  s.seq++;
+  return MMA_OK;
+}
+
+int checkSubmit(mma_ctx *ctx, uint32_t sample, const mma_hit_batch *b) {
+  if (!ctx) return MMA_ERR_INVALID;
+  if (!b) return ctx->fail(MMA_ERR_INVALID, "null batch");
+  if (!ctx->haveIndex) return ctx->fail(MMA_ERR_STATE, "mma_load_features must be called before hits are submitted");
+  if (sample >= ctx->samples.size()) return ctx->fail(MMA_ERR_INVALID, "sample index out of range");
+  if (b->n > ctx->params.max_batch_hits) return ctx->fail(MMA_ERR_INVALID, "batch larger than max_batch_hits");
+  if (b->n && (!b->start || !b->end || !b->meta || !b->nh || !b->read_key)) return ctx->fail(MMA_ERR_INVALID, "null hit array");
+  return MMA_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *mma_version(void) { return "mmannot_b200 0.1 (sm_100a)"; }
+
+const char *mma_last_error(const mma_ctx *ctx) { return ctx ? ctx->error.c_str() : g_createError.c_str(); }
+
+int mma_create(mma_ctx **out, const mma_params *p) {
+  if (!out || !p) { g_createError = "null argument"; return MMA_ERR_INVALID; }
+  *out = nullptr;
+  if (p->n_elements == 0 || p->n_elements > MMA_MAX_ELEMENTS || !p->elem_line || !p->elem_strand || !p->elem_vicinity) {
+    g_createError = "n_elements must be in 1..64 and the element tables must be given";
+    return MMA_ERR_INVALID;
+  }
+  if (p->strategy < 0 || p->strategy > 3) { g_createError = "unknown strategy"; return MMA_ERR_INVALID; }
+  if (p->strategy == MMA_STRATEGY_RATIO && p->n_elements > NH_SHIFT) {
+    g_createError = "-y ratio supports at most 40 elements in the Order section";
+    return MMA_ERR_INVALID;
+  }
+  if (p->n_samples == 0 || p->max_batch_hits == 0) { g_createError = "n_samples and max_batch_hits must be positive"; return MMA_ERR_INVALID; }
+  for (uint32_t i = 0; i < p->n_elements; ++i)
+    if (p->elem_strand[i] > 2 || p->elem_vicinity[i] > 2) { g_createError = "bad element table entry"; return MMA_ERR_INVALID; }
+  int nDev = 0;
+  cudaError_t e = cudaGetDeviceCount(&nDev);
+  if (e != cudaSuccess || nDev == 0) {
+    g_createError = std::string("no CUDA device available (") + cudaGetErrorString(e) + "); mmannot_b200 has no CPU fallback";
+    return MMA_ERR_NO_DEVICE;
+  }
+  if (p->device < 0 || p->device >= nDev) { g_createError = "device ordinal out of range"; return MMA_ERR_INVALID; }
+  mma_ctx *ctx = new mma_ctx();
+  ctx->params = *p;
+  ctx->device = p->device;
+  ctx->elemLine.assign(p->elem_line, p->elem_line + p->n_elements);
+  ctx->elemStrand.assign(p->elem_strand, p->elem_strand + p->n_elements);
+  ctx->elemVic.assign(p->elem_vicinity, p->elem_vicinity + p->n_elements);
+  ctx->params.elem_line = ctx->elemLine.data();
+  ctx->params.elem_strand = ctx->elemStrand.data();
+  ctx->params.elem_vicinity = ctx->elemVic.data();
+  Rules &r = ctx->rules;
+  r.strategy = p->strategy;
+  r.overlap = p->overlap;
+  r.mode = (p->overlap < 0.0f) ? 0 : (p->overlap < 1.0f) ? 1 : 2;  // mm:1974-1976
+  r.rescueThreshold = p->rescue_threshold;
+  r.rescue = (p->read_stats != 0 && p->rescue_threshold < 1.0f) ? 1 : 0;  // mm:491, 2025
+  r.nElements = p->n_elements;
+  ctx->wideMask = p->n_elements > 32;
+  ctx->tableCap = 1u << (p->table_log2 ? std::min<uint32_t>(std::max<uint32_t>(p->table_log2, 8), 26) : 16);
+  auto bail = [&](const char *what, cudaError_t err) {
+    g_createError = std::string(what) + ": " + cudaGetErrorString(err);
+    mma_destroy(ctx);
+    return MMA_ERR_CUDA;
+  };
+  if ((e = cudaSetDevice(ctx->device)) != cudaSuccess) return bail("cudaSetDevice", e);
+  if ((e = cudaStreamCreateWithFlags(&ctx->sc, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
+  if ((e = cudaStreamCreateWithFlags(&ctx->sh, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
+  for (int k = 0; k < 2; ++k) {
+    if ((e = cudaEventCreateWithFlags(&ctx->stage[k].copied, cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
+    if ((e = cudaEventCreateWithFlags(&ctx->stage[k].done, cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
+  }
+  ctx->samples.resize(p->n_samples);
+  *out = ctx;
+  return MMA_OK;
+}
+
+void mma_destroy(mma_ctx *ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  if (ctx->sc) cudaStreamSynchronize(ctx->sc);
+  if (ctx->sh) cudaStreamSynchronize(ctx->sh);
+  for (Sample &s : ctx->samples) {
+    if (s.ctl) cudaFree(s.ctl);
+    s.tableKeys.release(); s.tableVals.release(); s.deltaKeys.release(); s.deltaVals.release();
+    s.slowKey.release(); s.slowOrd.release(); s.slowMask.release(); s.slowNh.release(); s.openKeys.release();
+    if (s.countRing) cudaFreeHost(s.countRing);
+    for (int i = 0; i < 4; ++i) if (s.ringEv[i]) cudaEventDestroy(s.ringEv[i]);
+  }
+  for (int k = 0; k < 2; ++k) {
+    Staging &g = ctx->stage[k];
+    g.start.release(); g.end.release(); g.meta.release(); g.nh.release(); g.key.release(); g.mask.release();
+    if (g.copied) cudaEventDestroy(g.copied);
+    if (g.done) cudaEventDestroy(g.done);
+  }
+  ctx->feat.release(); ctx->chrInfo.release(); ctx->bins.release(); ctx->spanIdx.release();
+  ctx->dElemLine.release(); ctx->dElemStrand.release(); ctx->dElemVic.release();
+  ctx->collectTiming();
+  for (cudaEvent_t e : ctx->eventPool) cudaEventDestroy(e);
+  if (ctx->sc) cudaStreamDestroy(ctx->sc);
+  if (ctx->sh) cudaStreamDestroy(ctx->sh);
+  delete ctx;
+}
+
+void *mma_alloc_pinned(size_t bytes) {
+  void *p = nullptr;
+  if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) return nullptr;
+  return p;
+}
+void mma_free_pinned(void *p) {
+  if (p) cudaFreeHost(p);
+}
+
+int mma_load_features(mma_ctx *ctx, const mma_features *f) {
+  if (!ctx) return MMA_ERR_INVALID;
+  if (!f || f->n == 0 || !f->chr || !f->start || !f->end || !f->type || !f->strand) return ctx->fail(MMA_ERR_INVALID, "empty or null feature buffer");
+  if (f->n_chr == 0 || f->n_chr >= MMA_HIT_CHR_NONE) return ctx->fail(MMA_ERR_INVALID, "n_chr out of range");
+  CK(cudaSetDevice(ctx->device));
+  const uint32_t n = f->n, nChr = f->n_chr;
+  // host pass: validate the order, find chromosome ranges and extents
+  std::vector<u32> chrStart(nChr + 1, 0);
+  std::vector<uint64_t> extent(nChr, 0);
+  for (uint32_t i = 0; i < n; ++i) {
+    if (f->chr[i] >= nChr) return ctx->fail(MMA_ERR_INVALID, "feature chromosome id >= n_chr");
+    if (f->type[i] >= ctx->params.n_elements) return ctx->fail(MMA_ERR_INVALID, "feature type >= n_elements");
+    if (f->start[i] == 0xFFFFFFFFu || f->end[i] == 0xFFFFFFFFu) return ctx->fail(MMA_ERR_INVALID, "feature coordinate 0xFFFFFFFF is reserved");
+    if (i > 0 && (f->chr[i] < f->chr[i - 1] || (f->chr[i] == f->chr[i - 1] && f->start[i] < f->start[i - 1])))
+      return ctx->fail(MMA_ERR_INVALID, "features must be sorted by (chromosome, start)");
+    chrStart[f->chr[i] + 1]++;
+    extent[f->chr[i]] = std::max<uint64_t>(extent[f->chr[i]], std::max(f->start[i], f->end[i]));
+  }
+  for (uint32_t c = 0; c < nChr; ++c) chrStart[c + 1] += chrStart[c];
+  uint32_t shift = ctx->params.bin_shift;
+  if (shift == 0) {
+    uint64_t total = 0;
+    for (uint32_t c = 0; c < nChr; ++c) total += extent[c];
+    shift = 5;
+    while (shift < 20 && (total >> shift) > (1ull << 21)) ++shift;
+  }
+  shift = std::min<uint32_t>(std::max<uint32_t>(shift, 1), 24);
+  std::vector<u32> chrBinBase(nChr + 1, 0);
+  std::vector<uint2> chrInfo(nChr);
+  uint64_t entries = 0;
+  for (uint32_t c = 0; c < nChr; ++c) {
+    const uint64_t nb = (chrStart[c + 1] > chrStart[c]) ? (extent[c] >> shift) + 2 : 1;
+    chrBinBase[c] = (u32)entries;
+    chrInfo[c] = make_uint2((u32)entries, (u32)nb);
+    entries += nb + 1;
+    if (entries > 0x7FFFFFFFull) return ctx->fail(MMA_ERR_INVALID, "position index too large; raise bin_shift");
+  }
+  chrBinBase[nChr] = (u32)entries;
+
+  DevBuf dChr, dStart, dEnd, dType, dStrand, dChrStart, dChrBinBase, dSpanCount, dTotal;
+  auto cleanup = [&]() { dChr.release(); dStart.release(); dEnd.release(); dType.release(); dStrand.release(); dChrStart.release(); dChrBinBase.release(); dSpanCount.release(); dTotal.release(); };
+#define CKL(call)                                                                                  \
+  do {                                                                                             \
+    cudaError_t _e = (call);                                                                       \
+    if (_e != cudaSuccess) { cleanup(); return ctx->fail(MMA_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(_e)); } \
+  } while (0)
+  CKL(dChr.ensure((size_t)n * 4)); CKL(dStart.ensure((size_t)n * 4)); CKL(dEnd.ensure((size_t)n * 4));
+  CKL(dType.ensure(n)); CKL(dStrand.ensure(n));
+  CKL(dChrStart.ensure((size_t)(nChr + 1) * 4)); CKL(dChrBinBase.ensure((size_t)(nChr + 1) * 4));
+  CKL(dSpanCount.ensure((size_t)entries * 4)); CKL(dTotal.ensure(4));
+  CKL(ctx->feat.ensure((size_t)n * sizeof(uint4)));
+  CKL(ctx->chrInfo.ensure((size_t)nChr * sizeof(uint2)));
+  CKL(ctx->bins.ensure((size_t)entries * sizeof(uint2)));
+  CKL(ctx->dElemLine.ensure(ctx->elemLine.size() * 2)); CKL(ctx->dElemStrand.ensure(ctx->elemStrand.size())); CKL(ctx->dElemVic.ensure(ctx->elemVic.size()));
+  cudaStream_t st = ctx->sc;
+  CKL(cudaMemcpyAsync(dChr.p, f->chr, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+  CKL(cudaMemcpyAsync(dStart.p, f->start, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+  CKL(cudaMemcpyAsync(dEnd.p, f->end, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+  CKL(cudaMemcpyAsync(dType.p, f->type, n, cudaMemcpyHostToDevice, st));
+  CKL(cudaMemcpyAsync(dStrand.p, f->strand, n, cudaMemcpyHostToDevice, st));
+  CKL(cudaMemcpyAsync(dChrStart.p, chrStart.data(), (size_t)(nChr + 1) * 4, cudaMemcpyHostToDevice, st));
+  CKL(cudaMemcpyAsync(dChrBinBase.p, chrBinBase.data(), (size_t)(nChr + 1) * 4, cudaMemcpyHostToDevice, st));
+  CKL(cudaMemcpyAsync(ctx->chrInfo.p, chrInfo.data(), (size_t)nChr * sizeof(uint2), cudaMemcpyHostToDevice, st));
+  CKL(cudaMemcpyAsync(ctx->dElemLine.p, ctx->elemLine.data(), ctx->elemLine.size() * 2, cudaMemcpyHostToDevice, st));
+  CKL(cudaMemcpyAsync(ctx->dElemStrand.p, ctx->elemStrand.data(), ctx->elemStrand.size(), cudaMemcpyHostToDevice, st));
+  CKL(cudaMemcpyAsync(ctx->dElemVic.p, ctx->elemVic.data(), ctx->elemVic.size(), cudaMemcpyHostToDevice, st));
+  BuildView b;
+  b.chr = dChr.as<u32>(); b.start = dStart.as<u32>(); b.end = dEnd.as<u32>();
+  b.type = dType.as<uint8_t>(); b.strand = dStrand.as<uint8_t>();
+  b.elemLine = ctx->dElemLine.as<uint16_t>(); b.elemStrand = ctx->dElemStrand.as<uint8_t>(); b.elemVic = ctx->dElemVic.as<uint8_t>();
+  b.chrStart = dChrStart.as<u32>(); b.chrBinBase = dChrBinBase.as<u32>();
+  b.nFeat = n; b.nChr = nChr; b.shift = shift; b.nEntries = (u32)entries;
+  u32 total = 0;
+  {
+    mma_ctx::Timed t(ctx, TC_INDEX);
+    k_pack_features<<<gridFor(n, 256), 256, 0, st>>>(b, ctx->feat.as<uint4>());
+    k_prefix_max_end<<<nChr, 256, 0, st>>>(b, ctx->feat.as<uint4>());
+    k_build_bins<<<gridFor(entries, 128), 128, 0, st>>>(b, ctx->feat.as<uint4>(), ctx->bins.as<uint2>(), dSpanCount.as<u32>(), nullptr, 0);
+    k_scan_spans<<<1, 1024, 0, st>>>(dSpanCount.as<u32>(), ctx->bins.as<uint2>(), (u32)entries, dTotal.as<u32>());
+    ctx->launches += 4;
+  }
+  CKL(cudaMemcpyAsync(&total, dTotal.p, 4, cudaMemcpyDeviceToHost, st));
+  CKL(cudaStreamSynchronize(st));
+  CKL(ctx->spanIdx.ensure((size_t)std::max<u32>(total, 1) * 4));
+  {
+    mma_ctx::Timed t(ctx, TC_INDEX);
+    k_build_bins<<<gridFor(entries, 128), 128, 0, st>>>(b, ctx->feat.as<uint4>(), ctx->bins.as<uint2>(), dSpanCount.as<u32>(), ctx->spanIdx.as<u32>(), 1);
+    ctx->launches++;
+  }
+  CKL(cudaStreamSynchronize(st));
+  CKL(cudaGetLastError());
+#undef CKL
+  cleanup();
+  ctx->index.feat = ctx->feat.as<uint4>();
+  ctx->index.chrInfo = ctx->chrInfo.as<uint2>();
+  ctx->index.bins = ctx->bins.as<uint2>();
+  ctx->index.spanIdx = ctx->spanIdx.as<u32>();
+  ctx->index.nChr = nChr;
+  ctx->index.shift = shift;
+  ctx->indexBytes = (uint64_t)n * sizeof(uint4) + (uint64_t)nChr * sizeof(uint2) + entries * sizeof(uint2) + (uint64_t)total * 4;
+  ctx->haveIndex = true;
+  return MMA_OK;
+}
+
+uint64_t mma_index_bytes(const mma_ctx *ctx) { return ctx ? ctx->indexBytes : 0; }
+
+static int submitCommon(mma_ctx *ctx, uint32_t sample, const mma_hit_batch *b, bool onDevice) {
+  int rc = checkSubmit(ctx, sample, b);
+  if (rc) return rc;
+  CK(cudaSetDevice(ctx->device));
+  Sample &s = ctx->samples[sample];
+  if ((rc = initSample(ctx, s))) return rc;
+  const uint64_t n = b->n;
+  const uint64_t k = ctx->submitSeq;
+  Staging &g = ctx->stage[k & 1];
+  // buffers handed to the previous submit are free once its copy has landed
+  if (k > 0) CK(cudaEventSynchronize(ctx->stage[(k - 1) & 1].copied));
+  if (n == 0) return MMA_OK;
+  if ((rc = ensureDeferred(ctx, s, n))) return rc;
+  // this staging slot was last used by batch k-2
+  if (k > 1) CK(cudaEventSynchronize(g.done));
+  HitView h;
+  h.n = (u32)n;
+  if (onDevice) {
+    h.start = b->start; h.end = b->end; h.meta = b->meta; h.nh = b->nh; h.key = (const u64 *)b->read_key;
+    CK(cudaEventRecord(g.copied, ctx->sh));
+  } else {
+    const size_t cap = ctx->params.max_batch_hits;
+    CK(g.start.ensure(cap * 4)); CK(g.end.ensure(cap * 4)); CK(g.meta.ensure(cap * 4)); CK(g.nh.ensure(cap * 4)); CK(g.key.ensure(cap * 8));
+    CK(cudaMemcpyAsync(g.start.p, b->start, n * 4, cudaMemcpyHostToDevice, ctx->sh));
+    CK(cudaMemcpyAsync(g.end.p, b->end, n * 4, cudaMemcpyHostToDevice, ctx->sh));
+    CK(cudaMemcpyAsync(g.meta.p, b->meta, n * 4, cudaMemcpyHostToDevice, ctx->sh));
+    CK(cudaMemcpyAsync(g.nh.p, b->nh, n * 4, cudaMemcpyHostToDevice, ctx->sh));
+    CK(cudaMemcpyAsync(g.key.p, b->read_key, n * 8, cudaMemcpyHostToDevice, ctx->sh));
+    CK(cudaEventRecord(g.copied, ctx->sh));
+    CK(cudaStreamWaitEvent(ctx->sc, g.copied, 0));
+    h.start = g.start.as<u32>(); h.end = g.end.as<u32>(); h.meta = g.meta.as<u32>(); h.nh = g.nh.as<u32>(); h.key = g.key.as<u64>();
+  }
+  if (ctx->rules.strategy == MMA_STRATEGY_DEFAULT) CK(g.mask.ensure((size_t)ctx->params.max_batch_hits * (ctx->wideMask ? 8 : 4)));
+  if (ctx->wideMask) rc = launchBatch<u64>(ctx, s, h, g.mask.as<u64>());
+  else rc = launchBatch<u32>(ctx, s, h, g.mask.as<u32>());
+  if (rc) return rc;
+  CK(cudaEventRecord(g.done, ctx->sc));
+  if ((rc = afterBatch(ctx, s, n))) return rc;
+  ctx->submitSeq++;
+  return MMA_OK;
+}
+
+int mma_submit_hits(mma_ctx *ctx, uint32_t sample, const mma_hit_batch *batch) { return submitCommon(ctx, sample, batch, false); }
+int mma_submit_hits_device(mma_ctx *ctx, uint32_t sample, const mma_hit_batch *batch) { return submitCommon(ctx, sample, batch, true); }
+
+int mma_sync(mma_ctx *ctx) {
+  if (!ctx) return MMA_ERR_INVALID;
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaStreamSynchronize(ctx->sh));
+  CK(cudaStreamSynchronize(ctx->sc));
+  return MMA_OK;
+}
+
+void *mma_stream(mma_ctx *ctx) { return ctx ? (void *)ctx->sc : nullptr; }
+
+int mma_reset_sample(mma_ctx *ctx, uint32_t sample) {
+  if (!ctx) return MMA_ERR_INVALID;
+  if (sample >= ctx->samples.size()) return ctx->fail(MMA_ERR_INVALID, "sample index out of range");
+  CK(cudaSetDevice(ctx->device));
+  Sample &s = ctx->samples[sample];
+  if (!s.ctl) return MMA_OK;
+  const size_t tb = (size_t)ctx->tableCap * sizeof(u64);
+  CK(cudaMemsetAsync(s.ctl, 0, sizeof(SampleCtl), ctx->sc));
+  CK(cudaMemsetAsync(s.tableKeys.p, 0, tb, ctx->sc)); CK(cudaMemsetAsync(s.tableVals.p, 0, tb, ctx->sc));
+  CK(cudaMemsetAsync(s.deltaKeys.p, 0, tb, ctx->sc)); CK(cudaMemsetAsync(s.deltaVals.p, 0, tb, ctx->sc));
+  if (s.openCap) {
+    k_fill_u64<<<gridFor(s.openCap, 256), 256, 0, ctx->sc>>>(s.openKeys.as<u64>(), KEY_EMPTY, s.openCap);
+    ctx->launches++;
+  }
+  CK(cudaStreamSynchronize(ctx->sc));
+  s.cumHits = 0; s.knownCount = 0; s.knownCum = 0; s.seq = 0; s.touched = false;
+  for (int i = 0; i < 4; ++i) s.ringUsed[i] = false;
+  return MMA_OK;
+}
+
+static int finishDeferred(mma_ctx *ctx, Sample &s, u32 nSlow) {
+  const Rules &r = ctx->rules;
+  TableView table = tableView(s.tableKeys, s.tableVals, ctx->tableCap, s.ctl);
+  SlowView slow = slowView(s);
+  cudaStream_t st = ctx->sc;
+  // stable sort by ordinal, then by key  ==  ordered by (key, ordinal)
+  DevBuf permA, permB, keyA, keyB, tmp;
+  auto cleanup = [&]() { permA.release(); permB.release(); keyA.release(); keyB.release(); tmp.release(); };
+#define CKF(call)                                                                                  \
+  do {                                                                                             \
+    cudaError_t _e = (call);                                                                       \
+    if (_e != cudaSuccess) { cleanup(); return ctx->fail(MMA_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(_e)); } \
+  } while (0)
+  CKF(permA.ensure((size_t)nSlow * 4)); CKF(permB.ensure((size_t)nSlow * 4));
+  CKF(keyA.ensure((size_t)nSlow * 8)); CKF(keyB.ensure((size_t)nSlow * 8));
+  size_t tmpBytes = 0;
+  CKF(cub::DeviceRadixSort::SortPairs(nullptr, tmpBytes, keyA.as<u64>(), keyB.as<u64>(), permA.as<u32>(), permB.as<u32>(), (int)nSlow, 0, 64, st));
+  CKF(tmp.ensure(tmpBytes));
+  mma_ctx::Timed t(ctx, TC_FINISH);
+  const u32 g = gridFor(nSlow, 256);
+  k_iota<<<g, 256, 0, st>>>(permA.as<u32>(), nSlow);
+  CKF(cudaMemcpyAsync(keyA.p, slow.ord, (size_t)nSlow * 8, cudaMemcpyDeviceToDevice, st));
+  CKF(cub::DeviceRadixSort::SortPairs(tmp.p, tmpBytes, keyA.as<u64>(), keyB.as<u64>(), permA.as<u32>(), permB.as<u32>(), (int)nSlow, 0, 64, st));
+  k_gather_keys<<<g, 256, 0, st>>>(permB.as<u32>(), nSlow, slow.key, keyA.as<u64>());
+  CKF(cub::DeviceRadixSort::SortPairs(tmp.p, tmpBytes, keyA.as<u64>(), keyB.as<u64>(), permB.as<u32>(), permA.as<u32>(), (int)nSlow, 0, 64, st));
+  ctx->launches += 2;
+  const u32 *perm = permA.as<u32>();
+  if (r.strategy == MMA_STRATEGY_DEFAULT) {
+    k_slow_default<<<g, 256, 0, st>>>(perm, nSlow, slow, r, table, s.ctl);
+    ctx->launches++;
+  } else {  // random
+    DevBuf headOrd, headSorted, nHeadsDev, randDev;
+    auto cleanup2 = [&]() { headOrd.release(); headSorted.release(); nHeadsDev.release(); randDev.release(); };
+    cudaError_t e;
+    if ((e = headOrd.ensure((size_t)nSlow * 8)) != cudaSuccess || (e = headSorted.ensure((size_t)nSlow * 8)) != cudaSuccess ||
+        (e = nHeadsDev.ensure(4)) != cudaSuccess) { cleanup2(); cleanup(); return ctx->fail(MMA_ERR_CUDA, cudaGetErrorString(e)); }
+    cudaMemsetAsync(nHeadsDev.p, 0, 4, st);
+    k_slow_random_heads<<<g, 256, 0, st>>>(perm, nSlow, slow, headOrd.as<u64>(), nHeadsDev.as<u32>());
+    ctx->launches++;
+    u32 nHeads = 0;
+    cudaMemcpyAsync(&nHeads, nHeadsDev.p, 4, cudaMemcpyDeviceToHost, st);
+    if ((e = cudaStreamSynchronize(st)) != cudaSuccess) { cleanup2(); cleanup(); return ctx->fail(MMA_ERR_CUDA, cudaGetErrorString(e)); }
+    size_t tb2 = 0;
+    cub::DeviceRadixSort::SortKeys(nullptr, tb2, headOrd.as<u64>(), headSorted.as<u64>(), (int)nHeads, 0, 64, st);
+    DevBuf tmp2;
+    if ((e = tmp2.ensure(tb2 ? tb2 : 1)) != cudaSuccess) { cleanup2(); cleanup(); return ctx->fail(MMA_ERR_CUDA, cudaGetErrorString(e)); }
+    cub::DeviceRadixSort::SortKeys(tmp2.p, tb2, headOrd.as<u64>(), headSorted.as<u64>(), (int)nHeads, 0, 64, st);
+    // the reference's rand() stream (glibc TYPE_3 additive feedback generator, mm:1711; never seeded => seed 1)
+    std::vector<u32> stream((size_t)nHeads + 344);
+    {
+      u32 seed = ctx->params.rand_seed ? ctx->params.rand_seed : 1u;
+      std::vector<u32> &q = stream;
+      q[0] = seed;
+      for (int i = 1; i < 31; ++i) {
+        int32_t hi = (int32_t)q[i - 1] / 127773, lo = (int32_t)q[i - 1] % 127773;
+        int32_t w = 16807 * lo - 2836 * hi;
+        if (w < 0) w += 2147483647;
+        q[i] = (u32)w;
+      }
+      for (int i = 31; i < 34; ++i) q[i] = q[i - 31];
+      for (size_t i = 34; i < q.size(); ++i) q[i] = q[i - 31] + q[i - 3];
+      for (size_t i = 0; i < nHeads; ++i) q[i] = q[i + 344] >> 1;
+    }
+    if ((e = randDev.ensure((size_t)std::max<u32>(nHeads, 1) * 4)) != cudaSuccess) { tmp2.release(); cleanup2(); cleanup(); return ctx->fail(MMA_ERR_CUDA, cudaGetErrorString(e)); }
+    cudaMemcpyAsync(randDev.p, stream.data(), (size_t)nHeads * 4, cudaMemcpyHostToDevice, st);
+    k_slow_random_pick<<<g, 256, 0, st>>>(perm, nSlow, slow, headSorted.as<u64>(), nHeads, randDev.as<u32>(), r, table);
+    ctx->launches++;
+    e = cudaStreamSynchronize(st);
+    tmp2.release();
+    cleanup2();
+    if (e != cudaSuccess) { cleanup(); return ctx->fail(MMA_ERR_CUDA, cudaGetErrorString(e)); }
+  }
+  CKF(cudaStreamSynchronize(st));
+#undef CKF
+  cleanup();
+  return MMA_OK;
+}
+
+int mma_finish_sample(mma_ctx *ctx, uint32_t sample, mma_sample_result *out) {
+  if (!ctx) return MMA_ERR_INVALID;
+  if (!out) return ctx->fail(MMA_ERR_INVALID, "null result");
+  if (sample >= ctx->samples.size()) return ctx->fail(MMA_ERR_INVALID, "sample index out of range");
+  CK(cudaSetDevice(ctx->device));
+  Sample &s = ctx->samples[sample];
+  std::memset(out, 0, sizeof(*out));
+  s.rowMask.clear(); s.rowNh.clear(); s.rowCount.clear();
+  if (!s.ctl) return MMA_OK;  // nothing was ever submitted
+  CK(cudaStreamSynchronize(ctx->sh));
+  CK(cudaStreamSynchronize(ctx->sc));
+  SampleCtl hc;
+  CK(cudaMemcpy(&hc, s.ctl, sizeof(hc), cudaMemcpyDeviceToHost));
+  if (hc.overflow) return ctx->fail(MMA_ERR_CAPACITY, "a device table overflowed (combination table, deferred list or NH range under -y ratio)");
+  if (hc.slowCount > 0) {
+    int rc = finishDeferred(ctx, s, hc.slowCount);
+    if (rc) return rc;
+    // the deferred records are consumed: a later finish must not count them twice
+    CK(cudaMemsetAsync(&s.ctl->slowCount, 0, sizeof(u32), ctx->sc));
+    CK(cudaMemsetAsync(&s.ctl->slowCountAtBatch, 0, sizeof(u32), ctx->sc));
+    CK(cudaStreamSynchronize(ctx->sc));
+    CK(cudaMemcpy(&hc, s.ctl, sizeof(hc), cudaMemcpyDeviceToHost));
+    if (hc.overflow) return ctx->fail(MMA_ERR_CAPACITY, "the combination table overflowed");
+    s.knownCount = 0; s.knownCum = s.cumHits;
+  }
+  std::vector<u64> keys(ctx->tableCap), vals(ctx->tableCap);
+  CK(cudaMemcpy(keys.data(), s.tableKeys.p, (size_t)ctx->tableCap * 8, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(vals.data(), s.tableVals.p, (size_t)ctx->tableCap * 8, cudaMemcpyDeviceToHost));
+  const bool ratio = ctx->rules.strategy == MMA_STRATEGY_RATIO;
+  const u64 lowMask = (1ull << NH_SHIFT) - 1;
+  for (u32 i = 0; i < ctx->tableCap; ++i) {
+    if (!keys[i]) continue;
+    s.rowMask.push_back(ratio ? (keys[i] & lowMask) : keys[i]);
+    s.rowNh.push_back(ratio ? (uint32_t)(keys[i] >> NH_SHIFT) : 0u);
+    s.rowCount.push_back(vals[i]);
+  }
+  out->stats.n_hits = hc.stats[ST_HITS];
+  out->stats.n_reads = hc.stats[ST_READS];
+  out->stats.n_unique = hc.stats[ST_UNIQUE];
+  out->stats.n_ambiguous = hc.stats[ST_AMBIGUOUS];
+  out->stats.n_multiple = hc.stats[ST_MULTIPLE];
+  out->stats.n_unassigned = hc.stats[ST_UNASSIGNED];
+  out->stats.n_rescued = hc.stats[ST_RESCUED];
+  out->n_rows = s.rowMask.size();
+  out->row_mask = s.rowMask.data();
+  out->row_nh = s.rowNh.data();
+  out->row_count = s.rowCount.data();
+  return MMA_OK;
+}
+
+int mma_dense_counts(mma_ctx *ctx, uint32_t sample, const uint64_t *mask, const uint32_t *nh, uint64_t n, uint64_t *out_dev) {
+  if (!ctx) return MMA_ERR_INVALID;
+  if (sample >= ctx->samples.size()) return ctx->fail(MMA_ERR_INVALID, "sample index out of range");
+  if (n == 0) return MMA_OK;
+  if (!mask || !out_dev) return ctx->fail(MMA_ERR_INVALID, "null argument");
+  CK(cudaSetDevice(ctx->device));
+  Sample &s = ctx->samples[sample];
+  int rc = initSample(ctx, s);
+  if (rc) return rc;
+  const bool ratio = ctx->rules.strategy == MMA_STRATEGY_RATIO;
+  std::vector<u64> ck(n);
+  for (uint64_t i = 0; i < n; ++i) ck[i] = mask[i] | ((ratio && nh) ? ((u64)nh[i] << NH_SHIFT) : 0ull);
+  DevBuf d;
+  CK(d.ensure(n * 8));
+  CK(cudaMemcpyAsync(d.p, ck.data(), n * 8, cudaMemcpyHostToDevice, ctx->sc));
+  k_dense_counts<<<gridFor(n, 256), 256, 0, ctx->sc>>>(tableView(s.tableKeys, s.tableVals, ctx->tableCap, s.ctl), d.as<u64>(), n, (u64 *)out_dev);
+  ctx->launches++;
+  cudaError_t e = cudaStreamSynchronize(ctx->sc);
+  d.release();
+  if (e != cudaSuccess) return ctx->fail(MMA_ERR_CUDA, cudaGetErrorString(e));
+  return MMA_OK;
+}
+
+int mma_timing_enable(mma_ctx *ctx, int on) {
+  if (!ctx) return MMA_ERR_INVALID;
+  ctx->timing = on != 0;
+  return MMA_OK;
+}
+int mma_timing_reset(mma_ctx *ctx) {
+  if (!ctx) return MMA_ERR_INVALID;
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaStreamSynchronize(ctx->sc));
+  ctx->collectTiming();
+  for (int i = 0; i < TC_N; ++i) ctx->ms[i] = 0;
+  ctx->launches = 0;
+  ctx->hitsSubmitted = 0;
+  return MMA_OK;
+}
+int mma_timing_get(mma_ctx *ctx, mma_timing *out) {
+  if (!ctx || !out) return MMA_ERR_INVALID;
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaStreamSynchronize(ctx->sc));
+  ctx->collectTiming();
+  out->ms_index = ctx->ms[TC_INDEX];
+  out->ms_annotate = ctx->ms[TC_ANNOTATE];
+  out->ms_resolve = ctx->ms[TC_RESOLVE];
+  out->ms_merge = ctx->ms[TC_MERGE];
+  out->ms_finish = ctx->ms[TC_FINISH];
+  out->launches = ctx->launches;
+  out->hits = ctx->hitsSubmitted;
+  return MMA_OK;
+}
+
+}  // extern "C"

@@ -189,3 +189,30 @@ def read_hits(annotation, path, strandedness="F", fmt=0, batch=1 << 20):
 def name_key(name):
     b = name.encode() if isinstance(name, str) else name
     return int(lib().mmh_name_key(b, len(b)))
+
+
+class ElementTable:
+    """Element table without a config file behind it (e.g. loaded from a fixture)."""
+
+    def __init__(self, elem_line, elem_strand, elem_vicinity, names=None):
+        self.elem_line = np.ascontiguousarray(elem_line, np.uint16)
+        self.elem_strand = np.ascontiguousarray(elem_strand, np.uint8)
+        self.elem_vicinity = np.ascontiguousarray(elem_vicinity, np.uint8)
+        self.n_elements = len(self.elem_line)
+        self.names = list(names) if names is not None else ["e%d" % i for i in range(self.n_elements)]
+
+    def row_name(self, mask):
+        return "--".join(self.names[i] for i in range(self.n_elements) if (int(mask) >> i) & 1)
+
+
+class FeatureArrays:
+    """Feature buffer without a GTF behind it."""
+
+    def __init__(self, chr, start, end, type, strand, n_chr):
+        self.chr = np.ascontiguousarray(chr, np.uint32)
+        self.start = np.ascontiguousarray(start, np.uint32)
+        self.end = np.ascontiguousarray(end, np.uint32)
+        self.type = np.ascontiguousarray(type, np.uint8)
+        self.strand = np.ascontiguousarray(strand, np.uint8)
+        self.n_chr = int(n_chr)
+        self.n = len(self.start)
