@@ -12,7 +12,8 @@ CXXFLAGS  := -O3 -std=c++17 -fPIC -Wall -Wextra -Iinclude
 NVFLAGS   := $(ARCH) -O3 -std=c++17 -lineinfo -Xcompiler -fPIC -Iinclude
 
 HOST_SRC  := $(wildcard mmannot_b200/csrc/host/*.cpp)
-HOST_LIB_SRC := $(filter-out mmannot_b200/csrc/host/main.cpp,$(HOST_SRC))
+CLI_SRC   := mmannot_b200/csrc/host/main.cpp mmannot_b200/csrc/host/counter.cpp
+HOST_LIB_SRC := $(filter-out $(CLI_SRC),$(HOST_SRC))
 HOST_HDR  := $(wildcard mmannot_b200/csrc/host/*.hpp) $(wildcard include/*.h)
 CU_SRC    := $(wildcard mmannot_b200/csrc/*.cu)
 CU_HDR    := $(wildcard mmannot_b200/csrc/*.cuh) $(wildcard include/*.h)
@@ -32,9 +33,9 @@ mmannot_b200/lib/libmmannot_b200.so: $(CU_SRC) $(CU_HDR)
 	@mkdir -p mmannot_b200/lib
 	$(NVCC) $(NVFLAGS) -shared -o $@ $(CU_SRC)
 
-mmannot_b200/bin/mmannot_b200: mmannot_b200/csrc/host/main.cpp mmannot_b200/lib/libmmannot_host.so mmannot_b200/lib/libmmannot_b200.so
+mmannot_b200/bin/mmannot_b200: $(CLI_SRC) $(HOST_HDR) mmannot_b200/lib/libmmannot_host.so mmannot_b200/lib/libmmannot_b200.so
 	@mkdir -p mmannot_b200/bin
-	$(CXX) $(CXXFLAGS) -o $@ mmannot_b200/csrc/host/main.cpp -Lmmannot_b200/lib -lmmannot_host -lmmannot_b200 -lz -pthread -Wl,-rpath,'$$ORIGIN/../lib'
+	$(CXX) $(CXXFLAGS) -o $@ $(CLI_SRC) -Lmmannot_b200/lib -lmmannot_host -lmmannot_b200 -lz -pthread -Wl,-rpath,'$$ORIGIN/../lib'
 
 oracle/_build/liboracle.so: oracle/oracle.c oracle/oracle.h
 	@mkdir -p oracle/_build

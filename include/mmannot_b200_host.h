@@ -58,6 +58,27 @@ size_t mmh_reader_warnings(mmh_reader *r, char *buf, size_t cap);
 
 uint64_t mmh_name_key(const char *name, size_t len);
 
+/* ---- synthetic inputs of the benchmark shapes (BASELINE.json configs 2-5) ---- */
+typedef struct mmh_synth mmh_synth;
+typedef struct mmh_synth_reads {
+  uint32_t max_nh;
+  int32_t paired;       /* two records per placement, mate flags set */
+  int32_t flip_mate2;   /* store mate 2 with the strand bit flipped (-s FR as -s F for the reference) */
+  int32_t rna_seq;      /* read length 50..150 instead of 18..30 */
+  double p_in_feature;  /* probability that a placement falls inside a gene */
+  double p_same_class;  /* probability that all hits of a multi-mapper fall into one gene class */
+} mmh_synth_reads;
+/* shape: "tair10" | "hs38" | "flybase6"; gene_scale 1.0 = full-size annotation */
+int mmh_synth_create(const char *shape, uint64_t seed, double gene_scale, mmh_synth **out);
+void mmh_synth_free(mmh_synth *s);
+uint64_t mmh_synth_n_genes(const mmh_synth *s);
+int mmh_synth_write_annotation(const mmh_synth *s, const char *path);
+int mmh_synth_write_bam(const mmh_synth *s, const char *path, uint64_t first_read, uint64_t n_reads, const mmh_synth_reads *spec, int coordinate_sorted);
+uint64_t mmh_synth_count_hits(const mmh_synth *s, uint64_t first_read, uint64_t n_reads, const mmh_synth_reads *spec);
+/* packed hits of reads [first_read, first_read + n_reads), identical to decoding the BAM written for them */
+uint64_t mmh_synth_fill_hits(const mmh_synth *s, const mmh_annotation *a, char strandedness, uint64_t first_read, uint64_t n_reads,
+                             const mmh_synth_reads *spec, uint64_t cap, uint32_t *start, uint32_t *end, uint32_t *meta, uint32_t *nh, uint64_t *read_key);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,131 @@
+#include "counter.hpp"
+
+#include <algorithm>
+#include <cstdio>
+#include <iomanip>
+#include <sstream>
+
+namespace mmb {
+
+std::string withThousands(uint64_t n) {
+  std::string digits = std::to_string(n), out;
+  for (size_t i = 0; i < digits.size(); ++i) {
+    if (i && (digits.size() - i) % 3 == 0) out += ',';
+    out += digits[i];
+  }
+  return out;
+}
+
+namespace {
+
+// printStats, mm:139-143
+void printStats(std::ostream &log, uint64_t n, const char *label, uint64_t total) {
+  unsigned int size = static_cast<unsigned int>(std::log10(static_cast<double>(total)) + 1);
+  size += static_cast<unsigned int>(size / 3.0);
+  char pct[64];
+  std::snprintf(pct, sizeof(pct), "%5.1f", static_cast<double>(static_cast<float>(n) / total * 100));
+  log << "\t" << label << std::setw(static_cast<int>(size)) << withThousands(n) << " (" << pct << "%)\n";
+}
+
+bool allocPinned(HitBuffers &b, size_t cap) {
+  b.capacity = cap;
+  b.start = static_cast<uint32_t *>(mma_alloc_pinned(cap * 4));
+  b.end = static_cast<uint32_t *>(mma_alloc_pinned(cap * 4));
+  b.meta = static_cast<uint32_t *>(mma_alloc_pinned(cap * 4));
+  b.nh = static_cast<uint32_t *>(mma_alloc_pinned(cap * 4));
+  b.key = static_cast<uint64_t *>(mma_alloc_pinned(cap * 8));
+  return b.start && b.end && b.meta && b.nh && b.key;
+}
+void freePinned(HitBuffers &b) {
+  mma_free_pinned(b.start); mma_free_pinned(b.end); mma_free_pinned(b.meta); mma_free_pinned(b.nh); mma_free_pinned(b.key);
+  b = HitBuffers();
+}
+
+}  // namespace
+
+Counter::Counter(mma_ctx *ctx, const FeatureTable &features, const Config &config, const RunOptions &opt)
+    : ctx_(ctx), features_(features), config_(config), opt_(opt), stats_() {
+  allocPinned(pinned_[0], opt.batchHits);
+  allocPinned(pinned_[1], opt.batchHits);
+}
+
+Counter::~Counter() {
+  freePinned(pinned_[0]);
+  freePinned(pinned_[1]);
+}
+
+bool Counter::read(const std::string &fileName, uint32_t column, std::string &err, std::ostream &log) {
+  fileName_ = fileName;
+  counts_.clear();
+  stats_ = mma_sample_stats();
+  if (!pinned_[0].start || !pinned_[1].key) { err = "Cannot allocate page-locked hit buffers."; return false; }
+  XamReader reader(fileName, opt_.format, opt_.strandedness, features_);
+  if (!reader.open(err)) return false;
+  log << (reader.isBam() ? "Reading BAM file " : "Reading SAM file ") << fileName << std::endl;
+  if (mma_reset_sample(ctx_, column) != MMA_OK) { err = mma_last_error(ctx_); return false; }
+  // decode batch k+1 on the host while batch k is copied and annotated on the device
+  for (unsigned which = 0;; which ^= 1) {
+    const HitBuffers &buf = pinned_[which];
+    size_t n = reader.nextBatch(buf, nullptr);
+    std::string w = reader.takeWarnings();
+    if (!w.empty()) log << w;
+    if (n == 0) break;
+    mma_hit_batch b;
+    b.n = n; b.start = buf.start; b.end = buf.end; b.meta = buf.meta; b.nh = buf.nh; b.read_key = buf.key;
+    if (mma_submit_hits(ctx_, column, &b) != MMA_OK) { err = mma_last_error(ctx_); return false; }
+    if (opt_.progress) log << "\t" << withThousands(reader.recordsRead()) << " lines read.\r" << std::flush;
+  }
+  log << "\t" << withThousands(reader.recordsRead()) << " lines read, done." << std::endl;
+  mma_sample_result res;
+  if (mma_finish_sample(ctx_, column, &res) != MMA_OK) { err = mma_last_error(ctx_); return false; }
+  stats_ = res.stats;
+  // regionCounts value of every element set (mm:1658, 1730): count * 1/NH summed over NH under -y ratio
+  std::vector<size_t> order(res.n_rows);
+  for (size_t i = 0; i < order.size(); ++i) order[i] = i;
+  std::sort(order.begin(), order.end(), [&res](size_t a, size_t b) {
+    return res.row_mask[a] != res.row_mask[b] ? res.row_mask[a] < res.row_mask[b] : res.row_nh[a] < res.row_nh[b];
+  });
+  for (size_t i : order) {
+    const double w = res.row_nh[i] ? 1.0 / res.row_nh[i] : 1.0;
+    counts_[res.row_mask[i]] += static_cast<double>(res.row_count[i]) * w;
+  }
+  return true;
+}
+
+void Counter::dump(std::ostream &log) const {
+  log << "Results for " << fileName_ << ":" << std::endl;
+  if (stats_.n_hits == 0) {
+    log << "\tNo hit." << std::endl;
+    return;
+  }
+  log << "\t# reads:                       " << withThousands(stats_.n_reads) << "\n";
+  printStats(log, stats_.n_unique, "# uniquely mapped reads:       ", stats_.n_reads);
+  printStats(log, stats_.n_rescued, "# multi-mapping rescued reads: ", stats_.n_reads);
+  log << "\t# hits:                        " << withThousands(stats_.n_hits) << "\n";
+  printStats(log, stats_.n_ambiguous, "# ambiguous hits:              ", stats_.n_hits);
+  printStats(log, stats_.n_unassigned, "# unassigned hits:             ", stats_.n_hits);
+}
+
+void TableCount::addCounter(const Counter &counter) {
+  for (const auto &kv : counter.getCounts()) {
+    std::vector<size_t> elements;
+    for (size_t i = 0; i < 64; ++i) if ((kv.first >> i) & 1) elements.push_back(i);
+    std::vector<unsigned int> &row = rows_[elements];
+    if (row.empty()) row.assign(nInputs_, 0);
+    row[nColumns_] = static_cast<unsigned int>(std::round(kv.second));
+  }
+  ++nColumns_;
+}
+
+void TableCount::dump(std::ostream &out, const std::vector<std::string> &samples) const {
+  out << "Type";
+  for (const std::string &s : samples) out << "\t" << s;
+  out << "\n";
+  for (const auto &row : rows_) {
+    for (size_t k = 0; k < row.first.size(); ++k) out << (k ? "--" : "") << config_.getName(row.first[k]);
+    for (unsigned int v : row.second) out << "\t" << v;
+    out << "\n";
+  }
+}
+
+}  // namespace mmb

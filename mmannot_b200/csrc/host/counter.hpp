@@ -1,0 +1,65 @@
+// Host mirror of the reference's Counter / TableCount (mmannot.cpp:1653-1901) on top of the
+// device C ABI.  Same method names and meaning: Counter::read(file) annotates one input,
+// dump() prints its statistics, TableCount::addCounter()/dump() build and print the table.
+// The per-hit and per-read work happens on the GPU (mma_submit_hits / mma_finish_sample).
+#pragma once
+#include <cmath>
+#include <map>
+#include <ostream>
+#include <string>
+#include <vector>
+
+#include "annotation.hpp"
+#include "config.hpp"
+#include "mmannot_b200.h"
+#include "xam.hpp"
+
+namespace mmb {
+
+struct RunOptions {
+  Strandedness strandedness = Strandedness::F;  // mm:1938
+  ReadsFormat format = ReadsFormat::UNKNOWN;
+  int strategy = MMA_STRATEGY_DEFAULT;
+  float overlap = -1.0f;          // mm:1932
+  float rescueThreshold = 1.0f;   // mm:1933
+  bool readStats = false, intervalStats = false, progress = false;
+  uint32_t batchHits = 1u << 22;
+};
+
+std::string withThousands(uint64_t n);  // the comma_numpunct locale of mm:111-115, 2092-2093
+
+class Counter {
+ public:
+  Counter(mma_ctx *ctx, const FeatureTable &features, const Config &config, const RunOptions &opt);
+  ~Counter();
+  // Annotates one SAM/BAM file as sample `column`; false + message on a fatal problem.
+  bool read(const std::string &fileName, uint32_t column, std::string &err, std::ostream &log);
+  void dump(std::ostream &log) const;  // mm:1806-1818
+  // element set (bitmask) -> the reference's regionCounts value
+  const std::map<uint64_t, double> &getCounts() const { return counts_; }
+  const mma_sample_stats &getStats() const { return stats_; }
+
+ private:
+  mma_ctx *ctx_;
+  const FeatureTable &features_;
+  const Config &config_;
+  RunOptions opt_;
+  std::string fileName_;
+  mma_sample_stats stats_;
+  std::map<uint64_t, double> counts_;
+  HitBuffers pinned_[2];
+};
+
+class TableCount {
+ public:
+  TableCount(const Config &config, uint32_t nInputs) : config_(config), nInputs_(nInputs), nColumns_(0) {}
+  void addCounter(const Counter &counter);                                     // mm:1861-1876
+  void dump(std::ostream &out, const std::vector<std::string> &samples) const;  // mm:1877-1900
+
+ private:
+  const Config &config_;
+  uint32_t nInputs_, nColumns_;
+  std::map<std::vector<size_t>, std::vector<unsigned int> > rows_;  // ordered like the reference's sorted lineNames
+};
+
+}  // namespace mmb

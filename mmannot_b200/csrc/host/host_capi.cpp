@@ -6,6 +6,7 @@
 
 #include "annotation.hpp"
 #include "config.hpp"
+#include "synth.hpp"
 #include "xam.hpp"
 
 using namespace mmb;
@@ -13,6 +14,7 @@ using namespace mmb;
 struct mmh_config { Config config; };
 struct mmh_annotation { FeatureTable table; std::string warnings; };
 struct mmh_reader { XamReader *reader; };
+struct mmh_synth { SynthGenome *genome; };
 
 namespace {
 thread_local std::string g_error;
@@ -96,5 +98,40 @@ uint64_t mmh_reader_records(const mmh_reader *r) { return r->reader->recordsRead
 size_t mmh_reader_warnings(mmh_reader *r, char *buf, size_t cap) { return copyOut(r->reader->takeWarnings(), buf, cap); }
 
 uint64_t mmh_name_key(const char *name, size_t len) { return name_key(name, len); }
+
+static SynthReadSpec toSpec(const mmh_synth_reads *r) {
+  SynthReadSpec s;
+  if (r) {
+    s.maxNH = r->max_nh; s.paired = r->paired != 0; s.flipMate2 = r->flip_mate2 != 0; s.rnaSeq = r->rna_seq != 0;
+    s.pInFeature = r->p_in_feature; s.pSameClass = r->p_same_class;
+  }
+  return s;
+}
+static Strandedness toStrand(char c) { return c == 'U' ? Strandedness::U : c == 'R' ? Strandedness::R : Strandedness::F; }
+
+int mmh_synth_create(const char *shape, uint64_t seed, double gene_scale, mmh_synth **out) {
+  SynthGenome *g = new SynthGenome(shape, seed, gene_scale);
+  if (!g->ok()) { g_error = std::string("unknown synthetic shape '") + shape + "'"; delete g; return -1; }
+  *out = new mmh_synth{g};
+  return 0;
+}
+void mmh_synth_free(mmh_synth *s) {
+  if (s) { delete s->genome; delete s; }
+}
+uint64_t mmh_synth_n_genes(const mmh_synth *s) { return s->genome->genes.size(); }
+int mmh_synth_write_annotation(const mmh_synth *s, const char *path) { s->genome->writeAnnotation(path); return 0; }
+int mmh_synth_write_bam(const mmh_synth *s, const char *path, uint64_t first_read, uint64_t n_reads, const mmh_synth_reads *spec, int coordinate_sorted) {
+  if (!s->genome->writeBam(path, first_read, n_reads, toSpec(spec), coordinate_sorted != 0)) { g_error = std::string("cannot write '") + path + "'"; return -1; }
+  return 0;
+}
+uint64_t mmh_synth_count_hits(const mmh_synth *s, uint64_t first_read, uint64_t n_reads, const mmh_synth_reads *spec) {
+  return s->genome->countHits(first_read, n_reads, toSpec(spec));
+}
+uint64_t mmh_synth_fill_hits(const mmh_synth *s, const mmh_annotation *a, char strandedness, uint64_t first_read, uint64_t n_reads,
+                             const mmh_synth_reads *spec, uint64_t cap, uint32_t *start, uint32_t *end, uint32_t *meta, uint32_t *nh, uint64_t *read_key) {
+  HitBuffers b;
+  b.start = start; b.end = end; b.meta = meta; b.nh = nh; b.key = read_key; b.capacity = cap;
+  return s->genome->fillHits(a->table, toStrand(strandedness), first_read, n_reads, toSpec(spec), b);
+}
 
 }  // extern "C"

@@ -216,3 +216,80 @@ class FeatureArrays:
         self.strand = np.ascontiguousarray(strand, np.uint8)
         self.n_chr = int(n_chr)
         self.n = len(self.start)
+
+
+class _SynthReads(C.Structure):
+    _fields_ = [("max_nh", C.c_uint32), ("paired", C.c_int32), ("flip_mate2", C.c_int32), ("rna_seq", C.c_int32),
+                ("p_in_feature", C.c_double), ("p_same_class", C.c_double)]
+
+
+class Synth:
+    """Synthetic annotation + reads of a benchmark shape ("tair10", "hs38", "flybase6")."""
+
+    def __init__(self, shape, seed, gene_scale=1.0, max_nh=20, paired=False, flip_mate2=False, rna_seq=False,
+                 p_in_feature=0.5, p_same_class=0.6):
+        L = lib()
+        L.mmh_synth_create.argtypes = [C.c_char_p, C.c_uint64, C.c_double, C.POINTER(C.c_void_p)]
+        L.mmh_synth_free.argtypes = [C.c_void_p]
+        L.mmh_synth_n_genes.argtypes = [C.c_void_p]
+        L.mmh_synth_n_genes.restype = C.c_uint64
+        L.mmh_synth_write_annotation.argtypes = [C.c_void_p, C.c_char_p]
+        L.mmh_synth_write_bam.argtypes = [C.c_void_p, C.c_char_p, C.c_uint64, C.c_uint64, C.POINTER(_SynthReads), C.c_int]
+        L.mmh_synth_count_hits.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.POINTER(_SynthReads)]
+        L.mmh_synth_count_hits.restype = C.c_uint64
+        L.mmh_synth_fill_hits.argtypes = [C.c_void_p, C.c_void_p, C.c_char, C.c_uint64, C.c_uint64, C.POINTER(_SynthReads), C.c_uint64] + [C.c_void_p] * 5
+        L.mmh_synth_fill_hits.restype = C.c_uint64
+        self.shape = shape
+        self.spec = _SynthReads(max_nh, int(paired), int(flip_mate2), int(rna_seq), p_in_feature, p_same_class)
+        self._h = C.c_void_p()
+        if L.mmh_synth_create(shape.encode(), seed, gene_scale, C.byref(self._h)) != 0:
+            raise _err()
+        self.n_genes = L.mmh_synth_n_genes(self._h)
+
+    def write_annotation(self, path):
+        lib().mmh_synth_write_annotation(self._h, os.fsencode(path))
+
+    def write_bam(self, path, first_read, n_reads, coordinate_sorted=False):
+        if lib().mmh_synth_write_bam(self._h, os.fsencode(path), first_read, n_reads, C.byref(self.spec), int(coordinate_sorted)) != 0:
+            raise _err()
+
+    def count_hits(self, first_read, n_reads):
+        return int(lib().mmh_synth_count_hits(self._h, first_read, n_reads, C.byref(self.spec)))
+
+    def fill_hits(self, annotation, strandedness, first_read, n_reads, out=None, offset=0):
+        """Packed hits of the read range.  `out` = dict of preallocated arrays (filled at `offset`) or None."""
+        if out is None:
+            n = self.count_hits(first_read, n_reads)
+            out = {"start": np.empty(n, np.uint32), "end": np.empty(n, np.uint32), "meta": np.empty(n, np.uint32),
+                   "nh": np.empty(n, np.uint32), "read_key": np.empty(n, np.uint64)}
+        cap = len(out["start"]) - offset
+        ptrs = [out[k][offset:].ctypes.data for k in ("start", "end", "meta", "nh", "read_key")]
+        n = lib().mmh_synth_fill_hits(self._h, annotation._h, strandedness.encode()[0:1], first_read, n_reads, C.byref(self.spec), cap, *ptrs)
+        return out, int(n)
+
+    def hits(self, annotation, strandedness, first_read, n_reads, threads=1):
+        """All hits of the range as one Hits object; `threads` > 1 fills disjoint slices in parallel."""
+        if threads <= 1 or n_reads < 4 * threads:
+            out, n = self.fill_hits(annotation, strandedness, first_read, n_reads)
+            return Hits(*[out[k][:n] for k in ("start", "end", "meta", "nh", "read_key")])
+        from concurrent.futures import ThreadPoolExecutor
+        chunks = []
+        step = (n_reads + threads - 1) // threads
+        for t in range(threads):
+            a = first_read + t * step
+            b = min(first_read + n_reads, a + step)
+            if a < b:
+                chunks.append((a, b - a))
+        with ThreadPoolExecutor(threads) as ex:
+            counts = list(ex.map(lambda c: self.count_hits(*c), chunks))
+            total = sum(counts)
+            out = {"start": np.empty(total, np.uint32), "end": np.empty(total, np.uint32), "meta": np.empty(total, np.uint32),
+                   "nh": np.empty(total, np.uint32), "read_key": np.empty(total, np.uint64)}
+            offs = np.concatenate([[0], np.cumsum(counts)[:-1]]).astype(np.int64)
+            list(ex.map(lambda co: self.fill_hits(annotation, strandedness, co[0][0], co[0][1], out, int(co[1])), zip(chunks, offs)))
+        return Hits(*[out[k] for k in ("start", "end", "meta", "nh", "read_key")])
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().mmh_synth_free(self._h)
+            self._h = None
