@@ -1,0 +1,410 @@
+#!/usr/bin/env python
+"""Benchmark of the read-annotation hot path (BASELINE.json metric: alignment records/s annotated).
+
+A "step" is one pass of the hot path over one whole sample: Counter::clear, every hit batch through
+scan + addCount (mma_submit_hits*), the end-of-file flush and the table read-back (mma_finish_sample),
+and for N > 1 the cross-GPU merge of the integer tables.
+
+    value     : hits/s with the packed hit buffers already resident in HBM (CUDA events, max over ranks)
+    e2e       : hits/s through mma_submit_hits with HOST (page-locked) hit buffers; the host->device copies of
+                every batch and the device->host read of the table are inside the timed region
+    roofline  : the dominant kernel's algorithmic bytes / its average launch duration (CUDA events on the
+                library's own compute stream) against the measured HBM copy peak (MEASURED_PEAKS.json)
+    cpu_baseline : the reference itself (oracle/_ref, compiled from /root/reference in the build container)
+                timed on this box's host cores on a bounded sample of the same workload
+
+`--impl reference` times only the reference's CPU path (same workload/metric/unit).
+Workload: BASELINE.json configs[1] -- synthetic sRNA-Seq single-end reads (NH <= 20) on a TAIR10-shaped
+annotation with configTAIR10.txt, 50 M reads per GPU, name-grouped (mapper order).
+"""
+import argparse
+import json
+import os
+import shutil
+import statistics
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (shape, config key, seed, reads per GPU, read spec, strandedness, reference args)
+    "tair10_srna": dict(shape="tair10", config="configTAIR10", seed=20261018 + 2, reads=50_000_000,
+                        spec=dict(max_nh=20), strand="F", strategy="default", overlap=-1.0,
+                        describe="synthetic sRNA-Seq single-end, NH<=20, TAIR10-shaped GFF3, configTAIR10.txt, -s F, -y default, -l -1"),
+    "hs38_multi": dict(shape="hs38", config="configHS38", seed=20261018 + 3, reads=20_000_000,
+                       spec=dict(max_nh=100), strand="F", strategy="default", overlap=-1.0,
+                       describe="synthetic heavy multi-mapping reads, NH<=100, GRCh38-shaped GTF, configHS38.txt"),
+}
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def dist_env():
+    return int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+
+
+class Workload:
+    """Config + synthetic annotation (files in a scratch directory) of one benchmark shape."""
+
+    def __init__(self, name, tmp, gene_scale=1.0):
+        from mmannot_b200 import host
+        self.w = WORKLOADS[name]
+        self.name = name
+        self.tmp = tmp
+        cfgs = json.load(open(os.path.join(ROOT, "tests", "golden", "configs.json")))
+        self.config_path = os.path.join(tmp, self.w["config"] + ".txt")
+        with open(self.config_path, "w") as f:
+            f.write(cfgs[self.w["config"]])
+        self.synth = host.Synth(self.w["shape"], self.w["seed"], gene_scale=gene_scale, **self.w["spec"])
+        self.gtf_path = os.path.join(tmp, "annotation.gff")
+        self.synth.write_annotation(self.gtf_path)
+        self.config = host.Config(self.config_path)
+        self.annotation = host.Annotation(self.config, self.gtf_path)
+
+    def fill_pinned(self, first_read, n_reads, threads):
+        """Packed hits of the read range, generated straight into page-locked buffers."""
+        from concurrent.futures import ThreadPoolExecutor
+        from mmannot_b200 import device
+        threads = max(1, min(threads, n_reads // 1000 or 1))
+        step = (n_reads + threads - 1) // threads
+        chunks = [(first_read + t * step, min(step, n_reads - t * step)) for t in range(threads) if t * step < n_reads]
+        with ThreadPoolExecutor(threads) as ex:
+            counts = list(ex.map(lambda c: self.synth.count_hits(*c), chunks))
+            total = int(sum(counts))
+            pinned = device.PinnedHits(max(total, 1))
+            offs = np.concatenate([[0], np.cumsum(counts)[:-1]]).astype(np.int64)
+            out = pinned.arrays
+            got = list(ex.map(lambda co: self.synth.fill_hits(self.annotation, self.w["strand"], co[0][0], co[0][1], out, int(co[1]))[1],
+                              zip(chunks, offs)))
+        assert [int(g) for g in got] == [int(c) for c in counts]
+        return pinned, total
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
+        "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        exe = shutil.which("nvidia-smi")
+        if not exe:
+            return
+        fd, self.path = tempfile.mkstemp(suffix=".clocks.csv")
+        os.close(fd)
+        self.proc = subprocess.Popen([exe, "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                     stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if not self.proc:
+            return out
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in open(self.path):
+            p = [x.strip() for x in line.split(",")]
+            if len(p) < 9:
+                continue
+            try:
+                sm.append(float(p[1])); mx.append(float(p[2]))
+            except ValueError:
+                continue
+            for k, nme in enumerate(names):
+                if p[5 + k].lower().startswith("active"):
+                    reasons.add(nme)
+        os.unlink(self.path)
+        if sm:
+            out.update(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+# ------------------------------------------------------------------------------------------ reference arm
+
+def reference_binary():
+    from oracle import pyoracle
+    return pyoracle.ref_binary("fixed")
+
+
+def time_reference(wl, n_files, reads_per_file, first_read=0, reps=1, warmup=0):
+    """The reference's own CPU path (oracle/_ref/mmannot_fixed: unmodified mmannot.cpp + the one-line setFlags repair
+    without which its strand is undefined) on `n_files` BAM files of the workload, -t n_files (one thread per
+    BAM is all it can use).  Returns (records/s list per rep, records, cores used, description)."""
+    exe = reference_binary()
+    if exe is None:
+        raise FileNotFoundError("oracle/_ref/mmannot_fixed missing (built by oracle/build_ref.sh where /root/reference exists)")
+    from concurrent.futures import ThreadPoolExecutor
+    bams = [os.path.join(wl.tmp, "ref_%d.bam" % i) for i in range(n_files)]
+    with ThreadPoolExecutor(n_files) as ex:
+        list(ex.map(lambda i: wl.synth.write_bam(bams[i], first_read + i * reads_per_file, reads_per_file), range(n_files)))
+        records = sum(ex.map(lambda i: wl.synth.count_hits(first_read + i * reads_per_file, reads_per_file), range(n_files)))
+    empty = os.path.join(wl.tmp, "ref_empty.bam")
+    wl.synth.write_bam(empty, 0, 0)
+    w = wl.w
+    base = [exe, "-a", wl.gtf_path, "-c", wl.config_path, "-s", w["strand"], "-y", w["strategy"], "-l", repr(w["overlap"]), "-o", os.devnull]
+
+    def run(files, threads):
+        t0 = time.perf_counter()
+        pr = subprocess.run(base + ["-r"] + files + ["-t", str(threads)], capture_output=True, text=True)
+        return time.perf_counter() - t0, pr
+
+    # fixed cost of a run (config + annotation load), subtracted: at the full size of the workload it is negligible
+    t_load = min(run([empty], 1)[0] for _ in range(2))
+    out = []
+    mode = "-t %d in one process" % n_files
+    for it in range(warmup + reps):
+        dt, pr = run(bams, n_files)
+        if pr.returncode != 0:  # the reference's -t > 1 path has unsynchronised table updates (mmannot.cpp:2136)
+            mode = "%d independent -t 1 processes" % n_files
+            t0 = time.perf_counter()
+            procs = [subprocess.Popen(base + ["-r", b, "-t", "1"], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL) for b in bams]
+            rcs = [p.wait() for p in procs]
+            dt = time.perf_counter() - t0
+            if any(rcs):
+                raise RuntimeError("reference run failed: " + pr.stderr[-500:])
+        if it >= warmup:
+            out.append(records / max(dt - t_load, 1e-9))
+    for b in bams + [empty]:
+        os.unlink(b)
+    desc = "%d BAM x %d reads (%d records) of the workload, reads %d.., %s, wall minus %.2fs annotation load" % (
+        n_files, reads_per_file, records, first_read, mode, t_load)
+    return out, records, n_files, desc
+
+
+def run_reference_arm(args):
+    rank, _, world = dist_env()
+    if rank != 0:
+        return 0
+    tmp = tempfile.mkdtemp(prefix="mmannot_bench_")
+    try:
+        wl = Workload(args.workload, tmp)
+        cores = os.cpu_count() or 1
+        n_files = args.ref_threads or max(1, min(cores, 32))
+        vals, records, used, desc = time_reference(wl, n_files, args.ref_reads, reps=args.steps, warmup=args.warmup)
+        v = statistics.median(vals)
+        line = {"impl": "reference", "metric": "alignment_records_per_sec", "value": v, "unit": "records/s", "n_gpus": args.gpus,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * records / v, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+                "config": {"workload": wl.w["describe"], "name": args.workload},
+                "cpu_baseline": {"value": v, "unit": "records/s", "cores": used, "kind": "reference", "sample": desc},
+                "e2e": {"value": v, "unit": "records/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0, "host_cores": cores}
+        print(json.dumps(line), flush=True)
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+    return 0
+
+
+# ------------------------------------------------------------------------------------------ product arm
+
+def run_product_arm(args):
+    import ctypes as C
+
+    import torch
+    import torch.distributed as dist
+
+    from mmannot_b200 import device, multi
+
+    rank, local_rank, world = dist_env()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    cores = os.cpu_count() or 1
+    threads = max(1, min(64, cores // max(1, world)))
+    tmp = tempfile.mkdtemp(prefix="mmannot_bench_%d_" % rank)
+    try:
+        t0 = time.time()
+        wl = Workload(args.workload, tmp)
+        w = wl.w
+        reads = args.reads or w["reads"]
+        # read-name-range sharding: rank r owns reads [r*reads, (r+1)*reads) -- every record of a read stays on one GPU
+        pinned, n_hits = wl.fill_pinned(rank * reads, reads, threads)
+        log("[rank %d] workload %s: %d features, %d reads -> %d hits generated in %.1fs (%d threads)" % (
+            rank, args.workload, wl.annotation.n, reads, n_hits, time.time() - t0, threads))
+        batch = args.batch
+        ann = device.Annotator(wl.config, strategy=w["strategy"], overlap=w["overlap"], n_samples=1, max_batch_hits=batch,
+                               device=local_rank, table_log2=args.table_log2)
+        ann.load_features(wl.annotation)
+        index_bytes = ann.index_bytes()
+        # device-resident copy of the packed hit buffers
+        dev_arrays = {k: torch.from_numpy(pinned.arrays[k][:max(n_hits, 1)].view(np.int32 if k != "read_key" else np.int64)).to(dev)
+                      for k in ("start", "end", "meta", "nh", "read_key")}
+        torch.cuda.synchronize()
+        isz = {"start": 4, "end": 4, "meta": 4, "nh": 4, "read_key": 8}
+
+        def batches(ptr_of):
+            out = []
+            for a in range(0, n_hits, batch):
+                n = min(batch, n_hits - a)
+                out.append(device.HitBatch(n, *[ptr_of(k) + a * isz[k] for k in ("start", "end", "meta", "nh", "read_key")]))
+            return out
+
+        dev_batches = batches(lambda k: dev_arrays[k].data_ptr())
+        host_batches = batches(lambda k: pinned.arrays[k].ctypes.data)
+        stream = torch.cuda.ExternalStream(ann.stream_ptr(), device=dev)
+
+        def merge(res):
+            return multi.merge_tables(res, dev) if world > 1 else res
+
+        def step_device():
+            ann.reset(0)
+            for b in dev_batches:
+                ann.submit_device(0, b)
+            return merge(ann.finish(0))
+
+        def step_e2e():
+            ann.reset(0)
+            for b in host_batches:
+                ann.submit_batch(0, b)
+            return merge(ann.finish(0))
+
+        def barrier():
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+
+        def timed(fn, steps, with_events):
+            barrier()
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+            t0 = time.perf_counter()
+            if with_events:
+                ev[0].record(stream)
+            res = None
+            for _ in range(steps):
+                res = fn()
+            if with_events:
+                ev[1].record(stream)
+            torch.cuda.synchronize()
+            wall_ms = (time.perf_counter() - t0) * 1e3
+            ms = ev[0].elapsed_time(ev[1]) if with_events else wall_ms
+            ms = max(ms, 0.0)
+            if world > 1:
+                t = torch.tensor([ms, wall_ms], device=dev, dtype=torch.float64)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                ms, wall_ms = float(t[0]), float(t[1])
+            return ms, wall_ms, res
+
+        for _ in range(args.warmup):
+            step_device()
+        for _ in range(min(args.warmup, 2)):
+            step_e2e()
+
+        sampler = ClockSampler(local_rank)
+        if rank == 0:
+            sampler.start()
+        ann.timing_enable(True)
+        ann.timing_reset()
+        ms_dev, wall_dev, res_dev = timed(step_device, args.steps, True)
+        tm = ann.timing()
+        ann.timing_enable(False)
+        _, wall_e2e, res_e2e = timed(step_e2e, args.steps, False)
+        clocks = sampler.stop() if rank == 0 else None
+
+        assert res_dev["rows"] == res_e2e["rows"] and res_dev["stats"] == res_e2e["stats"], "device-resident and host-buffer passes disagree"
+        total_hits = n_hits
+        if world > 1:
+            t = torch.tensor([n_hits], device=dev, dtype=torch.int64)
+            dist.all_reduce(t)
+            total_hits = int(t[0])
+        ms_per_step = ms_dev / args.steps
+        value = total_hits / (ms_per_step * 1e-3)
+        e2e_value = total_hits / (wall_e2e / args.steps * 1e-3)
+
+        if rank == 0:
+            peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+            if os.path.exists(peaks_path):
+                peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)"
+            else:
+                peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+            n_batches = len(dev_batches) * args.steps
+            k_ms = tm["ms_annotate"] + tm["ms_resolve"] + tm["ms_merge"]
+            # algorithmic bytes of the per-batch kernel group: 24 B per hit read once, the 16 B/feature
+            # index and the 8 B/row table are per sample and negligible (index %d B)
+            bytes_per_launch = 24.0 * n_hits / len(dev_batches)
+            avg_ms = k_ms / n_batches
+            achieved = bytes_per_launch / (avg_ms * 1e-3) / 1e9
+            roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                        "kernel": ann.dominant_kernel(), "bytes_per_launch": bytes_per_launch, "avg_launch_ms": avg_ms,
+                        "launches_timed": n_batches, "peak_source": peak_src,
+                        "kernel_ms_per_step": {k: tm[k] / args.steps for k in ("ms_annotate", "ms_resolve", "ms_merge", "ms_finish")}}
+            cpu = None
+            if not args.no_cpu_baseline:
+                try:
+                    n_files = args.ref_threads or 1
+                    vals, records, used, desc = time_reference(wl, n_files, args.cpu_reads, reps=1)
+                    cpu = {"value": vals[0], "unit": "records/s", "cores": used, "kind": "reference", "sample": desc}
+                except Exception as e:  # noqa: BLE001
+                    cpu = {"value": None, "unit": "records/s", "cores": 0, "kind": "reference", "sample": "unavailable: %s" % e}
+            h2d = 24 * n_hits
+            d2h = ann.table_readback_bytes()
+            line = {"metric": "alignment_records_per_sec", "value": value, "unit": "records/s", "n_gpus": world, "steps": args.steps,
+                    "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                    "dtype": "u32", "data": "synthetic",
+                    "config": {"workload": w["describe"], "name": args.workload, "reads_per_gpu": reads, "hits_per_gpu": n_hits,
+                               "features": int(wl.annotation.n), "elements": int(wl.config.n_elements), "batch_hits": batch,
+                               "sharding": "read-name ranges, index replicated, tables merged by one allreduce" if world > 1 else "single GPU",
+                               "l2": "inputs (%.2f GB per pass) larger than L2; no explicit flush" % (24e-9 * n_hits),
+                               "order": "name-grouped (mapper order)"},
+                    "e2e": {"value": e2e_value, "unit": "records/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                            "ms_per_step": wall_e2e / args.steps, "timer": "host wall clock around synchronize"},
+                    "gpu_launches": int(tm["launches"]),
+                    "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks, "host_cores": cores,
+                    "wall_ms_per_step_device_resident": wall_dev / args.steps,
+                    "stats": res_dev["stats"], "table_rows": len(res_dev["rows"])}
+            print(json.dumps(line), flush=True)
+        ann.close()
+        pinned.close()
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="tair10_srna", choices=sorted(WORKLOADS))
+    ap.add_argument("--reads", type=int, default=0, help="reads per GPU (default: the workload's full size)")
+    ap.add_argument("--batch", type=int, default=1 << 23, help="hits per mma_submit_hits call")
+    ap.add_argument("--table-log2", type=int, default=0)
+    ap.add_argument("--cpu-reads", type=int, default=3_000_000, help="reads of the bounded cpu_baseline sample (per BAM)")
+    ap.add_argument("--ref-reads", type=int, default=500_000, help="--impl reference: reads per BAM per step")
+    ap.add_argument("--ref-threads", type=int, default=0, help="BAM files / threads of the reference run (default: 1 for cpu_baseline, host cores up to 32 for --impl reference)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        log("bench.py: note: fewer than 3 warm-up steps requested")
+    if args.impl == "reference":
+        return run_reference_arm(args)
+    return run_product_arm(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -177,7 +177,12 @@ int mma_timing_get(mma_ctx *ctx, mma_timing *out); /* synchronises */
 /* Size in bytes of the device index built by mma_load_features (0 before). */
 uint64_t mma_index_bytes(const mma_ctx *ctx);
 
+/* Bytes mma_finish_sample copies back from the device per sample (table + control block). */
+uint64_t mma_readback_bytes(const mma_ctx *ctx);
+
 const char *mma_version(void);
+/* Name of the kernel that dominates a batch (for profiles / the roofline line of bench.py). */
+const char *mma_dominant_kernel(void);
 
 #ifdef __cplusplus
 }

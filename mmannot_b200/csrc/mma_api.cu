@@ -501,6 +501,8 @@ int mma_load_features(mma_ctx *ctx, const mma_features *f) {
 }
 
 uint64_t mma_index_bytes(const mma_ctx *ctx) { return ctx ? ctx->indexBytes : 0; }
+uint64_t mma_readback_bytes(const mma_ctx *ctx) { return ctx ? (uint64_t)ctx->tableCap * 16 + sizeof(SampleCtl) : 0; }
+const char *mma_dominant_kernel(void) { return "k_annotate+k_resolve"; }
 
 static int submitCommon(mma_ctx *ctx, uint32_t sample, const mma_hit_batch *b, bool onDevice) {
   int rc = checkSubmit(ctx, sample, b);

@@ -19,7 +19,7 @@ STRATEGIES = {"default": 0, "unique": 1, "random": 2, "ratio": 3}
 EXPORTS = [
     "mma_create", "mma_destroy", "mma_last_error", "mma_load_features", "mma_alloc_pinned", "mma_free_pinned",
     "mma_submit_hits", "mma_submit_hits_device", "mma_finish_sample", "mma_reset_sample", "mma_dense_counts",
-    "mma_sync", "mma_stream", "mma_timing_enable", "mma_timing_reset", "mma_timing_get", "mma_index_bytes", "mma_version",
+    "mma_sync", "mma_stream", "mma_timing_enable", "mma_timing_reset", "mma_timing_get", "mma_index_bytes", "mma_version", "mma_readback_bytes", "mma_dominant_kernel",
 ]
 
 
@@ -96,6 +96,9 @@ def lib():
         L.mma_index_bytes.argtypes = [C.c_void_p]
         L.mma_index_bytes.restype = C.c_uint64
         L.mma_version.restype = C.c_char_p
+        L.mma_readback_bytes.argtypes = [C.c_void_p]
+        L.mma_readback_bytes.restype = C.c_uint64
+        L.mma_dominant_kernel.restype = C.c_char_p
         _lib = L
     return _lib
 
@@ -232,6 +235,17 @@ class Annotator:
 
     def index_bytes(self):
         return int(lib().mma_index_bytes(self._h))
+
+    def stream_ptr(self):
+        """cudaStream_t (as an integer) of the context's compute stream."""
+        return int(lib().mma_stream(self._h) or 0)
+
+    def table_readback_bytes(self):
+        """Bytes mma_finish_sample reads back from the device per sample."""
+        return int(lib().mma_readback_bytes(self._h))
+
+    def dominant_kernel(self):
+        return lib().mma_dominant_kernel().decode()
 
     def close(self):
         if getattr(self, "_h", None):
