@@ -44,7 +44,12 @@ oracle/_build/liboracle.so: oracle/oracle.c oracle/oracle.h
 ref:
 	bash oracle/build_ref.sh
 
+# tuning builds (not shipped): make variants; MMANNOT_B200_LIB=mmannot_b200/lib/variants/b4.so python bench.py ...
+variants: $(CU_SRC) $(CU_HDR)
+	@mkdir -p mmannot_b200/lib/variants
+	for b in 3 5; do $(NVCC) $(NVFLAGS) -DMMA_BLOCKS_PER_SM=$$b -shared -o mmannot_b200/lib/variants/b$$b.so $(CU_SRC) & done; wait
+
 clean:
 	rm -rf mmannot_b200/lib mmannot_b200/bin oracle/_build
 
-.PHONY: all host cuda cli oracle ref clean
+.PHONY: all host cuda cli oracle ref clean variants

@@ -244,7 +244,7 @@ def run_product_arm(args):
             rank, args.workload, wl.annotation.n, reads, n_hits, time.time() - t0, threads))
         batch = args.batch
         ann = device.Annotator(wl.config, strategy=w["strategy"], overlap=w["overlap"], n_samples=1, max_batch_hits=batch,
-                               device=local_rank, table_log2=args.table_log2)
+                               device=local_rank, table_log2=args.table_log2, fast_bin_shift=args.fast_shift, bin_shift=args.bin_shift)
         ann.load_features(wl.annotation)
         index_bytes = ann.index_bytes()
         # device-resident copy of the packed hit buffers
@@ -338,17 +338,18 @@ def run_product_arm(args):
                 peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)"
             else:
                 peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
-            n_batches = len(dev_batches) * args.steps
-            k_ms = tm["ms_annotate"] + tm["ms_resolve"] + tm["ms_merge"]
-            # algorithmic bytes of the per-batch kernel group: 24 B per hit read once, the 16 B/feature
-            # index and the 8 B/row table are per sample and negligible (index %d B)
-            bytes_per_launch = 24.0 * n_hits / len(dev_batches)
+            n_batches = int(tm["batches"])
+            k_ms = tm["ms_batch"]
+            # algorithmic bytes of one k_batch launch: 24 B per hit read once (start, end, meta, nh u32 +
+            # read key u64); the 16 B/feature index and the 8 B/row table are per sample, not per launch
+            bytes_per_launch = 24.0 * n_hits * args.steps / n_batches
             avg_ms = k_ms / n_batches
             achieved = bytes_per_launch / (avg_ms * 1e-3) / 1e9
             roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
                         "kernel": ann.dominant_kernel(), "bytes_per_launch": bytes_per_launch, "avg_launch_ms": avg_ms,
                         "launches_timed": n_batches, "peak_source": peak_src,
-                        "kernel_ms_per_step": {k: tm[k] / args.steps for k in ("ms_annotate", "ms_resolve", "ms_merge", "ms_finish")}}
+                        "kernel_ms_per_step": {k: tm[k] / args.steps for k in ("ms_batch", "ms_close", "ms_finish")},
+                        "segment_table_miss_frac": tm["fast_miss"] / max(1, n_hits)}
             cpu = None
             if not args.no_cpu_baseline:
                 try:
@@ -364,6 +365,7 @@ def run_product_arm(args):
                     "dtype": "u32", "data": "synthetic",
                     "config": {"workload": w["describe"], "name": args.workload, "reads_per_gpu": reads, "hits_per_gpu": n_hits,
                                "features": int(wl.annotation.n), "elements": int(wl.config.n_elements), "batch_hits": batch,
+                               "index_bytes": index_bytes, "segments": ann.index_segments(),
                                "sharding": "read-name ranges, index replicated, tables merged by one allreduce" if world > 1 else "single GPU",
                                "l2": "inputs (%.2f GB per pass) larger than L2; no explicit flush" % (24e-9 * n_hits),
                                "order": "name-grouped (mapper order)"},
@@ -394,11 +396,15 @@ def main():
     ap.add_argument("--reads", type=int, default=0, help="reads per GPU (default: the workload's full size)")
     ap.add_argument("--batch", type=int, default=1 << 23, help="hits per mma_submit_hits call")
     ap.add_argument("--table-log2", type=int, default=0)
+    ap.add_argument("--fast-shift", type=int, default=0, help="log2 bin width of the segment answer table (0 = auto, -1 = no table)")
+    ap.add_argument("--bin-shift", type=int, default=0)
     ap.add_argument("--cpu-reads", type=int, default=3_000_000, help="reads of the bounded cpu_baseline sample (per BAM)")
     ap.add_argument("--ref-reads", type=int, default=500_000, help="--impl reference: reads per BAM per step")
     ap.add_argument("--ref-threads", type=int, default=0, help="BAM files / threads of the reference run (default: 1 for cpu_baseline, host cores up to 32 for --impl reference)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    if args.fast_shift < 0:
+        args.fast_shift = None
     if args.warmup < 3:
         log("bench.py: note: fewer than 3 warm-up steps requested")
     if args.impl == "reference":

@@ -59,6 +59,7 @@ extern "C" {
 #define MMA_HIT_STRAND_BIT 0x80000000u /* bit 31: read strand after the -s mapping (mmannot.cpp:836-844, 884) */
 
 #define MMA_MAX_ELEMENTS 64
+#define MMA_FAST_OFF 0xFFFFFFFFu
 
 typedef struct mma_ctx mma_ctx; /* one per GPU, opaque */
 
@@ -79,7 +80,7 @@ typedef struct mma_params {
   uint32_t table_log2;     /* log2(slots) of the per-sample combination table; 0 = 16 */
   uint32_t bin_shift;      /* log2(bin width) of the position index; 0 = chosen from the annotation extent */
   uint32_t rand_seed;      /* -y random: seed of the glibc rand() stream the reference draws from (1 = unseeded) */
-  uint32_t reserved;
+  uint32_t fast_bin_shift; /* log2(bin width) of the segment answer table; 0 = chosen from the annotation, MMA_FAST_OFF = no table */
 } mma_params;
 
 /* Typed intervals in REFERENCE ORDER (mmannot.cpp:1267: sorted by chromosome id then start,
@@ -123,13 +124,14 @@ typedef struct mma_sample_result {
 /* Per-kernel device time since mma_timing_reset(), from CUDA events recorded on the
  * context's own compute stream (timing must have been switched on). */
 typedef struct mma_timing {
-  double ms_index;    /* K1 feature index build */
-  double ms_annotate; /* K2 per-hit overlap + priority pick (+ single-hit counting) */
-  double ms_resolve;  /* K3 per-read resolution of multi-mapping reads */
-  double ms_merge;    /* K4 table merge / bookkeeping kernels */
+  double ms_index;    /* K1 feature index + segment answer table build */
+  double ms_batch;    /* k_batch: K2 per-hit annotation + K3 per-read resolution + K4 counting, one kernel per batch */
+  double ms_close;    /* k_batch_close: end-of-batch bookkeeping (+ re-routing of reads left unfinished mid-batch) */
   double ms_finish;   /* deferred (name-sorted) resolution at mma_finish_sample */
   uint64_t launches;  /* kernels launched by this library since the reset */
   uint64_t hits;      /* hits submitted since the reset */
+  uint64_t batches;   /* k_batch launches since the reset */
+  uint64_t fast_miss; /* hits the segment table could not answer (since the sample was reset) */
 } mma_timing;
 
 int mma_create(mma_ctx **out, const mma_params *params);
@@ -159,6 +161,10 @@ int mma_submit_hits_device(mma_ctx *ctx, uint32_t sample, const mma_hit_batch *d
  * mma_finish_sample / mma_reset_sample / mma_destroy. */
 int mma_finish_sample(mma_ctx *ctx, uint32_t sample, mma_sample_result *out);
 
+/* IntervalList::scan alone (mmannot.cpp:1291-1332): the element set (bit i <=> element i) of every hit of a HOST
+ * batch, written to out_masks[0..n) (host memory).  Synchronous; nothing is counted; nh / read_key are ignored. */
+int mma_annotate_hits(mma_ctx *ctx, const mma_hit_batch *batch, uint64_t *out_masks);
+
 /* Forget everything counted for `sample` (Counter::clear, mmannot.cpp:1742-1747). */
 int mma_reset_sample(mma_ctx *ctx, uint32_t sample);
 
@@ -174,8 +180,9 @@ int mma_timing_enable(mma_ctx *ctx, int on);
 int mma_timing_reset(mma_ctx *ctx);
 int mma_timing_get(mma_ctx *ctx, mma_timing *out); /* synchronises */
 
-/* Size in bytes of the device index built by mma_load_features (0 before). */
+/* Size in bytes of the device index built by mma_load_features (0 before), and its number of segments. */
 uint64_t mma_index_bytes(const mma_ctx *ctx);
+uint64_t mma_index_segments(const mma_ctx *ctx);
 
 /* Bytes mma_finish_sample copies back from the device per sample (table + control block). */
 uint64_t mma_readback_bytes(const mma_ctx *ctx);

@@ -4,6 +4,7 @@
 #include "mmannot_b200.h"
 
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
 
 #include <algorithm>
 #include <cstdio>
@@ -25,7 +26,7 @@ thread_local std::string g_createError;
     if (_e != cudaSuccess) return ctx->fail(MMA_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(_e)); \
   } while (0)
 
-enum TimeCat { TC_INDEX = 0, TC_ANNOTATE, TC_RESOLVE, TC_MERGE, TC_FINISH, TC_N };
+enum TimeCat { TC_INDEX = 0, TC_BATCH, TC_CLOSE, TC_FINISH, TC_N };
 
 struct DevBuf {
   void *p = nullptr;
@@ -43,14 +44,14 @@ struct DevBuf {
 };
 
 struct Staging {  // one batch resident on the device
-  DevBuf start, end, meta, nh, key, mask;
+  DevBuf start, end, meta, nh, key;
   cudaEvent_t copied = nullptr, done = nullptr;
 };
 
 struct Sample {
   SampleCtl *ctl = nullptr;
-  DevBuf tableKeys, tableVals, deltaKeys, deltaVals;
-  DevBuf slowKey, slowOrd, slowMask, slowNh, openKeys;
+  DevBuf tableKeys, tableVals;
+  DevBuf slowKey, slowOrd, slowMask, slowNh, openKeys, openSeq;
   u32 slowCap = 0, openCap = 0;
   // host-side bound on the number of deferred records (see ensureDeferred)
   u32 *countRing = nullptr;  // pinned, 4 entries
@@ -81,7 +82,10 @@ struct mma_ctx {
   // index
   bool haveIndex = false;
   DevBuf feat, chrInfo, bins, spanIdx, dElemLine, dElemStrand, dElemVic;
+  DevBuf fastBin, fastSeg, fastVic, fastChrInfo;
   IndexView index;
+  FastView fast;
+  uint64_t nSegments = 0;
   uint64_t indexBytes = 0;
   std::vector<Sample> samples;
   std::string error;
@@ -90,8 +94,9 @@ struct mma_ctx {
   struct Span { int cat; cudaEvent_t a, b; };
   std::vector<Span> spans;
   std::vector<cudaEvent_t> eventPool;
-  double ms[TC_N] = {0, 0, 0, 0, 0};
-  uint64_t launches = 0, hitsSubmitted = 0;
+  double ms[TC_N] = {0, 0, 0, 0};
+  uint64_t launches = 0, hitsSubmitted = 0, batches = 0;
+  int nSM = 148;
 
   int fail(int code, const std::string &msg) {
     error = msg;
@@ -138,7 +143,7 @@ SlowView slowView(const Sample &s) {
 }
 KeySetView openView(const Sample &s) {
   KeySetView v;
-  v.keys = s.openKeys.as<u64>(); v.capMask = s.openCap ? s.openCap - 1 : 0;
+  v.keys = s.openKeys.as<u64>(); v.seq = s.openSeq.as<u32>(); v.capMask = s.openCap ? s.openCap - 1 : 0;
   return v;
 }
 
@@ -147,15 +152,14 @@ int initSample(mma_ctx *ctx, Sample &s) {
   CK(cudaMalloc(&s.ctl, sizeof(SampleCtl)));
   CK(cudaMemsetAsync(s.ctl, 0, sizeof(SampleCtl), ctx->sc));
   const size_t tb = (size_t)ctx->tableCap * sizeof(u64);
-  CK(s.tableKeys.ensure(tb)); CK(s.tableVals.ensure(tb)); CK(s.deltaKeys.ensure(tb)); CK(s.deltaVals.ensure(tb));
+  CK(s.tableKeys.ensure(tb)); CK(s.tableVals.ensure(tb));
   CK(cudaMemsetAsync(s.tableKeys.p, 0, tb, ctx->sc)); CK(cudaMemsetAsync(s.tableVals.p, 0, tb, ctx->sc));
-  CK(cudaMemsetAsync(s.deltaKeys.p, 0, tb, ctx->sc)); CK(cudaMemsetAsync(s.deltaVals.p, 0, tb, ctx->sc));
   CK(cudaHostAlloc(&s.countRing, 4 * sizeof(u32), cudaHostAllocDefault));
   for (int i = 0; i < 4; ++i) CK(cudaEventCreateWithFlags(&s.ringEv[i], cudaEventDisableTiming));
   return MMA_OK;
 }
 
-__global__ void k_keyset_rehash(KeySetView from, KeySetView to, SampleCtl *ctl) {
+__global__ void k_keyset_rehash(KeySetView from, KeySetView to) {
   const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i > from.capMask) return;
   const u64 k = from.keys[i];
@@ -163,17 +167,19 @@ __global__ void k_keyset_rehash(KeySetView from, KeySetView to, SampleCtl *ctl) 
   u32 slot = (u32)mix64(k) & to.capMask;
   for (;;) {
     const u64 o = atomicCAS(&to.keys[slot], KEY_EMPTY, k);
-    if (o == KEY_EMPTY || o == k) return;
+    if (o == KEY_EMPTY || o == k) { to.seq[slot] = from.seq[i]; return; }
     slot = (slot + 1) & to.capMask;
   }
 }
 
 // Deferred list / open-key set sizing.  The device appends without asking; the host keeps an
-// upper bound on the list length (last count read back asynchronously + hits submitted since)
-// and only synchronises when that bound says the next batch might not fit.
+// upper bound on the list length (last count read back asynchronously + hits submitted since,
+// plus one stand-in record per batch for a carried read) and only synchronises when that bound
+// says the next batch might not fit.
 int ensureDeferred(mma_ctx *ctx, Sample &s, uint64_t n) {
   const bool needs = (ctx->rules.strategy == MMA_STRATEGY_DEFAULT || ctx->rules.strategy == MMA_STRATEGY_RANDOM);
   if (!needs) return MMA_OK;
+  n += 2;
   // freshest completed read-back
   for (int k = 0; k < 4; ++k) {
     const int slot = (int)((s.seq + 3 - k) & 3);  // newest first
@@ -194,7 +200,7 @@ int ensureDeferred(mma_ctx *ctx, Sample &s, uint64_t n) {
     s.knownCount = actual; s.knownCum = s.cumHits;
     if (actual + n <= s.slowCap) return MMA_OK;
   }
-  uint64_t want = std::max<uint64_t>(std::max<uint64_t>(4ull * ctx->params.max_batch_hits, 1u << 16), 2 * (actual + n));
+  uint64_t want = std::max<uint64_t>(std::max<uint64_t>(2ull * ctx->params.max_batch_hits, 1u << 16), 2 * (actual + n));
   if (want > 0xFFFFFFF0ull) return ctx->fail(MMA_ERR_CAPACITY, "deferred read list would exceed 2^32 records");
   u32 newCap = (u32)want;
   DevBuf nk, no, nm, nn;
@@ -207,73 +213,75 @@ int ensureDeferred(mma_ctx *ctx, Sample &s, uint64_t n) {
   }
   u32 newOpen = 1;
   while (newOpen < 2ull * newCap && newOpen < 0x80000000u) newOpen <<= 1;
-  DevBuf nopen;
-  CK(nopen.ensure((size_t)newOpen * 8));
+  DevBuf nopen, nseq;
+  CK(nopen.ensure((size_t)newOpen * 8)); CK(nseq.ensure((size_t)newOpen * 4));
   k_fill_u64<<<gridFor(newOpen, 256), 256, 0, ctx->sc>>>(nopen.as<u64>(), KEY_EMPTY, newOpen);
-  ctx->launches++;
+  k_fill_u32<<<gridFor(newOpen, 256), 256, 0, ctx->sc>>>(nseq.as<u32>(), 0xFFFFFFFFu, newOpen);
+  ctx->launches += 2;
   if (s.openCap) {
     KeySetView from = openView(s), to;
-    to.keys = nopen.as<u64>(); to.capMask = newOpen - 1;
-    k_keyset_rehash<<<gridFor(s.openCap, 256), 256, 0, ctx->sc>>>(from, to, s.ctl);
+    to.keys = nopen.as<u64>(); to.seq = nseq.as<u32>(); to.capMask = newOpen - 1;
+    k_keyset_rehash<<<gridFor(s.openCap, 256), 256, 0, ctx->sc>>>(from, to);
     ctx->launches++;
   }
   CK(cudaStreamSynchronize(ctx->sc));
-  s.slowKey.release(); s.slowOrd.release(); s.slowMask.release(); s.slowNh.release(); s.openKeys.release();
-  s.slowKey = nk; s.slowOrd = no; s.slowMask = nm; s.slowNh = nn; s.openKeys = nopen;
+  s.slowKey.release(); s.slowOrd.release(); s.slowMask.release(); s.slowNh.release(); s.openKeys.release(); s.openSeq.release();
+  s.slowKey = nk; s.slowOrd = no; s.slowMask = nm; s.slowNh = nn; s.openKeys = nopen; s.openSeq = nseq;
   s.slowCap = newCap; s.openCap = newOpen;
   return MMA_OK;
 }
 
-template <typename MaskT>
-int launchBatch(mma_ctx *ctx, Sample &s, const HitView &h, MaskT *maskBuf) {
+template <int MODE, int STRAT, bool FAST, typename MaskT>
+void launchBatchKernels(mma_ctx *ctx, Sample &s, const HitView &h) {
   const Rules &r = ctx->rules;
   TableView table = tableView(s.tableKeys, s.tableVals, ctx->tableCap, s.ctl);
-  TableView delta = tableView(s.deltaKeys, s.deltaVals, ctx->tableCap, s.ctl);
   SlowView slow = slowView(s);
   KeySetView open = openView(s);
-  const u32 gA = gridFor(h.n, ANNOTATE_THREADS);
+  // one contiguous chunk of 128-hit warp tiles per warp; enough warps to fill the GPU, chunks of >= 8 tiles when possible
+  const u32 nWT = (h.n + WT_HITS - 1) / WT_HITS;
+  const u32 perSM = (sizeof(MaskT) == 4) ? MMA_BLOCKS_PER_SM : 2;
+  const u32 grid = std::max<u32>(1u, std::min<u32>((nWT + BATCH_WARPS - 1) / BATCH_WARPS, (u32)ctx->nSM * perSM));
   {
-    mma_ctx::Timed t(ctx, TC_ANNOTATE);
-    if (r.mode == 0) k_annotate<0, MaskT><<<gA, ANNOTATE_THREADS, 0, ctx->sc>>>(ctx->index, h, r, maskBuf, table, s.ctl, slow);
-    else if (r.mode == 1) k_annotate<1, MaskT><<<gA, ANNOTATE_THREADS, 0, ctx->sc>>>(ctx->index, h, r, maskBuf, table, s.ctl, slow);
-    else k_annotate<2, MaskT><<<gA, ANNOTATE_THREADS, 0, ctx->sc>>>(ctx->index, h, r, maskBuf, table, s.ctl, slow);
-    ctx->launches++;
+    mma_ctx::Timed t(ctx, TC_BATCH);
+    k_batch<MODE, STRAT, FAST, MaskT><<<grid, BATCH_THREADS, 0, ctx->sc>>>(ctx->index, ctx->fast, h, r, table, s.ctl, slow, open);
   }
-  if (r.strategy == MMA_STRATEGY_DEFAULT) {
-    const u32 gR = gridFor(h.n, RESOLVE_THREADS);
-    const u32 gT = gridFor(ctx->tableCap, 256);
-    {
-      mma_ctx::Timed t(ctx, TC_RESOLVE);
-      k_resolve<MaskT><<<gR, RESOLVE_THREADS, 0, ctx->sc>>>(h, r, maskBuf, delta, s.ctl, slow, open, 0);
-      ctx->launches++;
-    }
-    {
-      mma_ctx::Timed t(ctx, TC_MERGE);
-      k_batch_mid<<<gT, 256, 0, ctx->sc>>>(delta, s.ctl);
-      ctx->launches++;
-    }
-    {
-      mma_ctx::Timed t(ctx, TC_RESOLVE);
-      k_resolve<MaskT><<<gR, RESOLVE_THREADS, 0, ctx->sc>>>(h, r, maskBuf, delta, s.ctl, slow, open, 1);
-      ctx->launches++;
-    }
-    {
-      mma_ctx::Timed t(ctx, TC_MERGE);
-      k_batch_merge<<<gT, 256, 0, ctx->sc>>>(delta, table, s.ctl, h.n);
-      ctx->launches++;
-    }
-  } else {
-    mma_ctx::Timed t(ctx, TC_MERGE);
-    k_batch_advance<<<1, 1, 0, ctx->sc>>>(s.ctl, h.n);
-    ctx->launches++;
+  {
+    mma_ctx::Timed t(ctx, TC_CLOSE);
+    const u32 gridC = (STRAT == 0) ? std::min<u32>(gridFor(h.n, 256), (u32)ctx->nSM) : 1u;
+    k_batch_close<MODE, FAST><<<gridC, 256, 0, ctx->sc>>>(ctx->index, ctx->fast, h, r, table, s.ctl, slow, open);
   }
+  ctx->launches += 2;
+  ctx->batches++;
+}
+
+template <int MODE, bool FAST, typename MaskT>
+void launchBatchStrategy(mma_ctx *ctx, Sample &s, const HitView &h) {
+  switch (ctx->rules.strategy) {
+    case MMA_STRATEGY_DEFAULT: launchBatchKernels<MODE, 0, FAST, MaskT>(ctx, s, h); break;
+    case MMA_STRATEGY_UNIQUE: launchBatchKernels<MODE, 1, FAST, MaskT>(ctx, s, h); break;
+    case MMA_STRATEGY_RANDOM: launchBatchKernels<MODE, 2, FAST, MaskT>(ctx, s, h); break;
+    default: launchBatchKernels<MODE, 3, FAST, MaskT>(ctx, s, h); break;
+  }
+}
+
+template <int MODE>
+void launchBatchMode(mma_ctx *ctx, Sample &s, const HitView &h) {
+  if (ctx->wideMask) launchBatchStrategy<MODE, false, u64>(ctx, s, h);
+  else if (ctx->fast.enabled) launchBatchStrategy<MODE, true, u32>(ctx, s, h);
+  else launchBatchStrategy<MODE, false, u32>(ctx, s, h);
+}
+
+int launchBatch(mma_ctx *ctx, Sample &s, const HitView &h) {
+  if (ctx->rules.mode == 0) launchBatchMode<0>(ctx, s, h);
+  else if (ctx->rules.mode == 1) launchBatchMode<1>(ctx, s, h);
+  else launchBatchMode<2>(ctx, s, h);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return ctx->fail(MMA_ERR_CUDA, std::string("kernel launch: ") + cudaGetErrorString(e));
   return MMA_OK;
 }
 
 int afterBatch(mma_ctx *ctx, Sample &s, uint64_t n) {
-  s.cumHits += n;
+  s.cumHits += n + 2;
   s.touched = true;
   ctx->hitsSubmitted += n;
   const int slot = (int)(s.seq & 3);
@@ -341,7 +349,7 @@ int mma_create(mma_ctx **out, const mma_params *p) {
   r.rescueThreshold = p->rescue_threshold;
   r.rescue = (p->read_stats != 0 && p->rescue_threshold < 1.0f) ? 1 : 0;  // mm:491, 2025
   r.nElements = p->n_elements;
-  ctx->wideMask = p->n_elements > 32;
+  ctx->wideMask = p->n_elements > 30;  // bits 30 and 31 of a 32-bit element set serve as flags (segment table, run scan)
   ctx->tableCap = 1u << (p->table_log2 ? std::min<uint32_t>(std::max<uint32_t>(p->table_log2, 8), 26) : 16);
   auto bail = [&](const char *what, cudaError_t err) {
     g_createError = std::string(what) + ": " + cudaGetErrorString(err);
@@ -349,6 +357,8 @@ int mma_create(mma_ctx **out, const mma_params *p) {
     return MMA_ERR_CUDA;
   };
   if ((e = cudaSetDevice(ctx->device)) != cudaSuccess) return bail("cudaSetDevice", e);
+  if ((e = cudaDeviceGetAttribute(&ctx->nSM, cudaDevAttrMultiProcessorCount, ctx->device)) != cudaSuccess) return bail("cudaDeviceGetAttribute", e);
+  ctx->fast = FastView();
   if ((e = cudaStreamCreateWithFlags(&ctx->sc, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
   if ((e = cudaStreamCreateWithFlags(&ctx->sh, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
   for (int k = 0; k < 2; ++k) {
@@ -367,18 +377,19 @@ void mma_destroy(mma_ctx *ctx) {
   if (ctx->sh) cudaStreamSynchronize(ctx->sh);
   for (Sample &s : ctx->samples) {
     if (s.ctl) cudaFree(s.ctl);
-    s.tableKeys.release(); s.tableVals.release(); s.deltaKeys.release(); s.deltaVals.release();
-    s.slowKey.release(); s.slowOrd.release(); s.slowMask.release(); s.slowNh.release(); s.openKeys.release();
+    s.tableKeys.release(); s.tableVals.release();
+    s.slowKey.release(); s.slowOrd.release(); s.slowMask.release(); s.slowNh.release(); s.openKeys.release(); s.openSeq.release();
     if (s.countRing) cudaFreeHost(s.countRing);
     for (int i = 0; i < 4; ++i) if (s.ringEv[i]) cudaEventDestroy(s.ringEv[i]);
   }
   for (int k = 0; k < 2; ++k) {
     Staging &g = ctx->stage[k];
-    g.start.release(); g.end.release(); g.meta.release(); g.nh.release(); g.key.release(); g.mask.release();
+    g.start.release(); g.end.release(); g.meta.release(); g.nh.release(); g.key.release();
     if (g.copied) cudaEventDestroy(g.copied);
     if (g.done) cudaEventDestroy(g.done);
   }
   ctx->feat.release(); ctx->chrInfo.release(); ctx->bins.release(); ctx->spanIdx.release();
+  ctx->fastBin.release(); ctx->fastSeg.release(); ctx->fastVic.release(); ctx->fastChrInfo.release();
   ctx->dElemLine.release(); ctx->dElemStrand.release(); ctx->dElemVic.release();
   ctx->collectTiming();
   for (cudaEvent_t e : ctx->eventPool) cudaEventDestroy(e);
@@ -408,7 +419,7 @@ int mma_load_features(mma_ctx *ctx, const mma_features *f) {
   for (uint32_t i = 0; i < n; ++i) {
     if (f->chr[i] >= nChr) return ctx->fail(MMA_ERR_INVALID, "feature chromosome id >= n_chr");
     if (f->type[i] >= ctx->params.n_elements) return ctx->fail(MMA_ERR_INVALID, "feature type >= n_elements");
-    if (f->start[i] == 0xFFFFFFFFu || f->end[i] == 0xFFFFFFFFu) return ctx->fail(MMA_ERR_INVALID, "feature coordinate 0xFFFFFFFF is reserved");
+    if (f->start[i] >= 0xFFFFFFF0u || f->end[i] >= 0xFFFFFFF0u) return ctx->fail(MMA_ERR_INVALID, "feature coordinates >= 0xFFFFFFF0 are reserved");
     if (i > 0 && (f->chr[i] < f->chr[i - 1] || (f->chr[i] == f->chr[i - 1] && f->start[i] < f->start[i - 1])))
       return ctx->fail(MMA_ERR_INVALID, "features must be sorted by (chromosome, start)");
     chrStart[f->chr[i] + 1]++;
@@ -487,6 +498,103 @@ int mma_load_features(mma_ctx *ctx, const mma_features *f) {
   }
   CKL(cudaStreamSynchronize(st));
   CKL(cudaGetLastError());
+  // ---- segment answer table (E <= 31 only: bit 31 of an answer word is the "position dependent" flag)
+  ctx->index.feat = ctx->feat.as<uint4>();
+  ctx->index.chrInfo = ctx->chrInfo.as<uint2>();
+  ctx->index.bins = ctx->bins.as<uint2>();
+  ctx->index.spanIdx = ctx->spanIdx.as<u32>();
+  ctx->index.nChr = nChr;
+  ctx->index.shift = shift;
+  ctx->fast = FastView();
+  ctx->nSegments = 0;
+  uint64_t fastBytes = 0;
+  if (ctx->params.n_elements <= 30 && ctx->params.fast_bin_shift != MMA_FAST_OFF) {
+    const uint64_t nKeys = 2ull * n + nChr;
+    DevBuf kA, kB, flag, pos, tmp, segKey, fChrBinBase;
+    auto cleanupFast = [&]() { kA.release(); kB.release(); flag.release(); pos.release(); tmp.release(); segKey.release(); fChrBinBase.release(); };
+#define CKS(call)                                                                                  \
+  do {                                                                                             \
+    cudaError_t _e = (call);                                                                       \
+    if (_e != cudaSuccess) { cleanupFast(); cleanup(); return ctx->fail(MMA_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(_e)); } \
+  } while (0)
+    CKS(kA.ensure(nKeys * 8)); CKS(kB.ensure(nKeys * 8)); CKS(flag.ensure(nKeys * 4)); CKS(pos.ensure(nKeys * 4));
+    size_t tb1 = 0, tb2 = 0;
+    CKS(cub::DeviceRadixSort::SortKeys(nullptr, tb1, kA.as<u64>(), kB.as<u64>(), (int)nKeys, 0, 64, st));
+    CKS(cub::DeviceScan::ExclusiveSum(nullptr, tb2, flag.as<u32>(), pos.as<u32>(), (int)nKeys, st));
+    CKS(tmp.ensure(std::max(tb1, tb2)));
+    u32 lastFlag = 0, lastPos = 0;
+    {
+      mma_ctx::Timed t(ctx, TC_INDEX);
+      k_seg_keys<<<gridFor(std::max<u32>(n, nChr), 256), 256, 0, st>>>(b, kA.as<u64>());
+      CKS(cub::DeviceRadixSort::SortKeys(tmp.p, tb1, kA.as<u64>(), kB.as<u64>(), (int)nKeys, 0, 64, st));
+      k_seg_flag<<<gridFor(nKeys, 256), 256, 0, st>>>(kB.as<u64>(), (u32)nKeys, flag.as<u32>());
+      CKS(cub::DeviceScan::ExclusiveSum(tmp.p, tb2, flag.as<u32>(), pos.as<u32>(), (int)nKeys, st));
+      ctx->launches += 2;
+    }
+    CKS(cudaMemcpyAsync(&lastFlag, flag.as<u32>() + (nKeys - 1), 4, cudaMemcpyDeviceToHost, st));
+    CKS(cudaMemcpyAsync(&lastPos, pos.as<u32>() + (nKeys - 1), 4, cudaMemcpyDeviceToHost, st));
+    CKS(cudaStreamSynchronize(st));
+    const u32 nSeg = lastPos + lastFlag;
+    // bin grid of the table: about two bins per segment, at most 2^21 bins
+    uint32_t fshift = ctx->params.fast_bin_shift;
+    if (fshift == 0) {
+      uint64_t totalExtent = 0;
+      for (uint32_t c = 0; c < nChr; ++c) totalExtent += extent[c];
+      fshift = 5;
+      const uint64_t wantBins = std::min<uint64_t>(std::max<uint64_t>(2ull * nSeg, 1u << 16), 1ull << 21);
+      while (fshift < 24 && (totalExtent >> fshift) > wantBins) ++fshift;
+    }
+    fshift = std::min<uint32_t>(std::max<uint32_t>(fshift, 2), 24);
+    std::vector<u32> fBase(nChr + 1, 0);
+    std::vector<uint2> fInfo(nChr);
+    uint64_t fEntries = 0;
+    for (uint32_t c = 0; c < nChr; ++c) {
+      const uint64_t nb = (chrStart[c + 1] > chrStart[c]) ? (extent[c] >> fshift) + 2 : 1;
+      fBase[c] = (u32)fEntries;
+      fInfo[c] = make_uint2((u32)fEntries, (u32)nb);
+      fEntries += nb;
+    }
+    fBase[nChr] = (u32)fEntries;
+    if (fEntries <= 0x7FFFFFFFull && nSeg < (1u << 24)) {
+      CKS(segKey.ensure((size_t)nSeg * 8));
+      CKS(ctx->fastSeg.ensure(((size_t)nSeg + 16) * 2 * sizeof(uint4)));
+      CKS(ctx->fastVic.ensure(((size_t)nSeg + 16) * 4 * sizeof(uint2)));
+      u32 upMask = 0, downMask = 0;
+      for (uint32_t q = 0; q < ctx->params.n_elements; ++q) {
+        if (ctx->elemVic[q] == MMA_VICINITY_UP) upMask |= 1u << q;
+        if (ctx->elemVic[q] == MMA_VICINITY_DOWN) downMask |= 1u << q;
+      }
+      CKS(ctx->fastBin.ensure((size_t)fEntries * sizeof(uint4)));
+      CKS(ctx->fastChrInfo.ensure((size_t)nChr * sizeof(uint2)));
+      CKS(fChrBinBase.ensure((size_t)(nChr + 1) * 4));
+      CKS(cudaMemsetAsync(ctx->fastSeg.p, 0, ((size_t)nSeg + 16) * 2 * sizeof(uint4), st));
+      CKS(cudaMemcpyAsync(ctx->fastChrInfo.p, fInfo.data(), (size_t)nChr * sizeof(uint2), cudaMemcpyHostToDevice, st));
+      CKS(cudaMemcpyAsync(fChrBinBase.p, fBase.data(), (size_t)(nChr + 1) * 4, cudaMemcpyHostToDevice, st));
+      {
+        mma_ctx::Timed t(ctx, TC_INDEX);
+        k_seg_scatter<<<gridFor(nKeys, 256), 256, 0, st>>>(kB.as<u64>(), flag.as<u32>(), pos.as<u32>(), (u32)nKeys, segKey.as<u64>());
+        k_seg_eval<<<gridFor(nSeg, 128), 128, 0, st>>>(ctx->index, segKey.as<u64>(), nSeg, upMask, downMask, ctx->fastSeg.as<uint4>(), ctx->fastVic.as<uint2>());
+        k_fast_bins<<<gridFor(fEntries, 256), 256, 0, st>>>(segKey.as<u64>(), nSeg, ctx->fastSeg.as<uint4>(), fChrBinBase.as<u32>(), nChr, fshift,
+                                                            (u32)fEntries, ctx->fastBin.as<uint4>());
+        ctx->launches += 3;
+      }
+      CKS(cudaStreamSynchronize(st));
+      CKS(cudaGetLastError());
+      ctx->fast.bin = ctx->fastBin.as<uint4>();
+      ctx->fast.seg = ctx->fastSeg.as<uint4>();
+      ctx->fast.vic = ctx->fastVic.as<uint2>();
+      ctx->fast.upMask = upMask;
+      ctx->fast.downMask = downMask;
+      ctx->fast.chrInfo = ctx->fastChrInfo.as<uint2>();
+      ctx->fast.nChr = nChr;
+      ctx->fast.shift = fshift;
+      ctx->fast.enabled = 1;
+      ctx->nSegments = nSeg;
+      fastBytes = (uint64_t)nSeg * (2 * sizeof(uint4) + 4 * sizeof(uint2)) + fEntries * sizeof(uint4) + (uint64_t)nChr * sizeof(uint2);
+    }
+#undef CKS
+    cleanupFast();
+  }
 #undef CKL
   cleanup();
   ctx->index.feat = ctx->feat.as<uint4>();
@@ -495,14 +603,15 @@ int mma_load_features(mma_ctx *ctx, const mma_features *f) {
   ctx->index.spanIdx = ctx->spanIdx.as<u32>();
   ctx->index.nChr = nChr;
   ctx->index.shift = shift;
-  ctx->indexBytes = (uint64_t)n * sizeof(uint4) + (uint64_t)nChr * sizeof(uint2) + entries * sizeof(uint2) + (uint64_t)total * 4;
+  ctx->indexBytes = (uint64_t)n * sizeof(uint4) + (uint64_t)nChr * sizeof(uint2) + entries * sizeof(uint2) + (uint64_t)total * 4 + fastBytes;
   ctx->haveIndex = true;
   return MMA_OK;
 }
 
 uint64_t mma_index_bytes(const mma_ctx *ctx) { return ctx ? ctx->indexBytes : 0; }
+uint64_t mma_index_segments(const mma_ctx *ctx) { return ctx ? ctx->nSegments : 0; }
 uint64_t mma_readback_bytes(const mma_ctx *ctx) { return ctx ? (uint64_t)ctx->tableCap * 16 + sizeof(SampleCtl) : 0; }
-const char *mma_dominant_kernel(void) { return "k_annotate+k_resolve"; }
+const char *mma_dominant_kernel(void) { return "k_batch"; }
 
 static int submitCommon(mma_ctx *ctx, uint32_t sample, const mma_hit_batch *b, bool onDevice) {
   int rc = checkSubmit(ctx, sample, b);
@@ -536,10 +645,8 @@ static int submitCommon(mma_ctx *ctx, uint32_t sample, const mma_hit_batch *b, b
     CK(cudaStreamWaitEvent(ctx->sc, g.copied, 0));
     h.start = g.start.as<u32>(); h.end = g.end.as<u32>(); h.meta = g.meta.as<u32>(); h.nh = g.nh.as<u32>(); h.key = g.key.as<u64>();
   }
-  if (ctx->rules.strategy == MMA_STRATEGY_DEFAULT) CK(g.mask.ensure((size_t)ctx->params.max_batch_hits * (ctx->wideMask ? 8 : 4)));
-  if (ctx->wideMask) rc = launchBatch<u64>(ctx, s, h, g.mask.as<u64>());
-  else rc = launchBatch<u32>(ctx, s, h, g.mask.as<u32>());
-  if (rc) return rc;
+  h.vec = ((((uintptr_t)h.start | (uintptr_t)h.end | (uintptr_t)h.meta | (uintptr_t)h.nh | (uintptr_t)h.key) & 15u) == 0) ? 1u : 0u;
+  if ((rc = launchBatch(ctx, s, h))) return rc;
   CK(cudaEventRecord(g.done, ctx->sc));
   if ((rc = afterBatch(ctx, s, n))) return rc;
   ctx->submitSeq++;
@@ -548,6 +655,44 @@ static int submitCommon(mma_ctx *ctx, uint32_t sample, const mma_hit_batch *b, b
 
 int mma_submit_hits(mma_ctx *ctx, uint32_t sample, const mma_hit_batch *batch) { return submitCommon(ctx, sample, batch, false); }
 int mma_submit_hits_device(mma_ctx *ctx, uint32_t sample, const mma_hit_batch *batch) { return submitCommon(ctx, sample, batch, true); }
+
+int mma_annotate_hits(mma_ctx *ctx, const mma_hit_batch *b, uint64_t *out_masks) {
+  if (!ctx) return MMA_ERR_INVALID;
+  if (!b || (b->n && (!b->start || !b->end || !b->meta || !out_masks))) return ctx->fail(MMA_ERR_INVALID, "null argument");
+  if (!ctx->haveIndex) return ctx->fail(MMA_ERR_STATE, "mma_load_features must be called before hits are submitted");
+  if (b->n == 0) return MMA_OK;
+  if (b->n > 0xFFFFFFF0ull) return ctx->fail(MMA_ERR_INVALID, "too many hits in one call");
+  CK(cudaSetDevice(ctx->device));
+  const size_t n = b->n;
+  DevBuf ds, de, dm, dout;
+  auto cleanup = [&]() { ds.release(); de.release(); dm.release(); dout.release(); };
+  cudaError_t e;
+  if ((e = ds.ensure(n * 4)) != cudaSuccess || (e = de.ensure(n * 4)) != cudaSuccess || (e = dm.ensure(n * 4)) != cudaSuccess ||
+      (e = dout.ensure(n * 8)) != cudaSuccess) { cleanup(); return ctx->fail(MMA_ERR_CUDA, cudaGetErrorString(e)); }
+  cudaStream_t st = ctx->sc;
+  cudaMemcpyAsync(ds.p, b->start, n * 4, cudaMemcpyHostToDevice, st);
+  cudaMemcpyAsync(de.p, b->end, n * 4, cudaMemcpyHostToDevice, st);
+  cudaMemcpyAsync(dm.p, b->meta, n * 4, cudaMemcpyHostToDevice, st);
+  HitView h = HitView();
+  h.start = ds.as<u32>(); h.end = de.as<u32>(); h.meta = dm.as<u32>(); h.n = (u32)n;
+  const u32 grid = std::min<u32>(gridFor(n, 256), (u32)ctx->nSM * 8);
+  const Rules &r = ctx->rules;
+  const bool fast = ctx->fast.enabled && !ctx->wideMask;
+#define LAUNCH_AO(M)                                                                                                        \
+  do {                                                                                                                      \
+    if (fast) k_annotate_only<M, true><<<grid, 256, 0, st>>>(ctx->index, ctx->fast, h, r, dout.as<u64>());                  \
+    else k_annotate_only<M, false><<<grid, 256, 0, st>>>(ctx->index, ctx->fast, h, r, dout.as<u64>());                      \
+  } while (0)
+  if (r.mode == 0) LAUNCH_AO(0); else if (r.mode == 1) LAUNCH_AO(1); else LAUNCH_AO(2);
+#undef LAUNCH_AO
+  ctx->launches++;
+  cudaMemcpyAsync(out_masks, dout.p, n * 8, cudaMemcpyDeviceToHost, st);
+  e = cudaStreamSynchronize(st);
+  if (e == cudaSuccess) e = cudaGetLastError();
+  cleanup();
+  if (e != cudaSuccess) return ctx->fail(MMA_ERR_CUDA, cudaGetErrorString(e));
+  return MMA_OK;
+}
 
 int mma_sync(mma_ctx *ctx) {
   if (!ctx) return MMA_ERR_INVALID;
@@ -568,10 +713,10 @@ int mma_reset_sample(mma_ctx *ctx, uint32_t sample) {
   const size_t tb = (size_t)ctx->tableCap * sizeof(u64);
   CK(cudaMemsetAsync(s.ctl, 0, sizeof(SampleCtl), ctx->sc));
   CK(cudaMemsetAsync(s.tableKeys.p, 0, tb, ctx->sc)); CK(cudaMemsetAsync(s.tableVals.p, 0, tb, ctx->sc));
-  CK(cudaMemsetAsync(s.deltaKeys.p, 0, tb, ctx->sc)); CK(cudaMemsetAsync(s.deltaVals.p, 0, tb, ctx->sc));
   if (s.openCap) {
     k_fill_u64<<<gridFor(s.openCap, 256), 256, 0, ctx->sc>>>(s.openKeys.as<u64>(), KEY_EMPTY, s.openCap);
-    ctx->launches++;
+    k_fill_u32<<<gridFor(s.openCap, 256), 256, 0, ctx->sc>>>(s.openSeq.as<u32>(), 0xFFFFFFFFu, s.openCap);
+    ctx->launches += 2;
   }
   CK(cudaStreamSynchronize(ctx->sc));
   s.cumHits = 0; s.knownCount = 0; s.knownCum = 0; s.seq = 0; s.touched = false;
@@ -667,6 +812,10 @@ int mma_finish_sample(mma_ctx *ctx, uint32_t sample, mma_sample_result *out) {
   s.rowMask.clear(); s.rowNh.clear(); s.rowCount.clear();
   if (!s.ctl) return MMA_OK;  // nothing was ever submitted
   CK(cudaStreamSynchronize(ctx->sh));
+  if (ctx->rules.strategy == MMA_STRATEGY_DEFAULT && s.slowCap) {
+    k_flush_carry<<<1, 1, 0, ctx->sc>>>(s.ctl, slowView(s));
+    ctx->launches++;
+  }
   CK(cudaStreamSynchronize(ctx->sc));
   SampleCtl hc;
   CK(cudaMemcpy(&hc, s.ctl, sizeof(hc), cudaMemcpyDeviceToHost));
@@ -676,7 +825,6 @@ int mma_finish_sample(mma_ctx *ctx, uint32_t sample, mma_sample_result *out) {
     if (rc) return rc;
     // the deferred records are consumed: a later finish must not count them twice
     CK(cudaMemsetAsync(&s.ctl->slowCount, 0, sizeof(u32), ctx->sc));
-    CK(cudaMemsetAsync(&s.ctl->slowCountAtBatch, 0, sizeof(u32), ctx->sc));
     CK(cudaStreamSynchronize(ctx->sc));
     CK(cudaMemcpy(&hc, s.ctl, sizeof(hc), cudaMemcpyDeviceToHost));
     if (hc.overflow) return ctx->fail(MMA_ERR_CAPACITY, "the combination table overflowed");
@@ -688,7 +836,7 @@ int mma_finish_sample(mma_ctx *ctx, uint32_t sample, mma_sample_result *out) {
   const bool ratio = ctx->rules.strategy == MMA_STRATEGY_RATIO;
   const u64 lowMask = (1ull << NH_SHIFT) - 1;
   for (u32 i = 0; i < ctx->tableCap; ++i) {
-    if (!keys[i]) continue;
+    if (!keys[i] || !vals[i]) continue;  // a count taken back by k_batch_close can leave an empty row
     s.rowMask.push_back(ratio ? (keys[i] & lowMask) : keys[i]);
     s.rowNh.push_back(ratio ? (uint32_t)(keys[i] >> NH_SHIFT) : 0u);
     s.rowCount.push_back(vals[i]);
@@ -743,6 +891,7 @@ int mma_timing_reset(mma_ctx *ctx) {
   for (int i = 0; i < TC_N; ++i) ctx->ms[i] = 0;
   ctx->launches = 0;
   ctx->hitsSubmitted = 0;
+  ctx->batches = 0;
   return MMA_OK;
 }
 int mma_timing_get(mma_ctx *ctx, mma_timing *out) {
@@ -751,12 +900,18 @@ int mma_timing_get(mma_ctx *ctx, mma_timing *out) {
   CK(cudaStreamSynchronize(ctx->sc));
   ctx->collectTiming();
   out->ms_index = ctx->ms[TC_INDEX];
-  out->ms_annotate = ctx->ms[TC_ANNOTATE];
-  out->ms_resolve = ctx->ms[TC_RESOLVE];
-  out->ms_merge = ctx->ms[TC_MERGE];
+  out->ms_batch = ctx->ms[TC_BATCH];
+  out->ms_close = ctx->ms[TC_CLOSE];
   out->ms_finish = ctx->ms[TC_FINISH];
   out->launches = ctx->launches;
   out->hits = ctx->hitsSubmitted;
+  out->batches = ctx->batches;
+  out->fast_miss = 0;
+  for (Sample &sm : ctx->samples)
+    if (sm.ctl) {
+      u32 fm = 0;
+      if (cudaMemcpy(&fm, &sm.ctl->fastMiss, sizeof(u32), cudaMemcpyDeviceToHost) == cudaSuccess) out->fast_miss += fm;
+    }
   return MMA_OK;
 }
 

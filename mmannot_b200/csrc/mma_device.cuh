@@ -1,11 +1,17 @@
 // Device-side data model and kernels of the read-annotation hot path (sm_100a).
 //
-// K1  index build      : packed features, running max-end, position bins (first-start + spanning lists)
-// K2  k_annotate       : per hit -> element set (strand / -l test / Order priority), hit statistics,
-//                        immediate counting of the reads that need no grouping
-// K3  k_resolve        : per read -> NH countdown over the run of records sharing a read key
-// K4  table kernels    : block-privatised shared-memory tables flushed into a device hash table,
-//                        batch delta merge, deferred (name-sorted) resolution at end of sample
+// K1  index build : packed features, running max-end, position bins (first-start + spanning lists), and the
+//                   SEGMENT ANSWER TABLE: the chromosome cut at every feature boundary; inside one segment the
+//                   set of covering features is constant, so the element set of a read that stays inside a
+//                   segment (or crosses exactly one boundary, inclusion mode) is precomputed per strand.
+// K2-K4 k_batch   : ONE kernel per hit batch.  Per tile of 1024 hits: 16-byte vector loads of the packed hit
+//                   arrays -> per-hit element set (segment table, 1-2 L2 gathers; hits the table cannot answer
+//                   are compacted through shared memory and evaluated against the feature index) -> per-read
+//                   NH countdown over the run of records sharing a read key, in shared memory -> counts in a
+//                   block-private shared-memory table flushed once per block into the device hash table.
+//     k_batch_close : end-of-batch bookkeeping; when the batch left an unfinished read in its middle, re-routes
+//                   the other runs of that read name to the deferred list (undoing what k_batch counted for them).
+//     k_slow_*    : deferred (name-sorted) resolution at end of sample.
 //
 // Reference semantics are cited per function as mm:LINE (= /root/reference/mmannot.cpp).
 #pragma once
@@ -39,10 +45,34 @@ struct IndexView {
   u32 nChr, shift;
 };
 
+// Segment answer table (only built when E <= 31: bit 31 of an answer word flags "position dependent")
+//   bin entry  {end of the segment A holding the bin's first position, answer F, answer R,
+//               index of A (24 bits) | for each quarter k = 1..3 of the bin, 2 bits: min(3, index of the segment holding
+//               the quarter's first position - index of A) at bits 24 + 2k}
+//   segment i  seg[2i]   = {start, end, answer F, answer R}                   read inside the segment
+//              seg[2i+1] = {end of segment i+1, cross answer F, cross answer R, 0}  read = tail of i + head of i+1
+// "answer F" is for a read whose strand bit is set (MMA_HIT_STRAND_BIT), "answer R" for the other one.
+// An answer word is the element set (E <= 30), or carries one of two flags:
+//   ANS_VICPAIR  the winning Order line matched exactly one upstream and one downstream element (bits 0..29 hold both):
+//                the pick goes to the nearer one (mm:1066-1075); the two reference coordinates (end of the upstream
+//                feature, start of the downstream one) are in vic[4 * segment + {0 in F, 1 in R, 2 cross F, 3 cross R}]
+//   ANS_GENERAL  any other position-dependent pick: the table cannot answer
+#define ANS_VICPAIR 0x80000000u
+#define ANS_GENERAL 0x40000000u
+struct FastView {
+  const uint4 *bin;
+  const uint4 *seg;
+  const uint2 *vic;
+  const uint2 *chrInfo;  // per chromosome {first bin entry, number of bins}
+  u32 nChr, shift, enabled;
+  u32 upMask, downMask;  // upstream / downstream elements (Config::isUpstream / isDownstream, mm:463-470)
+};
+
 struct HitView {
   const u32 *start, *end, *meta, *nh;
   const u64 *key;
   u32 n;
+  u32 vec;  // all five arrays are 16-byte aligned: the tile loads may use 128-bit accesses
 };
 
 // open-addressing table: combination key -> count.  key 0 = empty (an empty element set is never counted)
@@ -55,16 +85,27 @@ struct TableView {
 
 enum StatSlot { ST_HITS = 0, ST_READS, ST_UNIQUE, ST_AMBIGUOUS, ST_MULTIPLE, ST_UNASSIGNED, ST_RESCUED, ST_N = 8 };
 
+// an open multi-mapping read whose run of records reaches the end of a batch
+struct Carry {
+  u64 key;        // normalised read key
+  u64 ord;        // ordinal of the read's first record
+  u64 gm;         // union of the element sets seen so far
+  u32 remaining;  // records still expected (mm:1673)
+  u32 valid;
+};
+
 // control block of one sample (device memory)
 struct SampleCtl {
-  u64 stats[ST_N];       // committed counters
-  u64 dstats[ST_N];      // counters of the batch in flight (reads / rescued of multi-mapping reads)
-  u64 ordBase;           // ordinal of the first hit of the batch in flight
-  u32 slowCount;         // deferred records
-  u32 slowCountAtBatch;  // value when the batch in flight started
-  u32 openCount;         // entries in the open-key set
-  u32 dirty;             // the batch in flight found an unfinished read
-  u32 overflow;          // any capacity problem (tables, deferred list, key set)
+  u64 stats[ST_N];   // Counter's counters (mm:1663)
+  u64 ordBase;       // ordinal of the first hit of the batch in flight
+  Carry carry[2];    // [batchSeq & 1] = carried into the batch in flight, the other one = carried out of it
+  u32 batchSeq;      // number of batches closed so far
+  u32 slowCount;     // deferred records
+  u32 openCount;     // entries in the open-key set
+  u32 dirty;         // the batch in flight left an unfinished read in its middle
+  u32 overflow;      // any capacity problem (tables, deferred list, key set)
+  u32 closeCount;    // blocks of k_batch_close that are done
+  u32 fastMiss;      // hits the segment table could not answer (diagnostics)
   u32 pad;
 };
 
@@ -74,8 +115,9 @@ struct SlowView {  // deferred records: resolved after a (key, ordinal) sort at 
   u32 cap;
 };
 
-struct KeySetView {  // keys whose records must all take the deferred path
+struct KeySetView {  // read names whose multi-mapping records must all take the deferred path
   u64 *keys;
+  u32 *seq;  // batch in which the key was inserted
   u32 capMask;
 };
 
@@ -96,6 +138,11 @@ struct Rules {
 __device__ __forceinline__ u64 mix64(u64 x) {
   x ^= x >> 33; x *= 0xff51afd7ed558ccdull; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ull; x ^= x >> 33;
   return x;
+}
+__device__ __forceinline__ u32 mix32(u64 x) {
+  u32 h = (u32)x ^ ((u32)(x >> 32) * 0x9E3779B1u);
+  h ^= h >> 15; h *= 0x2C1B3C6Du; h ^= h >> 12;
+  return h;
 }
 __device__ __forceinline__ u64 normKey(u64 k) { return k == KEY_EMPTY ? KEY_EMPTY - 1 : k; }
 
@@ -122,8 +169,8 @@ struct BlockTable {
   __device__ void init() {
     for (int i = threadIdx.x; i < SLOTS; i += blockDim.x) { keys[i] = 0; cnt[i] = 0; }
   }
-  __device__ void add(u64 ckey, u32 n, const TableView &g) {
-    u32 slot = (u32)mix64(ckey) & (SLOTS - 1);
+  __device__ __noinline__ void add(u64 ckey, u32 n, const TableView &g) {
+    u32 slot = mix32(ckey) & (SLOTS - 1);
 #pragma unroll 1
     for (int probe = 0; probe < 8; ++probe) {
       u64 old = keys[slot];
@@ -145,28 +192,34 @@ struct BlockTable {
 // every lane of the warp calls this (ckey = 0 for lanes with nothing to count)
 template <int SLOTS>
 __device__ __forceinline__ void warpCount(BlockTable<SLOTS> &bt, u64 ckey, const TableView &g) {
-  u32 peers = __match_any_sync(0xffffffffu, ckey);
+  if (__ballot_sync(0xffffffffu, ckey != 0) == 0) return;
+  const u32 peers = __match_any_sync(0xffffffffu, ckey);
   if (ckey != 0 && (u32)(__ffs(peers) - 1) == (threadIdx.x & 31u)) bt.add(ckey, __popc(peers), g);
 }
 
-__device__ __forceinline__ bool keySetContains(const KeySetView &s, u64 key) {
+// returns 0 = absent, 1 = present from an earlier batch, 2 = inserted during batch `curSeq` (or later)
+__device__ __forceinline__ int keySetLookup(const KeySetView &s, u64 key, u32 curSeq) {
   u32 slot = (u32)mix64(key) & s.capMask;
   for (u32 probe = 0; probe <= s.capMask; ++probe) {
-    u64 k = s.keys[slot];
-    if (k == key) return true;
-    if (k == KEY_EMPTY) return false;
+    const u64 k = s.keys[slot];
+    if (k == key) return (*(volatile const u32 *)&s.seq[slot] < curSeq) ? 1 : 2;
+    if (k == KEY_EMPTY) return 0;
     slot = (slot + 1) & s.capMask;
   }
-  return false;
+  return 0;
 }
-__device__ __forceinline__ void keySetInsert(const KeySetView &s, u64 key, SampleCtl *ctl) {
+__device__ __forceinline__ void keySetInsert(const KeySetView &s, u64 key, u32 curSeq, SampleCtl *ctl) {
   u32 slot = (u32)mix64(key) & s.capMask;
   for (u32 probe = 0; probe <= s.capMask; ++probe) {
     u64 k = s.keys[slot];
     if (k == key) return;
     if (k == KEY_EMPTY) {
       k = atomicCAS(&s.keys[slot], KEY_EMPTY, key);
-      if (k == KEY_EMPTY) { atomicAdd(&ctl->openCount, 1u); return; }
+      if (k == KEY_EMPTY) {
+        *(volatile u32 *)&s.seq[slot] = curSeq;
+        atomicAdd(&ctl->openCount, 1u);
+        return;
+      }
       if (k == key) return;
     }
     slot = (slot + 1) & s.capMask;
@@ -175,23 +228,30 @@ __device__ __forceinline__ void keySetInsert(const KeySetView &s, u64 key, Sampl
 }
 
 __device__ __forceinline__ void slowAppend(const SlowView &s, SampleCtl *ctl, u64 key, u64 ord, u64 mask, u32 nh) {
-  u32 at = atomicAdd(&ctl->slowCount, 1u);
+  const u32 at = atomicAdd(&ctl->slowCount, 1u);
   if (at >= s.cap) { atomicExch(&ctl->overflow, 1u); return; }
   s.key[at] = key; s.ord[at] = ord; s.mask[at] = mask; s.nh[at] = nh;
 }
 
-// ----------------------------------------------------------------------------- K2: per-hit annotation
+// ----------------------------------------------------------------------------- per-hit annotation against the feature index
 
 struct HitEval {  // running best of the winning Order line (EvaluationStructure::getFirst, mm:1029-1076)
   u64 seen;       // element types already decided (we walk the candidates backwards: the first
                   // passing interval met for a type is the LAST one in feature order, mm:1023-1028)
   u64 chosen;
+  u64 lineAll;    // TRACK only: every matched element of the winning line
   u32 bestLine, bestOv, bestDist;
+  u32 pUp, pDown; // TRACK only: reference coordinate of the line's upstream / downstream match (mm:1316-1322)
 };
 
-template <int MODE>
+template <int MODE, bool TRACK>
 __device__ __forceinline__ void evalCandidate(const uint4 f, u32 rs, u32 re, u32 rstrand, float ovl, HitEval &ev) {
   if (f.x > re) return;  // the reference stops its walk at the first interval starting after the read (mm:1311)
+  // ... and starts it at the first interval, from the bin of the read start on, that does not end before the read
+  // (mm:1303-1308).  Everything before that bin ends before the read too, so an interval is walked iff the running
+  // maximum of the ends up to it reaches the read start.  Only matters for an empty CIGAR (end = start - 1, mm:874)
+  // against a feature ending exactly at that end: it is "included" (mm:638) unless the walk skipped it.
+  if (f.w < rs) return;
   const u32 m = f.z;
   const u32 t = FM_TYPE(m);
   if ((ev.seen >> t) & 1ull) return;
@@ -223,8 +283,11 @@ __device__ __forceinline__ void evalCandidate(const uint4 f, u32 rs, u32 re, u32
   ev.seen |= 1ull << t;
   const u32 line = FM_LINE(m);
   const u64 bit = 1ull << t;
-  if (line < ev.bestLine) { ev.bestLine = line; ev.bestOv = sc; ev.bestDist = d; ev.chosen = bit; }
-  else if (line == ev.bestLine) {
+  if (line < ev.bestLine) {
+    ev.bestLine = line; ev.bestOv = sc; ev.bestDist = d; ev.chosen = bit;
+    if (TRACK) { ev.lineAll = bit; ev.pUp = f.y; ev.pDown = f.x; }
+  } else if (line == ev.bestLine) {
+    if (TRACK) { ev.lineAll |= bit; if (vic == 1) ev.pUp = f.y; if (vic == 2) ev.pDown = f.x; }
     if (sc > ev.bestOv) { ev.bestOv = sc; ev.bestDist = d; ev.chosen = bit; }
     else if (sc == ev.bestOv) {
       if (d < ev.bestDist) { ev.bestDist = d; ev.chosen = bit; }
@@ -235,9 +298,12 @@ __device__ __forceinline__ void evalCandidate(const uint4 f, u32 rs, u32 re, u32
 
 // IntervalList::scan, mm:1291-1332, as an index lookup: the candidates are the features that reach
 // into the bin of the read start (spanning list) plus those that start in the bins the read covers.
-template <int MODE>
-__device__ __forceinline__ u64 annotateHit(const IndexView &ix, u32 rs, u32 re, u32 meta, float ovl) {
+struct EvalTrack { u64 lineAll; u32 pUp, pDown; };
+
+template <int MODE, bool TRACK>
+__device__ __forceinline__ u64 annotateEval(const IndexView &ix, u32 rs, u32 re, u32 meta, float ovl, EvalTrack *track) {
   const u32 chr = meta & 0x00FFFFFFu;
+  if (TRACK) { track->lineAll = 0; track->pUp = 0; track->pDown = 0; }
   if (chr >= ix.nChr) return 0;
   const uint2 ci = __ldg(&ix.chrInfo[chr]);
   const u32 lastBin = ci.y - 1;
@@ -248,204 +314,577 @@ __device__ __forceinline__ u64 annotateHit(const IndexView &ix, u32 rs, u32 re, 
   const u32 hi = (b1 == b0) ? e1.x : __ldg(&ix.bins[ci.x + b1 + 1]).x;
   const u32 rstrand = meta >> 31;
   HitEval ev;
-  ev.seen = 0; ev.chosen = 0; ev.bestLine = 0xFFFFFFFFu; ev.bestOv = 0; ev.bestDist = 0;
-  for (u32 i = hi; i-- > e0.x;) evalCandidate<MODE>(__ldg(&ix.feat[i]), rs, re, rstrand, ovl, ev);
-  for (u32 k = e1.y; k-- > e0.y;) evalCandidate<MODE>(__ldg(&ix.feat[__ldg(&ix.spanIdx[k])]), rs, re, rstrand, ovl, ev);
+  ev.seen = 0; ev.chosen = 0; ev.lineAll = 0; ev.bestLine = 0xFFFFFFFFu; ev.bestOv = 0; ev.bestDist = 0; ev.pUp = 0; ev.pDown = 0;
+  for (u32 i = hi; i-- > e0.x;) evalCandidate<MODE, TRACK>(__ldg(&ix.feat[i]), rs, re, rstrand, ovl, ev);
+  for (u32 k = e1.y; k-- > e0.y;) evalCandidate<MODE, TRACK>(__ldg(&ix.feat[__ldg(&ix.spanIdx[k])]), rs, re, rstrand, ovl, ev);
+  if (TRACK) { track->lineAll = ev.lineAll; track->pUp = ev.pUp; track->pDown = ev.pDown; }
   return ev.chosen;
 }
 
-#define ANNOTATE_THREADS 256
-#define BT_SLOTS 256
-
-// One thread per hit.  Writes the element set of every hit (default strategy only, for K3),
-// accumulates the per-hit counters of Counter::addCount (mm:1666-1668) and counts at once the
-// reads that are their own group (mm:1703-1738): NH <= 1 under `default`, every visited hit under
-// `unique` / `ratio`.  Under `random` the annotated hits are deferred (order-dependent draw).
-template <int MODE, typename MaskT>
-__global__ void __launch_bounds__(ANNOTATE_THREADS)
-k_annotate(IndexView ix, HitView h, Rules r, MaskT *__restrict__ outMask, TableView table, SampleCtl *ctl, SlowView slow) {
-  __shared__ BlockTable<BT_SLOTS> bt;
-  __shared__ u32 sstat[ST_N];
-  bt.init();
-  if (threadIdx.x < ST_N) sstat[threadIdx.x] = 0;
-  __syncthreads();
-  const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
-  const bool valid = i < h.n;
-  u32 rs = 0, re = 0, meta = 0x00FFFFFFu, nh = 1;
-  if (valid) { rs = __ldcs(&h.start[i]); re = __ldcs(&h.end[i]); meta = __ldcs(&h.meta[i]); nh = __ldcs(&h.nh[i]); }
-  const bool visited = valid && !(r.strategy == 1 && nh != 1);  // unique: only NH == 1 is looked at (mm:1773)
-  u64 mask = 0;
-  if (visited) mask = annotateHit<MODE>(ix, rs, re, meta, r.overlap);
-  const int nreg = __popcll(mask);
-  const bool multi = visited && r.strategy == 0 && nh > 1;  // joins the by-name countdown (mm:1669)
-  if (r.strategy == 0 && valid) outMask[i] = (MaskT)mask;
-  // per-hit counters, one shared atomic per warp and counter
-  const u32 lane = threadIdx.x & 31u;
-  const u32 bVisited = __ballot_sync(0xffffffffu, visited);
-  const u32 bUnassigned = __ballot_sync(0xffffffffu, visited && nreg == 0);
-  const u32 bAmbiguous = __ballot_sync(0xffffffffu, visited && nreg > 1);
-  const u32 bUnique = __ballot_sync(0xffffffffu, visited && nreg == 1 && nh == 1);
-  const u32 bMulti = __ballot_sync(0xffffffffu, multi);
-  if (lane == 0) {
-    if (bVisited) atomicAdd(&sstat[ST_HITS], __popc(bVisited));
-    if (bUnassigned) atomicAdd(&sstat[ST_UNASSIGNED], __popc(bUnassigned));
-    if (bAmbiguous) atomicAdd(&sstat[ST_AMBIGUOUS], __popc(bAmbiguous));
-    if (bUnique) atomicAdd(&sstat[ST_UNIQUE], __popc(bUnique));
-    if (bMulti) atomicAdd(&sstat[ST_MULTIPLE], __popc(bMulti));
-    const u32 own = bVisited & ~bMulti;  // each of these is a read of its own (mm:1737)
-    if (own) atomicAdd(&sstat[ST_READS], __popc(own));
-  }
-  u64 ckey = 0;
-  if (visited && !multi && mask != 0) {
-    if (r.strategy == 2) {
-      slowAppend(slow, ctl, normKey(__ldcs(&h.key[i])), ctl->ordBase + i, mask, nh);
-    } else {
-      u64 m = mask;
-      if (r.rescue && nreg > 1) {  // rescue() on a single ambiguous hit (mm:1728 -> 491 -> 497-509): every multiplicity is 1
-        const u32 t = (u32)ceilf(__fmul_rn((float)nreg, r.rescueThreshold));
-        if (t <= 1u) m = m & (0 - m);  // lowest element reaches the threshold first
-      }
-      ckey = m;
-      if (r.strategy == 3) {
-        if (nh >= (1u << (64 - NH_SHIFT))) atomicExch(&ctl->overflow, 1u);
-        ckey |= (u64)nh << NH_SHIFT;
-      }
-    }
-  }
-  warpCount(bt, ckey, table);
-  __syncthreads();
-  bt.flush(table);
-  if (threadIdx.x < ST_N && sstat[threadIdx.x]) atomicAdd(&ctl->stats[threadIdx.x], (u64)sstat[threadIdx.x]);
+template <int MODE>
+__device__ __noinline__ u64 annotateHit(const IndexView &ix, u32 rs, u32 re, u32 meta, float ovl) {
+  return annotateEval<MODE, false>(ix, rs, re, meta, ovl, nullptr);
 }
 
-// ----------------------------------------------------------------------------- K3: per-read resolution
+// Segment-table lookup.  true: `out` is the element set of the hit; false: the table cannot answer (read over three
+// or more segments or starting beyond the second segment of its bin, position-dependent pick, degenerate interval).
+//   * a read inside one segment is covered by exactly the features covering the segment; they all score alike
+//     (1 under inclusion, end - start under the overlap modes), so the pick is the precomputed one -- provided the
+//     read is long enough to match anything at all under -l (mm:995-1002);
+//   * under inclusion a read over two adjacent segments is included in exactly the features covering both.
+// One gather (the bin entry) answers a read inside segment A; otherwise the bin entry names the segment holding the
+// first position of the read's quarter of the bin, whose 32-byte record (one L2 sector) answers a read inside it or
+// over it and its right neighbour; a read starting one segment further costs one more gather.
+template <int MODE>
+__device__ __forceinline__ bool fastAnnotate(const FastView &fx, u32 rs, u32 re, u32 meta, float ovl, u32 &out) {
+  out = 0;
+  const u32 chr = meta & 0x00FFFFFFu;
+  if (chr >= fx.nChr) return true;
+  if (re < rs || re >= 0xFFFFFFF0u) return false;
+  if (MODE != 0) {  // no feature can overlap the read by more than end - start
+    const u32 o = re - rs;
+    if (o == 0) return true;
+    if (MODE == 1) { if (!(__fmul_rn((float)(o + 1u), ovl) <= (float)o)) return true; }
+    else { if (!((float)o >= ovl)) return true; }
+  }
+  const uint2 ci = __ldg(&fx.chrInfo[chr]);
+  const u32 bRaw = rs >> fx.shift;
+  const u32 b = min(bRaw, ci.y - 1);
+  const uint4 e = __ldg(&fx.bin[ci.x + b]);
+  const u32 strandIdx = (meta >> 31) ? 0u : 1u;
+  u32 a, i = e.w & 0x00FFFFFFu, kind = 0;
+  if (re <= e.x) {
+    a = strandIdx ? e.z : e.y;
+  } else {
+    const u32 quarter = (bRaw == b) ? ((rs >> (fx.shift - 2)) & 3u) : 3u;
+    i += (e.w >> (24 + 2 * quarter)) & 3u;
+    uint4 t = __ldg(&fx.seg[2 * i]);  // {start, end, answer F, answer R}
+#pragma unroll 1
+    for (int g = 0; rs > t.y; ++g) {
+      if (g == 3) return false;
+      ++i;
+      t = __ldg(&fx.seg[2 * i]);
+    }
+    if (re <= t.y) {
+      a = strandIdx ? t.w : t.z;
+    } else {
+      if (MODE != 0) return false;
+      const uint4 x = __ldg(&fx.seg[2 * i + 1]);  // {end of the next segment, cross answer F, cross answer R, 0}
+      if (re > x.x) return false;
+      a = strandIdx ? x.z : x.y;
+      kind = 2;
+    }
+  }
+  if (a & (ANS_VICPAIR | ANS_GENERAL)) {
+    if (a & ANS_GENERAL) return false;
+    const uint2 v = __ldg(&fx.vic[4 * i + kind + strandIdx]);
+    const u32 dUp = v.x - re, dDown = rs - v.y;  // Interval::getDistance of the read to the two coordinates (mm:661-665)
+    a &= ~ANS_VICPAIR;
+    if (dUp < dDown) a &= fx.upMask;
+    else if (dDown < dUp) a &= fx.downMask;
+  }
+  out = a;
+  return true;
+}
 
-// rescue(), mm:497-509, for a group of records [first, end) of one read (only reachable with -m and -e < 100)
-template <typename MaskT>
-__device__ u64 rescueGroup(const Rules &r, const MaskT *mask, const u32 *nh, const u64 *key, u64 k, u32 first, u32 end, u64 gm) {
-  u32 n = 0;
-  for (u32 j = first; j < end; ++j)
-    if (normKey(key[j]) == k && nh[j] > 1) n += __popcll((u64)mask[j]);
-  if (n == 1) return gm;
-  const u32 t = (u32)ceilf(__fmul_rn((float)n, r.rescueThreshold));
+// ----------------------------------------------------------------------------- the batch kernel
+
+// Work decomposition: a WARP TILE is 128 consecutive hits, 4 per lane (one 16-byte load per array and lane).  Every
+// warp of the grid owns one contiguous chunk of warp tiles and walks it front to back WITHOUT any block-wide barrier:
+// the state of the read that is still open at the end of a tile stays in registers for the next tile, so only the read
+// open at the end of a chunk (one per ~16 tiles) has to be finished by a serial walk through global memory.
+#define BATCH_THREADS 256
+#define BATCH_WARPS (BATCH_THREADS / 32)
+#define WT_HITS 128
+#ifndef MMA_BLOCKS_PER_SM
+#define MMA_BLOCKS_PER_SM 4  // resident k_batch blocks per SM the register allocation is tuned for
+#endif
+#define BT_SLOTS 256
+#define HIST_ROWS 32
+
+// rescue(), mm:497-509, on a single ambiguous hit (mm:1728 -> 491): every multiplicity is 1
+__device__ __forceinline__ u64 rescueSingle(const Rules &r, u64 mask) {
+  const int nreg = __popcll(mask);
+  if (r.rescue && nreg > 1) {
+    const u32 t = (u32)ceilf(__fmul_rn((float)nreg, r.rescueThreshold));
+    if (t <= 1u) return mask & (0 - mask);  // lowest element reaches the threshold first
+  }
+  return mask;
+}
+
+// rescue(), mm:497-509, from per-element multiplicities gathered by `multiplicity(bit)`
+template <typename F>
+__device__ __forceinline__ u64 rescueFromCounts(const Rules &r, u64 gm, u32 total, F multiplicity) {
+  if (total == 1) return gm;
+  const u32 t = (u32)ceilf(__fmul_rn((float)total, r.rescueThreshold));
   for (u64 rest = gm; rest; rest &= rest - 1) {
     const u64 bit = rest & (0 - rest);
-    u32 c = 0;
-    for (u32 j = first; j < end; ++j)
-      if (normKey(key[j]) == k && nh[j] > 1 && ((u64)mask[j] & bit)) ++c;
-    if (c >= t) return bit;
+    if (multiplicity(bit) >= t) return bit;
   }
   return gm;
 }
 
-#define RESOLVE_THREADS 256
+template <int MODE, bool FAST>
+struct Annotator {
+  const IndexView &ix;
+  const FastView &fx;
+  float ovl;
+  __device__ __forceinline__ u64 operator()(u32 rs, u32 re, u32 meta) const {
+    if (FAST) {
+      u32 a;
+      if (fastAnnotate<MODE>(fx, rs, re, meta, ovl, a)) return a;
+    }
+    return annotateHit<MODE>(ix, rs, re, meta, ovl);
+  }
+};
 
-// One thread per hit; the thread of the first record of a run of equal read keys walks the run and
-// applies the NH countdown of Counter::addCount (mm:1669-1702): a read opens at a record with NH > 1,
-// takes the following NH-1 records of its name (NH <= 1 records are reads of their own and do not
-// count down), then its element set is counted.  A read still open at the end of its run cannot be
-// finished here (its remaining records may come later in the file, or never): its records and key go
-// to the deferred path, and the batch is marked dirty so that pass 1 re-routes every run of such keys.
-//   pass 0: normal.   pass 1: only runs if pass 0 left the batch dirty (the delta was discarded).
-template <typename MaskT>
-__global__ void __launch_bounds__(RESOLVE_THREADS)
-k_resolve(HitView h, Rules r, const MaskT *__restrict__ mask, TableView delta, SampleCtl *ctl, SlowView slow, KeySetView open, int pass) {
-  if (pass == 1 && ctl->dirty == 0) return;
-  __shared__ BlockTable<BT_SLOTS> bt;
-  __shared__ u32 sReads, sRescued;
-  bt.init();
-  if (threadIdx.x == 0) { sReads = 0; sRescued = 0; }
+// Shared memory of one block: only the count tables
+template <bool HIST>
+struct BatchSmem {
+  BlockTable<BT_SLOTS> bt;  // element sets of two or more elements (and everything under -y ratio / wide sets)
+  // reads counted per single-element set: one private column per thread, no atomics.  A thread adds at most 4 per
+  // warp tile and sees < 2^14 warp tiles of one batch: no overflow
+  unsigned short hist[HIST ? HIST_ROWS : 1][BATCH_THREADS];
+  u32 walkQ[4][BATCH_THREADS];  // per thread: first records of the runs of the current tile that need the serial walk
+  u32 stat[ST_N];
+};
+
+// The NH countdown of Counter::addCount (mm:1669-1702) over one run of records sharing a read key, as a serial walk
+// through global memory (element sets recomputed).  A read opens at a record with NH > 1, takes the following NH-1
+// records of its name (NH <= 1 records are reads of their own and do not count down), then its element set is
+// counted.  This is the path of every run that is not the clean "n records carrying NH = n" and of the one run per
+// chunk that crosses into the next warp's chunk.  What happens to a read still open at the end of its run:
+//   run ends inside the batch : the read cannot be finished here (its remaining records may come later in the file,
+//                               or never): its records and key go to the deferred path, the batch is marked dirty;
+//   run reaches the batch end : the open state is carried into the next batch (ctl->carry).
+template <int MODE, bool FAST, typename Count>
+struct RunWalker {
+  const HitView &h;
+  const Rules &r;
+  const Annotator<MODE, FAST> &annot;
+  SampleCtl *ctl;
+  const SlowView &slow;
+  const KeySetView &open;
+  Count &count;
+  u32 seq;
+  u32 nReads, nRescued;
+
+  __device__ __forceinline__ u64 maskAt(u32 j) const { return annot(h.start[j], h.end[j], h.meta[j]); }
+
+  __device__ u64 rescueGroup(u32 first, u32 end, u64 gm) const {
+    u32 total = 0;
+    for (u32 j = first; j < end; ++j)
+      if (h.nh[j] > 1) total += __popcll(maskAt(j));
+    return rescueFromCounts(r, gm, total, [&](u64 bit) {
+      u32 c = 0;
+      for (u32 j = first; j < end; ++j)
+        if (h.nh[j] > 1 && (maskAt(j) & bit)) ++c;
+      return c;
+    });
+  }
+
+  // i = first record of the run inside this batch, k = its key; `cin` = state carried into the batch (or null)
+  __device__ __noinline__ void walk(u32 i, u64 k, const Carry *cin) {
+    const bool routed = (ctl->openCount != 0) && keySetLookup(open, k, seq) == 1;
+    bool isOpen = false, fromCarry = false;
+    u32 remaining = 0, first = i;
+    u64 gm = 0;
+    if (cin) { isOpen = true; fromCarry = true; remaining = cin->remaining; gm = cin->gm; }
+    u32 j = i;
+    for (; j < h.n; ++j) {
+      if (j != i && normKey(h.key[j]) != k) break;  // end of the run
+      const u32 nhj = h.nh[j];
+      if (!(nhj > 1)) continue;
+      const u64 mj = maskAt(j);
+      if (routed) { slowAppend(slow, ctl, k, ctl->ordBase + j, mj, nhj); continue; }
+      if (!isOpen) { isOpen = true; fromCarry = false; remaining = nhj - 1; gm = mj; first = j; ++nReads; }
+      else { --remaining; gm |= mj; }
+      if (remaining == 0) {
+        if (gm != 0) {
+          if (r.rescue) gm = rescueGroup(first, j + 1, gm);  // never a carried read: rescue mode does not carry
+          count(gm);
+          if (__popcll(gm) == 1) ++nRescued;
+        }
+        isOpen = false;
+      }
+    }
+    if (!isOpen) return;
+    if (routed) return;  // (a carried read is never routed: its name would have been deferred instead of carried)
+    if (j >= h.n && !r.rescue) {  // the run reaches the end of the batch: carry the open read over
+      Carry &c = ctl->carry[(seq + 1) & 1];
+      c.key = k; c.gm = gm; c.remaining = remaining;
+      c.ord = fromCarry ? cin->ord : ctl->ordBase + first;
+      __threadfence();
+      c.valid = 1;
+      return;
+    }
+    // unfinished read: the deferred path opens it again
+    --nReads;
+    if (fromCarry) slowAppend(slow, ctl, k, cin->ord, cin->gm, cin->remaining + 1);  // stands for the records of earlier batches
+    for (u32 q = fromCarry ? i : first; q < j; ++q) {
+      const u32 nhq = h.nh[q];
+      if (nhq > 1) slowAppend(slow, ctl, k, ctl->ordBase + q, maskAt(q), nhq);
+    }
+    keySetInsert(open, k, seq, ctl);
+    ctl->dirty = 1;
+  }
+};
+
+// STRAT: MMA_STRATEGY_* (0 default, 1 unique, 2 random, 3 ratio)
+template <int MODE, int STRAT, bool FAST, typename MaskT>
+__global__ void __launch_bounds__(BATCH_THREADS, (sizeof(MaskT) == 4) ? MMA_BLOCKS_PER_SM : 2)
+k_batch(IndexView ix, FastView fx, HitView h, Rules r, TableView table, SampleCtl *ctl, SlowView slow, KeySetView open) {
+  constexpr bool HIST = (sizeof(MaskT) == 4) && STRAT != 2 && STRAT != 3;  // single-element sets go to the private histogram
+  __shared__ BatchSmem<HIST> sm;
+  const u32 tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+  sm.bt.init();
+  if (HIST) {
+#pragma unroll
+    for (int e = 0; e < HIST_ROWS; ++e) sm.hist[e][tid] = 0;
+  }
+  if (tid < ST_N) sm.stat[tid] = 0;
   __syncthreads();
-  const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
-  u64 commit[1];
-  commit[0] = 0;
-  u32 nReads = 0, nRescued = 0;
-  if (i < h.n) {
-    const u64 k = normKey(h.key[i]);
-    const bool head = (i == 0) || (normKey(h.key[i - 1]) != k);
-    if (head) {
-      // find the run and whether it holds any multi-mapping record at all
-      const bool anyOpenKeys = (ctl->openCount != 0) || pass == 1;
-      bool routed = false;
-      if (anyOpenKeys && keySetContains(open, k)) routed = true;
-      bool isOpen = false;
-      u32 remaining = 0, first = 0;
-      u64 gm = 0;
-      u32 j = i;
-      for (; j < h.n && normKey(h.key[j]) == k; ++j) {
-        const u32 nhj = h.nh[j];
-        if (!(nhj > 1)) continue;
-        const u64 mj = (u64)mask[j];
-        if (routed) { slowAppend(slow, ctl, k, ctl->ordBase + j, mj, nhj); continue; }
-        if (!isOpen) { isOpen = true; remaining = nhj - 1; gm = mj; first = j; ++nReads; }
-        else { --remaining; gm |= mj; }
-        if (isOpen && remaining == 0) {
-          if (gm != 0) {
-            if (r.rescue) gm = rescueGroup(r, mask, h.nh, h.key, k, first, j + 1, gm);
-            if (commit[0] == 0) commit[0] = gm;
-            else bt.add(gm, 1, delta);  // more than one read closed inside one run: rare
-            if (__popcll(gm) == 1) ++nRescued;
-          }
-          isOpen = false;
+  const Annotator<MODE, FAST> annot{ix, fx, r.overlap};
+  const u32 seq = ctl->batchSeq;
+  // parallel countdown only when no read name is known as unfinished (then nothing has to be routed to the deferred
+  // path) and rescue() is off (it needs multiplicities); the value is uniform over the warp
+  const bool parallelRuns = (STRAT == 0) && (sizeof(MaskT) == 4) && !r.rescue && (__shfl_sync(0xffffffffu, ctl->openCount, 0) == 0);
+  u32 cHits = 0, cUnassigned = 0, cAmbiguous = 0, cUnique = 0, cMultiple = 0, cReads = 0, cRescued = 0, cMiss = 0;
+
+  // one read counted for the element set `ckey` (0 = nothing)
+  auto count = [&](u64 ckey) {
+    if (HIST && (ckey & (ckey - 1)) == 0) {
+      if (ckey) sm.hist[__ffs((u32)ckey) - 1][tid] += 1;
+    } else if (ckey) {
+      sm.bt.add(ckey, 1, table);
+    }
+  };
+  RunWalker<MODE, FAST, decltype(count)> w{h, r, annot, ctl, slow, open, count, seq, 0u, 0u};
+
+  // this warp's chunk of warp tiles
+  const u32 nWT = (h.n + WT_HITS - 1) / WT_HITS;
+  const u32 nWarps = gridDim.x * BATCH_WARPS;
+  const u32 per = (nWT + nWarps - 1) / nWarps;
+  const u32 t0 = min(nWT, (blockIdx.x * BATCH_WARPS + warp) * per), t1 = min(nWT, t0 + per);
+
+  // the run that is open at the end of the previous tile of the chunk (all lanes hold the same values)
+  bool cValid = false;  // ... and it starts inside this chunk (else the previous chunk's warp finishes it)
+  u32 cStart = 0;       // its first record
+  u32 cTot = 0;         // union of its element sets so far | bit 31: NH changed inside it
+  u32 cNh = 0;          // NH of the last record of the previous tile
+  u64 cKey = KEY_EMPTY; // key of the last record of the previous tile
+
+  for (u32 t = t0; t < t1; ++t) {
+    const u32 base = t * WT_HITS + lane * 4;
+    u32 rs[4], re[4], meta[4], nh[4];
+    u64 key[4];
+    bool valid[4];
+    // ---- load (128-bit accesses on full tiles of aligned arrays)
+    if (h.vec && (t + 1) * WT_HITS <= h.n) {
+      const uint4 a = __ldcs(reinterpret_cast<const uint4 *>(h.start + base));
+      const uint4 b = __ldcs(reinterpret_cast<const uint4 *>(h.end + base));
+      const uint4 c = __ldcs(reinterpret_cast<const uint4 *>(h.meta + base));
+      const uint4 d = __ldcs(reinterpret_cast<const uint4 *>(h.nh + base));
+      rs[0] = a.x; rs[1] = a.y; rs[2] = a.z; rs[3] = a.w;
+      re[0] = b.x; re[1] = b.y; re[2] = b.z; re[3] = b.w;
+      meta[0] = c.x; meta[1] = c.y; meta[2] = c.z; meta[3] = c.w;
+      nh[0] = d.x; nh[1] = d.y; nh[2] = d.z; nh[3] = d.w;
+      if (STRAT == 0 || STRAT == 2) {
+        const ulonglong2 k0 = __ldcs(reinterpret_cast<const ulonglong2 *>(h.key + base));
+        const ulonglong2 k1 = __ldcs(reinterpret_cast<const ulonglong2 *>(h.key + base + 2));
+        key[0] = normKey(k0.x); key[1] = normKey(k0.y); key[2] = normKey(k1.x); key[3] = normKey(k1.y);
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) valid[j] = true;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const u32 i = base + j;
+        valid[j] = i < h.n;
+        rs[j] = 0; re[j] = 0; meta[j] = 0x00FFFFFFu; nh[j] = 1; key[j] = KEY_EMPTY;
+        if (valid[j]) {
+          rs[j] = __ldcs(&h.start[i]); re[j] = __ldcs(&h.end[i]); meta[j] = __ldcs(&h.meta[i]); nh[j] = __ldcs(&h.nh[i]);
+          if (STRAT == 0 || STRAT == 2) key[j] = normKey(__ldcs(&h.key[i]));
         }
       }
-      if (isOpen) {  // unfinished read
-        --nReads;    // it will be opened again on the deferred path
-        for (u32 q = first; q < j; ++q) {
-          const u32 nhq = h.nh[q];
-          if (nhq > 1) slowAppend(slow, ctl, k, ctl->ordBase + q, (u64)mask[q], nhq);
+    }
+    // ---- element set of every hit that is looked at (unique: only NH == 1 is, mm:1773)
+    bool visited[4];
+    MaskT m[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      visited[j] = valid[j] && !(STRAT == 1 && nh[j] != 1);
+      m[j] = 0;
+      if (!visited[j]) continue;
+      if (FAST) {
+        u32 a;
+        if (fastAnnotate<MODE>(fx, rs[j], re[j], meta[j], r.overlap, a)) m[j] = (MaskT)a;
+        else { m[j] = (MaskT)annotateHit<MODE>(ix, rs[j], re[j], meta[j], r.overlap); ++cMiss; }
+      } else {
+        m[j] = (MaskT)annotateHit<MODE>(ix, rs[j], re[j], meta[j], r.overlap);
+      }
+    }
+    // ---- per-hit counters (mm:1666-1668) and the reads that are their own group (mm:1703-1738)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int nreg = __popcll((u64)m[j]);
+      const bool multi = visited[j] && STRAT == 0 && nh[j] > 1;  // joins the by-name countdown (mm:1669)
+      cHits += visited[j];
+      cUnassigned += visited[j] && nreg == 0;
+      cAmbiguous += visited[j] && nreg > 1;
+      cUnique += visited[j] && nreg == 1 && nh[j] == 1;
+      cMultiple += multi;
+      cReads += visited[j] && !multi;  // each of these is a read of its own (mm:1737)
+      if (visited[j] && !multi && m[j] != 0) {
+        if (STRAT == 2) {
+          slowAppend(slow, ctl, key[j], ctl->ordBase + base + j, (u64)m[j], nh[j]);  // order-dependent draw: deferred
+        } else {
+          u64 ckey = rescueSingle(r, (u64)m[j]);
+          if (STRAT == 3) {
+            if (nh[j] >= (1u << (64 - NH_SHIFT))) atomicExch(&ctl->overflow, 1u);
+            ckey |= (u64)nh[j] << NH_SHIFT;
+          }
+          count(ckey);
         }
-        keySetInsert(open, k, ctl);
+      }
+    }
+    if (STRAT != 0) continue;
+
+    // ---- per-read countdown (mm:1669-1702)
+    // run starts: a record whose read key differs from the previous record's
+    u64 prev = __shfl_up_sync(0xffffffffu, key[3], 1);
+    const Carry *carryIn = nullptr;
+    if (lane == 0) {
+      if (t != t0) prev = cKey;
+      else if (base == 0) {
+        const Carry &c = ctl->carry[seq & 1];
+        prev = KEY_EMPTY;
+        if (c.valid) { carryIn = &c; prev = c.key; }
+      } else prev = normKey(h.key[base - 1]);
+    }
+    const u32 hbits = ((key[0] != prev || !valid[0]) ? 1u : 0u) | ((key[1] != key[0] || !valid[1]) ? 2u : 0u) |
+                      ((key[2] != key[1] || !valid[2]) ? 4u : 0u) | ((key[3] != key[2] || !valid[3]) ? 8u : 0u);
+    const u32 F = __ballot_sync(0xffffffffu, hbits != 0);  // lanes in which a run starts
+    if (carryIn) {  // lane 0 of the batch's first tile: the read carried into this batch
+      if (!(hbits & 1u)) w.walk(0, carryIn->key, carryIn);
+      else {  // its name does not continue: unfinished
+        --w.nReads;
+        slowAppend(slow, ctl, carryIn->key, carryIn->ord, carryIn->gm, carryIn->remaining + 1);
+        keySetInsert(open, carryIn->key, seq, ctl);
         ctl->dirty = 1;
       }
     }
-  }
-  warpCount(bt, commit[0], delta);
-  if (nReads) atomicAdd(&sReads, nReads);
-  if (nRescued) atomicAdd(&sRescued, nRescued);
-  __syncthreads();
-  bt.flush(delta);
-  if (threadIdx.x == 0) {
-    if (sReads) atomicAdd(&ctl->dstats[ST_READS], (u64)sReads);
-    if (sRescued) atomicAdd(&ctl->dstats[ST_RESCUED], (u64)sRescued);
-  }
-}
-
-// between pass 0 and pass 1: a dirty batch throws its delta away and rolls the deferred list back
-__global__ void k_batch_mid(TableView delta, SampleCtl *ctl) {
-  if (ctl->dirty == 0) return;
-  const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i <= delta.capMask) { delta.keys[i] = 0; delta.vals[i] = 0; }
-  if (i == 0) {
-    ctl->dstats[ST_READS] = 0; ctl->dstats[ST_RESCUED] = 0;
-    ctl->slowCount = ctl->slowCountAtBatch;
-  }
-}
-
-// end of batch: delta -> sample table, batch counters -> sample counters
-__global__ void k_batch_merge(TableView delta, TableView table, SampleCtl *ctl, u32 nHits) {
-  const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i <= delta.capMask) {
-    const u64 k = delta.keys[i];
-    if (k != 0) {
-      tableAdd(table, k, delta.vals[i]);
-      delta.keys[i] = 0; delta.vals[i] = 0;
+    u32 nWalk = 0;
+    if (!parallelRuns) {
+      // serial walk of every run from its first record (rescue mode, wide element sets, or some read name is unfinished)
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (valid[j] && ((hbits >> j) & 1u)) sm.walkQ[nWalk++][tid] = base + j;
+#pragma unroll 1
+      for (u32 q = 0; q < nWalk; ++q) { const u32 i0 = sm.walkQ[q][tid]; w.walk(i0, normKey(h.key[i0]), nullptr); }
+      continue;
+    }
+    // Parallel countdown for the regular case: a run of n records that all carry NH = n (> 1) is one read; its
+    // element set is the union over the run: a segmented OR scan over the 128 hits of the warp tile (bit 31 of the
+    // scanned word = "NH changes inside the run"), seeded with the state carried from the previous tile.  The lane
+    // owning the run's LAST record closes it.  Runs of another shape take the serial walk (RunWalker), started by the
+    // same lane.
+    u32 prevNh = __shfl_up_sync(0xffffffffu, nh[3], 1);
+    if (lane == 0) prevNh = cNh;
+    u32 pre[4], acc = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const bool isHead = (hbits >> j) & 1u;
+      const bool bad = !isHead && nh[j] != (j ? nh[j > 0 ? j - 1 : 0] : prevNh);
+      const u32 x = (u32)m[j] | (bad ? 0x80000000u : 0u);
+      acc = isHead ? x : (acc | x);
+      pre[j] = acc;
+    }
+    u32 inc = acc;  // inclusive scan over lanes: OR of `acc` from the nearest lane with a run start up to this lane
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const u32 tt = __shfl_up_sync(0xffffffffu, inc, d);
+      if (lane >= (u32)d && ((F >> (lane - d + 1)) & ((1u << d) - 1u)) == 0) inc |= tt;
+    }
+    u32 X = __shfl_up_sync(0xffffffffu, inc, 1);
+    if (lane == 0) X = 0;
+    const u32 before = F & ((1u << lane) - 1u);
+    const u32 lastHeadPos = base + (31 - __clz(hbits | 1u));
+    const u32 sPrev = __shfl_sync(0xffffffffu, lastHeadPos, before ? (31 - __clz(before)) : 0);
+    const u32 nextHead0 = __shfl_down_sync(0xffffffffu, hbits & 1u, 1);
+    // bit j: the next record starts another run, i.e. this record ends its run.  The tile's last record: only known at
+    // the end of the batch (it does end there)
+    const u32 lastBits = (hbits >> 1) | ((lane < 31u ? nextHead0 : ((t + 1) * WT_HITS >= h.n ? 1u : 0u)) << 3);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (!(valid[j] && ((lastBits >> j) & 1u))) continue;
+      const u32 hbLe = hbits & ((2u << j) - 1u);
+      u32 tot, runStart;
+      if (hbLe) { tot = pre[j]; runStart = base + (31 - __clz(hbLe)); }
+      else if (before) { tot = X | pre[j]; runStart = sPrev; }
+      else if (cValid) { tot = cTot | X | pre[j]; runStart = cStart; }
+      else continue;  // the run starts in another warp's chunk: that warp finishes it
+      if (tot & 0x80000000u) { sm.walkQ[nWalk++][tid] = runStart; continue; }
+      if (!(nh[j] > 1)) continue;  // a run of reads that are their own group
+      if (nh[j] != base + j + 1 - runStart) { sm.walkQ[nWalk++][tid] = runStart; continue; }
+      ++cReads;
+      const u32 gm = tot & 0x7FFFFFFFu;
+      cRescued += (__popc(gm) == 1);
+      count(gm);
+    }
+#pragma unroll 1
+    for (u32 q = 0; q < nWalk; ++q) { const u32 i0 = sm.walkQ[q][tid]; w.walk(i0, normKey(h.key[i0]), nullptr); }
+    // the run still open at the end of the tile
+    {
+      const u32 incLast = __shfl_sync(0xffffffffu, inc, 31);
+      if (F) {
+        cTot = incLast;
+        cStart = __shfl_sync(0xffffffffu, lastHeadPos, 31 - __clz(F));
+        cValid = true;
+      } else if (cValid) {
+        cTot |= incLast;
+      }
+      cNh = __shfl_sync(0xffffffffu, nh[3], 31);
+      cKey = __shfl_sync(0xffffffffu, key[3], 31);
     }
   }
-  if (i == 0) {
-    ctl->stats[ST_READS] += ctl->dstats[ST_READS];
-    ctl->stats[ST_RESCUED] += ctl->dstats[ST_RESCUED];
-    ctl->dstats[ST_READS] = 0; ctl->dstats[ST_RESCUED] = 0;
-    ctl->dirty = 0;
-    ctl->slowCountAtBatch = ctl->slowCount;
-    ctl->ordBase += nHits;
+  // ---- the read open at the end of the chunk continues in another warp's chunk: finish it by the serial walk.  (At the
+  //      end of the batch the tile's last record closed its run above.)
+  if (STRAT == 0 && parallelRuns && cValid && t1 > t0 && t1 * WT_HITS < h.n && lane == 0) w.walk(cStart, cKey, nullptr);
+  cReads += w.nReads; cRescued += w.nRescued;
+
+  // ---- block epilogue: counters, the private histogram columns and the private table
+  cHits = __reduce_add_sync(0xffffffffu, cHits); cUnassigned = __reduce_add_sync(0xffffffffu, cUnassigned);
+  cAmbiguous = __reduce_add_sync(0xffffffffu, cAmbiguous); cUnique = __reduce_add_sync(0xffffffffu, cUnique);
+  cMultiple = __reduce_add_sync(0xffffffffu, cMultiple); cReads = __reduce_add_sync(0xffffffffu, cReads);
+  cRescued = __reduce_add_sync(0xffffffffu, cRescued); cMiss = __reduce_add_sync(0xffffffffu, cMiss);
+  if (lane == 0) {
+    atomicAdd(&sm.stat[ST_HITS], cHits); atomicAdd(&sm.stat[ST_UNASSIGNED], cUnassigned); atomicAdd(&sm.stat[ST_AMBIGUOUS], cAmbiguous);
+    atomicAdd(&sm.stat[ST_UNIQUE], cUnique); atomicAdd(&sm.stat[ST_MULTIPLE], cMultiple); atomicAdd(&sm.stat[ST_READS], cReads);
+    atomicAdd(&sm.stat[ST_RESCUED], cRescued); atomicAdd(&sm.stat[7], cMiss);
+  }
+  __syncthreads();
+  sm.bt.flush(table);
+  if (HIST) {
+    for (u32 e = warp; e < HIST_ROWS; e += BATCH_WARPS) {
+      u32 v = 0;
+#pragma unroll
+      for (int q = 0; q < BATCH_WARPS; ++q) v += sm.hist[e][lane + 32 * q];
+      v = __reduce_add_sync(0xffffffffu, v);
+      if (lane == 0 && v) tableAdd(table, 1ull << e, v);
+    }
+  }
+  if (tid < 7) {
+    const int sv = (int)sm.stat[tid];  // reads / rescued can be negative within a block (unfinished reads)
+    if (sv) atomicAdd(&ctl->stats[tid], (u64)(long long)sv);
+  }
+  if (tid == 7 && sm.stat[7]) atomicAdd(&ctl->fastMiss, sm.stat[7]);
+}
+
+// IntervalList::scan alone (mm:1291-1332): the element set of every hit, nothing counted
+template <int MODE, bool FAST>
+__global__ void __launch_bounds__(256)
+k_annotate_only(IndexView ix, FastView fx, HitView h, Rules r, u64 *__restrict__ out) {
+  const Annotator<MODE, FAST> annot{ix, fx, r.overlap};
+  for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < h.n; i += gridDim.x * blockDim.x)
+    out[i] = annot(h.start[i], h.end[i], h.meta[i]);
+}
+
+// End of batch.  When the batch is dirty, every run (of this batch) of a read name that became unfinished DURING the
+// batch was resolved by k_batch as if the name had no open read; such runs are walked again here, what k_batch counted
+// for them is taken back and their multi-mapping records are handed to the deferred path, which replays the name's
+// records in file order.  The last block to finish advances the batch state.
+template <int MODE, bool FAST>
+__global__ void __launch_bounds__(256)
+k_batch_close(IndexView ix, FastView fx, HitView h, Rules r, TableView table, SampleCtl *ctl, SlowView slow, KeySetView open) {
+  const Annotator<MODE, FAST> annot{ix, fx, r.overlap};
+  const u32 seq = ctl->batchSeq;
+  if (ctl->dirty) {
+    const Carry cin = ctl->carry[seq & 1];
+    Carry &cout = ctl->carry[(seq + 1) & 1];
+    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < h.n; i += gridDim.x * blockDim.x) {
+      const u64 k = normKey(h.key[i]);
+      const bool continues = (i == 0) && cin.valid && cin.key == k;
+      if (i > 0 && normKey(h.key[i - 1]) == k) continue;  // not the first record of a run
+      if (keySetLookup(open, k, seq) != 2) continue;      // only names that became unfinished during this batch
+      // pass A: replay what k_batch did with this run (it was not routed: the name was not known as unfinished)
+      bool isOpen = continues, fromCarry = continues;
+      u32 remaining = continues ? cin.remaining : 0, first = i;
+      u64 gm = continues ? cin.gm : 0;
+      long long dReads = 0, dRescued = 0;
+      u32 j = i;
+      for (; j < h.n && (j == i || normKey(h.key[j]) == k); ++j) {
+        const u32 nhj = h.nh[j];
+        if (!(nhj > 1)) continue;
+        const u64 mj = annot(h.start[j], h.end[j], h.meta[j]);
+        if (!isOpen) { isOpen = true; fromCarry = false; remaining = nhj - 1; gm = mj; first = j; }
+        else { --remaining; gm |= mj; }
+        if (remaining == 0) {
+          if (gm != 0) {
+            u64 g = gm;
+            if (r.rescue) {
+              u32 total = 0;
+              for (u32 q = first; q <= j; ++q)
+                if (h.nh[q] > 1) total += __popcll(annot(h.start[q], h.end[q], h.meta[q]));
+              g = rescueFromCounts(r, gm, total, [&](u64 bit) {
+                u32 c = 0;
+                for (u32 q = first; q <= j; ++q)
+                  if (h.nh[q] > 1 && (annot(h.start[q], h.end[q], h.meta[q]) & bit)) ++c;
+                return c;
+              });
+            }
+            tableAdd(table, g, (u64)(-1ll));  // take the count back
+            if (__popcll(g) == 1) --dRescued;
+          }
+          --dReads;
+          isOpen = false;
+        }
+      }
+      // the read still open at the end of the run: carried out (not yet deferred) or already deferred by k_batch
+      u32 appendEnd = j;
+      bool synth = continues;
+      if (isOpen) {
+        if (j >= h.n && !r.rescue) {  // k_batch carried it out of the batch: defer it instead
+          cout.valid = 0;
+          --dReads;
+        } else {  // k_batch deferred records [first, j) (and the carried part when the read came from the carry)
+          appendEnd = fromCarry ? i : first;
+          if (fromCarry) synth = false;
+        }
+      }
+      // pass B: defer every multi-mapping record of the run that k_batch did not
+      if (synth) slowAppend(slow, ctl, k, cin.ord, cin.gm, cin.remaining + 1);
+      for (u32 q = i; q < appendEnd; ++q) {
+        const u32 nhq = h.nh[q];
+        if (nhq > 1) slowAppend(slow, ctl, k, ctl->ordBase + q, annot(h.start[q], h.end[q], h.meta[q]), nhq);
+      }
+      if (dReads) atomicAdd(&ctl->stats[ST_READS], (u64)dReads);
+      if (dRescued) atomicAdd(&ctl->stats[ST_RESCUED], (u64)dRescued);
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const u32 done = atomicAdd(&ctl->closeCount, 1u) + 1;
+    if (done == gridDim.x) {
+      __threadfence();
+      ctl->carry[seq & 1].valid = 0;  // consumed by this batch
+      ctl->ordBase += h.n;
+      ctl->dirty = 0;
+      ctl->closeCount = 0;
+      __threadfence();
+      ctl->batchSeq = seq + 1;
+    }
   }
 }
 
-// batches that need no K3 still have to advance the ordinal base
-__global__ void k_batch_advance(SampleCtl *ctl, u32 nHits) {
-  ctl->slowCountAtBatch = ctl->slowCount;
-  ctl->ordBase += nHits;
+// end of sample: a read still carried becomes a deferred record (it is flushed with the other open reads, mm:1783-1792)
+__global__ void k_flush_carry(SampleCtl *ctl, SlowView slow) {
+  Carry &c = ctl->carry[ctl->batchSeq & 1];
+  if (!c.valid) return;
+  slowAppend(slow, ctl, c.key, c.ord, c.gm, c.remaining + 1);
+  ctl->stats[ST_READS] -= 1;  // the deferred path counts the read again when it opens it
+  c.valid = 0;
 }
 
 // ----------------------------------------------------------------------------- end of sample: deferred records
@@ -472,15 +911,11 @@ __global__ void k_slow_default(const u32 *__restrict__ perm, u32 n, SlowView s, 
         if (r.rescue) {
           u32 cnt = 0;
           for (u32 z = first; z <= q; ++z) cnt += __popcll(s.mask[perm[z]]);
-          if (cnt != 1) {
-            const u32 t = (u32)ceilf(__fmul_rn((float)cnt, r.rescueThreshold));
-            for (u64 rest = gm; rest; rest &= rest - 1) {
-              const u64 bit = rest & (0 - rest);
-              u32 c = 0;
-              for (u32 z = first; z <= q; ++z) if (s.mask[perm[z]] & bit) ++c;
-              if (c >= t) { gm = bit; break; }
-            }
-          }
+          gm = rescueFromCounts(r, gm, cnt, [&](u64 bit) {
+            u32 c = 0;
+            for (u32 z = first; z <= q; ++z) if (s.mask[perm[z]] & bit) ++c;
+            return c;
+          });
         }
         tableAdd(table, gm, 1);
         if (__popcll(gm) == 1) ++nRescued;
@@ -492,15 +927,11 @@ __global__ void k_slow_default(const u32 *__restrict__ perm, u32 n, SlowView s, 
     if (r.rescue) {
       u32 cnt = 0;
       for (u32 z = first; z < q; ++z) cnt += __popcll(s.mask[perm[z]]);
-      if (cnt != 1) {
-        const u32 t = (u32)ceilf(__fmul_rn((float)cnt, r.rescueThreshold));
-        for (u64 rest = gm; rest; rest &= rest - 1) {
-          const u64 bit = rest & (0 - rest);
-          u32 c = 0;
-          for (u32 z = first; z < q; ++z) if (s.mask[perm[z]] & bit) ++c;
-          if (c >= t) { gm = bit; break; }
-        }
-      }
+      gm = rescueFromCounts(r, gm, cnt, [&](u64 bit) {
+        u32 c = 0;
+        for (u32 z = first; z < q; ++z) if (s.mask[perm[z]] & bit) ++c;
+        return c;
+      });
     }
     tableAdd(table, gm, 1);
     if (__popcll(gm) == 1) ++nRescued;
@@ -534,15 +965,7 @@ __global__ void k_slow_random_pick(const u32 *__restrict__ perm, u32 n, SlowView
   const u32 q = p + pick;
   if (q < n && q >= p) {
     const u32 id = perm[q];
-    if (s.key[id] == k) {
-      u64 m = s.mask[id];
-      const int nreg = __popcll(m);
-      if (r.rescue && nreg > 1) {
-        const u32 t = (u32)ceilf(__fmul_rn((float)nreg, r.rescueThreshold));
-        if (t <= 1u) m = m & (0 - m);
-      }
-      tableAdd(table, m, 1);
-    }
+    if (s.key[id] == k) tableAdd(table, rescueSingle(r, s.mask[id]), 1);
   }
 }
 
@@ -555,6 +978,10 @@ __global__ void k_iota(u32 *dst, u32 n) {
   if (p < n) dst[p] = p;
 }
 __global__ void k_fill_u64(u64 *dst, u64 v, u64 n) {
+  const u64 p = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p < n) dst[p] = v;
+}
+__global__ void k_fill_u32(u32 *dst, u32 v, u64 n) {
   const u64 p = (u64)blockIdx.x * blockDim.x + threadIdx.x;
   if (p < n) dst[p] = v;
 }
@@ -628,9 +1055,9 @@ __global__ void k_prefix_max_end(BuildView b, uint4 *feat) {
   }
 }
 
-__device__ __forceinline__ u32 chrOfEntry(const BuildView &b, u32 e) {
-  u32 lo = 0, hi = b.nChr;  // last c with chrBinBase[c] <= e
-  while (hi - lo > 1) { const u32 mid = (lo + hi) >> 1; if (b.chrBinBase[mid] <= e) lo = mid; else hi = mid; }
+__device__ __forceinline__ u32 chrOfEntry(const u32 *chrBinBase, u32 nChr, u32 e) {
+  u32 lo = 0, hi = nChr;  // last c with chrBinBase[c] <= e
+  while (hi - lo > 1) { const u32 mid = (lo + hi) >> 1; if (chrBinBase[mid] <= e) lo = mid; else hi = mid; }
   return lo;
 }
 
@@ -639,7 +1066,7 @@ __device__ __forceinline__ u32 chrOfEntry(const BuildView &b, u32 e) {
 __global__ void k_build_bins(BuildView b, const uint4 *__restrict__ feat, uint2 *bins, u32 *spanCount, u32 *spanIdx, int fill) {
   const u32 e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= b.nEntries) return;
-  const u32 c = chrOfEntry(b, e);
+  const u32 c = chrOfEntry(b.chrBinBase, b.nChr, e);
   const u32 bin = e - b.chrBinBase[c];
   const u32 nBins = b.chrBinBase[c + 1] - b.chrBinBase[c] - 1;
   const u32 cs = b.chrStart[c], ce = b.chrStart[c + 1];
@@ -692,6 +1119,95 @@ __global__ void k_scan_spans(const u32 *__restrict__ spanCount, uint2 *bins, u32
     __syncthreads();
   }
   if (threadIdx.x == 0) *total = carry;
+}
+
+// ---- segment answer table
+
+// boundary keys (chromosome << 32 | position): position 0 of every chromosome, every feature start, every end + 1
+__global__ void k_seg_keys(BuildView b, u64 *keys) {
+  const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < b.nFeat) {
+    const u64 c = (u64)b.chr[i] << 32;
+    keys[2 * i] = c | b.start[i];
+    keys[2 * i + 1] = c | ((u64)b.end[i] + 1ull);
+  }
+  if (i < b.nChr) keys[2ull * b.nFeat + i] = (u64)i << 32;
+}
+
+// one answer word from the evaluation of a representative read (see FastView)
+__device__ __forceinline__ u32 answerWord(u64 chosen, const EvalTrack &tr, u32 upMask, u32 downMask, uint2 *vic) {
+  const u32 all = (u32)tr.lineAll, U = all & upMask, D = all & downMask;
+  *vic = make_uint2(tr.pUp, tr.pDown);
+  // the pick between several matched elements of one line depends on distances to the read (mm:1066-1075) only when one
+  // of them is an upstream / downstream element
+  if (__popc(all) <= 1 || (U | D) == 0) return (u32)chosen;
+  if ((all & ~(U | D)) == 0 && __popc(U) == 1 && __popc(D) == 1) return ANS_VICPAIR | all;
+  return ANS_GENERAL;
+}
+
+// one thread per segment: the answers of a read inside it and of a read over it and its right neighbour, per
+// strand, evaluated with the SAME candidate walk as any hit (inclusion scoring; see fastAnnotate for why that
+// also serves the overlap modes)
+__global__ void k_seg_eval(IndexView ix, const u64 *__restrict__ segKey, u32 nSeg, u32 upMask, u32 downMask, uint4 *seg, uint2 *vic) {
+  const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nSeg) return;
+  const u64 k = segKey[i];
+  const u32 chr = (u32)(k >> 32), start = (u32)k;
+  const bool hasNext = (i + 1 < nSeg) && (u32)(segKey[i + 1] >> 32) == chr;
+  const u32 end = hasNext ? (u32)segKey[i + 1] - 1u : 0xFFFFFFFEu;
+  u32 end2 = 0;
+  if (hasNext) {
+    const bool hasNext2 = (i + 2 < nSeg) && (u32)(segKey[i + 2] >> 32) == chr;
+    end2 = hasNext2 ? (u32)segKey[i + 2] - 1u : 0xFFFFFFFEu;
+  }
+  u32 in[2], cross[2];  // index 0: strand bit set ("F"), 1: not set
+  for (u32 s = 0; s < 2; ++s) {
+    const u32 meta = chr | (s == 0 ? 0x80000000u : 0u);
+    EvalTrack tr;
+    u64 a = annotateEval<0, true>(ix, start, start, meta, -1.0f, &tr);
+    in[s] = answerWord(a, tr, upMask, downMask, &vic[4 * i + s]);
+    cross[s] = ANS_GENERAL;
+    vic[4 * i + 2 + s] = make_uint2(0u, 0u);
+    if (hasNext) {
+      a = annotateEval<0, true>(ix, end, end + 1u, meta, -1.0f, &tr);
+      cross[s] = answerWord(a, tr, upMask, downMask, &vic[4 * i + 2 + s]);
+    }
+  }
+  seg[2 * i] = make_uint4(start, end, in[0], in[1]);
+  seg[2 * i + 1] = make_uint4(end2, cross[0], cross[1], 0u);
+}
+
+// one thread per bin entry of the segment table
+__global__ void k_fast_bins(const u64 *__restrict__ segKey, u32 nSeg, const uint4 *__restrict__ seg, const u32 *__restrict__ chrBinBase,
+                            u32 nChr, u32 shift, u32 nEntries, uint4 *bin) {
+  const u32 e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= nEntries) return;
+  const u32 c = chrOfEntry(chrBinBase, nChr, e);
+  const u64 pos = (u64)(e - chrBinBase[c]) << shift;
+  const u64 cap = 0xFFFFFFFEull;
+  const u64 want = ((u64)c << 32) | (pos > cap ? cap : pos);
+  u32 lo = 0, hi = nSeg;  // last segment whose key <= want (every chromosome has a segment starting at 0)
+  while (hi - lo > 1) { const u32 mid = (lo + hi) >> 1; if (segKey[mid] <= want) lo = mid; else hi = mid; }
+  u32 w = lo;
+  for (u32 k = 1; k < 4; ++k) {
+    const u64 pk = pos + ((u64)k << (shift - 2));
+    const u64 wk = ((u64)c << 32) | (pk > cap ? cap : pk);
+    u32 d = 0;
+    while (d < 3 && lo + d + 1 < nSeg && segKey[lo + d + 1] <= wk) ++d;
+    w |= d << (24 + 2 * k);
+  }
+  const uint4 s = seg[2 * lo];
+  bin[e] = make_uint4(s.y, s.z, s.w, w);
+}
+
+// adjacent-duplicate removal of the sorted boundary keys: flags, then a scatter through their prefix sums
+__global__ void k_seg_flag(const u64 *__restrict__ sorted, u32 n, u32 *flag) {
+  const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) flag[i] = (i == 0 || sorted[i] != sorted[i - 1]) ? 1u : 0u;
+}
+__global__ void k_seg_scatter(const u64 *__restrict__ sorted, const u32 *__restrict__ flag, const u32 *__restrict__ pos, u32 n, u64 *out) {
+  const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n && flag[i]) out[pos[i]] = sorted[i];
 }
 
 }  // namespace mma

@@ -12,14 +12,15 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_LIB_PATH = os.path.join(_HERE, "lib", "libmmannot_b200.so")
+_LIB_PATH = os.environ.get("MMANNOT_B200_LIB") or os.path.join(_HERE, "lib", "libmmannot_b200.so")  # env: tuning builds only
 
 STRATEGIES = {"default": 0, "unique": 1, "random": 2, "ratio": 3}
+FAST_OFF = 0xFFFFFFFF  # fast_bin_shift=None: no segment answer table
 
 EXPORTS = [
     "mma_create", "mma_destroy", "mma_last_error", "mma_load_features", "mma_alloc_pinned", "mma_free_pinned",
     "mma_submit_hits", "mma_submit_hits_device", "mma_finish_sample", "mma_reset_sample", "mma_dense_counts",
-    "mma_sync", "mma_stream", "mma_timing_enable", "mma_timing_reset", "mma_timing_get", "mma_index_bytes", "mma_version", "mma_readback_bytes", "mma_dominant_kernel",
+    "mma_sync", "mma_stream", "mma_timing_enable", "mma_timing_reset", "mma_timing_get", "mma_index_bytes", "mma_version", "mma_readback_bytes", "mma_dominant_kernel", "mma_index_segments", "mma_annotate_hits",
 ]
 
 
@@ -34,7 +35,7 @@ class Params(C.Structure):
                 ("read_stats", C.c_int32), ("interval_stats", C.c_int32), ("n_elements", C.c_uint32),
                 ("elem_line", C.c_void_p), ("elem_strand", C.c_void_p), ("elem_vicinity", C.c_void_p),
                 ("n_samples", C.c_uint32), ("max_batch_hits", C.c_uint32), ("table_log2", C.c_uint32),
-                ("bin_shift", C.c_uint32), ("rand_seed", C.c_uint32), ("reserved", C.c_uint32)]
+                ("bin_shift", C.c_uint32), ("rand_seed", C.c_uint32), ("fast_bin_shift", C.c_uint32)]
 
 
 class Features(C.Structure):
@@ -57,8 +58,8 @@ class SampleResult(C.Structure):
 
 
 class Timing(C.Structure):
-    _fields_ = [("ms_index", C.c_double), ("ms_annotate", C.c_double), ("ms_resolve", C.c_double), ("ms_merge", C.c_double),
-                ("ms_finish", C.c_double), ("launches", C.c_uint64), ("hits", C.c_uint64)]
+    _fields_ = [("ms_index", C.c_double), ("ms_batch", C.c_double), ("ms_close", C.c_double), ("ms_finish", C.c_double),
+                ("launches", C.c_uint64), ("hits", C.c_uint64), ("batches", C.c_uint64), ("fast_miss", C.c_uint64)]
 
 
 _lib = None
@@ -96,6 +97,9 @@ def lib():
         L.mma_index_bytes.argtypes = [C.c_void_p]
         L.mma_index_bytes.restype = C.c_uint64
         L.mma_version.restype = C.c_char_p
+        L.mma_annotate_hits.argtypes = [C.c_void_p, C.POINTER(HitBatch), C.c_void_p]
+        L.mma_index_segments.argtypes = [C.c_void_p]
+        L.mma_index_segments.restype = C.c_uint64
         L.mma_readback_bytes.argtypes = [C.c_void_p]
         L.mma_readback_bytes.restype = C.c_uint64
         L.mma_dominant_kernel.restype = C.c_char_p
@@ -152,14 +156,15 @@ class Annotator:
     """One device context (mma_ctx)."""
 
     def __init__(self, config, strategy="default", overlap=-1.0, rescue_threshold=1.0, read_stats=False,
-                 interval_stats=False, n_samples=1, max_batch_hits=1 << 22, device=0, table_log2=0, bin_shift=0, rand_seed=1):
+                 interval_stats=False, n_samples=1, max_batch_hits=1 << 22, device=0, table_log2=0, bin_shift=0, rand_seed=1,
+                 fast_bin_shift=0):
         self.config = config
         self._keep = (np.ascontiguousarray(config.elem_line, np.uint16), np.ascontiguousarray(config.elem_strand, np.uint8),
                       np.ascontiguousarray(config.elem_vicinity, np.uint8))
         self.strategy = STRATEGIES[strategy] if isinstance(strategy, str) else int(strategy)
         p = Params(device, self.strategy, float(overlap), float(rescue_threshold), int(bool(read_stats)), int(bool(interval_stats)),
                    len(self._keep[0]), self._keep[0].ctypes.data, self._keep[1].ctypes.data, self._keep[2].ctypes.data,
-                   n_samples, int(max_batch_hits), table_log2, bin_shift, rand_seed, 0)
+                   n_samples, int(max_batch_hits), table_log2, bin_shift, rand_seed, FAST_OFF if fast_bin_shift is None else fast_bin_shift)
         self.max_batch_hits = int(max_batch_hits)
         self._h = C.c_void_p()
         rc = lib().mma_create(C.byref(self._h), C.byref(p))
@@ -201,6 +206,13 @@ class Annotator:
         """Raw mma_submit_hits_device on a HitBatch struct holding device pointers; asynchronous."""
         self._check(lib().mma_submit_hits_device(self._h, sample, C.byref(hit_batch)))
 
+    def annotate(self, hits):
+        """Per-hit element sets (IntervalList::scan alone): uint64 bitmask per hit."""
+        out = np.zeros(max(hits.n, 1), np.uint64)
+        hb = HitBatch(hits.n, hits.start.ctypes.data, hits.end.ctypes.data, hits.meta.ctypes.data, hits.nh.ctypes.data, hits.read_key.ctypes.data)
+        self._check(lib().mma_annotate_hits(self._h, C.byref(hb), out.ctypes.data))
+        return out[:hits.n]
+
     def sync(self):
         self._check(lib().mma_sync(self._h))
 
@@ -235,6 +247,9 @@ class Annotator:
 
     def index_bytes(self):
         return int(lib().mma_index_bytes(self._h))
+
+    def index_segments(self):
+        return int(lib().mma_index_segments(self._h))
 
     def stream_ptr(self):
         """cudaStream_t (as an integer) of the context's compute stream."""

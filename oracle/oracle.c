@@ -47,15 +47,19 @@ static int strand_ok(uint8_t es, uint8_t fs, int rs) {
   return ((fs == 1) && !rs) || ((fs == 2) && rs);
 }
 
+#define BIN_SIZE 16384u /* binSize, mm:67 */
+
 typedef struct {
   const orc_params *p;
   const orc_features *f;
   uint32_t *chr_start; /* n_chr + 1 */
+  uint32_t *bin_first; /* per chromosome: bins[b] = first interval (in order) whose end / binSize >= b, mm:1277-1284 */
+  uint64_t *bin_base;  /* n_chr + 1 offsets into bin_first */
 } actx;
 
-/* IntervalList::scan + EvaluationStructure, mm:1291-1332, 1018-1076.  The bin lookup and the
- * first while-loop of scan() only skip intervals that end before the read; they cannot
- * match, so the walk here simply starts at the chromosome's first interval. */
+/* IntervalList::scan + EvaluationStructure, mm:1291-1332, 1018-1076: start at the bin of the read start
+ * (mm:1303-1305), skip the intervals that end before the read (mm:1306-1308), then walk while the
+ * interval does not start after the read (mm:1311). */
 static uint64_t annotate_one(const actx *a, uint32_t hstart, uint32_t hend, uint32_t meta) {
   const orc_params *p = a->p;
   const orc_features *f = a->f;
@@ -68,7 +72,15 @@ static uint64_t annotate_one(const actx *a, uint32_t hstart, uint32_t hend, uint
   pos_t ov[MAXE], di[MAXE];
   uint32_t E = p->n_elements, nset = 0;
   for (uint32_t i = 0; i < E; ++i) ov[i] = di[i] = 0;
-  for (uint32_t v = cs; v < ce && !((pos_t)f->start[v] > re); ++v) { /* ! isAfter(read), mm:1311 */
+  uint32_t v0 = cs;
+  if (a->bin_first) {
+    uint64_t nb = a->bin_base[chr + 1] - a->bin_base[chr];
+    uint64_t bin = rs / BIN_SIZE;
+    if (bin > nb - 1) bin = nb - 1;
+    v0 = a->bin_first[a->bin_base[chr] + bin];
+  }
+  while (v0 < ce && (pos_t)f->end[v0] < rs) ++v0; /* isBefore(read), mm:1306-1308 */
+  for (uint32_t v = v0; v < ce && !((pos_t)f->start[v] > re); ++v) { /* ! isAfter(read), mm:1311 */
     uint32_t t = f->type[v];
     if (!strand_ok(p->elem_strand[t], f->strand[v], rstrand)) continue;
     pos_t o = score(p->overlap, f->start[v], f->end[v], rs, re);
@@ -118,12 +130,41 @@ static int build_chr_start(const orc_features *f, uint32_t **out) {
   return 0;
 }
 
+/* the bins of mm:1277-1284 */
+static int build_bins(actx *a) {
+  const orc_features *f = a->f;
+  a->bin_base = (uint64_t *)calloc((size_t)f->n_chr + 1, sizeof(uint64_t));
+  if (!a->bin_base) return -1;
+  for (uint32_t c = 0; c < f->n_chr; ++c) {
+    uint64_t nb = 0;
+    for (uint32_t i = a->chr_start[c]; i < a->chr_start[c + 1]; ++i) {
+      uint64_t b = f->end[i] / BIN_SIZE;
+      if (nb <= b) nb = b + 1;
+    }
+    a->bin_base[c + 1] = a->bin_base[c] + nb;
+  }
+  a->bin_first = (uint32_t *)malloc((a->bin_base[f->n_chr] ? a->bin_base[f->n_chr] : 1) * sizeof(uint32_t));
+  if (!a->bin_first) return -1;
+  for (uint32_t c = 0; c < f->n_chr; ++c) {
+    uint64_t size = 0;
+    uint32_t *bins = a->bin_first + a->bin_base[c];
+    for (uint32_t i = a->chr_start[c]; i < a->chr_start[c + 1]; ++i) {
+      uint64_t b = f->end[i] / BIN_SIZE;
+      while (size <= b) bins[size++] = i;
+    }
+  }
+  return 0;
+}
+static void free_actx(actx *a) { free(a->chr_start); free(a->bin_first); free(a->bin_base); }
+
 void orc_annotate(const orc_params *p, const orc_features *f, const orc_hits *h, uint64_t *hit_mask) {
   actx a;
+  memset(&a, 0, sizeof(a));
   a.p = p; a.f = f;
   if (build_chr_start(f, &a.chr_start)) return;
+  if (build_bins(&a)) { free_actx(&a); return; }
   for (uint64_t i = 0; i < h->n; ++i) hit_mask[i] = annotate_one(&a, h->start[i], h->end[i], h->meta[i]);
-  free(a.chr_start);
+  free_actx(&a);
 }
 
 /* ------------------------------------------------------- small hash maps */
@@ -369,8 +410,10 @@ int orc_run(const orc_params *p, const orc_features *f, const orc_hits *h, int w
   if (p->n_elements > MAXE) return -1;
   memset(out, 0, sizeof(*out));
   actx a;
+  memset(&a, 0, sizeof(a));
   a.p = p; a.f = f;
   if (build_chr_start(f, &a.chr_start)) return -1;
+  if (build_bins(&a)) { free_actx(&a); return -1; }
   rctx r;
   memset(&r, 0, sizeof(r));
   r.p = p; r.out = out;
@@ -407,7 +450,7 @@ int orc_run(const orc_params *p, const orc_features *f, const orc_hits *h, int w
   for (k = 0; k < out->n_rows; ++k) out->row_value[k] = *cmap_slot(&r.counts, out->row_mask[k]);
   free(r.counts.key); free(r.counts.val);
   nmap_free(&r.names);
-  free(a.chr_start);
+  free_actx(&a);
   return 0;
 }
 

@@ -1,0 +1,183 @@
+"""CUDA path (through the C ABI) against the CPU oracle on adversarial synthetic inputs (tests/fuzz.py):
+every strategy, every -l mode, batch borders in arbitrary places, with and without the segment answer table."""
+import numpy as np
+import pytest
+
+from tests import fuzz
+from oracle import pyoracle
+
+pytestmark = pytest.mark.gpu
+
+
+def device_run(et, feats, hits, strategy="default", overlap=-1.0, max_batch=1 << 20, rescue_threshold=1.0, read_stats=False, **kw):
+    from mmannot_b200 import device
+    a = device.Annotator(et, strategy=strategy, overlap=overlap, rescue_threshold=rescue_threshold, read_stats=read_stats,
+                         max_batch_hits=max_batch, **kw)
+    try:
+        a.load_features(feats)
+        a.submit(0, hits)
+        res = a.finish(0)
+        res["values"] = device.values_by_mask(res["rows"])
+        return res
+    finally:
+        a.close()
+
+
+def oracle_run(et, feats, hits, **kw):
+    return pyoracle.run(et.elem_line, et.elem_strand, et.elem_vicinity, feats, hits, **kw)
+
+
+def check(res, ref, exact=True):
+    assert set(res["values"]) == set(ref["rows"])
+    for m, v in ref["rows"].items():
+        if exact:
+            assert res["values"][m] == v, (hex(m), res["values"][m], v)
+        else:
+            assert abs(res["values"][m] - v) <= 1e-9 * max(1.0, abs(v)), hex(m)
+    assert res["stats"] == ref["stats"]
+
+
+@pytest.mark.parametrize("seed", range(6))
+@pytest.mark.parametrize("overlap", [-1.0, 0.5, 1.0, 12.0])
+def test_per_hit_annotation(seed, overlap):
+    """NH = 1 everywhere: the table is the histogram of the per-hit element sets."""
+    rng = np.random.default_rng(1000 + seed)
+    et = fuzz.make_elements(rng)
+    feats = fuzz.make_features(rng, et, n_feat=int(rng.integers(50, 900)))
+    hits = fuzz.make_hits(rng, feats, n_reads=20000, max_nh=1, messy=0.0)
+    ref = oracle_run(et, feats, hits, overlap=overlap)
+    for fast in (0, None, 3, 9):
+        res = device_run(et, feats, hits, overlap=overlap, fast_bin_shift=fast, max_batch=7777)
+        check(res, ref)
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_scan_alone(seed):
+    """mma_annotate_hits (IntervalList::scan alone) against the oracle's per-hit element sets."""
+    from mmannot_b200 import device
+    rng = np.random.default_rng(1500 + seed)
+    et = fuzz.make_elements(rng, wide=(seed == 5))
+    feats = fuzz.make_features(rng, et, n_feat=int(rng.integers(50, 900)))
+    hits = fuzz.make_hits(rng, feats, n_reads=30000, max_nh=1, messy=0.0)
+    for overlap in (-1.0, 0.3, 0.99, 1.0, 25.0):
+        ref = oracle_run(et, feats, hits, overlap=overlap, want_hit_masks=True)
+        for fast in (0, None, 4):
+            a = device.Annotator(et, overlap=overlap, fast_bin_shift=fast)
+            try:
+                a.load_features(feats)
+                got = a.annotate(hits)
+            finally:
+                a.close()
+            bad = np.nonzero(got != ref["hit_mask"])[0]
+            assert len(bad) == 0, (overlap, fast, int(bad[0]), int(hits.start[bad[0]]), int(hits.end[bad[0]]), hex(int(got[bad[0]])), hex(int(ref["hit_mask"][bad[0]])))
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_per_hit_annotation_wide_masks(seed):
+    """More than 32 Order elements: 64-bit element sets, no segment table."""
+    rng = np.random.default_rng(2000 + seed)
+    et = fuzz.make_elements(rng, wide=True)
+    feats = fuzz.make_features(rng, et, n_feat=600)
+    hits = fuzz.make_hits(rng, feats, n_reads=6000, max_nh=5)
+    for overlap in (-1.0, 3.0):
+        ref = oracle_run(et, feats, hits, overlap=overlap)
+        check(device_run(et, feats, hits, overlap=overlap, max_batch=5000), ref)
+
+
+@pytest.mark.parametrize("seed", range(8))
+@pytest.mark.parametrize("batch", [1, 5, 64, 1000, 1024, 4099, 1 << 20])
+def test_read_resolution_name_grouped(seed, batch):
+    """default strategy: countdown over name-grouped reads incl. messy groups, batches cut anywhere."""
+    rng = np.random.default_rng(3000 + seed)
+    et = fuzz.make_elements(rng)
+    feats = fuzz.make_features(rng, et, n_feat=300)
+    n_reads = 300 if batch < 64 else 4000
+    hits = fuzz.make_hits(rng, feats, n_reads=n_reads, max_nh=int(rng.choice([3, 8, 40])), messy=float(rng.choice([0.0, 0.1, 0.5])))
+    overlap = float(rng.choice([-1.0, 1.0]))
+    ref = oracle_run(et, feats, hits, overlap=overlap)
+    check(device_run(et, feats, hits, overlap=overlap, max_batch=batch), ref)
+
+
+@pytest.mark.parametrize("seed", range(4))
+@pytest.mark.parametrize("batch", [3, 700, 1 << 20])
+def test_read_resolution_scattered(seed, batch):
+    """Records of a read not adjacent (coordinate-sorted files): everything goes through the deferred path."""
+    rng = np.random.default_rng(4000 + seed)
+    et = fuzz.make_elements(rng)
+    feats = fuzz.make_features(rng, et, n_feat=300)
+    hits = fuzz.make_hits(rng, feats, n_reads=250 if batch < 64 else 3000, max_nh=6, messy=0.2)
+    hits = fuzz.shuffle_hits(rng, hits, block=int(rng.choice([1, 16, 200])))
+    ref = oracle_run(et, feats, hits)
+    check(device_run(et, feats, hits, max_batch=batch), ref)
+
+
+@pytest.mark.parametrize("seed", range(4))
+@pytest.mark.parametrize("strategy", ["unique", "ratio", "random"])
+def test_other_strategies(seed, strategy):
+    rng = np.random.default_rng(5000 + seed)
+    et = fuzz.make_elements(rng)
+    feats = fuzz.make_features(rng, et, n_feat=300)
+    hits = fuzz.make_hits(rng, feats, n_reads=3000, max_nh=9, messy=0.2)
+    if seed % 2:
+        hits = fuzz.shuffle_hits(rng, hits, block=50)
+    ref = oracle_run(et, feats, hits, strategy=strategy, overlap=1.0)
+    for batch in (333, 1 << 20):
+        check(device_run(et, feats, hits, strategy=strategy, overlap=1.0, max_batch=batch), ref, exact=(strategy != "ratio"))
+
+
+@pytest.mark.parametrize("seed", range(6))
+@pytest.mark.parametrize("threshold", [0.5, 0.8])
+def test_rescue_threshold(seed, threshold):
+    """-e with -m: rescue() needs element multiplicities, on every path (in-batch, across batches, deferred)."""
+    rng = np.random.default_rng(6000 + seed)
+    et = fuzz.make_elements(rng)
+    feats = fuzz.make_features(rng, et, n_feat=200, extent=5000)
+    hits = fuzz.make_hits(rng, feats, n_reads=2500, extent=5000, max_nh=10, messy=0.15)
+    if seed % 3 == 2:
+        hits = fuzz.shuffle_hits(rng, hits, block=30)
+    thr = float(np.float32(threshold))
+    for strategy in ("default", "ratio", "random"):
+        ref = oracle_run(et, feats, hits, strategy=strategy, overlap=1.0, rescue_threshold=thr, read_stats=True)
+        for batch in (97, 1 << 20):
+            res = device_run(et, feats, hits, strategy=strategy, overlap=1.0, rescue_threshold=thr, read_stats=True, max_batch=batch)
+            check(res, ref, exact=(strategy != "ratio"))
+
+
+def test_sample_reuse_and_two_samples():
+    """reset + resubmit gives the same answer; two samples on one context stay separate."""
+    from mmannot_b200 import device
+    rng = np.random.default_rng(7000)
+    et = fuzz.make_elements(rng)
+    feats = fuzz.make_features(rng, et, n_feat=300)
+    h0 = fuzz.make_hits(rng, feats, n_reads=3000, max_nh=6, messy=0.2)
+    h1 = fuzz.make_hits(rng, feats, n_reads=2000, max_nh=3, messy=0.0)
+    r0, r1 = oracle_run(et, feats, h0), oracle_run(et, feats, h1)
+    a = device.Annotator(et, n_samples=2, max_batch_hits=900)
+    try:
+        a.load_features(feats)
+        for _ in range(2):
+            a.reset(0)
+            a.reset(1)
+            a.submit(0, h0)
+            a.submit(1, h1)
+            for s, ref in ((0, r0), (1, r1)):
+                res = a.finish(s)
+                res["values"] = device.values_by_mask(res["rows"])
+                check(res, ref)
+    finally:
+        a.close()
+
+
+def test_empty_and_tiny_inputs():
+    rng = np.random.default_rng(7100)
+    et = fuzz.make_elements(rng)
+    feats = fuzz.make_features(rng, et, n_feat=50)
+    hits = fuzz.make_hits(rng, feats, n_reads=5, max_nh=3)
+    from mmannot_b200 import host
+    z = np.zeros(0, np.uint32)
+    empty = host.Hits(z, z, z, z, np.zeros(0, np.uint64))
+    res = device_run(et, feats, empty)
+    assert res["rows"] == {} and res["stats"]["n_hits"] == 0
+    check(device_run(et, feats, hits), oracle_run(et, feats, hits))
+    one = hits.slice(0, 1)
+    check(device_run(et, feats, one), oracle_run(et, feats, one))
