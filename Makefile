@@ -47,7 +47,7 @@ ref:
 # tuning builds (not shipped): make variants; MMANNOT_B200_LIB=mmannot_b200/lib/variants/b4.so python bench.py ...
 variants: $(CU_SRC) $(CU_HDR)
 	@mkdir -p mmannot_b200/lib/variants
-	for b in 3 5; do $(NVCC) $(NVFLAGS) -DMMA_BLOCKS_PER_SM=$$b -shared -o mmannot_b200/lib/variants/b$$b.so $(CU_SRC) & done; wait
+	for b in 2 4; do $(NVCC) $(NVFLAGS) -DMMA_BLOCKS_PER_SM=$$b -shared -o mmannot_b200/lib/variants/b$$b.so $(CU_SRC) & done; wait
 
 clean:
 	rm -rf mmannot_b200/lib mmannot_b200/bin oracle/_build

@@ -61,6 +61,7 @@ struct Sample {
   uint64_t cumHits = 0, seq = 0;
   uint64_t knownCount = 0, knownCum = 0;
   bool touched = false;
+  bool openMaybeUsed = false;  // the open-key set may hold keys (unknown until the control block is read back)
   // results
   std::vector<uint64_t> rowMask, rowCount;
   std::vector<uint32_t> rowNh;
@@ -283,6 +284,7 @@ int launchBatch(mma_ctx *ctx, Sample &s, const HitView &h) {
 int afterBatch(mma_ctx *ctx, Sample &s, uint64_t n) {
   s.cumHits += n + 2;
   s.touched = true;
+  s.openMaybeUsed = true;
   ctx->hitsSubmitted += n;
   const int slot = (int)(s.seq & 3);
   CK(cudaMemcpyAsync(&s.countRing[slot], &s.ctl->slowCount, sizeof(u32), cudaMemcpyDeviceToHost, ctx->sc));
@@ -713,11 +715,12 @@ int mma_reset_sample(mma_ctx *ctx, uint32_t sample) {
   const size_t tb = (size_t)ctx->tableCap * sizeof(u64);
   CK(cudaMemsetAsync(s.ctl, 0, sizeof(SampleCtl), ctx->sc));
   CK(cudaMemsetAsync(s.tableKeys.p, 0, tb, ctx->sc)); CK(cudaMemsetAsync(s.tableVals.p, 0, tb, ctx->sc));
-  if (s.openCap) {
+  if (s.openCap && s.openMaybeUsed) {
     k_fill_u64<<<gridFor(s.openCap, 256), 256, 0, ctx->sc>>>(s.openKeys.as<u64>(), KEY_EMPTY, s.openCap);
     k_fill_u32<<<gridFor(s.openCap, 256), 256, 0, ctx->sc>>>(s.openSeq.as<u32>(), 0xFFFFFFFFu, s.openCap);
     ctx->launches += 2;
   }
+  s.openMaybeUsed = false;
   CK(cudaStreamSynchronize(ctx->sc));
   s.cumHits = 0; s.knownCount = 0; s.knownCum = 0; s.seq = 0; s.touched = false;
   for (int i = 0; i < 4; ++i) s.ringUsed[i] = false;
@@ -820,6 +823,7 @@ int mma_finish_sample(mma_ctx *ctx, uint32_t sample, mma_sample_result *out) {
   SampleCtl hc;
   CK(cudaMemcpy(&hc, s.ctl, sizeof(hc), cudaMemcpyDeviceToHost));
   if (hc.overflow) return ctx->fail(MMA_ERR_CAPACITY, "a device table overflowed (combination table, deferred list or NH range under -y ratio)");
+  s.openMaybeUsed = hc.openCount != 0;
   if (hc.slowCount > 0) {
     int rc = finishDeferred(ctx, s, hc.slowCount);
     if (rc) return rc;

@@ -326,65 +326,86 @@ __device__ __noinline__ u64 annotateHit(const IndexView &ix, u32 rs, u32 re, u32
   return annotateEval<MODE, false>(ix, rs, re, meta, ovl, nullptr);
 }
 
-// Segment-table lookup.  true: `out` is the element set of the hit; false: the table cannot answer (read over three
-// or more segments or starting beyond the second segment of its bin, position-dependent pick, degenerate interval).
+// Segment-table lookup.
 //   * a read inside one segment is covered by exactly the features covering the segment; they all score alike
 //     (1 under inclusion, end - start under the overlap modes), so the pick is the precomputed one -- provided the
 //     read is long enough to match anything at all under -l (mm:995-1002);
 //   * under inclusion a read over two adjacent segments is included in exactly the features covering both.
-// One gather (the bin entry) answers a read inside segment A; otherwise the bin entry names the segment holding the
-// first position of the read's quarter of the bin, whose 32-byte record (one L2 sector) answers a read inside it or
-// over it and its right neighbour; a read starting one segment further costs one more gather.
+// One gather (the bin entry) answers a read inside segment A; this part is inlined in the hot loop (fastAnnotate).
+// Everything else lives out of line (fastRest): the bin entry names the segment holding the first position of the
+// read's quarter of the bin, whose 32-byte record (one L2 sector) answers a read inside it or over it and its right
+// neighbour (a few more gathers when the read starts further right); upstream/downstream ties are settled from the
+// side table; what the table cannot answer (read over three or more segments, other position-dependent picks,
+// degenerate intervals) is evaluated against the feature index.  Bit 31 of fastRest's result says so (statistics).
+#define FAST_MISS 0x80000000u
 template <int MODE>
-__device__ __forceinline__ bool fastAnnotate(const FastView &fx, u32 rs, u32 re, u32 meta, float ovl, u32 &out) {
-  out = 0;
+__device__ __noinline__ u32 fastRest(const FastView &fx, const IndexView &ix, uint4 e, u32 rs, u32 re, u32 meta, float ovl, int stage) {
+  if (stage != 0) {  // stage 0: no table lookup was possible (degenerate interval)
+    const u32 strandIdx = (meta >> 31) ? 0u : 1u;
+    u32 a = 0, i = e.w & 0x00FFFFFFu, kind = 0;
+    bool ok = true;
+    if (re <= e.x) {
+      a = strandIdx ? e.z : e.y;
+    } else {
+      const u32 chr = meta & 0x00FFFFFFu;
+      const uint2 ci = __ldg(&fx.chrInfo[chr]);
+      const u32 bRaw = rs >> fx.shift;
+      const u32 quarter = (bRaw < ci.y) ? ((rs >> (fx.shift - 2)) & 3u) : 3u;
+      i += (e.w >> (24 + 2 * quarter)) & 3u;
+      uint4 t = __ldg(&fx.seg[2 * i]);  // {start, end, answer F, answer R}
+#pragma unroll 1
+      for (int g = 0; rs > t.y; ++g) {
+        if (g == 3) { ok = false; break; }
+        ++i;
+        t = __ldg(&fx.seg[2 * i]);
+      }
+      if (ok) {
+        if (re <= t.y) {
+          a = strandIdx ? t.w : t.z;
+        } else if (MODE != 0) {
+          ok = false;
+        } else {
+          const uint4 x = __ldg(&fx.seg[2 * i + 1]);  // {end of the next segment, cross answer F, cross answer R, 0}
+          if (re > x.x) ok = false;
+          a = strandIdx ? x.z : x.y;
+          kind = 2;
+        }
+      }
+    }
+    if (ok && (a & ANS_GENERAL)) ok = false;
+    if (ok) {
+      if (a & ANS_VICPAIR) {
+        const uint2 v = __ldg(&fx.vic[4 * i + kind + strandIdx]);
+        const u32 dUp = v.x - re, dDown = rs - v.y;  // Interval::getDistance of the read to the two coordinates (mm:661-665)
+        a &= ~ANS_VICPAIR;
+        if (dUp < dDown) a &= fx.upMask;
+        else if (dDown < dUp) a &= fx.downMask;
+      }
+      return a;
+    }
+  }
+  return (u32)annotateEval<MODE, false>(ix, rs, re, meta, ovl, nullptr) | FAST_MISS;
+}
+
+template <int MODE>
+__device__ __forceinline__ u32 fastAnnotate(const FastView &fx, const IndexView &ix, u32 rs, u32 re, u32 meta, float ovl) {
   const u32 chr = meta & 0x00FFFFFFu;
-  if (chr >= fx.nChr) return true;
-  if (re < rs || re >= 0xFFFFFFF0u) return false;
+  if (chr >= fx.nChr) return 0;
+  uint4 e = make_uint4(0u, 0u, 0u, 0u);
+  if (re < rs || re >= 0xFFFFFFF0u) return fastRest<MODE>(fx, ix, e, rs, re, meta, ovl, 0);
   if (MODE != 0) {  // no feature can overlap the read by more than end - start
     const u32 o = re - rs;
-    if (o == 0) return true;
-    if (MODE == 1) { if (!(__fmul_rn((float)(o + 1u), ovl) <= (float)o)) return true; }
-    else { if (!((float)o >= ovl)) return true; }
+    if (o == 0) return 0;
+    if (MODE == 1) { if (!(__fmul_rn((float)(o + 1u), ovl) <= (float)o)) return 0; }
+    else { if (!((float)o >= ovl)) return 0; }
   }
   const uint2 ci = __ldg(&fx.chrInfo[chr]);
-  const u32 bRaw = rs >> fx.shift;
-  const u32 b = min(bRaw, ci.y - 1);
-  const uint4 e = __ldg(&fx.bin[ci.x + b]);
-  const u32 strandIdx = (meta >> 31) ? 0u : 1u;
-  u32 a, i = e.w & 0x00FFFFFFu, kind = 0;
+  e = __ldg(&fx.bin[ci.x + min(rs >> fx.shift, ci.y - 1)]);
   if (re <= e.x) {
-    a = strandIdx ? e.z : e.y;
-  } else {
-    const u32 quarter = (bRaw == b) ? ((rs >> (fx.shift - 2)) & 3u) : 3u;
-    i += (e.w >> (24 + 2 * quarter)) & 3u;
-    uint4 t = __ldg(&fx.seg[2 * i]);  // {start, end, answer F, answer R}
-#pragma unroll 1
-    for (int g = 0; rs > t.y; ++g) {
-      if (g == 3) return false;
-      ++i;
-      t = __ldg(&fx.seg[2 * i]);
-    }
-    if (re <= t.y) {
-      a = strandIdx ? t.w : t.z;
-    } else {
-      if (MODE != 0) return false;
-      const uint4 x = __ldg(&fx.seg[2 * i + 1]);  // {end of the next segment, cross answer F, cross answer R, 0}
-      if (re > x.x) return false;
-      a = strandIdx ? x.z : x.y;
-      kind = 2;
-    }
+    const u32 a = (meta >> 31) ? e.y : e.z;
+    if (!(a & (ANS_VICPAIR | ANS_GENERAL))) return a;
   }
-  if (a & (ANS_VICPAIR | ANS_GENERAL)) {
-    if (a & ANS_GENERAL) return false;
-    const uint2 v = __ldg(&fx.vic[4 * i + kind + strandIdx]);
-    const u32 dUp = v.x - re, dDown = rs - v.y;  // Interval::getDistance of the read to the two coordinates (mm:661-665)
-    a &= ~ANS_VICPAIR;
-    if (dUp < dDown) a &= fx.upMask;
-    else if (dDown < dUp) a &= fx.downMask;
-  }
-  out = a;
-  return true;
+  return fastRest<MODE>(fx, ix, e, rs, re, meta, ovl, 1);
 }
 
 // ----------------------------------------------------------------------------- the batch kernel
@@ -397,7 +418,7 @@ __device__ __forceinline__ bool fastAnnotate(const FastView &fx, u32 rs, u32 re,
 #define BATCH_WARPS (BATCH_THREADS / 32)
 #define WT_HITS 128
 #ifndef MMA_BLOCKS_PER_SM
-#define MMA_BLOCKS_PER_SM 4  // resident k_batch blocks per SM the register allocation is tuned for
+#define MMA_BLOCKS_PER_SM 3  // resident k_batch blocks per SM the register allocation is tuned for (measured: 3 > 4 > 5)
 #endif
 #define BT_SLOTS 256
 #define HIST_ROWS 32
@@ -430,10 +451,7 @@ struct Annotator {
   const FastView &fx;
   float ovl;
   __device__ __forceinline__ u64 operator()(u32 rs, u32 re, u32 meta) const {
-    if (FAST) {
-      u32 a;
-      if (fastAnnotate<MODE>(fx, rs, re, meta, ovl, a)) return a;
-    }
+    if (FAST) return fastAnnotate<MODE>(fx, ix, rs, re, meta, ovl) & ~FAST_MISS;
     return annotateHit<MODE>(ix, rs, re, meta, ovl);
   }
 };
@@ -549,12 +567,20 @@ k_batch(IndexView ix, FastView fx, HitView h, Rules r, TableView table, SampleCt
   // parallel countdown only when no read name is known as unfinished (then nothing has to be routed to the deferred
   // path) and rescue() is off (it needs multiplicities); the value is uniform over the warp
   const bool parallelRuns = (STRAT == 0) && (sizeof(MaskT) == 4) && !r.rescue && (__shfl_sync(0xffffffffu, ctl->openCount, 0) == 0);
-  u32 cHits = 0, cUnassigned = 0, cAmbiguous = 0, cUnique = 0, cMultiple = 0, cReads = 0, cRescued = 0, cMiss = 0;
+  // per-thread counters, two 16-bit fields per register (a thread sees < 2^15 hits of one batch: 4 per warp tile,
+  // at most 2^32 / 128 / (gridDim.x * 8) tiles with gridDim.x >= 148 * 2 for such a batch)
+  u32 pUnasAmbi = 0;   // unassigned | ambiguous << 16      (mm:1666-1667)
+  u32 pUniqMult = 0;   // unique | multiple << 16           (mm:1668, 1670)
+  u32 pHitsMiss = 0;   // hits looked at | segment-table misses << 16
+  u32 pClosResc = 0;   // multi-mapping reads closed by the parallel countdown | of which rescued << 16
 
   // one read counted for the element set `ckey` (0 = nothing)
   auto count = [&](u64 ckey) {
-    if (HIST && (ckey & (ckey - 1)) == 0) {
-      if (ckey) sm.hist[__ffs((u32)ckey) - 1][tid] += 1;
+    if (HIST) {
+      const u32 c = (u32)ckey;
+      if (c == 0) return;
+      if (c & (c - 1)) sm.bt.add(ckey, 1, table);
+      else sm.hist[__ffs(c) - 1][tid] += 1;
     } else if (ckey) {
       sm.bt.add(ckey, 1, table);
     }
@@ -589,7 +615,7 @@ k_batch(IndexView ix, FastView fx, HitView h, Rules r, TableView table, SampleCt
       re[0] = b.x; re[1] = b.y; re[2] = b.z; re[3] = b.w;
       meta[0] = c.x; meta[1] = c.y; meta[2] = c.z; meta[3] = c.w;
       nh[0] = d.x; nh[1] = d.y; nh[2] = d.z; nh[3] = d.w;
-      if (STRAT == 0 || STRAT == 2) {
+      if (STRAT == 0) {
         const ulonglong2 k0 = __ldcs(reinterpret_cast<const ulonglong2 *>(h.key + base));
         const ulonglong2 k1 = __ldcs(reinterpret_cast<const ulonglong2 *>(h.key + base + 2));
         key[0] = normKey(k0.x); key[1] = normKey(k0.y); key[2] = normKey(k1.x); key[3] = normKey(k1.y);
@@ -604,9 +630,29 @@ k_batch(IndexView ix, FastView fx, HitView h, Rules r, TableView table, SampleCt
         rs[j] = 0; re[j] = 0; meta[j] = 0x00FFFFFFu; nh[j] = 1; key[j] = KEY_EMPTY;
         if (valid[j]) {
           rs[j] = __ldcs(&h.start[i]); re[j] = __ldcs(&h.end[i]); meta[j] = __ldcs(&h.meta[i]); nh[j] = __ldcs(&h.nh[i]);
-          if (STRAT == 0 || STRAT == 2) key[j] = normKey(__ldcs(&h.key[i]));
+          if (STRAT == 0) key[j] = normKey(__ldcs(&h.key[i]));
         }
       }
+    }
+    // ---- run starts (the keys are not needed after this)
+    u32 hbits = 0, F = 0;
+    const Carry *carryIn = nullptr;
+    u64 nextKey = KEY_EMPTY;
+    if (STRAT == 0) {
+      u64 prev = __shfl_up_sync(0xffffffffu, key[3], 1);
+      if (lane == 0) {
+        if (t != t0) prev = cKey;
+        else if (base == 0) {
+          const Carry &c = ctl->carry[seq & 1];
+          prev = KEY_EMPTY;
+          if (c.valid) { carryIn = &c; prev = c.key; }
+        } else prev = normKey(h.key[base - 1]);
+      }
+      // a record whose read key differs from the previous record's starts a run
+      hbits = ((key[0] != prev || !valid[0]) ? 1u : 0u) | ((key[1] != key[0] || !valid[1]) ? 2u : 0u) |
+              ((key[2] != key[1] || !valid[2]) ? 4u : 0u) | ((key[3] != key[2] || !valid[3]) ? 8u : 0u);
+      F = __ballot_sync(0xffffffffu, hbits != 0);  // lanes in which a run starts
+      nextKey = __shfl_sync(0xffffffffu, key[3], 31);
     }
     // ---- element set of every hit that is looked at (unique: only NH == 1 is, mm:1773)
     bool visited[4];
@@ -617,9 +663,9 @@ k_batch(IndexView ix, FastView fx, HitView h, Rules r, TableView table, SampleCt
       m[j] = 0;
       if (!visited[j]) continue;
       if (FAST) {
-        u32 a;
-        if (fastAnnotate<MODE>(fx, rs[j], re[j], meta[j], r.overlap, a)) m[j] = (MaskT)a;
-        else { m[j] = (MaskT)annotateHit<MODE>(ix, rs[j], re[j], meta[j], r.overlap); ++cMiss; }
+        const u32 a = fastAnnotate<MODE>(fx, ix, rs[j], re[j], meta[j], r.overlap);
+        m[j] = (MaskT)(a & ~FAST_MISS);
+        pHitsMiss += (a >> 31) << 16;
       } else {
         m[j] = (MaskT)annotateHit<MODE>(ix, rs[j], re[j], meta[j], r.overlap);
       }
@@ -629,15 +675,12 @@ k_batch(IndexView ix, FastView fx, HitView h, Rules r, TableView table, SampleCt
     for (int j = 0; j < 4; ++j) {
       const int nreg = __popcll((u64)m[j]);
       const bool multi = visited[j] && STRAT == 0 && nh[j] > 1;  // joins the by-name countdown (mm:1669)
-      cHits += visited[j];
-      cUnassigned += visited[j] && nreg == 0;
-      cAmbiguous += visited[j] && nreg > 1;
-      cUnique += visited[j] && nreg == 1 && nh[j] == 1;
-      cMultiple += multi;
-      cReads += visited[j] && !multi;  // each of these is a read of its own (mm:1737)
+      pHitsMiss += visited[j] ? 1u : 0u;  // a hit that is not multi is a read of its own (mm:1737)
+      pUnasAmbi += (visited[j] && nreg == 0 ? 1u : 0u) | (visited[j] && nreg > 1 ? 0x10000u : 0u);
+      pUniqMult += (visited[j] && nreg == 1 && nh[j] == 1 ? 1u : 0u) | (multi ? 0x10000u : 0u);
       if (visited[j] && !multi && m[j] != 0) {
         if (STRAT == 2) {
-          slowAppend(slow, ctl, key[j], ctl->ordBase + base + j, (u64)m[j], nh[j]);  // order-dependent draw: deferred
+          slowAppend(slow, ctl, normKey(h.key[base + j]), ctl->ordBase + base + j, (u64)m[j], nh[j]);  // order-dependent draw: deferred
         } else {
           u64 ckey = rescueSingle(r, (u64)m[j]);
           if (STRAT == 3) {
@@ -651,20 +694,6 @@ k_batch(IndexView ix, FastView fx, HitView h, Rules r, TableView table, SampleCt
     if (STRAT != 0) continue;
 
     // ---- per-read countdown (mm:1669-1702)
-    // run starts: a record whose read key differs from the previous record's
-    u64 prev = __shfl_up_sync(0xffffffffu, key[3], 1);
-    const Carry *carryIn = nullptr;
-    if (lane == 0) {
-      if (t != t0) prev = cKey;
-      else if (base == 0) {
-        const Carry &c = ctl->carry[seq & 1];
-        prev = KEY_EMPTY;
-        if (c.valid) { carryIn = &c; prev = c.key; }
-      } else prev = normKey(h.key[base - 1]);
-    }
-    const u32 hbits = ((key[0] != prev || !valid[0]) ? 1u : 0u) | ((key[1] != key[0] || !valid[1]) ? 2u : 0u) |
-                      ((key[2] != key[1] || !valid[2]) ? 4u : 0u) | ((key[3] != key[2] || !valid[3]) ? 8u : 0u);
-    const u32 F = __ballot_sync(0xffffffffu, hbits != 0);  // lanes in which a run starts
     if (carryIn) {  // lane 0 of the batch's first tile: the read carried into this batch
       if (!(hbits & 1u)) w.walk(0, carryIn->key, carryIn);
       else {  // its name does not continue: unfinished
@@ -727,9 +756,8 @@ k_batch(IndexView ix, FastView fx, HitView h, Rules r, TableView table, SampleCt
       if (tot & 0x80000000u) { sm.walkQ[nWalk++][tid] = runStart; continue; }
       if (!(nh[j] > 1)) continue;  // a run of reads that are their own group
       if (nh[j] != base + j + 1 - runStart) { sm.walkQ[nWalk++][tid] = runStart; continue; }
-      ++cReads;
       const u32 gm = tot & 0x7FFFFFFFu;
-      cRescued += (__popc(gm) == 1);
+      pClosResc += 1u | (__popc(gm) == 1 ? 0x10000u : 0u);
       count(gm);
     }
 #pragma unroll 1
@@ -745,13 +773,15 @@ k_batch(IndexView ix, FastView fx, HitView h, Rules r, TableView table, SampleCt
         cTot |= incLast;
       }
       cNh = __shfl_sync(0xffffffffu, nh[3], 31);
-      cKey = __shfl_sync(0xffffffffu, key[3], 31);
+      cKey = nextKey;
     }
   }
   // ---- the read open at the end of the chunk continues in another warp's chunk: finish it by the serial walk.  (At the
   //      end of the batch the tile's last record closed its run above.)
   if (STRAT == 0 && parallelRuns && cValid && t1 > t0 && t1 * WT_HITS < h.n && lane == 0) w.walk(cStart, cKey, nullptr);
-  cReads += w.nReads; cRescued += w.nRescued;
+  u32 cHits = pHitsMiss & 0xFFFFu, cMiss = pHitsMiss >> 16, cUnassigned = pUnasAmbi & 0xFFFFu, cAmbiguous = pUnasAmbi >> 16;
+  u32 cUnique = pUniqMult & 0xFFFFu, cMultiple = pUniqMult >> 16;
+  u32 cReads = cHits - cMultiple + (pClosResc & 0xFFFFu) + w.nReads, cRescued = (pClosResc >> 16) + w.nRescued;
 
   // ---- block epilogue: counters, the private histogram columns and the private table
   cHits = __reduce_add_sync(0xffffffffu, cHits); cUnassigned = __reduce_add_sync(0xffffffffu, cUnassigned);

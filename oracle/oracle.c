@@ -375,7 +375,8 @@ static int add_count(rctx *r, uint64_t key, uint64_t mask, uint32_t nh) {
         if (!n) return -1;
         if (!n->seen) {
           if (!n->has_chosen) {
-            n->chosen = nh ? next_rand(r) % nh : 0;
+            uint32_t draw = next_rand(r); /* rand() is evaluated before the modulo (mm:1711); NH = 0 traps there in the reference */
+            n->chosen = nh ? draw % nh : 0;
             n->has_chosen = 1;
             n->number_seen = 0;
           } else {
