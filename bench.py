@@ -394,7 +394,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="tair10_srna", choices=sorted(WORKLOADS))
     ap.add_argument("--reads", type=int, default=0, help="reads per GPU (default: the workload's full size)")
-    ap.add_argument("--batch", type=int, default=1 << 23, help="hits per mma_submit_hits call")
+    ap.add_argument("--batch", type=int, default=1 << 25, help="hits per mma_submit_hits call")
     ap.add_argument("--table-log2", type=int, default=0)
     ap.add_argument("--fast-shift", type=int, default=0, help="log2 bin width of the segment answer table (0 = auto, -1 = no table)")
     ap.add_argument("--bin-shift", type=int, default=0)

@@ -98,6 +98,7 @@ struct mma_ctx {
   double ms[TC_N] = {0, 0, 0, 0};
   uint64_t launches = 0, hitsSubmitted = 0, batches = 0;
   int nSM = 148;
+  u64 *hostTable = nullptr;  // pinned, 2 x tableCap: keys then values of the sample being read back
 
   int fail(int code, const std::string &msg) {
     error = msg;
@@ -394,6 +395,7 @@ void mma_destroy(mma_ctx *ctx) {
   ctx->fastBin.release(); ctx->fastSeg.release(); ctx->fastVic.release(); ctx->fastChrInfo.release();
   ctx->dElemLine.release(); ctx->dElemStrand.release(); ctx->dElemVic.release();
   ctx->collectTiming();
+  if (ctx->hostTable) cudaFreeHost(ctx->hostTable);
   for (cudaEvent_t e : ctx->eventPool) cudaEventDestroy(e);
   if (ctx->sc) cudaStreamDestroy(ctx->sc);
   if (ctx->sh) cudaStreamDestroy(ctx->sh);
@@ -834,9 +836,11 @@ int mma_finish_sample(mma_ctx *ctx, uint32_t sample, mma_sample_result *out) {
     if (hc.overflow) return ctx->fail(MMA_ERR_CAPACITY, "the combination table overflowed");
     s.knownCount = 0; s.knownCum = s.cumHits;
   }
-  std::vector<u64> keys(ctx->tableCap), vals(ctx->tableCap);
-  CK(cudaMemcpy(keys.data(), s.tableKeys.p, (size_t)ctx->tableCap * 8, cudaMemcpyDeviceToHost));
-  CK(cudaMemcpy(vals.data(), s.tableVals.p, (size_t)ctx->tableCap * 8, cudaMemcpyDeviceToHost));
+  if (!ctx->hostTable) CK(cudaHostAlloc(&ctx->hostTable, (size_t)ctx->tableCap * 16, cudaHostAllocDefault));
+  const u64 *keys = ctx->hostTable, *vals = ctx->hostTable + ctx->tableCap;
+  CK(cudaMemcpyAsync(ctx->hostTable, s.tableKeys.p, (size_t)ctx->tableCap * 8, cudaMemcpyDeviceToHost, ctx->sc));
+  CK(cudaMemcpyAsync(ctx->hostTable + ctx->tableCap, s.tableVals.p, (size_t)ctx->tableCap * 8, cudaMemcpyDeviceToHost, ctx->sc));
+  CK(cudaStreamSynchronize(ctx->sc));
   const bool ratio = ctx->rules.strategy == MMA_STRATEGY_RATIO;
   const u64 lowMask = (1ull << NH_SHIFT) - 1;
   for (u32 i = 0; i < ctx->tableCap; ++i) {

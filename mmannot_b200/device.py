@@ -224,9 +224,14 @@ class Annotator:
         r = SampleResult()
         self._check(lib().mma_finish_sample(self._h, sample, C.byref(r)))
         stats = {k: int(getattr(r.stats, k)) for k, _ in SampleStats._fields_}
-        rows = {}
-        for i in range(r.n_rows):
-            rows[(int(r.row_mask[i]), int(r.row_nh[i]))] = int(r.row_count[i])
+        n = int(r.n_rows)
+        if n:
+            masks = np.ctypeslib.as_array(r.row_mask, shape=(n,)).tolist()
+            nhs = np.ctypeslib.as_array(r.row_nh, shape=(n,)).tolist()
+            counts = np.ctypeslib.as_array(r.row_count, shape=(n,)).tolist()
+            rows = dict(zip(zip(masks, nhs), counts))
+        else:
+            rows = {}
         return {"stats": stats, "rows": rows}
 
     def dense_counts(self, sample, masks, nhs, out_dev_ptr):

@@ -1,0 +1,98 @@
+"""GPU path on the benchmark shapes: (1) device == oracle on synthetic sRNA-Seq / RNA-Seq hits at a size the oracle
+finishes in seconds, for several batch sizes; (2) the drop-in command line (mmannot_b200/bin/mmannot_b200: BAM decode
+on the host, annotation on the GPU through the C ABI) writes the same table and counters as the reference binary
+(oracle/_ref/mmannot_fixed, compiled from the reference where it lies) on the same files."""
+import json
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from tests import common
+from oracle import pyoracle
+from mmannot_b200 import host
+
+pytestmark = pytest.mark.gpu
+
+CFGS = json.load(open(os.path.join(common.GOLDEN, "configs.json")))
+SHAPES = [("tair10", "configTAIR10", dict(max_nh=20)), ("hs38", "configHS38", dict(max_nh=100)),
+          ("flybase6", "configFlybase6", dict(max_nh=8, paired=True, rna_seq=True))]
+CLI = os.path.join(common.ROOT, "mmannot_b200", "bin", "mmannot_b200")
+
+
+@pytest.fixture(scope="module", params=SHAPES, ids=[s[0] for s in SHAPES])
+def workload(request, tmp_path_factory):
+    shape, cfg_key, spec = request.param
+    tmp = tmp_path_factory.mktemp(shape)
+    cfg_path = str(tmp / (cfg_key + ".txt"))
+    open(cfg_path, "w").write(CFGS[cfg_key])
+    synth = host.Synth(shape, 777, gene_scale=0.1, **spec)
+    gtf = str(tmp / "a.gtf")
+    synth.write_annotation(gtf)
+    cfg = host.Config(cfg_path)
+    ann = host.Annotation(cfg, gtf)
+    return dict(tmp=tmp, cfg_path=cfg_path, gtf=gtf, cfg=cfg, ann=ann, synth=synth)
+
+
+def _device(cfg, ann, hits, batch, **kw):
+    from mmannot_b200 import device
+    a = device.Annotator(cfg, max_batch_hits=batch, **kw)
+    try:
+        a.load_features(ann)
+        a.submit(0, hits)
+        r = a.finish(0)
+        r["values"] = device.values_by_mask(r["rows"])
+        return r
+    finally:
+        a.close()
+
+
+@pytest.mark.parametrize("strategy,overlap", [("default", -1.0), ("default", 10.0), ("ratio", -1.0), ("unique", 0.5), ("random", -1.0)])
+def test_device_equals_oracle_on_benchmark_shapes(workload, strategy, overlap):
+    w = workload
+    hits = w["synth"].hits(w["ann"], "F", 0, 150000, threads=4)
+    ref = pyoracle.run(w["cfg"].elem_line, w["cfg"].elem_strand, w["cfg"].elem_vicinity, w["ann"], hits, strategy=strategy, overlap=overlap)
+    for batch in (50021, 1 << 22):
+        res = _device(w["cfg"], w["ann"], hits, batch, strategy=strategy, overlap=overlap)
+        assert set(res["values"]) == set(ref["rows"])
+        for m, v in ref["rows"].items():
+            if strategy == "ratio":
+                assert abs(res["values"][m] - v) <= 1e-9 * max(1.0, abs(v))
+            else:
+                assert res["values"][m] == v
+        assert res["stats"] == ref["stats"]
+
+
+def test_coordinate_sorted_variant(workload):
+    """Same reads in coordinate order: the records of a read are scattered, everything takes the deferred path."""
+    w = workload
+    hits = w["synth"].hits(w["ann"], "F", 0, 60000, threads=4)
+    order = np.lexsort((hits.start, hits.meta & np.uint32(0xFFFFFF)))
+    shuffled = host.Hits(hits.start[order], hits.end[order], hits.meta[order], hits.nh[order], hits.read_key[order])
+    ref = pyoracle.run(w["cfg"].elem_line, w["cfg"].elem_strand, w["cfg"].elem_vicinity, w["ann"], shuffled)
+    res = _device(w["cfg"], w["ann"], shuffled, 30011)
+    assert res["values"] == ref["rows"] and res["stats"] == ref["stats"]
+
+
+@pytest.mark.skipif(pyoracle.ref_binary("fixed") is None or not os.path.exists(CLI), reason="needs oracle/_ref and the CLI binary")
+@pytest.mark.parametrize("args", [["-s", "F"], ["-s", "U", "-l", "1"], ["-s", "R", "-y", "ratio"], ["-s", "F", "-y", "unique", "-l", "0.5"]],
+                         ids=lambda a: " ".join(a))
+def test_cli_equals_reference(workload, args):
+    w = workload
+    bams = []
+    for i in range(2):
+        b = str(w["tmp"] / ("sample%d.bam" % i))
+        if not os.path.exists(b):
+            w["synth"].write_bam(b, i * 20000, 20000)
+        bams.append(b)
+    common_args = ["-a", w["gtf"], "-c", w["cfg_path"], "-r"] + bams + args
+    rc, ref_out, ref_err = pyoracle.run_reference(common_args, kind="fixed")
+    assert rc == 0, ref_err
+    pr = subprocess.run([CLI] + common_args, capture_output=True, text=True, timeout=300)
+    assert pr.returncode == 0, pr.stderr
+    assert pr.stdout == ref_out
+    assert pyoracle.parse_stats(pr.stderr) == pyoracle.parse_stats(ref_err)
+    # same report text for the per-sample blocks
+    pick = lambda t: [l for l in t.split("\n") if l.startswith("\t#") or l.startswith("Results for")]
+    assert pick(pr.stderr) == pick(ref_err)
