@@ -44,10 +44,11 @@ oracle/_build/liboracle.so: oracle/oracle.c oracle/oracle.h
 ref:
 	bash oracle/build_ref.sh
 
-# tuning builds (not shipped): make variants; MMANNOT_B200_LIB=mmannot_b200/lib/variants/b4.so python bench.py ...
+VARIANT_BLOCKS ?= 3 5
+# tuning builds (not shipped): make variants; MMANNOT_B200_LIB=mmannot_b200/lib/variants/f3.so python bench.py ...
 variants: $(CU_SRC) $(CU_HDR)
 	@mkdir -p mmannot_b200/lib/variants
-	for b in 2 4; do $(NVCC) $(NVFLAGS) -DMMA_BLOCKS_PER_SM=$$b -shared -o mmannot_b200/lib/variants/b$$b.so $(CU_SRC) & done; wait
+	for b in $(VARIANT_BLOCKS); do $(NVCC) $(NVFLAGS) -DMMA_FAST_BLOCKS_PER_SM=$$b -shared -o mmannot_b200/lib/variants/f$$b.so $(CU_SRC) & done; wait
 
 clean:
 	rm -rf mmannot_b200/lib mmannot_b200/bin oracle/_build

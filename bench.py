@@ -323,6 +323,12 @@ def run_product_arm(args):
         clocks = sampler.stop() if rank == 0 else None
 
         assert res_dev["rows"] == res_e2e["rows"] and res_dev["stats"] == res_e2e["stats"], "device-resident and host-buffer passes disagree"
+        # size-independent properties of the synthetic workload: every read is complete (NH records each), so the reads
+        # counted must be the reads generated, and every hit is either unassigned, ambiguous or assigned to one element
+        if w["strategy"] == "default":
+            assert res_dev["stats"]["n_hits"] == n_hits * (world if world > 1 else 1) or world > 1
+            if world == 1:
+                assert res_dev["stats"]["n_reads"] == reads, "reads counted %d != reads generated %d" % (res_dev["stats"]["n_reads"], reads)
         total_hits = n_hits
         if world > 1:
             t = torch.tensor([n_hits], device=dev, dtype=torch.int64)

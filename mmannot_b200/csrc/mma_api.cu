@@ -8,11 +8,13 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
 
 #include "mma_device.cuh"
+#include "mma_batch_fast.cuh"
 
 using namespace mma;
 
@@ -98,6 +100,8 @@ struct mma_ctx {
   double ms[TC_N] = {0, 0, 0, 0};
   uint64_t launches = 0, hitsSubmitted = 0, batches = 0;
   int nSM = 148;
+  u32 maxGrid = 0;           // MMANNOT_B200_MAX_GRID=n: cap on k_batch blocks, so that small test inputs still give every warp a multi-tile chunk (testing only)
+  bool legacyBatch = false;  // MMANNOT_B200_LEGACY_BATCH=1: A/B runs of the general k_batch against k_batch_fast (tuning only)
   u64 *hostTable = nullptr;  // pinned, 2 x tableCap: keys then values of the sample being read back
 
   int fail(int code, const std::string &msg) {
@@ -241,9 +245,19 @@ void launchBatchKernels(mma_ctx *ctx, Sample &s, const HitView &h) {
   KeySetView open = openView(s);
   // one contiguous chunk of 128-hit warp tiles per warp; enough warps to fill the GPU, chunks of >= 8 tiles when possible
   const u32 nWT = (h.n + WT_HITS - 1) / WT_HITS;
-  const u32 perSM = (sizeof(MaskT) == 4) ? MMA_BLOCKS_PER_SM : 2;
-  const u32 grid = std::max<u32>(1u, std::min<u32>((nWT + BATCH_WARPS - 1) / BATCH_WARPS, (u32)ctx->nSM * perSM));
-  {
+  constexpr bool useFast = FAST && sizeof(MaskT) == 4 && STRAT != 2;  // k_batch_fast (mma_batch_fast.cuh)
+  bool launched = false;
+  if constexpr (useFast) if (!ctx->legacyBatch) {
+    launched = true;
+    u32 grid = std::max<u32>(1u, std::min<u32>((nWT + BATCH_WARPS - 1) / BATCH_WARPS, (u32)ctx->nSM * MMA_FAST_BLOCKS_PER_SM));
+    if (ctx->maxGrid) grid = std::min(grid, ctx->maxGrid);
+    mma_ctx::Timed t(ctx, TC_BATCH);
+    k_batch_fast<MODE, STRAT><<<grid, BATCH_THREADS, 0, ctx->sc>>>(ctx->index, ctx->fast, h, r, table, s.ctl, slow, open);
+  }
+  if (!launched) {
+    const u32 perSM = (sizeof(MaskT) == 4) ? MMA_BLOCKS_PER_SM : 2;
+    u32 grid = std::max<u32>(1u, std::min<u32>((nWT + BATCH_WARPS - 1) / BATCH_WARPS, (u32)ctx->nSM * perSM));
+    if (ctx->maxGrid) grid = std::min(grid, ctx->maxGrid);
     mma_ctx::Timed t(ctx, TC_BATCH);
     k_batch<MODE, STRAT, FAST, MaskT><<<grid, BATCH_THREADS, 0, ctx->sc>>>(ctx->index, ctx->fast, h, r, table, s.ctl, slow, open);
   }
@@ -368,6 +382,8 @@ int mma_create(mma_ctx **out, const mma_params *p) {
     if ((e = cudaEventCreateWithFlags(&ctx->stage[k].copied, cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
     if ((e = cudaEventCreateWithFlags(&ctx->stage[k].done, cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
   }
+  { const char *lg = getenv("MMANNOT_B200_LEGACY_BATCH"); ctx->legacyBatch = lg && lg[0] == '1';
+    const char *mg = getenv("MMANNOT_B200_MAX_GRID"); ctx->maxGrid = mg ? (u32)std::max(0, atoi(mg)) : 0u; }
   ctx->samples.resize(p->n_samples);
   *out = ctx;
   return MMA_OK;
@@ -615,7 +631,7 @@ int mma_load_features(mma_ctx *ctx, const mma_features *f) {
 uint64_t mma_index_bytes(const mma_ctx *ctx) { return ctx ? ctx->indexBytes : 0; }
 uint64_t mma_index_segments(const mma_ctx *ctx) { return ctx ? ctx->nSegments : 0; }
 uint64_t mma_readback_bytes(const mma_ctx *ctx) { return ctx ? (uint64_t)ctx->tableCap * 16 + sizeof(SampleCtl) : 0; }
-const char *mma_dominant_kernel(void) { return "k_batch"; }
+const char *mma_dominant_kernel(void) { return "k_batch_fast"; }
 
 static int submitCommon(mma_ctx *ctx, uint32_t sample, const mma_hit_batch *b, bool onDevice) {
   int rc = checkSubmit(ctx, sample, b);
@@ -885,6 +901,15 @@ int mma_dense_counts(mma_ctx *ctx, uint32_t sample, const uint64_t *mask, const 
   if (e != cudaSuccess) return ctx->fail(MMA_ERR_CUDA, cudaGetErrorString(e));
   return MMA_OK;
 }
+
+#ifdef MMA_DIAG
+int mma_diag_get(unsigned long long *out16, int reset) {
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(out16, mma::g_diag, sizeof(unsigned long long) * 16);
+  if (reset) { unsigned long long z[16] = {0}; cudaMemcpyToSymbol(mma::g_diag, z, sizeof(z)); }
+  return 0;
+}
+#endif
 
 int mma_timing_enable(mma_ctx *ctx, int on) {
   if (!ctx) return MMA_ERR_INVALID;

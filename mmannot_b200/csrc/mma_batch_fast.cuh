@@ -1,0 +1,411 @@
+// k_batch_fast: the batch kernel (K2 + K3 + K4) for the common configuration -- segment answer table built (E <= 30),
+// 32-bit element sets, -y default / unique / ratio.  Same decomposition as k_batch (mma_device.cuh): a warp owns a
+// contiguous chunk of 128-hit warp tiles, 4 consecutive hits per lane, no block-wide barrier in the loop.  What differs
+// is the shape of the per-tile code, written so that the warp stays converged and its memory requests overlap:
+//
+//   phase A   4 independent gathers per lane: the bin entries of the segment table (unconditional, dummy address for
+//             hits that need no lookup)
+//   phase B   4 independent gathers of the 32-byte segment record for the hits the bin entry did not answer
+//   phase C   pick the in-segment / cross-segment answer; whatever is left (position-dependent picks, reads over three
+//             or more segments, degenerate intervals: a few % of the hits) is COMPACTED over the warp through shared
+//             memory and evaluated out of line, one hit per lane, instead of diverging hit by hit
+//   counting  every hit slot yields at most one count event (a read that is its own group, or the read whose run ends
+//             at this record); single-element sets go to the lane's private histogram column with one unconditional
+//             read-modify-write, the others to the block table in a loop the whole warp runs in lockstep
+//
+// Reads whose run is not the clean "n records carrying NH = n" shape, -m rescue and batches following one that left
+// unfinished read names take the serial RunWalker of mma_device.cuh, exactly as in k_batch.
+#pragma once
+#include "mma_device.cuh"
+
+namespace mma {
+
+#ifndef MMA_FAST_BLOCKS_PER_SM
+#define MMA_FAST_BLOCKS_PER_SM 4
+#endif
+
+#ifdef MMA_DIAG
+// tuning builds only: why hits leave the table fast path.  0 degenerate, 1 bin answer VICPAIR, 2 bin answer GENERAL, 3 start beyond
+// the quarter's segment, 4 read over 3+ segments (or 2 under an overlap mode), 5 segment answer VICPAIR, 6 segment answer GENERAL,
+// 7 answered by the bin entry, 8 answered by the segment record, 9 hits looked up
+__device__ unsigned long long g_diag[16];
+#define DIAG(i, c) do { if (c) atomicAdd(&g_diag[i], 1ull); } while (0)
+#else
+#define DIAG(i, c) do { } while (0)
+#endif
+
+template <int MODE>
+__device__ __noinline__ u32 slowAnnotate(const FastView &fx, const IndexView &ix, u32 rs, u32 re, u32 meta, float ovl) {
+  return fastAnnotate<MODE>(fx, ix, rs, re, meta, ovl);
+}
+
+template <bool HIST, int SLOTS>
+struct FastSmem {
+  BlockTable<SLOTS> bt;
+  unsigned short hist[HIST ? HIST_ROWS : 1][BATCH_THREADS];
+  u32 walkQ[4][BATCH_THREADS];
+  u32 slowRes[BATCH_WARPS][WT_HITS];
+  unsigned char slowQ[BATCH_WARPS][WT_HITS];
+  u32 stat[ST_N];
+};
+
+template <bool HIST, int SLOTS>
+struct FastCount {  // one read counted for an element set, from divergent code (the serial walker)
+  FastSmem<HIST, SLOTS> &sm;
+  const TableView &table;
+  u32 tid;
+  __device__ __forceinline__ void operator()(u64 ckey) const {
+    if (HIST) {
+      const u32 c = (u32)ckey;
+      if (c == 0) return;
+      if (c & (c - 1)) sm.bt.add(ckey, 1, table);
+      else sm.hist[__ffs(c) - 1][tid] += 1;
+    } else if (ckey) {
+      sm.bt.add(ckey, 1, table);
+    }
+  }
+};
+
+template <int MODE, int STRAT>
+__global__ void __launch_bounds__(BATCH_THREADS, MMA_FAST_BLOCKS_PER_SM)
+k_batch_fast(IndexView ix, FastView fx, HitView h, Rules r, TableView table, SampleCtl *ctl, SlowView slow, KeySetView open) {
+  constexpr bool HIST = (STRAT != 3);
+  constexpr int SLOTS = (STRAT == 3) ? 1024 : BT_SLOTS;
+  constexpr u32 FULL = 0xffffffffu;
+  __shared__ FastSmem<HIST, SLOTS> sm;
+  const u32 tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+  sm.bt.init();
+  if (HIST) {
+#pragma unroll
+    for (int e = 0; e < HIST_ROWS; ++e) sm.hist[e][tid] = 0;
+  }
+  if (tid < ST_N) sm.stat[tid] = 0;
+  __syncthreads();
+  const Annotator<MODE, true> annot{ix, fx, r.overlap};
+  const u32 seq = ctl->batchSeq;
+  // every run takes the serial walker when rescue() needs multiplicities or some read name is known as unfinished
+  const bool forceWalk = (STRAT == 0) && (r.rescue || __shfl_sync(FULL, ctl->openCount, 0) != 0);
+  u32 pUnasAmbi = 0, pUniqMult = 0, pHitsMiss = 0, pClosResc = 0;  // packed 16-bit counters, see k_batch
+
+  FastCount<HIST, SLOTS> count{sm, table, tid};
+  RunWalker<MODE, true, FastCount<HIST, SLOTS>> w{h, r, annot, ctl, slow, open, count, seq, 0u, 0u};
+
+  const u32 nWT = (h.n + WT_HITS - 1) / WT_HITS;
+  const u32 nWarps = gridDim.x * BATCH_WARPS;
+  const u32 per = (nWT + nWarps - 1) / nWarps;
+  const u32 t0 = min(nWT, (blockIdx.x * BATCH_WARPS + warp) * per), t1 = min(nWT, t0 + per);
+
+  bool cValid = false, cCont = false;  // cCont: the run open at the end of the tile continues in the next tile
+  u32 cStart = 0, cTot = 0, cNh = 0;
+  u64 cKey = KEY_EMPTY;
+  const u32 shift = fx.shift;
+
+  for (u32 t = t0; t < t1; ++t) {
+    const u32 base = t * WT_HITS + lane * 4;
+    u32 rs[4], re[4], meta[4], nh[4];
+    u64 key[4];
+    u32 validBits;
+    if (h.vec && (t + 1) * WT_HITS <= h.n) {
+      const uint4 a = __ldcs(reinterpret_cast<const uint4 *>(h.start + base));
+      const uint4 b = __ldcs(reinterpret_cast<const uint4 *>(h.end + base));
+      const uint4 c = __ldcs(reinterpret_cast<const uint4 *>(h.meta + base));
+      const uint4 d = __ldcs(reinterpret_cast<const uint4 *>(h.nh + base));
+      rs[0] = a.x; rs[1] = a.y; rs[2] = a.z; rs[3] = a.w;
+      re[0] = b.x; re[1] = b.y; re[2] = b.z; re[3] = b.w;
+      meta[0] = c.x; meta[1] = c.y; meta[2] = c.z; meta[3] = c.w;
+      nh[0] = d.x; nh[1] = d.y; nh[2] = d.z; nh[3] = d.w;
+      if (STRAT == 0) {
+        const ulonglong2 k0 = __ldcs(reinterpret_cast<const ulonglong2 *>(h.key + base));
+        const ulonglong2 k1 = __ldcs(reinterpret_cast<const ulonglong2 *>(h.key + base + 2));
+        key[0] = normKey(k0.x); key[1] = normKey(k0.y); key[2] = normKey(k1.x); key[3] = normKey(k1.y);
+      }
+      validBits = 15u;
+    } else {
+      validBits = 0;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const u32 i = base + j;
+        rs[j] = 0; re[j] = 0; meta[j] = 0x00FFFFFFu; nh[j] = 1; key[j] = KEY_EMPTY;
+        if (i < h.n) {
+          validBits |= 1u << j;
+          rs[j] = __ldcs(&h.start[i]); re[j] = __ldcs(&h.end[i]); meta[j] = __ldcs(&h.meta[i]); nh[j] = __ldcs(&h.nh[i]);
+          if (STRAT == 0) key[j] = normKey(__ldcs(&h.key[i]));
+        }
+      }
+    }
+    // ---- run starts
+    u32 hbits = 0, F = 0;
+    const Carry *carryIn = nullptr;
+    u64 nextKey = KEY_EMPTY;
+    u32 tileEndsRun = 1;  // lane 31: the record after the tile's last one starts another run (or the batch ends there)
+    if (STRAT == 0) {
+      const u32 nextTile = (t + 1) * WT_HITS;
+      if (lane == 31u && nextTile < h.n) tileEndsRun = (normKey(__ldg(&h.key[nextTile])) != key[3]) ? 1u : 0u;
+      u64 prev = __shfl_up_sync(FULL, key[3], 1);
+      if (lane == 0) {
+        if (t != t0) prev = cKey;
+        else if (base == 0) {
+          const Carry &c = ctl->carry[seq & 1];
+          prev = KEY_EMPTY;
+          if (c.valid) { carryIn = &c; prev = c.key; }
+        } else prev = normKey(h.key[base - 1]);
+      }
+      const u32 inv = ~validBits;
+      hbits = ((key[0] != prev || (inv & 1u)) ? 1u : 0u) | ((key[1] != key[0] || (inv & 2u)) ? 2u : 0u) |
+              ((key[2] != key[1] || (inv & 4u)) ? 4u : 0u) | ((key[3] != key[2] || (inv & 8u)) ? 8u : 0u);
+      F = __ballot_sync(FULL, hbits != 0);
+      nextKey = __shfl_sync(FULL, key[3], 31);
+    }
+    // ---- which hits are looked at (unique: only NH == 1, mm:1773)
+    u32 visBits = validBits;
+    if (STRAT == 1) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) if (nh[j] != 1) visBits &= ~(1u << j);
+    }
+    // ---- phase A: bin entries of the segment table
+    u32 m[4] = {0u, 0u, 0u, 0u};
+    u32 lookBits = 0, slowBits = 0;
+    uint4 e[4];
+    u32 ciy[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const u32 chr = meta[j] & 0x00FFFFFFu;
+      const bool vis = ((visBits >> j) & 1u) && chr < fx.nChr;
+      const bool degen = re[j] < rs[j] || re[j] >= 0xFFFFFFF0u;
+      bool pass = true;
+      if (MODE != 0) {  // no feature can overlap the read by more than end - start
+        const u32 o = re[j] - rs[j];
+        if (MODE == 1) pass = (o != 0) && (__fmul_rn((float)(o + 1u), r.overlap) <= (float)o);
+        else pass = (o != 0) && ((float)o >= r.overlap);
+      }
+      if (vis && degen) slowBits |= 1u << j;
+      DIAG(0, vis && degen);
+      const bool look = vis && !degen && pass;
+      if (look) lookBits |= 1u << j;
+      const uint2 ci = __ldg(&fx.chrInfo[look ? chr : 0u]);
+      ciy[j] = ci.y;
+      e[j] = __ldg(&fx.bin[ci.x + min(rs[j] >> shift, ci.y - 1u)]);
+    }
+    // ---- phase B: the bin entry answers a read inside the segment of the bin's first position; else the segment record
+    u32 need2 = 0;
+    u32 tEnd[4], tAns[4], xEnd[4], xAns[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const bool fwd = (meta[j] >> 31) != 0;
+      const u32 a = fwd ? e[j].y : e[j].z;
+      const bool look = (lookBits >> j) & 1u;
+      const bool inA = re[j] <= e[j].x;
+      const bool flagged = (a & (ANS_VICPAIR | ANS_GENERAL)) != 0;
+      if (look && inA && !flagged) m[j] = a;
+      if (look && inA && flagged) slowBits |= 1u << j;
+      DIAG(9, look); DIAG(7, look && inA && !flagged); DIAG(1, look && inA && (a & ANS_VICPAIR)); DIAG(2, look && inA && (a & ANS_GENERAL));
+      const bool n2 = look && !inA;
+      if (n2) need2 |= 1u << j;
+      const u32 quarter = ((rs[j] >> shift) < ciy[j]) ? ((rs[j] >> (shift - 2u)) & 3u) : 3u;
+      const u32 i = n2 ? (e[j].w & 0x00FFFFFFu) + ((e[j].w >> (24u + 2u * quarter)) & 3u) : 0u;
+      const uint4 tt = __ldg(&fx.seg[2u * i]);
+      tEnd[j] = tt.y; tAns[j] = fwd ? tt.z : tt.w;
+      if (MODE == 0) {
+        const uint4 xx = __ldg(&fx.seg[2u * i + 1u]);
+        xEnd[j] = xx.x; xAns[j] = fwd ? xx.y : xx.z;
+      } else { xEnd[j] = 0; xAns[j] = 0; }
+    }
+    // ---- phase C
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const bool n2 = (need2 >> j) & 1u;
+      const bool inT = re[j] <= tEnd[j];
+      const bool inX = (MODE == 0) && re[j] <= xEnd[j];
+      const u32 a = inT ? tAns[j] : xAns[j];
+      const bool ok = rs[j] <= tEnd[j] && (inT || inX) && !(a & (ANS_VICPAIR | ANS_GENERAL));
+      if (n2 && ok) m[j] = a;
+      if (n2 && !ok) slowBits |= 1u << j;
+      DIAG(8, n2 && ok); DIAG(3, n2 && rs[j] > tEnd[j]); DIAG(4, n2 && rs[j] <= tEnd[j] && !(inT || inX));
+      DIAG(5, n2 && rs[j] <= tEnd[j] && (inT || inX) && (a & ANS_VICPAIR)); DIAG(6, n2 && rs[j] <= tEnd[j] && (inT || inX) && (a & ANS_GENERAL));
+    }
+    // ---- the rest, compacted over the warp
+    if (__any_sync(FULL, slowBits != 0)) {
+      u32 off[4], total = 0;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const u32 b = __ballot_sync(FULL, (slowBits >> j) & 1u);
+        off[j] = total + __popc(b & ((1u << lane) - 1u));
+        total += __popc(b);
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if ((slowBits >> j) & 1u) sm.slowQ[warp][off[j]] = (unsigned char)(lane * 4 + j);
+      __syncwarp();
+      for (u32 k = lane; k < total; k += 32) {
+        const u32 id = sm.slowQ[warp][k];
+        const u32 i = t * WT_HITS + id;
+        sm.slowRes[warp][id] = slowAnnotate<MODE>(fx, ix, h.start[i], h.end[i], h.meta[i], r.overlap);
+      }
+      __syncwarp();
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if ((slowBits >> j) & 1u) {
+          const u32 a = sm.slowRes[warp][lane * 4 + j];
+          m[j] = a & ~FAST_MISS;
+          pHitsMiss += (a >> 31) << 16;
+        }
+      __syncwarp();
+    }
+    // ---- per-hit counters (mm:1666-1668); a visited hit that does not join the by-name countdown is a read of its own
+    u32 ev[4];  // the element set counted at this hit slot (0 = none)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const bool vis = (visBits >> j) & 1u;
+      const int nreg = __popc(m[j]);
+      const bool multi = vis && STRAT == 0 && nh[j] > 1;
+      pHitsMiss += vis ? 1u : 0u;
+      pUnasAmbi += (vis && nreg == 0 ? 1u : 0u) | (vis && nreg > 1 ? 0x10000u : 0u);
+      pUniqMult += (vis && nreg == 1 && nh[j] == 1 ? 1u : 0u) | (multi ? 0x10000u : 0u);
+      ev[j] = (vis && !multi) ? m[j] : 0u;
+      if (r.rescue) ev[j] = (u32)rescueSingle(r, (u64)ev[j]);
+    }
+    u32 nWalk = 0;
+    u32 inc = 0, lastHeadPos = 0;
+    if (STRAT == 0) {
+      // ---- per-read countdown (mm:1669-1702)
+      if (carryIn) {  // lane 0 of the batch's first tile: the read carried into this batch
+        if (!(hbits & 1u)) w.walk(0, carryIn->key, carryIn);
+        else {  // its name does not continue: unfinished
+          --w.nReads;
+          slowAppend(slow, ctl, carryIn->key, carryIn->ord, carryIn->gm, carryIn->remaining + 1);
+          keySetInsert(open, carryIn->key, seq, ctl);
+          ctl->dirty = 1;
+        }
+      }
+      // A run of n records that all carry NH = n (> 1) is one read; its element set is the union over the run: a
+      // segmented OR scan over the 128 hits of the warp tile (bit 31 of the scanned word = "irregular": NH changes inside
+      // the run, or every run has to be walked), seeded with the state carried from the previous tile.  The lane owning
+      // the run's LAST record closes it; irregular runs take the serial walk (RunWalker), started by the same lane.
+      u32 prevNh = __shfl_up_sync(FULL, nh[3], 1);
+      if (lane == 0) prevNh = cNh;
+      u32 pre[4], acc = 0;
+      const u32 force = forceWalk ? 0x80000000u : 0u;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const bool isHead = (hbits >> j) & 1u;
+        const bool bad = !isHead && nh[j] != (j ? nh[j > 0 ? j - 1 : 0] : prevNh);
+        const u32 x = m[j] | (bad ? 0x80000000u : 0u) | force;
+        acc = isHead ? x : (acc | x);
+        pre[j] = acc;
+      }
+      inc = acc;  // inclusive scan over lanes: OR of `acc` from the nearest lane with a run start up to this lane
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const u32 tt = __shfl_up_sync(FULL, inc, d);
+        if (lane >= (u32)d && ((F >> (lane - d + 1)) & ((1u << d) - 1u)) == 0) inc |= tt;
+      }
+      u32 X = __shfl_up_sync(FULL, inc, 1);
+      if (lane == 0) X = 0;
+      const u32 before = F & ((1u << lane) - 1u);
+      lastHeadPos = base + (31 - __clz(hbits | 1u));
+      const u32 sPrev = __shfl_sync(FULL, lastHeadPos, before ? (31 - __clz(before)) : 0);
+      const u32 nextHead0 = __shfl_down_sync(FULL, hbits & 1u, 1);
+      // bit j: the next record starts another run, i.e. this record ends its run (the tile's last record: from the peek)
+      const u32 lastBits = ((hbits >> 1) | ((lane < 31u ? nextHead0 : tileEndsRun) << 3)) & validBits;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const bool last = (lastBits >> j) & 1u;
+        const u32 hbLe = hbits & ((2u << j) - 1u);
+        // union of the run's element sets and its first record, wherever the run starts
+        const u32 tot = hbLe ? pre[j] : before ? (X | pre[j]) : (cTot | X | pre[j]);
+        const u32 runStart = hbLe ? base + (31 - __clz(hbLe)) : before ? sPrev : cStart;
+        const bool mine = hbLe || before || cValid;  // else the run starts in another warp's chunk: that warp finishes it
+        const bool flagged = (tot & 0x80000000u) != 0;
+        // a run of reads that are their own group (NH <= 1 throughout) has nothing to close
+        const bool irregular = flagged || (nh[j] > 1 && nh[j] != base + j + 1 - runStart);
+        if (last && mine && irregular) sm.walkQ[nWalk++][tid] = runStart;
+        if (last && mine && !irregular && nh[j] > 1) {
+          const u32 gm = tot & 0x7FFFFFFFu;
+          ev[j] = gm;
+          pClosResc += 1u | (__popc(gm) == 1 ? 0x10000u : 0u);
+        }
+      }
+    }
+    // ---- counting: single-element sets into the lane's histogram column, the rest into the block table
+    {
+      u32 pend = 0;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const u32 c = ev[j];
+        if (HIST) {
+          const bool single = c != 0 && (c & (c - 1)) == 0;
+          const u32 row = single ? (u32)(__ffs(c) - 1) : (u32)(HIST_ROWS - 1);  // E <= 30: the last row only ever receives zeros
+          sm.hist[row][tid] += single ? 1 : 0;
+          if (c != 0 && !single) pend |= 1u << j;
+        } else {
+          if (c != 0) pend |= 1u << j;
+        }
+      }
+      while (__any_sync(FULL, pend != 0)) {
+        if (pend) {
+          const int j = __ffs(pend) - 1;
+          pend &= pend - 1;
+          const u32 c = (j == 0) ? ev[0] : (j == 1) ? ev[1] : (j == 2) ? ev[2] : ev[3];
+          u64 ckey = c;
+          if (STRAT == 3) {
+            const u32 n = (j == 0) ? nh[0] : (j == 1) ? nh[1] : (j == 2) ? nh[2] : nh[3];
+            if (n >= (1u << (64 - NH_SHIFT))) atomicExch(&ctl->overflow, 1u);
+            ckey |= (u64)n << NH_SHIFT;
+          }
+          sm.bt.add(ckey, 1, table);
+        }
+      }
+    }
+    if (STRAT == 0) {
+#pragma unroll 1
+      for (u32 q = 0; q < nWalk; ++q) { const u32 i0 = sm.walkQ[q][tid]; w.walk(i0, normKey(h.key[i0]), nullptr); }
+      // the run still open at the end of the tile
+      const u32 incLast = __shfl_sync(FULL, inc, 31);
+      if (F) {
+        cTot = incLast;
+        cStart = __shfl_sync(FULL, lastHeadPos, 31 - __clz(F));
+        cValid = true;
+      } else if (cValid) {
+        cTot |= incLast;
+      }
+      cNh = __shfl_sync(FULL, nh[3], 31);
+      cKey = nextKey;
+      cCont = __shfl_sync(FULL, tileEndsRun, 31) == 0;
+    }
+  }
+  // ---- a read open at the end of the chunk that continues in another warp's chunk: finished by the serial walk.  (A run
+  //      ending exactly at the chunk's last record was closed above, like the last run of the batch.)
+  if (STRAT == 0 && cValid && cCont && t1 > t0 && lane == 0) w.walk(cStart, cKey, nullptr);
+  u32 cHits = pHitsMiss & 0xFFFFu, cMiss = pHitsMiss >> 16, cUnassigned = pUnasAmbi & 0xFFFFu, cAmbiguous = pUnasAmbi >> 16;
+  u32 cUnique = pUniqMult & 0xFFFFu, cMultiple = pUniqMult >> 16;
+  u32 cReads = cHits - cMultiple + (pClosResc & 0xFFFFu) + w.nReads, cRescued = (pClosResc >> 16) + w.nRescued;
+
+  // ---- block epilogue: counters, the private histogram columns and the private table
+  cHits = __reduce_add_sync(FULL, cHits); cUnassigned = __reduce_add_sync(FULL, cUnassigned);
+  cAmbiguous = __reduce_add_sync(FULL, cAmbiguous); cUnique = __reduce_add_sync(FULL, cUnique);
+  cMultiple = __reduce_add_sync(FULL, cMultiple); cReads = __reduce_add_sync(FULL, cReads);
+  cRescued = __reduce_add_sync(FULL, cRescued); cMiss = __reduce_add_sync(FULL, cMiss);
+  if (lane == 0) {
+    atomicAdd(&sm.stat[ST_HITS], cHits); atomicAdd(&sm.stat[ST_UNASSIGNED], cUnassigned); atomicAdd(&sm.stat[ST_AMBIGUOUS], cAmbiguous);
+    atomicAdd(&sm.stat[ST_UNIQUE], cUnique); atomicAdd(&sm.stat[ST_MULTIPLE], cMultiple); atomicAdd(&sm.stat[ST_READS], cReads);
+    atomicAdd(&sm.stat[ST_RESCUED], cRescued); atomicAdd(&sm.stat[7], cMiss);
+  }
+  __syncthreads();
+  sm.bt.flush(table);
+  if (HIST) {
+    for (u32 e = warp; e < HIST_ROWS; e += BATCH_WARPS) {
+      u32 v = 0;
+#pragma unroll
+      for (int q = 0; q < BATCH_WARPS; ++q) v += sm.hist[e][lane + 32 * q];
+      v = __reduce_add_sync(FULL, v);
+      if (lane == 0 && v) tableAdd(table, 1ull << e, v);
+    }
+  }
+  if (tid < 7) {
+    const int sv = (int)sm.stat[tid];  // reads / rescued can be negative within a block (unfinished reads)
+    if (sv) atomicAdd(&ctl->stats[tid], (u64)(long long)sv);
+  }
+  if (tid == 7 && sm.stat[7]) atomicAdd(&ctl->fastMiss, sm.stat[7]);
+}
+
+}  // namespace mma

@@ -594,6 +594,7 @@ k_batch(IndexView ix, FastView fx, HitView h, Rules r, TableView table, SampleCt
   const u32 t0 = min(nWT, (blockIdx.x * BATCH_WARPS + warp) * per), t1 = min(nWT, t0 + per);
 
   // the run that is open at the end of the previous tile of the chunk (all lanes hold the same values)
+  bool cCont = false;   // ... continues in the next tile
   bool cValid = false;  // ... and it starts inside this chunk (else the previous chunk's warp finishes it)
   u32 cStart = 0;       // its first record
   u32 cTot = 0;         // union of its element sets so far | bit 31: NH changed inside it
@@ -638,7 +639,10 @@ k_batch(IndexView ix, FastView fx, HitView h, Rules r, TableView table, SampleCt
     u32 hbits = 0, F = 0;
     const Carry *carryIn = nullptr;
     u64 nextKey = KEY_EMPTY;
+    u32 tileEndsRun = 1;  // lane 31: the record after the tile's last one starts another run (or the batch ends there)
     if (STRAT == 0) {
+      const u32 nextTile = (t + 1) * WT_HITS;
+      if (lane == 31u && nextTile < h.n) tileEndsRun = (normKey(__ldg(&h.key[nextTile])) != key[3]) ? 1u : 0u;
       u64 prev = __shfl_up_sync(0xffffffffu, key[3], 1);
       if (lane == 0) {
         if (t != t0) prev = cKey;
@@ -711,6 +715,7 @@ k_batch(IndexView ix, FastView fx, HitView h, Rules r, TableView table, SampleCt
         if (valid[j] && ((hbits >> j) & 1u)) sm.walkQ[nWalk++][tid] = base + j;
 #pragma unroll 1
       for (u32 q = 0; q < nWalk; ++q) { const u32 i0 = sm.walkQ[q][tid]; w.walk(i0, normKey(h.key[i0]), nullptr); }
+      cKey = nextKey;  // the next tile of the chunk compares its first record with this tile's last one
       continue;
     }
     // Parallel countdown for the regular case: a run of n records that all carry NH = n (> 1) is one read; its
@@ -741,9 +746,8 @@ k_batch(IndexView ix, FastView fx, HitView h, Rules r, TableView table, SampleCt
     const u32 lastHeadPos = base + (31 - __clz(hbits | 1u));
     const u32 sPrev = __shfl_sync(0xffffffffu, lastHeadPos, before ? (31 - __clz(before)) : 0);
     const u32 nextHead0 = __shfl_down_sync(0xffffffffu, hbits & 1u, 1);
-    // bit j: the next record starts another run, i.e. this record ends its run.  The tile's last record: only known at
-    // the end of the batch (it does end there)
-    const u32 lastBits = (hbits >> 1) | ((lane < 31u ? nextHead0 : ((t + 1) * WT_HITS >= h.n ? 1u : 0u)) << 3);
+    // bit j: the next record starts another run, i.e. this record ends its run (the tile's last record: from the peek)
+    const u32 lastBits = (hbits >> 1) | ((lane < 31u ? nextHead0 : tileEndsRun) << 3);
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       if (!(valid[j] && ((lastBits >> j) & 1u))) continue;
@@ -774,11 +778,12 @@ k_batch(IndexView ix, FastView fx, HitView h, Rules r, TableView table, SampleCt
       }
       cNh = __shfl_sync(0xffffffffu, nh[3], 31);
       cKey = nextKey;
+      cCont = __shfl_sync(0xffffffffu, tileEndsRun, 31) == 0;
     }
   }
   // ---- the read open at the end of the chunk continues in another warp's chunk: finish it by the serial walk.  (At the
   //      end of the batch the tile's last record closed its run above.)
-  if (STRAT == 0 && parallelRuns && cValid && t1 > t0 && t1 * WT_HITS < h.n && lane == 0) w.walk(cStart, cKey, nullptr);
+  if (STRAT == 0 && parallelRuns && cValid && cCont && t1 > t0 && lane == 0) w.walk(cStart, cKey, nullptr);
   u32 cHits = pHitsMiss & 0xFFFFu, cMiss = pHitsMiss >> 16, cUnassigned = pUnasAmbi & 0xFFFFu, cAmbiguous = pUnasAmbi >> 16;
   u32 cUnique = pUniqMult & 0xFFFFu, cMultiple = pUniqMult >> 16;
   u32 cReads = cHits - cMultiple + (pClosResc & 0xFFFFu) + w.nReads, cRescued = (pClosResc >> 16) + w.nRescued;

@@ -181,3 +181,34 @@ def test_empty_and_tiny_inputs():
     check(device_run(et, feats, hits), oracle_run(et, feats, hits))
     one = hits.slice(0, 1)
     check(device_run(et, feats, one), oracle_run(et, feats, one))
+
+
+@pytest.mark.parametrize("seed", range(4))
+@pytest.mark.parametrize("grid", [1, 3])
+def test_multi_tile_chunks(seed, grid, monkeypatch):
+    """Few blocks => every warp walks a chunk of many 128-hit tiles: runs that cross tile borders inside a chunk, runs
+    that end exactly on a tile border, and the state carried from tile to tile (regression: reads ending on a tile
+    border inside a chunk were dropped)."""
+    monkeypatch.setenv("MMANNOT_B200_MAX_GRID", str(grid))
+    rng = np.random.default_rng(9000 + seed)
+    et = fuzz.make_elements(rng)
+    feats = fuzz.make_features(rng, et, n_feat=500)
+    hits = fuzz.make_hits(rng, feats, n_reads=40000, max_nh=(70 if seed & 1 else 6), messy=(0.0 if seed < 2 else 0.1))
+    for strategy in ("default", "unique", "ratio"):
+        ref = oracle_run(et, feats, hits, strategy=strategy)
+        for batch in (1 << 20, 33333):
+            res = device_run(et, feats, hits, strategy=strategy, max_batch=batch)
+            check(res, ref, exact=(strategy != "ratio"))
+    ref = oracle_run(et, feats, hits, rescue_threshold=0.6, read_stats=True)
+    check(device_run(et, feats, hits, rescue_threshold=0.6, read_stats=True, max_batch=50000), ref)
+
+
+def test_natural_grid_two_tiles_per_warp():
+    """Enough hits that the full-size grid gives each warp more than one tile (> 148 SMs x 5 blocks x 8 warps x 128 hits)."""
+    rng = np.random.default_rng(4242)
+    et = fuzz.make_elements(rng)
+    feats = fuzz.make_features(rng, et, n_feat=800)
+    hits = fuzz.make_hits(rng, feats, n_reads=450000, max_nh=5, messy=0.02)
+    assert hits.n > 148 * 5 * 8 * 128
+    ref = oracle_run(et, feats, hits)
+    check(device_run(et, feats, hits, max_batch=1 << 21), ref)
