@@ -85,7 +85,7 @@ struct mma_ctx {
   // index
   bool haveIndex = false;
   DevBuf feat, chrInfo, bins, spanIdx, dElemLine, dElemStrand, dElemVic;
-  DevBuf fastBin, fastSeg, fastVic, fastChrInfo;
+  DevBuf fastBin, fastSeg, fastChrInfo;
   IndexView index;
   FastView fast;
   uint64_t nSegments = 0;
@@ -408,7 +408,7 @@ void mma_destroy(mma_ctx *ctx) {
     if (g.done) cudaEventDestroy(g.done);
   }
   ctx->feat.release(); ctx->chrInfo.release(); ctx->bins.release(); ctx->spanIdx.release();
-  ctx->fastBin.release(); ctx->fastSeg.release(); ctx->fastVic.release(); ctx->fastChrInfo.release();
+  ctx->fastBin.release(); ctx->fastSeg.release(); ctx->fastChrInfo.release();
   ctx->dElemLine.release(); ctx->dElemStrand.release(); ctx->dElemVic.release();
   ctx->collectTiming();
   if (ctx->hostTable) cudaFreeHost(ctx->hostTable);
@@ -555,16 +555,17 @@ int mma_load_features(mma_ctx *ctx, const mma_features *f) {
     CKS(cudaMemcpyAsync(&lastPos, pos.as<u32>() + (nKeys - 1), 4, cudaMemcpyDeviceToHost, st));
     CKS(cudaStreamSynchronize(st));
     const u32 nSeg = lastPos + lastFlag;
-    // bin grid of the table: about two bins per segment, at most 2^21 bins
+    // position map: 32 granules per entry; one position per granule when the map stays within 2^22 entries (32 MB),
+    // coarser granules for larger annotations
     uint32_t fshift = ctx->params.fast_bin_shift;
     if (fshift == 0) {
       uint64_t totalExtent = 0;
       for (uint32_t c = 0; c < nChr; ++c) totalExtent += extent[c];
       fshift = 5;
-      const uint64_t wantBins = std::min<uint64_t>(std::max<uint64_t>(2ull * nSeg, 1u << 16), 1ull << 21);
-      while (fshift < 24 && (totalExtent >> fshift) > wantBins) ++fshift;
+      while (fshift < 24 && (totalExtent >> fshift) > (1ull << 22)) ++fshift;
     }
-    fshift = std::min<uint32_t>(std::max<uint32_t>(fshift, 2), 24);
+    fshift = std::min<uint32_t>(std::max<uint32_t>(fshift, 5), 24);
+    const uint32_t gshift = fshift - 5;
     std::vector<u32> fBase(nChr + 1, 0);
     std::vector<uint2> fInfo(nChr);
     uint64_t fEntries = 0;
@@ -575,16 +576,15 @@ int mma_load_features(mma_ctx *ctx, const mma_features *f) {
       fEntries += nb;
     }
     fBase[nChr] = (u32)fEntries;
-    if (fEntries <= 0x7FFFFFFFull && nSeg < (1u << 24)) {
+    if (fEntries <= 0x7FFFFFFFull && nSeg < (1u << 30)) {
       CKS(segKey.ensure((size_t)nSeg * 8));
       CKS(ctx->fastSeg.ensure(((size_t)nSeg + 16) * 2 * sizeof(uint4)));
-      CKS(ctx->fastVic.ensure(((size_t)nSeg + 16) * 4 * sizeof(uint2)));
       u32 upMask = 0, downMask = 0;
       for (uint32_t q = 0; q < ctx->params.n_elements; ++q) {
         if (ctx->elemVic[q] == MMA_VICINITY_UP) upMask |= 1u << q;
         if (ctx->elemVic[q] == MMA_VICINITY_DOWN) downMask |= 1u << q;
       }
-      CKS(ctx->fastBin.ensure((size_t)fEntries * sizeof(uint4)));
+      CKS(ctx->fastBin.ensure((size_t)fEntries * sizeof(uint2)));
       CKS(ctx->fastChrInfo.ensure((size_t)nChr * sizeof(uint2)));
       CKS(fChrBinBase.ensure((size_t)(nChr + 1) * 4));
       CKS(cudaMemsetAsync(ctx->fastSeg.p, 0, ((size_t)nSeg + 16) * 2 * sizeof(uint4), st));
@@ -593,24 +593,24 @@ int mma_load_features(mma_ctx *ctx, const mma_features *f) {
       {
         mma_ctx::Timed t(ctx, TC_INDEX);
         k_seg_scatter<<<gridFor(nKeys, 256), 256, 0, st>>>(kB.as<u64>(), flag.as<u32>(), pos.as<u32>(), (u32)nKeys, segKey.as<u64>());
-        k_seg_eval<<<gridFor(nSeg, 128), 128, 0, st>>>(ctx->index, segKey.as<u64>(), nSeg, upMask, downMask, ctx->fastSeg.as<uint4>(), ctx->fastVic.as<uint2>());
-        k_fast_bins<<<gridFor(fEntries, 256), 256, 0, st>>>(segKey.as<u64>(), nSeg, ctx->fastSeg.as<uint4>(), fChrBinBase.as<u32>(), nChr, fshift,
-                                                            (u32)fEntries, ctx->fastBin.as<uint4>());
+        k_seg_eval<<<gridFor(nSeg, 128), 128, 0, st>>>(ctx->index, segKey.as<u64>(), nSeg, upMask, downMask, ctx->fastSeg.as<uint4>());
+        k_fast_bitmap<<<gridFor(fEntries, 256), 256, 0, st>>>(segKey.as<u64>(), nSeg, fChrBinBase.as<u32>(), nChr, fshift, gshift, (u32)fEntries,
+                                                              ctx->fastBin.as<uint2>());
         ctx->launches += 3;
       }
       CKS(cudaStreamSynchronize(st));
       CKS(cudaGetLastError());
-      ctx->fast.bin = ctx->fastBin.as<uint4>();
+      ctx->fast.bm = ctx->fastBin.as<uint2>();
       ctx->fast.seg = ctx->fastSeg.as<uint4>();
-      ctx->fast.vic = ctx->fastVic.as<uint2>();
       ctx->fast.upMask = upMask;
       ctx->fast.downMask = downMask;
       ctx->fast.chrInfo = ctx->fastChrInfo.as<uint2>();
       ctx->fast.nChr = nChr;
       ctx->fast.shift = fshift;
+      ctx->fast.gshift = gshift;
       ctx->fast.enabled = 1;
       ctx->nSegments = nSeg;
-      fastBytes = (uint64_t)nSeg * (2 * sizeof(uint4) + 4 * sizeof(uint2)) + fEntries * sizeof(uint4) + (uint64_t)nChr * sizeof(uint2);
+      fastBytes = (uint64_t)nSeg * 2 * sizeof(uint4) + fEntries * sizeof(uint2) + (uint64_t)nChr * sizeof(uint2);
     }
 #undef CKS
     cleanupFast();

@@ -21,13 +21,13 @@
 namespace mma {
 
 #ifndef MMA_FAST_BLOCKS_PER_SM
-#define MMA_FAST_BLOCKS_PER_SM 4
+#define MMA_FAST_BLOCKS_PER_SM 3
 #endif
 
 #ifdef MMA_DIAG
-// tuning builds only: why hits leave the table fast path.  0 degenerate, 1 bin answer VICPAIR, 2 bin answer GENERAL, 3 start beyond
-// the quarter's segment, 4 read over 3+ segments (or 2 under an overlap mode), 5 segment answer VICPAIR, 6 segment answer GENERAL,
-// 7 answered by the bin entry, 8 answered by the segment record, 9 hits looked up
+// tuning builds only: why hits leave the table fast path.  0 degenerate, 3 start beyond the looked-up segment (coarse granules),
+// 4 read over 3+ segments (or 2 under an overlap mode), 6 answer GENERAL, 7 answered in-segment, 8 answered cross-segment,
+// 9 hits looked up
 __device__ unsigned long long g_diag[16];
 #define DIAG(i, c) do { if (c) atomicAdd(&g_diag[i], 1ull); } while (0)
 #else
@@ -39,9 +39,42 @@ __device__ __noinline__ u32 slowAnnotate(const FastView &fx, const IndexView &ix
   return fastAnnotate<MODE>(fx, ix, rs, re, meta, ovl);
 }
 
+// Block-private table for 32-bit element sets (multi-element sets only: a few thousand distinct keys per sample);
+// flushed once per block.  Sized so that it does not fill up: a full neighbourhood falls through to the device table.
+template <int SLOTS>
+struct BlockTable32 {
+  u32 keys[SLOTS];
+  u32 cnt[SLOTS];
+  __device__ void init() {
+    for (int i = threadIdx.x; i < SLOTS; i += blockDim.x) { keys[i] = 0; cnt[i] = 0; }
+  }
+  __device__ __forceinline__ void add(u64 ckey64, u32 n, const TableView &g) {
+    const u32 ckey = (u32)ckey64;
+    u32 slot = (ckey * 0x9E3779B1u) >> (32 - __builtin_ctz(SLOTS));
+#pragma unroll 1
+    for (int probe = 0; probe < 16; ++probe) {
+      u32 old = keys[slot];
+      if (old != ckey) {
+        if (old == 0) old = atomicCAS(&keys[slot], 0u, ckey);
+        if (old != 0 && old != ckey) { slot = (slot + 1) & (SLOTS - 1); continue; }
+      }
+      atomicAdd(&cnt[slot], n);
+      return;
+    }
+    tableAdd(g, ckey64, n);
+  }
+  __device__ void flush(const TableView &g) {
+    for (int i = threadIdx.x; i < SLOTS; i += blockDim.x)
+      if (cnt[i]) tableAdd(g, (u64)keys[i], cnt[i]);
+  }
+};
+
+template <bool HIST, int SLOTS> struct BlockTableOf { typedef BlockTable<SLOTS> type; };
+template <int SLOTS> struct BlockTableOf<true, SLOTS> { typedef BlockTable32<SLOTS> type; };
+
 template <bool HIST, int SLOTS>
 struct FastSmem {
-  BlockTable<SLOTS> bt;
+  typename BlockTableOf<HIST, SLOTS>::type bt;
   unsigned short hist[HIST ? HIST_ROWS : 1][BATCH_THREADS];
   u32 walkQ[4][BATCH_THREADS];
   u32 slowRes[BATCH_WARPS][WT_HITS];
@@ -70,7 +103,7 @@ template <int MODE, int STRAT>
 __global__ void __launch_bounds__(BATCH_THREADS, MMA_FAST_BLOCKS_PER_SM)
 k_batch_fast(IndexView ix, FastView fx, HitView h, Rules r, TableView table, SampleCtl *ctl, SlowView slow, KeySetView open) {
   constexpr bool HIST = (STRAT != 3);
-  constexpr int SLOTS = (STRAT == 3) ? 1024 : BT_SLOTS;
+  constexpr int SLOTS = (STRAT == 3) ? 1024 : 2048;
   constexpr u32 FULL = 0xffffffffu;
   __shared__ FastSmem<HIST, SLOTS> sm;
   const u32 tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
@@ -98,7 +131,7 @@ k_batch_fast(IndexView ix, FastView fx, HitView h, Rules r, TableView table, Sam
   bool cValid = false, cCont = false;  // cCont: the run open at the end of the tile continues in the next tile
   u32 cStart = 0, cTot = 0, cNh = 0;
   u64 cKey = KEY_EMPTY;
-  const u32 shift = fx.shift;
+  const u32 shift = fx.shift, gshift = fx.gshift;
 
   for (u32 t = t0; t < t1; ++t) {
     const u32 base = t * WT_HITS + lane * 4;
@@ -162,11 +195,11 @@ k_batch_fast(IndexView ix, FastView fx, HitView h, Rules r, TableView table, Sam
 #pragma unroll
       for (int j = 0; j < 4; ++j) if (nh[j] != 1) visBits &= ~(1u << j);
     }
-    // ---- phase A: bin entries of the segment table
+    // ---- phase A: position map entries of the read starts
     u32 m[4] = {0u, 0u, 0u, 0u};
     u32 lookBits = 0, slowBits = 0;
-    uint4 e[4];
-    u32 ciy[4];
+    uint2 en[4];
+    u32 pm[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const u32 chr = meta[j] & 0x00FFFFFFu;
@@ -183,45 +216,38 @@ k_batch_fast(IndexView ix, FastView fx, HitView h, Rules r, TableView table, Sam
       const bool look = vis && !degen && pass;
       if (look) lookBits |= 1u << j;
       const uint2 ci = __ldg(&fx.chrInfo[look ? chr : 0u]);
-      ciy[j] = ci.y;
-      e[j] = __ldg(&fx.bin[ci.x + min(rs[j] >> shift, ci.y - 1u)]);
+      const u32 bRaw = rs[j] >> shift;
+      en[j] = __ldg(&fx.bm[ci.x + min(bRaw, ci.y - 1u)]);
+      const u32 p = (bRaw < ci.y) ? ((rs[j] >> gshift) & 31u) : 31u;
+      pm[j] = (gshift == 0) ? (0xFFFFFFFFu >> (31u - p)) : ((1u << p) - 1u);
     }
-    // ---- phase B: the bin entry answers a read inside the segment of the bin's first position; else the segment record
-    u32 need2 = 0;
-    u32 tEnd[4], tAns[4], xEnd[4], xAns[4];
+    // ---- phase B: the 32-byte record of the segment holding the read start
+    u32 tEnd[4], tEnd2[4], tAns[4], xAns[4], tie[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const bool fwd = (meta[j] >> 31) != 0;
-      const u32 a = fwd ? e[j].y : e[j].z;
       const bool look = (lookBits >> j) & 1u;
-      const bool inA = re[j] <= e[j].x;
-      const bool flagged = (a & (ANS_VICPAIR | ANS_GENERAL)) != 0;
-      if (look && inA && !flagged) m[j] = a;
-      if (look && inA && flagged) slowBits |= 1u << j;
-      DIAG(9, look); DIAG(7, look && inA && !flagged); DIAG(1, look && inA && (a & ANS_VICPAIR)); DIAG(2, look && inA && (a & ANS_GENERAL));
-      const bool n2 = look && !inA;
-      if (n2) need2 |= 1u << j;
-      const u32 quarter = ((rs[j] >> shift) < ciy[j]) ? ((rs[j] >> (shift - 2u)) & 3u) : 3u;
-      const u32 i = n2 ? (e[j].w & 0x00FFFFFFu) + ((e[j].w >> (24u + 2u * quarter)) & 3u) : 0u;
+      const bool fwd = (meta[j] >> 31) != 0;
+      const u32 i = look ? en[j].y + __popc(en[j].x & pm[j]) : 0u;
       const uint4 tt = __ldg(&fx.seg[2u * i]);
-      tEnd[j] = tt.y; tAns[j] = fwd ? tt.z : tt.w;
-      if (MODE == 0) {
-        const uint4 xx = __ldg(&fx.seg[2u * i + 1u]);
-        xEnd[j] = xx.x; xAns[j] = fwd ? xx.y : xx.z;
-      } else { xEnd[j] = 0; xAns[j] = 0; }
+      const uint4 xx = __ldg(&fx.seg[2u * i + 1u]);
+      tEnd[j] = tt.x; tAns[j] = fwd ? tt.y : tt.z; tEnd2[j] = tt.w;
+      xAns[j] = fwd ? xx.x : xx.y; tie[j] = fwd ? xx.z : xx.w;
     }
-    // ---- phase C
+    // ---- phase C: in-segment answer (with the upstream/downstream tie settled from the tie point) or cross-segment answer
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const bool n2 = (need2 >> j) & 1u;
+      const bool look = (lookBits >> j) & 1u;
       const bool inT = re[j] <= tEnd[j];
-      const bool inX = (MODE == 0) && re[j] <= xEnd[j];
-      const u32 a = inT ? tAns[j] : xAns[j];
+      const bool inX = (MODE == 0) && re[j] <= tEnd2[j];
+      u32 a = inT ? tAns[j] : xAns[j];
+      const u64 sum = (u64)rs[j] + (u64)re[j];
+      const u32 keep = (sum > (u64)tie[j]) ? fx.upMask : (sum < (u64)tie[j]) ? fx.downMask : 0xFFFFFFFFu;
+      if (inT && (a & ANS_VICPAIR)) a = (a & ~ANS_VICPAIR) & keep;
       const bool ok = rs[j] <= tEnd[j] && (inT || inX) && !(a & (ANS_VICPAIR | ANS_GENERAL));
-      if (n2 && ok) m[j] = a;
-      if (n2 && !ok) slowBits |= 1u << j;
-      DIAG(8, n2 && ok); DIAG(3, n2 && rs[j] > tEnd[j]); DIAG(4, n2 && rs[j] <= tEnd[j] && !(inT || inX));
-      DIAG(5, n2 && rs[j] <= tEnd[j] && (inT || inX) && (a & ANS_VICPAIR)); DIAG(6, n2 && rs[j] <= tEnd[j] && (inT || inX) && (a & ANS_GENERAL));
+      if (look && ok) m[j] = a;
+      if (look && !ok) slowBits |= 1u << j;
+      DIAG(9, look); DIAG(7, look && ok && inT); DIAG(8, look && ok && !inT); DIAG(3, look && rs[j] > tEnd[j]);
+      DIAG(4, look && rs[j] <= tEnd[j] && !(inT || inX)); DIAG(6, look && rs[j] <= tEnd[j] && (inT || inX) && (a & ANS_GENERAL));
     }
     // ---- the rest, compacted over the warp
     if (__any_sync(FULL, slowBits != 0)) {

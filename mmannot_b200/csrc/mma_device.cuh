@@ -45,26 +45,31 @@ struct IndexView {
   u32 nChr, shift;
 };
 
-// Segment answer table (only built when E <= 31: bit 31 of an answer word flags "position dependent")
-//   bin entry  {end of the segment A holding the bin's first position, answer F, answer R,
-//               index of A (24 bits) | for each quarter k = 1..3 of the bin, 2 bits: min(3, index of the segment holding
-//               the quarter's first position - index of A) at bits 24 + 2k}
-//   segment i  seg[2i]   = {start, end, answer F, answer R}                   read inside the segment
-//              seg[2i+1] = {end of segment i+1, cross answer F, cross answer R, 0}  read = tail of i + head of i+1
+// Segment answer table (only built when E <= 30: bits 30 and 31 of an answer word are flags)
+//   The chromosomes are cut at every feature boundary; segment i of a chromosome spans [start_i, end_i].
+//   position map  bm[chromosome base + (pos >> shift)] = {bits, rank}: the bin of 2^shift positions is cut into 32 granules of
+//               2^gshift positions (shift = gshift + 5).  rank = index of the segment holding the bin's first position; bit p =
+//               "a segment starts inside granule p" (the bin's first position itself excluded).  With gshift = 0 (one position
+//               per bit: annotations up to ~128 Mb) the segment holding position x is EXACTLY rank + popc(bits up to x's bit);
+//               with coarser granules it is a lower bound, corrected by stepping right (a boundary in x's own granule, or two in
+//               one granule).
+//   segment i   seg[2i]   = {end_i, answer F, answer R, end_{i+1}}                            read inside the segment
+//               seg[2i+1] = {cross answer F, cross answer R, tie point F, tie point R}          read = tail of i + head of i+1
 // "answer F" is for a read whose strand bit is set (MMA_HIT_STRAND_BIT), "answer R" for the other one.
 // An answer word is the element set (E <= 30), or carries one of two flags:
-//   ANS_VICPAIR  the winning Order line matched exactly one upstream and one downstream element (bits 0..29 hold both):
-//                the pick goes to the nearer one (mm:1066-1075); the two reference coordinates (end of the upstream
-//                feature, start of the downstream one) are in vic[4 * segment + {0 in F, 1 in R, 2 cross F, 3 cross R}]
+//   ANS_VICPAIR  the winning Order line matched exactly one upstream and one downstream element (bits 0..29 hold both): the
+//                pick goes to the nearer one (mm:1066-1075).  With U = end of the upstream feature and D = start of the
+//                downstream one, the read [s, e] is at distance U - e from the first and s - D from the second, so the pick
+//                is upstream iff s + e > U + D, downstream iff s + e < U + D, both on a tie: "tie point" = U + D.  Only
+//                in-segment answers carry the flag (a cross answer of that kind is stored as ANS_GENERAL).
 //   ANS_GENERAL  any other position-dependent pick: the table cannot answer
 #define ANS_VICPAIR 0x80000000u
 #define ANS_GENERAL 0x40000000u
 struct FastView {
-  const uint4 *bin;
+  const uint2 *bm;
   const uint4 *seg;
-  const uint2 *vic;
-  const uint2 *chrInfo;  // per chromosome {first bin entry, number of bins}
-  u32 nChr, shift, enabled;
+  const uint2 *chrInfo;  // per chromosome {first entry of bm, number of bins}
+  u32 nChr, shift, gshift, enabled;
   u32 upMask, downMask;  // upstream / downstream elements (Config::isUpstream / isDownstream, mm:463-470)
 };
 
@@ -331,59 +336,31 @@ __device__ __noinline__ u64 annotateHit(const IndexView &ix, u32 rs, u32 re, u32
 //     (1 under inclusion, end - start under the overlap modes), so the pick is the precomputed one -- provided the
 //     read is long enough to match anything at all under -l (mm:995-1002);
 //   * under inclusion a read over two adjacent segments is included in exactly the features covering both.
-// One gather (the bin entry) answers a read inside segment A; this part is inlined in the hot loop (fastAnnotate).
-// Everything else lives out of line (fastRest): the bin entry names the segment holding the first position of the
-// read's quarter of the bin, whose 32-byte record (one L2 sector) answers a read inside it or over it and its right
-// neighbour (a few more gathers when the read starts further right); upstream/downstream ties are settled from the
-// side table; what the table cannot answer (read over three or more segments, other position-dependent picks,
-// degenerate intervals) is evaluated against the feature index.  Bit 31 of fastRest's result says so (statistics).
+// Two dependent gathers: the position map entry of the read start, then the 32-byte record of its segment.  What the
+// table cannot answer (read over three or more segments, position-dependent picks other than the upstream/downstream
+// tie, degenerate intervals) is evaluated against the feature index; bit 31 of the result says so (statistics).
 #define FAST_MISS 0x80000000u
+
+// segment index (lower bound, exact when gshift == 0) of position rs on chromosome info ci
+__device__ __forceinline__ u32 fastSegIndex(const FastView &fx, uint2 ci, u32 rs) {
+  const u32 bRaw = rs >> fx.shift;
+  const uint2 en = __ldg(&fx.bm[ci.x + min(bRaw, ci.y - 1u)]);
+  const u32 p = (bRaw < ci.y) ? ((rs >> fx.gshift) & 31u) : 31u;
+  const u32 m = (fx.gshift == 0) ? (0xFFFFFFFFu >> (31u - p)) : ((1u << p) - 1u);
+  return en.y + __popc(en.x & m);
+}
+
+// the pick of an ANS_VICPAIR answer for the read [rs, re]
+__device__ __forceinline__ u32 vicPick(const FastView &fx, u32 a, u32 tie, u32 rs, u32 re) {
+  const u64 sum = (u64)rs + (u64)re;
+  a &= ~ANS_VICPAIR;
+  if (sum > (u64)tie) a &= fx.upMask;
+  else if (sum < (u64)tie) a &= fx.downMask;
+  return a;
+}
+
 template <int MODE>
-__device__ __noinline__ u32 fastRest(const FastView &fx, const IndexView &ix, uint4 e, u32 rs, u32 re, u32 meta, float ovl, int stage) {
-  if (stage != 0) {  // stage 0: no table lookup was possible (degenerate interval)
-    const u32 strandIdx = (meta >> 31) ? 0u : 1u;
-    u32 a = 0, i = e.w & 0x00FFFFFFu, kind = 0;
-    bool ok = true;
-    if (re <= e.x) {
-      a = strandIdx ? e.z : e.y;
-    } else {
-      const u32 chr = meta & 0x00FFFFFFu;
-      const uint2 ci = __ldg(&fx.chrInfo[chr]);
-      const u32 bRaw = rs >> fx.shift;
-      const u32 quarter = (bRaw < ci.y) ? ((rs >> (fx.shift - 2)) & 3u) : 3u;
-      i += (e.w >> (24 + 2 * quarter)) & 3u;
-      uint4 t = __ldg(&fx.seg[2 * i]);  // {start, end, answer F, answer R}
-#pragma unroll 1
-      for (int g = 0; rs > t.y; ++g) {
-        if (g == 3) { ok = false; break; }
-        ++i;
-        t = __ldg(&fx.seg[2 * i]);
-      }
-      if (ok) {
-        if (re <= t.y) {
-          a = strandIdx ? t.w : t.z;
-        } else if (MODE != 0) {
-          ok = false;
-        } else {
-          const uint4 x = __ldg(&fx.seg[2 * i + 1]);  // {end of the next segment, cross answer F, cross answer R, 0}
-          if (re > x.x) ok = false;
-          a = strandIdx ? x.z : x.y;
-          kind = 2;
-        }
-      }
-    }
-    if (ok && (a & ANS_GENERAL)) ok = false;
-    if (ok) {
-      if (a & ANS_VICPAIR) {
-        const uint2 v = __ldg(&fx.vic[4 * i + kind + strandIdx]);
-        const u32 dUp = v.x - re, dDown = rs - v.y;  // Interval::getDistance of the read to the two coordinates (mm:661-665)
-        a &= ~ANS_VICPAIR;
-        if (dUp < dDown) a &= fx.upMask;
-        else if (dDown < dUp) a &= fx.downMask;
-      }
-      return a;
-    }
-  }
+__device__ __noinline__ u32 fastMissEval(const IndexView &ix, u32 rs, u32 re, u32 meta, float ovl) {
   return (u32)annotateEval<MODE, false>(ix, rs, re, meta, ovl, nullptr) | FAST_MISS;
 }
 
@@ -391,21 +368,37 @@ template <int MODE>
 __device__ __forceinline__ u32 fastAnnotate(const FastView &fx, const IndexView &ix, u32 rs, u32 re, u32 meta, float ovl) {
   const u32 chr = meta & 0x00FFFFFFu;
   if (chr >= fx.nChr) return 0;
-  uint4 e = make_uint4(0u, 0u, 0u, 0u);
-  if (re < rs || re >= 0xFFFFFFF0u) return fastRest<MODE>(fx, ix, e, rs, re, meta, ovl, 0);
+  if (re < rs || re >= 0xFFFFFFF0u) return fastMissEval<MODE>(ix, rs, re, meta, ovl);
   if (MODE != 0) {  // no feature can overlap the read by more than end - start
     const u32 o = re - rs;
     if (o == 0) return 0;
     if (MODE == 1) { if (!(__fmul_rn((float)(o + 1u), ovl) <= (float)o)) return 0; }
     else { if (!((float)o >= ovl)) return 0; }
   }
-  const uint2 ci = __ldg(&fx.chrInfo[chr]);
-  e = __ldg(&fx.bin[ci.x + min(rs >> fx.shift, ci.y - 1)]);
-  if (re <= e.x) {
-    const u32 a = (meta >> 31) ? e.y : e.z;
-    if (!(a & (ANS_VICPAIR | ANS_GENERAL))) return a;
+  u32 i = fastSegIndex(fx, __ldg(&fx.chrInfo[chr]), rs);
+  uint4 t = __ldg(&fx.seg[2u * i]);  // {end, answer F, answer R, end of the next segment}
+#pragma unroll 1
+  for (int g = 0; rs > t.x; ++g) {   // coarse granules only
+    if (g == 3) return fastMissEval<MODE>(ix, rs, re, meta, ovl);
+    ++i;
+    t = __ldg(&fx.seg[2u * i]);
   }
-  return fastRest<MODE>(fx, ix, e, rs, re, meta, ovl, 1);
+  const bool fwd = (meta >> 31) != 0;
+  u32 a;
+  if (re <= t.x) {
+    a = fwd ? t.y : t.z;
+    if (a & ANS_VICPAIR) {
+      const uint4 x = __ldg(&fx.seg[2u * i + 1u]);
+      a = vicPick(fx, a, fwd ? x.z : x.w, rs, re);
+    }
+  } else if (MODE == 0 && re <= t.w) {
+    const uint4 x = __ldg(&fx.seg[2u * i + 1u]);  // {cross answer F, cross answer R, tie F, tie R}
+    a = fwd ? x.x : x.y;
+  } else {
+    return fastMissEval<MODE>(ix, rs, re, meta, ovl);
+  }
+  if (a & ANS_GENERAL) return fastMissEval<MODE>(ix, rs, re, meta, ovl);
+  return a;
 }
 
 // ----------------------------------------------------------------------------- the batch kernel
@@ -1169,21 +1162,24 @@ __global__ void k_seg_keys(BuildView b, u64 *keys) {
   if (i < b.nChr) keys[2ull * b.nFeat + i] = (u64)i << 32;
 }
 
-// one answer word from the evaluation of a representative read (see FastView)
-__device__ __forceinline__ u32 answerWord(u64 chosen, const EvalTrack &tr, u32 upMask, u32 downMask, uint2 *vic) {
+// one answer word from the evaluation of a representative read (see FastView); *tie = U + D for an ANS_VICPAIR answer
+__device__ __forceinline__ u32 answerWord(u64 chosen, const EvalTrack &tr, u32 upMask, u32 downMask, u32 *tie) {
   const u32 all = (u32)tr.lineAll, U = all & upMask, D = all & downMask;
-  *vic = make_uint2(tr.pUp, tr.pDown);
+  *tie = 0;
   // the pick between several matched elements of one line depends on distances to the read (mm:1066-1075) only when one
   // of them is an upstream / downstream element
   if (__popc(all) <= 1 || (U | D) == 0) return (u32)chosen;
-  if ((all & ~(U | D)) == 0 && __popc(U) == 1 && __popc(D) == 1) return ANS_VICPAIR | all;
+  if ((all & ~(U | D)) == 0 && __popc(U) == 1 && __popc(D) == 1) {
+    const u64 sum = (u64)tr.pUp + (u64)tr.pDown;
+    if (sum <= 0xFFFFFFFFull) { *tie = (u32)sum; return ANS_VICPAIR | all; }
+  }
   return ANS_GENERAL;
 }
 
 // one thread per segment: the answers of a read inside it and of a read over it and its right neighbour, per
 // strand, evaluated with the SAME candidate walk as any hit (inclusion scoring; see fastAnnotate for why that
 // also serves the overlap modes)
-__global__ void k_seg_eval(IndexView ix, const u64 *__restrict__ segKey, u32 nSeg, u32 upMask, u32 downMask, uint4 *seg, uint2 *vic) {
+__global__ void k_seg_eval(IndexView ix, const u64 *__restrict__ segKey, u32 nSeg, u32 upMask, u32 downMask, uint4 *seg) {
   const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= nSeg) return;
   const u64 k = segKey[i];
@@ -1195,44 +1191,46 @@ __global__ void k_seg_eval(IndexView ix, const u64 *__restrict__ segKey, u32 nSe
     const bool hasNext2 = (i + 2 < nSeg) && (u32)(segKey[i + 2] >> 32) == chr;
     end2 = hasNext2 ? (u32)segKey[i + 2] - 1u : 0xFFFFFFFEu;
   }
-  u32 in[2], cross[2];  // index 0: strand bit set ("F"), 1: not set
+  u32 in[2], cross[2], tie[2];  // index 0: strand bit set ("F"), 1: not set
   for (u32 s = 0; s < 2; ++s) {
     const u32 meta = chr | (s == 0 ? 0x80000000u : 0u);
     EvalTrack tr;
     u64 a = annotateEval<0, true>(ix, start, start, meta, -1.0f, &tr);
-    in[s] = answerWord(a, tr, upMask, downMask, &vic[4 * i + s]);
+    in[s] = answerWord(a, tr, upMask, downMask, &tie[s]);
     cross[s] = ANS_GENERAL;
-    vic[4 * i + 2 + s] = make_uint2(0u, 0u);
     if (hasNext) {
+      u32 crossTie;
       a = annotateEval<0, true>(ix, end, end + 1u, meta, -1.0f, &tr);
-      cross[s] = answerWord(a, tr, upMask, downMask, &vic[4 * i + 2 + s]);
+      cross[s] = answerWord(a, tr, upMask, downMask, &crossTie);
+      if (cross[s] & ANS_VICPAIR) cross[s] = ANS_GENERAL;  // no room for a second tie point: left to the index walk
     }
   }
-  seg[2 * i] = make_uint4(start, end, in[0], in[1]);
-  seg[2 * i + 1] = make_uint4(end2, cross[0], cross[1], 0u);
+  seg[2 * i] = make_uint4(end, in[0], in[1], end2);
+  seg[2 * i + 1] = make_uint4(cross[0], cross[1], tie[0], tie[1]);
 }
 
-// one thread per bin entry of the segment table
-__global__ void k_fast_bins(const u64 *__restrict__ segKey, u32 nSeg, const uint4 *__restrict__ seg, const u32 *__restrict__ chrBinBase,
-                            u32 nChr, u32 shift, u32 nEntries, uint4 *bin) {
+// one thread per entry of the position map
+__global__ void k_fast_bitmap(const u64 *__restrict__ segKey, u32 nSeg, const u32 *__restrict__ chrBinBase, u32 nChr, u32 shift, u32 gshift,
+                              u32 nEntries, uint2 *bm) {
   const u32 e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= nEntries) return;
   const u32 c = chrOfEntry(chrBinBase, nChr, e);
   const u64 pos = (u64)(e - chrBinBase[c]) << shift;
   const u64 cap = 0xFFFFFFFEull;
-  const u64 want = ((u64)c << 32) | (pos > cap ? cap : pos);
+  const u64 first = pos > cap ? cap : pos;
+  const u64 want = ((u64)c << 32) | first;
   u32 lo = 0, hi = nSeg;  // last segment whose key <= want (every chromosome has a segment starting at 0)
   while (hi - lo > 1) { const u32 mid = (lo + hi) >> 1; if (segKey[mid] <= want) lo = mid; else hi = mid; }
-  u32 w = lo;
-  for (u32 k = 1; k < 4; ++k) {
-    const u64 pk = pos + ((u64)k << (shift - 2));
-    const u64 wk = ((u64)c << 32) | (pk > cap ? cap : pk);
-    u32 d = 0;
-    while (d < 3 && lo + d + 1 < nSeg && segKey[lo + d + 1] <= wk) ++d;
-    w |= d << (24 + 2 * k);
+  u32 bits = 0;
+  const u64 binEnd = pos + (1ull << shift);  // exclusive
+  for (u32 k = lo + 1; k < nSeg; ++k) {
+    const u64 sk = segKey[k];
+    if ((u32)(sk >> 32) != c) break;
+    const u64 sp = sk & 0xFFFFFFFFull;
+    if (sp >= binEnd) break;
+    bits |= 1u << (u32)((sp - pos) >> gshift);
   }
-  const uint4 s = seg[2 * lo];
-  bin[e] = make_uint4(s.y, s.z, s.w, w);
+  bm[e] = make_uint2(bits, lo);
 }
 
 // adjacent-duplicate removal of the sorted boundary keys: flags, then a scatter through their prefix sums
