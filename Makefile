@@ -48,7 +48,7 @@ VARIANT_BLOCKS ?= 3 5
 # tuning builds (not shipped): make variants; MMANNOT_B200_LIB=mmannot_b200/lib/variants/f3.so python bench.py ...
 variants: $(CU_SRC) $(CU_HDR)
 	@mkdir -p mmannot_b200/lib/variants
-	for b in $(VARIANT_BLOCKS); do $(NVCC) $(NVFLAGS) -DMMA_FAST_BLOCKS_PER_SM=$$b -shared -o mmannot_b200/lib/variants/f$$b.so $(CU_SRC) & done; wait
+	for b in $(VARIANT_BLOCKS); do $(NVCC) $(NVFLAGS) -DMMA_FAST_BLOCKS_PER_SM=$$b $(VARIANT_DEFS) -shared -o mmannot_b200/lib/variants/f$${b}$(VARIANT_TAG).so mmannot_b200/csrc/mma_api.cu & done; wait
 
 clean:
 	rm -rf mmannot_b200/lib mmannot_b200/bin oracle/_build
