@@ -165,6 +165,13 @@ int mma_finish_sample(mma_ctx *ctx, uint32_t sample, mma_sample_result *out);
  * batch, written to out_masks[0..n) (host memory).  Synchronous; nothing is counted; nh / read_key are ignored. */
 int mma_annotate_hits(mma_ctx *ctx, const mma_hit_batch *batch, uint64_t *out_masks);
 
+/* scan with -M (EvaluationStructure::getIds, mmannot.cpp:1077-1081, 1328-1330): besides the element set of every hit, the
+ * indices (into the feature buffer given to mma_load_features) of the intervals behind it -- every interval of a chosen
+ * element that passes the strand rule and the -l test.  out_offsets has n + 1 entries: the intervals of hit i are
+ * (*out_ids)[out_offsets[i] .. out_offsets[i+1]), in no particular order (every consumer in the reference sorts them).
+ * *out_ids belongs to the context and stays valid until the next call.  Synchronous; nothing is counted. */
+int mma_annotate_intervals(mma_ctx *ctx, const mma_hit_batch *batch, uint64_t *out_masks, uint64_t *out_offsets, const uint32_t **out_ids);
+
 /* Forget everything counted for `sample` (Counter::clear, mmannot.cpp:1742-1747). */
 int mma_reset_sample(mma_ctx *ctx, uint32_t sample);
 

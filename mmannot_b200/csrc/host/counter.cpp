@@ -64,18 +64,33 @@ bool Counter::read(const std::string &fileName, uint32_t column, std::string &er
   log << (reader.isBam() ? "Reading BAM file " : "Reading SAM file ") << fileName << std::endl;
   if (mma_reset_sample(ctx_, column) != MMA_OK) { err = mma_last_error(ctx_); return false; }
   // decode batch k+1 on the host while batch k is copied and annotated on the device
+  std::vector<std::string> names;
+  std::vector<uint64_t> masks, offsets;
   for (unsigned which = 0;; which ^= 1) {
     const HitBuffers &buf = pinned_[which];
-    size_t n = reader.nextBatch(buf, nullptr);
+    size_t n = reader.nextBatch(buf, writers_ ? &names : nullptr);
     std::string w = reader.takeWarnings();
     if (!w.empty()) log << w;
     if (n == 0) break;
     mma_hit_batch b;
     b.n = n; b.start = buf.start; b.end = buf.end; b.meta = buf.meta; b.nh = buf.nh; b.read_key = buf.key;
     if (mma_submit_hits(ctx_, column, &b) != MMA_OK) { err = mma_last_error(ctx_); return false; }
+    if (writers_) {  // -m / -M: scan alone for the same hits, then the name-keyed text bookkeeping on the host
+      masks.resize(n);
+      offsets.assign(n + 1, 0);
+      const uint32_t *ids = nullptr;
+      const int rc = opt_.intervalStats ? mma_annotate_intervals(ctx_, &b, masks.data(), offsets.data(), &ids)
+                                        : mma_annotate_hits(ctx_, &b, masks.data());
+      if (rc != MMA_OK) { err = mma_last_error(ctx_); return false; }
+      for (size_t i = 0; i < n; ++i) {
+        if (opt_.strategy == MMA_STRATEGY_UNIQUE && buf.nh[i] != 1) continue;  // mm:1773
+        writers_->addHit(names[i], buf.nh[i], masks[i], ids ? ids + offsets[i] : nullptr, ids ? offsets[i + 1] - offsets[i] : 0);
+      }
+    }
     if (opt_.progress) log << "\t" << withThousands(reader.recordsRead()) << " lines read.\r" << std::flush;
   }
   log << "\t" << withThousands(reader.recordsRead()) << " lines read, done." << std::endl;
+  if (writers_) writers_->endOfFile();
   mma_sample_result res;
   if (mma_finish_sample(ctx_, column, &res) != MMA_OK) { err = mma_last_error(ctx_); return false; }
   stats_ = res.stats;

@@ -12,6 +12,7 @@
 #include "annotation.hpp"
 #include "config.hpp"
 #include "mmannot_b200.h"
+#include "stats_writers.hpp"
 #include "xam.hpp"
 
 namespace mmb {
@@ -38,6 +39,8 @@ class Counter {
   // element set (bitmask) -> the reference's regionCounts value
   const std::map<uint64_t, double> &getCounts() const { return counts_; }
   const mma_sample_stats &getStats() const { return stats_; }
+  // -m / -M: the per-hit element sets (and interval ids) of every batch are also handed to `w` in file order
+  void setStatsWriters(StatsWriters *w) { writers_ = w; }
 
  private:
   mma_ctx *ctx_;
@@ -48,6 +51,7 @@ class Counter {
   mma_sample_stats stats_;
   std::map<uint64_t, double> counts_;
   HitBuffers pinned_[2];
+  StatsWriters *writers_ = nullptr;
 };
 
 class TableCount {

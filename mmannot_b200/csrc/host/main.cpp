@@ -158,9 +158,6 @@ int main(int argc, char **argv) {
     printUsage();
     return EXIT_FAILURE;
   }
-  if (opt.readStats || opt.intervalStats)
-    return fail("Error: the per-read (-m) and per-interval (-M) statistics files are not produced by this build yet.");
-
   std::string err, warnings;
   Config config;
   if (!config.parse(configFileName, err)) return fail(err);
@@ -208,9 +205,15 @@ int main(int argc, char **argv) {
   {
     TableCount table(config, nInputs);
     Counter counter(ctx, features, config, opt);
+    std::ofstream readStatsStream, intervalStatsStream;
+    if (opt.readStats) readStatsStream.open(readStatsFile.c_str());            // mm:2000
+    if (opt.intervalStats) intervalStatsStream.open(intervalStatsFile.c_str());  // mm:2005
+    StatsWriters writers(config, features, opt.strategy, opt.rescueThreshold, opt.readStats ? &readStatsStream : nullptr, opt.intervalStats);
+    if (opt.readStats || opt.intervalStats) counter.setStatsWriters(&writers);
     for (uint32_t i = 0; i < nInputs; i++) {
       if (!counter.read(readsFileNames[i], i, err, std::cerr)) { std::cerr << err << std::endl; rc = EXIT_FAILURE; break; }
       counter.dump(std::cerr);
+      if (opt.intervalStats) writers.dumpIntervals(intervalStatsStream);
       table.addCounter(counter);
     }
     if (rc == 0) table.dump(outputFile, names);

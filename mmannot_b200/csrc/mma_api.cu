@@ -102,6 +102,7 @@ struct mma_ctx {
   int nSM = 148;
   u32 maxGrid = 0;           // MMANNOT_B200_MAX_GRID=n: cap on k_batch blocks, so that small test inputs still give every warp a multi-tile chunk (testing only)
   bool legacyBatch = false;  // MMANNOT_B200_LEGACY_BATCH=1: A/B runs of the general k_batch against k_batch_fast (tuning only)
+  std::vector<uint32_t> intervalIds;  // result of the last mma_annotate_intervals
   u64 *hostTable = nullptr;  // pinned, 2 x tableCap: keys then values of the sample being read back
 
   int fail(int code, const std::string &msg) {
@@ -711,6 +712,73 @@ int mma_annotate_hits(mma_ctx *ctx, const mma_hit_batch *b, uint64_t *out_masks)
   if (e == cudaSuccess) e = cudaGetLastError();
   cleanup();
   if (e != cudaSuccess) return ctx->fail(MMA_ERR_CUDA, cudaGetErrorString(e));
+  return MMA_OK;
+}
+
+int mma_annotate_intervals(mma_ctx *ctx, const mma_hit_batch *b, uint64_t *out_masks, uint64_t *out_offsets, const uint32_t **out_ids) {
+  if (!ctx) return MMA_ERR_INVALID;
+  if (!b || !out_offsets || !out_ids || (b->n && (!b->start || !b->end || !b->meta || !out_masks))) return ctx->fail(MMA_ERR_INVALID, "null argument");
+  if (!ctx->haveIndex) return ctx->fail(MMA_ERR_STATE, "mma_load_features must be called before hits are submitted");
+  *out_ids = nullptr;
+  out_offsets[0] = 0;
+  if (b->n == 0) return MMA_OK;
+  if (b->n > 0x7FFFFFF0ull) return ctx->fail(MMA_ERR_INVALID, "too many hits in one call");
+  CK(cudaSetDevice(ctx->device));
+  const size_t n = b->n;
+  DevBuf ds, de, dm, dmask, dcnt, doff, dtmp, dids;
+  auto cleanup = [&]() { ds.release(); de.release(); dm.release(); dmask.release(); dcnt.release(); doff.release(); dtmp.release(); dids.release(); };
+#define CKI(call)                                                                                  \
+  do {                                                                                             \
+    cudaError_t _e = (call);                                                                       \
+    if (_e != cudaSuccess) { cleanup(); return ctx->fail(MMA_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(_e)); } \
+  } while (0)
+  CKI(ds.ensure(n * 4)); CKI(de.ensure(n * 4)); CKI(dm.ensure(n * 4)); CKI(dmask.ensure(n * 8)); CKI(dcnt.ensure(n * 4)); CKI(doff.ensure((n + 1) * 8));
+  cudaStream_t st = ctx->sc;
+  CKI(cudaMemcpyAsync(ds.p, b->start, n * 4, cudaMemcpyHostToDevice, st));
+  CKI(cudaMemcpyAsync(de.p, b->end, n * 4, cudaMemcpyHostToDevice, st));
+  CKI(cudaMemcpyAsync(dm.p, b->meta, n * 4, cudaMemcpyHostToDevice, st));
+  HitView h = HitView();
+  h.start = ds.as<u32>(); h.end = de.as<u32>(); h.meta = dm.as<u32>(); h.n = (u32)n;
+  const u32 grid = std::min<u32>(gridFor(n, 256), (u32)ctx->nSM * 8);
+  const Rules &r = ctx->rules;
+  if (r.mode == 0) k_intervals_count<0><<<grid, 256, 0, st>>>(ctx->index, h, r, dmask.as<u64>(), dcnt.as<u32>());
+  else if (r.mode == 1) k_intervals_count<1><<<grid, 256, 0, st>>>(ctx->index, h, r, dmask.as<u64>(), dcnt.as<u32>());
+  else k_intervals_count<2><<<grid, 256, 0, st>>>(ctx->index, h, r, dmask.as<u64>(), dcnt.as<u32>());
+  // exclusive scan of the per-hit counts (64-bit offsets) with the total in the extra last slot
+  DevBuf dwide;
+  auto cleanup2 = [&]() { dwide.release(); cleanup(); };
+#define CKJ(call)                                                                                  \
+  do {                                                                                             \
+    cudaError_t _e = (call);                                                                       \
+    if (_e != cudaSuccess) { cleanup2(); return ctx->fail(MMA_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(_e)); } \
+  } while (0)
+  CKJ(dwide.ensure((n + 1) * 8));
+  CKJ(cudaMemsetAsync(dwide.p, 0, (n + 1) * 8, st));
+  k_widen_counts<<<gridFor(n, 256), 256, 0, st>>>(dcnt.as<u32>(), dwide.as<u64>(), (u32)n);
+  size_t tb = 0;
+  CKJ(cub::DeviceScan::ExclusiveSum(nullptr, tb, dwide.as<u64>(), doff.as<u64>(), (int)(n + 1), st));
+  CKJ(dtmp.ensure(tb ? tb : 1));
+  CKJ(cub::DeviceScan::ExclusiveSum(dtmp.p, tb, dwide.as<u64>(), doff.as<u64>(), (int)(n + 1), st));
+  ctx->launches += 2;
+  CKJ(cudaMemcpyAsync(out_offsets, doff.p, (n + 1) * 8, cudaMemcpyDeviceToHost, st));
+  CKJ(cudaMemcpyAsync(out_masks, dmask.p, n * 8, cudaMemcpyDeviceToHost, st));
+  CKJ(cudaStreamSynchronize(st));
+  const uint64_t total = out_offsets[n];
+  ctx->intervalIds.resize(total);
+  if (total) {
+    CKJ(dids.ensure(total * 4));
+    if (r.mode == 0) k_intervals_fill<0><<<grid, 256, 0, st>>>(ctx->index, h, r, dmask.as<u64>(), doff.as<u64>(), dids.as<u32>());
+    else if (r.mode == 1) k_intervals_fill<1><<<grid, 256, 0, st>>>(ctx->index, h, r, dmask.as<u64>(), doff.as<u64>(), dids.as<u32>());
+    else k_intervals_fill<2><<<grid, 256, 0, st>>>(ctx->index, h, r, dmask.as<u64>(), doff.as<u64>(), dids.as<u32>());
+    ctx->launches++;
+    CKJ(cudaMemcpyAsync(ctx->intervalIds.data(), dids.p, total * 4, cudaMemcpyDeviceToHost, st));
+    CKJ(cudaStreamSynchronize(st));
+  }
+  CKJ(cudaGetLastError());
+#undef CKI
+#undef CKJ
+  cleanup2();
+  *out_ids = ctx->intervalIds.data();
   return MMA_OK;
 }
 

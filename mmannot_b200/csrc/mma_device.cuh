@@ -818,6 +818,72 @@ k_annotate_only(IndexView ix, FastView fx, HitView h, Rules r, u64 *__restrict__
     out[i] = annot(h.start[i], h.end[i], h.meta[i]);
 }
 
+// -M (mm:1077-1081, 1328-1330): the intervals behind the element set of a hit = every candidate of a chosen element that
+// passes the strand rule and scores > 0 (EvaluationStructure::set appends each of them to ids[type], mm:1023-1028).  The
+// reference concatenates them element by element, but every consumer sorts the list (mm:1693, 1732, 1795), so they are
+// emitted here in candidate order.  `emit(featureIndex)` is called once per such interval; returns their number.
+template <int MODE, typename Emit>
+__device__ __forceinline__ u32 chosenIntervals(const IndexView &ix, u32 rs, u32 re, u32 meta, float ovl, u64 chosen, Emit emit) {
+  const u32 chr = meta & 0x00FFFFFFu;
+  if (chosen == 0 || chr >= ix.nChr) return 0;
+  const uint2 ci = __ldg(&ix.chrInfo[chr]);
+  const u32 lastBin = ci.y - 1;
+  const u32 qlo = min(rs, re), qhi = max(rs, re);
+  const u32 b0 = min(qlo >> ix.shift, lastBin), b1 = min(qhi >> ix.shift, lastBin);
+  const uint2 e0 = __ldg(&ix.bins[ci.x + b0]);
+  const uint2 e1 = __ldg(&ix.bins[ci.x + b0 + 1]);
+  const u32 hi = (b1 == b0) ? e1.x : __ldg(&ix.bins[ci.x + b1 + 1]).x;
+  const u32 rstrand = meta >> 31;
+  u32 n = 0;
+  auto visit = [&](u32 i) {
+    const uint4 f = __ldg(&ix.feat[i]);
+    if (f.x > re || f.w < rs) return;  // outside the reference's walk (see evalCandidate)
+    const u32 m = f.z;
+    if (!((chosen >> FM_TYPE(m)) & 1ull)) return;
+    const u32 es = FM_ESTRAND(m);
+    if (es != 0 && ((es == 1) != (FM_FWD(m) == rstrand))) return;  // Config::checkStrand, mm:438-443
+    u32 sc;
+    if (MODE == 0) {
+      sc = (rs >= f.x && re <= f.y) ? 1u : 0u;
+    } else {
+      const u32 s = max(f.x, rs), e = min(f.y, re);
+      const u32 o = (s >= e) ? 0u : e - s;
+      if (MODE == 1) sc = (__fmul_rn((float)(re - rs + 1u), ovl) <= (float)o) ? o : 0u;
+      else sc = ((float)o >= ovl) ? o : 0u;
+    }
+    if (sc == 0) return;
+    emit(i);
+    ++n;
+  };
+  for (u32 k = e0.y; k < e1.y; ++k) visit(__ldg(&ix.spanIdx[k]));  // spanning features come first in feature order
+  for (u32 i = e0.x; i < hi; ++i) visit(i);
+  return n;
+}
+
+// pass 1: element set and number of intervals per hit; pass 2 (after an exclusive scan of the counts): the interval ids
+template <int MODE>
+__global__ void __launch_bounds__(256)
+k_intervals_count(IndexView ix, HitView h, Rules r, u64 *__restrict__ masks, u32 *__restrict__ counts) {
+  for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < h.n; i += gridDim.x * blockDim.x) {
+    const u32 rs = h.start[i], re = h.end[i], meta = h.meta[i];
+    const u64 c = annotateEval<MODE, false>(ix, rs, re, meta, r.overlap, nullptr);
+    masks[i] = c;
+    counts[i] = chosenIntervals<MODE>(ix, rs, re, meta, r.overlap, c, [](u32) {});
+  }
+}
+template <int MODE>
+__global__ void __launch_bounds__(256)
+k_intervals_fill(IndexView ix, HitView h, Rules r, const u64 *__restrict__ masks, const u64 *__restrict__ offsets, u32 *__restrict__ ids) {
+  for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < h.n; i += gridDim.x * blockDim.x) {
+    u64 at = offsets[i];
+    chosenIntervals<MODE>(ix, h.start[i], h.end[i], h.meta[i], r.overlap, masks[i], [&](u32 f) { ids[at++] = f; });
+  }
+}
+__global__ void k_widen_counts(const u32 *__restrict__ in, u64 *__restrict__ out, u32 n) {
+  const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = in[i];
+}
+
 // End of batch.  When the batch is dirty, every run (of this batch) of a read name that became unfinished DURING the
 // batch was resolved by k_batch as if the name had no open read; such runs are walked again here, what k_batch counted
 // for them is taken back and their multi-mapping records are handed to the deferred path, which replays the name's

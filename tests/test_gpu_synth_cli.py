@@ -96,3 +96,37 @@ def test_cli_equals_reference(workload, args):
     # same report text for the per-sample blocks
     pick = lambda t: [l for l in t.split("\n") if l.startswith("\t#") or l.startswith("Results for")]
     assert pick(pr.stderr) == pick(ref_err)
+
+
+STATS_CASES = [["-s", "F"], ["-s", "F", "-e", "60"], ["-s", "U", "-l", "1", "-e", "75"], ["-s", "R", "-y", "ratio", "-e", "50"],
+               ["-s", "F", "-y", "unique"], ["-s", "F", "-y", "random", "-e", "80"]]
+
+
+@pytest.mark.skipif(pyoracle.ref_binary("fixed") is None or not os.path.exists(CLI), reason="needs oracle/_ref and the CLI binary")
+@pytest.mark.parametrize("args", STATS_CASES, ids=lambda a: " ".join(a))
+@pytest.mark.parametrize("sorted_input", [False, True], ids=["grouped", "coordinate-sorted"])
+def test_cli_read_and_interval_statistics(workload, args, sorted_input):
+    """-m (per read) and -M (per interval) files, the table and the counters against the reference binary, byte for byte.
+    With -m the -e threshold becomes active (mmannot.cpp:491).  The coordinate-sorted input leaves many reads open until
+    the end of the file: their -m lines come out in the iteration order of the reference's name-keyed map."""
+    w = workload
+    tag = "s" if sorted_input else "g"
+    bam = str(w["tmp"] / ("stats_%s.bam" % tag))
+    if not os.path.exists(bam):
+        w["synth"].write_bam(bam, 50000, 6000, coordinate_sorted=sorted_input)
+    out = {}
+    for who, exe in (("ref", None), ("b200", CLI)):
+        m, M = str(w["tmp"] / ("%s_m.txt" % who)), str(w["tmp"] / ("%s_M.txt" % who))
+        a = ["-a", w["gtf"], "-c", w["cfg_path"], "-r", bam, "-m", m, "-M", M] + args
+        if exe is None:
+            rc, so, se = pyoracle.run_reference(a, kind="fixed")
+        else:
+            pr = subprocess.run([exe] + a, capture_output=True, text=True, timeout=300)
+            rc, so, se = pr.returncode, pr.stdout, pr.stderr
+        assert rc == 0, se
+        out[who] = (so, pyoracle.parse_stats(se), open(m).read(), open(M).read())
+    assert out["b200"][0] == out["ref"][0]
+    assert out["b200"][1] == out["ref"][1]
+    assert out["b200"][3] == out["ref"][3], "-M differs"
+    assert out["b200"][2] == out["ref"][2], "-m differs"
+    assert len(out["ref"][2]) > 1000 and len(out["ref"][3]) > 1000
