@@ -106,6 +106,33 @@ typedef struct mma_hit_batch {
   const uint64_t *read_key;  /* 64-bit key of the read name (the reference keys by the name string) */
 } mma_hit_batch;
 
+/* The same batch in the compact transfer format (8 bytes per hit + 8 bytes per run of records sharing a read name, instead
+ * of 24 bytes per hit): what crosses PCIe when the host decoder packs its output with mma_pack_hits().  The device expands
+ * it back into the five arrays of mma_hit_batch (k_expand_packed) before the batch kernel runs; results are identical.
+ *   packed[i]  bits 0..7   end - start + 1  (0 for the empty-CIGAR case end = start - 1; 255 = look the hit up in the escapes)
+ *              bits 8..15  NH               (255 = look the hit up in the escapes)
+ *              bits 16..29 annotation chromosome id (MMA_PACKED_CHR_NONE = unknown to the annotation)
+ *              bit  30     first record of a run: its read key differs from the previous record's (always set for record 0)
+ *              bit  31     read strand (MMA_HIT_STRAND_BIT)
+ *   run_key[r]             read key of the r-th run of the batch
+ *   tile_run_base[t]       number of runs that start before hit t * MMA_PACK_TILE
+ *   esc_*                  ascending hit indices with their full end and NH, for hits a field of which did not fit */
+#define MMA_PACK_TILE 1024
+#define MMA_PACKED_CHR_NONE 0x3FFFu
+#define MMA_PACKED_RUN_START 0x40000000u
+typedef struct mma_packed_batch {
+  uint64_t n;
+  const uint32_t *start;
+  const uint32_t *packed;
+  uint64_t n_runs;
+  const uint64_t *run_key;
+  const uint32_t *tile_run_base;  /* [(n + MMA_PACK_TILE - 1) / MMA_PACK_TILE] */
+  uint64_t n_escapes;
+  const uint32_t *esc_index;
+  const uint32_t *esc_end;
+  const uint32_t *esc_nh;
+} mma_packed_batch;
+
 typedef struct mma_sample_stats { /* Counter's counters, mmannot.cpp:1663, printed at 1807-1818 */
   uint64_t n_hits, n_reads, n_unique, n_ambiguous, n_multiple, n_unassigned, n_rescued;
 } mma_sample_stats;
@@ -155,6 +182,16 @@ int mma_submit_hits(mma_ctx *ctx, uint32_t sample, const mma_hit_batch *batch);
 /* Same, but the arrays already live in device memory of ctx's GPU (no copy is made; they
  * must stay valid until mma_sync / mma_finish_sample). */
 int mma_submit_hits_device(mma_ctx *ctx, uint32_t sample, const mma_hit_batch *device_batch);
+
+/* Host-side packer (no device work): fills the caller's buffers -- packed[n], run_key[n] (worst case one run per hit),
+ * tile_run_base[(n + MMA_PACK_TILE - 1) / MMA_PACK_TILE], esc_*[esc_capacity] -- from a batch in the wide format and points
+ * `out` at them (out->start aliases wide->start).  MMA_ERR_CAPACITY when the batch cannot be packed (more escapes than
+ * esc_capacity, or a chromosome id >= MMA_PACKED_CHR_NONE): submit it in the wide format instead. */
+int mma_pack_hits(const mma_hit_batch *wide, uint32_t *packed, uint64_t *run_key, uint32_t *tile_run_base, uint32_t *esc_index,
+                  uint32_t *esc_end, uint32_t *esc_nh, uint64_t esc_capacity, mma_packed_batch *out);
+
+/* mma_submit_hits for a batch in the compact format (same asynchrony and buffer lifetime rules). */
+int mma_submit_hits_packed(mma_ctx *ctx, uint32_t sample, const mma_packed_batch *batch);
 
 /* Synchronous: end-of-file flush of the sample (mmannot.cpp:1783-1792) and read-back of its
  * counters and rows.  The arrays belong to the context and stay valid until the next

@@ -47,11 +47,25 @@ Counter::Counter(mma_ctx *ctx, const FeatureTable &features, const Config &confi
     : ctx_(ctx), features_(features), config_(config), opt_(opt), stats_() {
   allocPinned(pinned_[0], opt.batchHits);
   allocPinned(pinned_[1], opt.batchHits);
+  for (PackedBuffers &p : packedBuf_) {
+    const size_t cap = opt.batchHits;
+    p.escCapacity = cap / 64 + 16;
+    p.packed = static_cast<uint32_t *>(mma_alloc_pinned(cap * 4));
+    p.runKey = static_cast<uint64_t *>(mma_alloc_pinned(cap * 8));
+    p.tileRunBase = static_cast<uint32_t *>(mma_alloc_pinned((cap / MMA_PACK_TILE + 1) * 4));
+    p.escIndex = static_cast<uint32_t *>(mma_alloc_pinned(p.escCapacity * 4));
+    p.escEnd = static_cast<uint32_t *>(mma_alloc_pinned(p.escCapacity * 4));
+    p.escNh = static_cast<uint32_t *>(mma_alloc_pinned(p.escCapacity * 4));
+  }
 }
 
 Counter::~Counter() {
   freePinned(pinned_[0]);
   freePinned(pinned_[1]);
+  for (PackedBuffers &p : packedBuf_) {
+    mma_free_pinned(p.packed); mma_free_pinned(p.runKey); mma_free_pinned(p.tileRunBase);
+    mma_free_pinned(p.escIndex); mma_free_pinned(p.escEnd); mma_free_pinned(p.escNh);
+  }
 }
 
 bool Counter::read(const std::string &fileName, uint32_t column, std::string &err, std::ostream &log) {
@@ -74,7 +88,13 @@ bool Counter::read(const std::string &fileName, uint32_t column, std::string &er
     if (n == 0) break;
     mma_hit_batch b;
     b.n = n; b.start = buf.start; b.end = buf.end; b.meta = buf.meta; b.nh = buf.nh; b.read_key = buf.key;
-    if (mma_submit_hits(ctx_, column, &b) != MMA_OK) { err = mma_last_error(ctx_); return false; }
+    // compact format over PCIe when the batch fits it (short reads, NH < 255 with a few escapes), else the wide arrays
+    const PackedBuffers &pk = packedBuf_[which];
+    mma_packed_batch pb;
+    const bool canPack = pk.packed && pk.runKey && pk.tileRunBase && pk.escIndex && pk.escEnd && pk.escNh &&
+                         mma_pack_hits(&b, pk.packed, pk.runKey, pk.tileRunBase, pk.escIndex, pk.escEnd, pk.escNh, pk.escCapacity, &pb) == MMA_OK;
+    const int src = canPack ? mma_submit_hits_packed(ctx_, column, &pb) : mma_submit_hits(ctx_, column, &b);
+    if (src != MMA_OK) { err = mma_last_error(ctx_); return false; }
     if (writers_) {  // -m / -M: scan alone for the same hits, then the name-keyed text bookkeeping on the host
       masks.resize(n);
       offsets.assign(n + 1, 0);

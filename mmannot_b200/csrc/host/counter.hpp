@@ -51,6 +51,12 @@ class Counter {
   mma_sample_stats stats_;
   std::map<uint64_t, double> counts_;
   HitBuffers pinned_[2];
+  // compact transfer format of each slot (mma_pack_hits): what actually crosses PCIe
+  struct PackedBuffers {
+    uint32_t *packed = nullptr, *tileRunBase = nullptr, *escIndex = nullptr, *escEnd = nullptr, *escNh = nullptr;
+    uint64_t *runKey = nullptr;
+    uint64_t escCapacity = 0;
+  } packedBuf_[2];
   StatsWriters *writers_ = nullptr;
 };
 

@@ -47,6 +47,7 @@ struct DevBuf {
 
 struct Staging {  // one batch resident on the device
   DevBuf start, end, meta, nh, key;
+  DevBuf packed, runKey, tileBase, escIndex, escEnd, escNh;  // compact transfer format, expanded into the five arrays above
   cudaEvent_t copied = nullptr, done = nullptr;
 };
 
@@ -405,6 +406,7 @@ void mma_destroy(mma_ctx *ctx) {
   for (int k = 0; k < 2; ++k) {
     Staging &g = ctx->stage[k];
     g.start.release(); g.end.release(); g.meta.release(); g.nh.release(); g.key.release();
+    g.packed.release(); g.runKey.release(); g.tileBase.release(); g.escIndex.release(); g.escEnd.release(); g.escNh.release();
     if (g.copied) cudaEventDestroy(g.copied);
     if (g.done) cudaEventDestroy(g.done);
   }
@@ -667,6 +669,94 @@ static int submitCommon(mma_ctx *ctx, uint32_t sample, const mma_hit_batch *b, b
     h.start = g.start.as<u32>(); h.end = g.end.as<u32>(); h.meta = g.meta.as<u32>(); h.nh = g.nh.as<u32>(); h.key = g.key.as<u64>();
   }
   h.vec = ((((uintptr_t)h.start | (uintptr_t)h.end | (uintptr_t)h.meta | (uintptr_t)h.nh | (uintptr_t)h.key) & 15u) == 0) ? 1u : 0u;
+  if ((rc = launchBatch(ctx, s, h))) return rc;
+  CK(cudaEventRecord(g.done, ctx->sc));
+  if ((rc = afterBatch(ctx, s, n))) return rc;
+  ctx->submitSeq++;
+  return MMA_OK;
+}
+
+int mma_pack_hits(const mma_hit_batch *w, uint32_t *packed, uint64_t *run_key, uint32_t *tile_run_base, uint32_t *esc_index,
+                  uint32_t *esc_end, uint32_t *esc_nh, uint64_t esc_capacity, mma_packed_batch *out) {
+  if (!w || !out || (w->n && (!w->start || !w->end || !w->meta || !w->nh || !w->read_key || !packed || !run_key || !tile_run_base)))
+    return MMA_ERR_INVALID;
+  uint64_t runs = 0, esc = 0;
+  for (uint64_t i = 0; i < w->n; ++i) {
+    if ((i % MMA_PACK_TILE) == 0) tile_run_base[i / MMA_PACK_TILE] = (uint32_t)runs;
+    const uint32_t chrWide = w->meta[i] & MMA_HIT_CHR_MASK;
+    uint32_t chr = MMA_PACKED_CHR_NONE;
+    if (chrWide != MMA_HIT_CHR_NONE) {
+      if (chrWide >= MMA_PACKED_CHR_NONE) return MMA_ERR_CAPACITY;
+      chr = chrWide;
+    }
+    const uint32_t len = w->end[i] - w->start[i] + 1u;  // 0 for end = start - 1
+    uint32_t lenField = len < 255u ? len : 255u, nhField = w->nh[i] < 255u ? w->nh[i] : 255u;
+    if (lenField == 255u || nhField == 255u) {
+      if (esc >= esc_capacity || !esc_index || !esc_end || !esc_nh) return MMA_ERR_CAPACITY;
+      esc_index[esc] = (uint32_t)i; esc_end[esc] = w->end[i]; esc_nh[esc] = w->nh[i];
+      ++esc;
+    }
+    uint32_t p = lenField | (nhField << 8) | (chr << 16) | (w->meta[i] & MMA_HIT_STRAND_BIT);
+    // runs are defined on the normalised keys the kernels compare (the all-ones key is reserved, see normKey)
+    const uint64_t kn = (w->read_key[i] == ~0ull) ? ~0ull - 1 : w->read_key[i];
+    const uint64_t kp = (i == 0) ? 0 : ((w->read_key[i - 1] == ~0ull) ? ~0ull - 1 : w->read_key[i - 1]);
+    if (i == 0 || kn != kp) { p |= MMA_PACKED_RUN_START; run_key[runs++] = kn; }
+    packed[i] = p;
+  }
+  out->n = w->n; out->start = w->start; out->packed = packed; out->n_runs = runs; out->run_key = run_key;
+  out->tile_run_base = tile_run_base; out->n_escapes = esc; out->esc_index = esc_index; out->esc_end = esc_end; out->esc_nh = esc_nh;
+  return MMA_OK;
+}
+
+int mma_submit_hits_packed(mma_ctx *ctx, uint32_t sample, const mma_packed_batch *pb) {
+  if (!ctx) return MMA_ERR_INVALID;
+  if (!pb) return ctx->fail(MMA_ERR_INVALID, "null batch");
+  if (!ctx->haveIndex) return ctx->fail(MMA_ERR_STATE, "mma_load_features must be called before hits are submitted");
+  if (sample >= ctx->samples.size()) return ctx->fail(MMA_ERR_INVALID, "sample index out of range");
+  if (pb->n > ctx->params.max_batch_hits) return ctx->fail(MMA_ERR_INVALID, "batch larger than max_batch_hits");
+  const uint64_t n = pb->n;
+  if (n && (!pb->start || !pb->packed || !pb->run_key || !pb->tile_run_base || pb->n_runs == 0 || pb->n_runs > n ||
+            !(pb->packed[0] & MMA_PACKED_RUN_START) || (pb->n_escapes && (!pb->esc_index || !pb->esc_end || !pb->esc_nh))))
+    return ctx->fail(MMA_ERR_INVALID, "malformed packed batch");
+  CK(cudaSetDevice(ctx->device));
+  Sample &s = ctx->samples[sample];
+  int rc = initSample(ctx, s);
+  if (rc) return rc;
+  const uint64_t k = ctx->submitSeq;
+  Staging &g = ctx->stage[k & 1];
+  if (k > 0) CK(cudaEventSynchronize(ctx->stage[(k - 1) & 1].copied));
+  if (n == 0) return MMA_OK;
+  if ((rc = ensureDeferred(ctx, s, n))) return rc;
+  if (k > 1) CK(cudaEventSynchronize(g.done));
+  const size_t cap = ctx->params.max_batch_hits;
+  const size_t nTiles = (n + PACK_TILE - 1) / PACK_TILE;
+  CK(g.start.ensure(cap * 4)); CK(g.end.ensure(cap * 4)); CK(g.meta.ensure(cap * 4)); CK(g.nh.ensure(cap * 4)); CK(g.key.ensure(cap * 8));
+  CK(g.packed.ensure(cap * 4)); CK(g.runKey.ensure(cap * 8)); CK(g.tileBase.ensure(((cap + PACK_TILE - 1) / PACK_TILE) * 4));
+  if (pb->n_escapes) { CK(g.escIndex.ensure(pb->n_escapes * 4)); CK(g.escEnd.ensure(pb->n_escapes * 4)); CK(g.escNh.ensure(pb->n_escapes * 4)); }
+  CK(cudaMemcpyAsync(g.start.p, pb->start, n * 4, cudaMemcpyHostToDevice, ctx->sh));
+  CK(cudaMemcpyAsync(g.packed.p, pb->packed, n * 4, cudaMemcpyHostToDevice, ctx->sh));
+  CK(cudaMemcpyAsync(g.runKey.p, pb->run_key, pb->n_runs * 8, cudaMemcpyHostToDevice, ctx->sh));
+  CK(cudaMemcpyAsync(g.tileBase.p, pb->tile_run_base, nTiles * 4, cudaMemcpyHostToDevice, ctx->sh));
+  if (pb->n_escapes) {
+    CK(cudaMemcpyAsync(g.escIndex.p, pb->esc_index, pb->n_escapes * 4, cudaMemcpyHostToDevice, ctx->sh));
+    CK(cudaMemcpyAsync(g.escEnd.p, pb->esc_end, pb->n_escapes * 4, cudaMemcpyHostToDevice, ctx->sh));
+    CK(cudaMemcpyAsync(g.escNh.p, pb->esc_nh, pb->n_escapes * 4, cudaMemcpyHostToDevice, ctx->sh));
+  }
+  CK(cudaEventRecord(g.copied, ctx->sh));
+  CK(cudaStreamWaitEvent(ctx->sc, g.copied, 0));
+  PackedView pv;
+  pv.start = g.start.as<u32>(); pv.packed = g.packed.as<u32>(); pv.tileRunBase = g.tileBase.as<u32>();
+  pv.escIndex = g.escIndex.as<u32>(); pv.escEnd = g.escEnd.as<u32>(); pv.escNh = g.escNh.as<u32>();
+  pv.runKey = g.runKey.as<u64>(); pv.n = (u32)n; pv.nEsc = (u32)pb->n_escapes;
+  {
+    mma_ctx::Timed t(ctx, TC_CLOSE);
+    k_expand_packed<<<(u32)nTiles, PACK_TILE / 4, 0, ctx->sc>>>(pv, g.end.as<u32>(), g.meta.as<u32>(), g.nh.as<u32>(), g.key.as<u64>());
+    ctx->launches++;
+  }
+  HitView h;
+  h.n = (u32)n;
+  h.start = g.start.as<u32>(); h.end = g.end.as<u32>(); h.meta = g.meta.as<u32>(); h.nh = g.nh.as<u32>(); h.key = g.key.as<u64>();
+  h.vec = 1u;
   if ((rc = launchBatch(ctx, s, h))) return rc;
   CK(cudaEventRecord(g.done, ctx->sc));
   if ((rc = afterBatch(ctx, s, n))) return rc;

@@ -884,6 +884,55 @@ __global__ void k_widen_counts(const u32 *__restrict__ in, u64 *__restrict__ out
   if (i < n) out[i] = in[i];
 }
 
+// Compact transfer format -> the five hit arrays (see mma_packed_batch in mmannot_b200.h).  One block per tile of
+// PACK_TILE hits, 4 consecutive hits per thread; the read key of a hit is the key of its run, found from the number of run
+// starts up to the hit (tile base from the host + a block-wide prefix sum of the run-start bits).
+#define PACK_TILE 1024
+struct PackedView {
+  const u32 *start, *packed, *tileRunBase, *escIndex, *escEnd, *escNh;
+  const u64 *runKey;
+  u32 n, nEsc;
+};
+__global__ void __launch_bounds__(PACK_TILE / 4)
+k_expand_packed(PackedView pv, u32 *__restrict__ end, u32 *__restrict__ meta, u32 *__restrict__ nh, u64 *__restrict__ key) {
+  __shared__ u32 warpSum[PACK_TILE / 4 / 32];
+  const u32 tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+  const u32 base = blockIdx.x * PACK_TILE + tid * 4;
+  u32 p[4], st[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const u32 i = base + j;
+    p[j] = (i < pv.n) ? pv.packed[i] : 0u;
+    st[j] = (i < pv.n) ? pv.start[i] : 0u;
+  }
+  const u32 mine = ((p[0] >> 30) & 1u) + ((p[1] >> 30) & 1u) + ((p[2] >> 30) & 1u) + ((p[3] >> 30) & 1u);
+  u32 inc = mine;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) { const u32 o = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= (u32)d) inc += o; }
+  if (lane == 31) warpSum[warp] = inc;
+  __syncthreads();
+  u32 before = pv.tileRunBase[blockIdx.x] + inc - mine;
+  for (u32 w = 0; w < warp; ++w) before += warpSum[w];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const u32 i = base + j;
+    if (i >= pv.n) break;
+    before += (p[j] >> 30) & 1u;
+    u32 len = p[j] & 255u, n = (p[j] >> 8) & 255u;
+    u32 e = st[j] + len - 1u;
+    if (len == 255u || n == 255u) {  // escaped: full values by binary search of the hit index
+      u32 lo = 0, hi = pv.nEsc;
+      while (lo < hi) { const u32 mid = (lo + hi) >> 1; if (pv.escIndex[mid] < i) lo = mid + 1; else hi = mid; }
+      if (lo < pv.nEsc && pv.escIndex[lo] == i) { e = pv.escEnd[lo]; n = pv.escNh[lo]; }
+    }
+    const u32 chr = (p[j] >> 16) & 0x3FFFu;
+    end[i] = e;
+    nh[i] = n;
+    meta[i] = (chr == 0x3FFFu ? 0x00FFFFFFu : chr) | (p[j] & 0x80000000u);
+    key[i] = pv.runKey[before - 1u];
+  }
+}
+
 // End of batch.  When the batch is dirty, every run (of this batch) of a read name that became unfinished DURING the
 // batch was resolved by k_batch as if the name had no open read; such runs are walked again here, what k_batch counted
 // for them is taken back and their multi-mapping records are handed to the deferred path, which replays the name's

@@ -20,7 +20,7 @@ FAST_OFF = 0xFFFFFFFF  # fast_bin_shift=None: no segment answer table
 EXPORTS = [
     "mma_create", "mma_destroy", "mma_last_error", "mma_load_features", "mma_alloc_pinned", "mma_free_pinned",
     "mma_submit_hits", "mma_submit_hits_device", "mma_finish_sample", "mma_reset_sample", "mma_dense_counts",
-    "mma_sync", "mma_stream", "mma_timing_enable", "mma_timing_reset", "mma_timing_get", "mma_index_bytes", "mma_version", "mma_readback_bytes", "mma_dominant_kernel", "mma_index_segments", "mma_annotate_hits", "mma_annotate_intervals",
+    "mma_sync", "mma_stream", "mma_timing_enable", "mma_timing_reset", "mma_timing_get", "mma_index_bytes", "mma_version", "mma_readback_bytes", "mma_dominant_kernel", "mma_index_segments", "mma_annotate_hits", "mma_annotate_intervals", "mma_pack_hits", "mma_submit_hits_packed",
 ]
 
 
@@ -46,6 +46,15 @@ class Features(C.Structure):
 class HitBatch(C.Structure):
     _fields_ = [("n", C.c_uint64), ("start", C.c_void_p), ("end", C.c_void_p), ("meta", C.c_void_p),
                 ("nh", C.c_void_p), ("read_key", C.c_void_p)]
+
+
+class PackedBatch(C.Structure):
+    _fields_ = [("n", C.c_uint64), ("start", C.c_void_p), ("packed", C.c_void_p), ("n_runs", C.c_uint64), ("run_key", C.c_void_p),
+                ("tile_run_base", C.c_void_p), ("n_escapes", C.c_uint64), ("esc_index", C.c_void_p), ("esc_end", C.c_void_p),
+                ("esc_nh", C.c_void_p)]
+
+
+PACK_TILE = 1024
 
 
 class SampleStats(C.Structure):
@@ -103,6 +112,12 @@ def lib():
         L.mma_readback_bytes.argtypes = [C.c_void_p]
         L.mma_readback_bytes.restype = C.c_uint64
         L.mma_dominant_kernel.restype = C.c_char_p
+        L.mma_alloc_pinned.argtypes = [C.c_size_t]
+        L.mma_alloc_pinned.restype = C.c_void_p
+        L.mma_free_pinned.argtypes = [C.c_void_p]
+        L.mma_pack_hits.argtypes = [C.POINTER(HitBatch)] + [C.c_void_p] * 6 + [C.c_uint64, C.POINTER(PackedBatch)]
+        L.mma_submit_hits_packed.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(PackedBatch)]
+        L.mma_annotate_intervals.argtypes = [C.c_void_p, C.POINTER(HitBatch), C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]
         _lib = L
     return _lib
 
@@ -144,6 +159,53 @@ class PinnedHits:
             lib().mma_free_pinned(p)
         self._ptrs = []
         self.arrays = {}
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class PackedHits:
+    """One batch in the compact transfer format (mma_packed_batch), in page-locked buffers filled by mma_pack_hits from
+    wide arrays (numpy views or a PinnedHits slice).  `start` is aliased, so the wide start array must stay alive."""
+
+    def __init__(self, start, end, meta, nh, read_key, esc_capacity=None):
+        L = lib()
+        n = int(len(start))
+        self.n = n
+        esc_capacity = max(16, n // 64) if esc_capacity is None else int(esc_capacity)
+        self._ptrs = []
+
+        def pinned(count, ct):
+            p = L.mma_alloc_pinned(max(1, count) * C.sizeof(ct))
+            if not p:
+                raise MemoryError("mma_alloc_pinned failed")
+            self._ptrs.append(p)
+            return p
+
+        self._keep = [np.ascontiguousarray(a) for a in (start, end, meta, nh, read_key)]
+        wide = HitBatch(n, *[a.ctypes.data for a in self._keep])
+        packed = pinned(n, C.c_uint32)
+        run_key = pinned(n, C.c_uint64)
+        tile = pinned((n + PACK_TILE - 1) // PACK_TILE, C.c_uint32)
+        ei, ee, en = pinned(esc_capacity, C.c_uint32), pinned(esc_capacity, C.c_uint32), pinned(esc_capacity, C.c_uint32)
+        self.batch = PackedBatch()
+        rc = L.mma_pack_hits(C.byref(wide), packed, run_key, tile, ei, ee, en, esc_capacity, C.byref(self.batch))
+        if rc != 0:
+            self.close()
+            raise MmaError(rc, "batch cannot be packed (too many escapes or chromosome ids): use the wide format")
+
+    @property
+    def h2d_bytes(self):
+        b = self.batch
+        return int(8 * b.n + 8 * b.n_runs + 4 * ((b.n + PACK_TILE - 1) // PACK_TILE) + 12 * b.n_escapes)
+
+    def close(self):
+        for p in self._ptrs:
+            lib().mma_free_pinned(p)
+        self._ptrs = []
 
     def __del__(self):
         try:
@@ -201,6 +263,10 @@ class Annotator:
     def submit_batch(self, sample, hit_batch):
         """Raw mma_submit_hits on a HitBatch struct (host pointers); asynchronous."""
         self._check(lib().mma_submit_hits(self._h, sample, C.byref(hit_batch)))
+
+    def submit_packed(self, sample, packed_batch):
+        """Raw mma_submit_hits_packed on a PackedBatch struct (host pointers); asynchronous."""
+        self._check(lib().mma_submit_hits_packed(self._h, sample, C.byref(packed_batch)))
 
     def submit_device(self, sample, hit_batch):
         """Raw mma_submit_hits_device on a HitBatch struct holding device pointers; asynchronous."""

@@ -212,3 +212,48 @@ def test_natural_grid_two_tiles_per_warp():
     assert hits.n > 148 * 5 * 8 * 128
     ref = oracle_run(et, feats, hits)
     check(device_run(et, feats, hits, max_batch=1 << 21), ref)
+
+
+@pytest.mark.parametrize("seed", range(5))
+def test_packed_transfer_format(seed):
+    """mma_pack_hits + mma_submit_hits_packed (8 B/hit + 8 B/run over PCIe, expanded on the device) must give exactly what
+    the wide arrays give: long reads and NH >= 255 (escapes), unknown chromosomes, empty-CIGAR intervals, cut batches."""
+    from mmannot_b200 import device
+    rng = np.random.default_rng(7000 + seed)
+    et = fuzz.make_elements(rng)
+    feats = fuzz.make_features(rng, et, n_feat=400)
+    hits = fuzz.make_hits(rng, feats, n_reads=30000, max_nh=(6 if seed < 3 else 300), messy=0.1, max_read=(60 if seed != 1 else 700))
+    strategy = ("default", "default", "ratio", "default", "unique")[seed]
+    ref = oracle_run(et, feats, hits, strategy=strategy)
+    batch = (1 << 20, 25000, 4099, 100000, 1 << 20)[seed]
+    a = device.Annotator(et, strategy=strategy, max_batch_hits=batch)
+    keep = []
+    try:
+        a.load_features(feats)
+        n_esc = 0
+        for lo in range(0, hits.n, batch):
+            part = hits.slice(lo, min(hits.n, lo + batch))
+            ph = device.PackedHits(part.start, part.end, part.meta, part.nh, part.read_key, esc_capacity=part.n)
+            n_esc += int(ph.batch.n_escapes)
+            assert ph.h2d_bytes < 24 * part.n
+            keep.append(ph)
+            a.submit_packed(0, ph.batch)
+        res = a.finish(0)
+    finally:
+        a.close()
+        for ph in keep:
+            ph.close()
+    res["values"] = device.values_by_mask(res["rows"])
+    check(res, ref, exact=(strategy != "ratio"))
+    if seed in (1, 3):
+        assert n_esc > 0
+
+
+def test_packed_refuses_what_does_not_fit():
+    from mmannot_b200 import device
+    n = 1000
+    start = np.arange(1, n + 1, dtype=np.uint32) * 1000
+    end = start + 5000  # every hit needs an escape
+    meta = np.zeros(n, np.uint32); nh = np.ones(n, np.uint32); key = np.arange(n, dtype=np.uint64)
+    with pytest.raises(device.MmaError):
+        device.PackedHits(start, end, meta, nh, key, esc_capacity=10)
