@@ -207,7 +207,7 @@ def run_reference_arm(args):
                 "cpu_baseline": {"value": v, "unit": "records/s", "cores": used, "kind": "reference", "sample": desc},
                 "e2e": {"value": v, "unit": "records/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0, "host_cores": cores}
-        print(json.dumps(line), flush=True)
+        emit(line)
     finally:
         shutil.rmtree(tmp, ignore_errors=True)
     return 0
@@ -270,14 +270,14 @@ def run_product_arm(args):
                 packed_batches.append(device.PackedHits(*[pinned.arrays[k][a:a + n] for k in ("start", "end", "meta", "nh", "read_key")]))
         stream = torch.cuda.ExternalStream(ann.stream_ptr(), device=dev)
 
-        def merge(res):
-            return multi.merge_tables(res, dev) if world > 1 else res
+        def merge(res):  # res = (stats int64[7], rows int64[n, 3]); one all-gather when there is more than one GPU
+            return multi.merge_arrays(res[0], res[1], dev) if world > 1 else res
 
         def step_device():
             ann.reset(0)
             for b in dev_batches:
                 ann.submit_device(0, b)
-            return merge(ann.finish(0))
+            return merge(ann.finish_arrays(0))
 
         def step_e2e():
             ann.reset(0)
@@ -287,13 +287,13 @@ def run_product_arm(args):
             else:
                 for b in host_batches:
                     ann.submit_batch(0, b)
-            return merge(ann.finish(0))
+            return merge(ann.finish_arrays(0))
 
         def step_e2e_wide():
             ann.reset(0)
             for b in host_batches:
                 ann.submit_batch(0, b)
-            return merge(ann.finish(0))
+            return merge(ann.finish_arrays(0))
 
         def barrier():
             torch.cuda.synchronize()
@@ -337,21 +337,22 @@ def run_product_arm(args):
         ann.timing_enable(False)
         _, wall_e2e, res_e2e = timed(step_e2e, args.steps, False)
         _, wall_e2e_wide, res_e2e_wide = timed(step_e2e_wide, max(1, args.steps // 2), False)
-        assert res_e2e_wide["rows"] == res_e2e["rows"] and res_e2e_wide["stats"] == res_e2e["stats"], "packed and wide host-buffer passes disagree"
+        same = lambda x, y: np.array_equal(x[0], y[0]) and np.array_equal(x[1], y[1])
+        assert same(res_e2e_wide, res_e2e), "packed and wide host-buffer passes disagree"
         clocks = sampler.stop() if rank == 0 else None
 
-        assert res_dev["rows"] == res_e2e["rows"] and res_dev["stats"] == res_e2e["stats"], "device-resident and host-buffer passes disagree"
-        # size-independent properties of the synthetic workload: every read is complete (NH records each), so the reads
-        # counted must be the reads generated, and every hit is either unassigned, ambiguous or assigned to one element
-        if w["strategy"] == "default":
-            assert res_dev["stats"]["n_hits"] == n_hits * (world if world > 1 else 1) or world > 1
-            if world == 1:
-                assert res_dev["stats"]["n_reads"] == reads, "reads counted %d != reads generated %d" % (res_dev["stats"]["n_reads"], reads)
+        assert same(res_dev, res_e2e), "device-resident and host-buffer passes disagree"
+        stats_dev = {k: int(v) for k, v in zip(multi.STAT_KEYS, res_dev[0])}
         total_hits = n_hits
         if world > 1:
             t = torch.tensor([n_hits], device=dev, dtype=torch.int64)
             dist.all_reduce(t)
             total_hits = int(t[0])
+        # size-independent properties of the synthetic workload: every read is complete (NH records each), so the reads
+        # counted must be the reads generated and the hits counted the hits submitted, over all ranks
+        if w["strategy"] == "default":
+            assert stats_dev["n_hits"] == total_hits, "hits counted %d != hits submitted %d" % (stats_dev["n_hits"], total_hits)
+            assert stats_dev["n_reads"] == reads * world, "reads counted %d != reads generated %d" % (stats_dev["n_reads"], reads * world)
         ms_per_step = ms_dev / args.steps
         value = total_hits / (ms_per_step * 1e-3)
         e2e_value = total_hits / (wall_e2e / args.steps * 1e-3)
@@ -400,8 +401,8 @@ def run_product_arm(args):
                     "gpu_launches": int(tm["launches"]),
                     "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks, "host_cores": cores,
                     "wall_ms_per_step_device_resident": wall_dev / args.steps,
-                    "stats": res_dev["stats"], "table_rows": len(res_dev["rows"])}
-            print(json.dumps(line), flush=True)
+                    "stats": stats_dev, "table_rows": int(len(res_dev[1]))}
+            emit(line)
         ann.close()
         for pb in packed_batches:
             pb.close()
@@ -414,7 +415,24 @@ def run_product_arm(args):
     return 0
 
 
+_REAL_STDOUT = None
+
+
+def emit(line):
+    """The one JSON line of the contract, on the process's real stdout."""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
+    # libraries (NCCL prints its version banner) must not write to stdout: everything but the JSON line goes to stderr
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)

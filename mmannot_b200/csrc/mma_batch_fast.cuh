@@ -150,6 +150,9 @@ k_batch_fast(const __grid_constant__ IndexView ix, const __grid_constant__ FastV
   u64 cKey = KEY_EMPTY;
   const u32 shift = fx.shift, gshift = fx.gshift;
 
+  u64 peekKey = KEY_EMPTY;  // lane 31: first key of the tile after the current one
+  if (STRAT == 0 && lane == 31u && t0 < t1 && (t0 + 1) * WT_HITS < h.n) peekKey = __ldg(&h.key[(t0 + 1) * WT_HITS]);
+
   for (u32 t = t0; t < t1; ++t) {
     const u32 base = t * WT_HITS + lane * 4;
     u32 rs[4], re[4], meta[4], nh[4];
@@ -194,8 +197,10 @@ k_batch_fast(const __grid_constant__ IndexView ix, const __grid_constant__ FastV
     u64 nextKey = KEY_EMPTY;
     u32 tileEndsRun = 1;  // lane 31: the record after the tile's last one starts another run (or the batch ends there)
     if (STRAT == 0) {
+      // the first key of the next tile was requested one tile ago (peekKey); request the one after it now
       const u32 nextTile = (t + 1) * WT_HITS;
-      if (lane == 31u && nextTile < h.n) tileEndsRun = (normKey(__ldg(&h.key[nextTile])) != key[3]) ? 1u : 0u;
+      if (lane == 31u && nextTile < h.n) tileEndsRun = (normKey(peekKey) != key[3]) ? 1u : 0u;
+      if (lane == 31u && nextTile + WT_HITS < h.n) peekKey = __ldg(&h.key[nextTile + WT_HITS]);
       u64 prev = __shfl_up_sync(FULL, key[3], 1);
       if (lane == 0) {
         if (t != t0) prev = cKey;
@@ -356,14 +361,18 @@ k_batch_fast(const __grid_constant__ IndexView ix, const __grid_constant__ FastV
       const u32 nextHead0 = __shfl_down_sync(FULL, hbits & 1u, 1);
       // bit j: the next record starts another run, i.e. this record ends its run (the tile's last record: from the peek)
       const u32 lastBits = ((hbits >> 1) | ((lane < 31u ? nextHead0 : tileEndsRun) << 3)) & validBits;
+      // a run that starts before this lane's hits: union so far, first record, and whether this warp owns it at all
+      const u32 inTot = before ? X : (cTot | X);
+      const u32 inStart = before ? sPrev : cStart;
+      const bool inMine = before || cValid;  // else the run starts in another warp's chunk: that warp finishes it
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const bool last = (lastBits >> j) & 1u;
         const u32 hbLe = hbits & ((2u << j) - 1u);
         // union of the run's element sets and its first record, wherever the run starts
-        const u32 tot = hbLe ? pre[j] : before ? (X | pre[j]) : (cTot | X | pre[j]);
-        const u32 runStart = hbLe ? base + (31 - __clz(hbLe)) : before ? sPrev : cStart;
-        const bool mine = hbLe || before || cValid;  // else the run starts in another warp's chunk: that warp finishes it
+        const u32 tot = hbLe ? pre[j] : (inTot | pre[j]);
+        const u32 runStart = hbLe ? base + (31 - __clz(hbLe)) : inStart;
+        const bool mine = hbLe || inMine;
         const bool flagged = (tot & 0x80000000u) != 0;
         // a run of reads that are their own group (NH <= 1 throughout) has nothing to close
         const bool irregular = flagged || (nh[j] > 1 && nh[j] != base + j + 1 - runStart);

@@ -1,7 +1,8 @@
 """Multi-GPU side of the hot path: one process per GPU, reads sharded by read name, the annotation index
 replicated, and ONE exchange step at the end -- the integer count tables and Counter's counters
 (mmannot.cpp:1663) summed over the ranks.  The reference merges per-file tables in one process
-(TableCount::addCounter, mmannot.cpp:1861-1876); here the same sum runs as an allreduce over NCCL.
+(TableCount::addCounter, mmannot.cpp:1861-1876); here the same sum runs as one NCCL all-gather of the
+compact (key, count) rows over NVLink, every rank adding up the few thousand rows it receives.
 
 There is no data-path collective: a read name (all its NH records, both mates) lives on exactly one rank,
 so the per-read resolution never crosses GPUs.  `-y random` draws from one global rand() stream in file
@@ -27,40 +28,62 @@ def read_range(rank, world, n_reads):
     return first, min(per, n_reads - first)
 
 
-def merge_tables(res, device, group=None):
-    """Sum of the per-rank results {"stats": {...}, "rows": {(mask, nh): count}} over the process group.
+def merge_arrays(stats, rows, device, group=None, capacity=4096):
+    """Sum of the per-rank results over the process group with ONE collective: an all-gather of the compact rows.
 
-    1. union of the combination keys: an allgather of the (padded) local key lists  -- a few KB
-    2. one allreduce(sum, int64) over the dense [union keys + 7 counters] vector
-    Every rank returns the merged result."""
+    stats int64[7], rows int64[n, 3] = (mask, nh, count) (Annotator.finish_arrays).  Every rank contributes a fixed-size
+    vector [n, 7 counters, capacity x (mask, nh, count)] (a few tens of KB), receives everybody's, and forms the union of
+    the keys and the sums itself -- the same sum TableCount::addCounter forms column by column (mmannot.cpp:1861-1876),
+    without a key-agreement round before it.  If some rank holds more rows than `capacity` the exchange is repeated once
+    with the capacity that fits.  Returns (stats, rows) merged, rows sorted by (mask, nh), identical on every rank."""
     import torch
     import torch.distributed as dist
 
     world = dist.get_world_size(group)
+    n = int(rows.shape[0])
+    while True:
+        payload = np.zeros(8 + 3 * capacity, np.int64)
+        payload[0] = n
+        payload[1:8] = stats
+        if n <= capacity:
+            payload[8:8 + 3 * n] = rows.reshape(-1)
+        mine = torch.from_numpy(payload).to(device, non_blocking=True)
+        out = torch.empty(world * payload.size, dtype=torch.int64, device=device)
+        if device.type == "cuda":
+            dist.all_gather_into_tensor(out, mine, group=group)
+        else:  # gloo (CPU tests)
+            parts = [torch.empty_like(mine) for _ in range(world)]
+            dist.all_gather(parts, mine, group=group)
+            out = torch.cat(parts)
+        got = out.cpu().numpy().reshape(world, -1)
+        n_max = int(got[:, 0].max())
+        if n_max <= capacity:
+            break
+        capacity = 1 << int(n_max - 1).bit_length()
+    merged_stats = got[:, 1:8].sum(axis=0)
+    parts = [got[r, 8:8 + 3 * int(got[r, 0])].reshape(-1, 3) for r in range(world)]
+    allrows = np.concatenate(parts) if parts else np.empty((0, 3), np.int64)
+    if len(allrows):
+        order = np.lexsort((allrows[:, 1], allrows[:, 0].view(np.uint64)))
+        allrows = allrows[order]
+        new_key = np.ones(len(allrows), bool)
+        new_key[1:] = (allrows[1:, 0] != allrows[:-1, 0]) | (allrows[1:, 1] != allrows[:-1, 1])
+        starts = np.nonzero(new_key)[0]
+        sums = np.add.reduceat(allrows[:, 2], starts)
+        merged = np.stack([allrows[starts, 0], allrows[starts, 1], sums], axis=1)
+        merged = merged[merged[:, 2] != 0]
+    else:
+        merged = allrows
+    return merged_stats, merged
+
+
+def merge_tables(res, device, group=None):
+    """Dictionary front-end of merge_arrays: {"stats": {...}, "rows": {(mask, nh): count}} summed over the process group;
+    every rank returns the merged result."""
     keys = sorted(res["rows"].keys())
-    local = np.array([[m, nh] for m, nh in keys], dtype=np.uint64).reshape(-1, 2)
-    n_local = torch.tensor([len(keys)], dtype=torch.int64, device=device)
-    sizes = [torch.zeros_like(n_local) for _ in range(world)]
-    dist.all_gather(sizes, n_local, group=group)
-    n_max = max(1, max(int(s[0]) for s in sizes))
-    padded = np.zeros((n_max, 2), np.uint64)
-    padded[:len(keys)] = local
-    mine = torch.from_numpy(padded.view(np.int64)).to(device)
-    gathered = [torch.zeros_like(mine) for _ in range(world)]
-    dist.all_gather(gathered, mine, group=group)
-    union = set()
-    for r in range(world):
-        g = gathered[r].cpu().numpy().view(np.uint64)[:int(sizes[r][0])]
-        union.update((int(a), int(b)) for a, b in g)
-    union = sorted(union)
-    dense = np.zeros(len(union) + len(STAT_KEYS), np.int64)
-    for i, k in enumerate(union):
-        dense[i] = res["rows"].get(k, 0)
-    for j, s in enumerate(STAT_KEYS):
-        dense[len(union) + j] = res["stats"][s]
-    t = torch.from_numpy(dense).to(device)
-    dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
-    out = t.cpu().numpy()
-    rows = {k: int(out[i]) for i, k in enumerate(union) if int(out[i]) != 0}
-    stats = {s: int(out[len(union) + j]) for j, s in enumerate(STAT_KEYS)}
-    return {"stats": stats, "rows": rows}
+    rows = np.array([[m, nh, res["rows"][(m, nh)]] for m, nh in keys], dtype=np.uint64).reshape(-1, 3).view(np.int64)
+    stats = np.array([res["stats"][s] for s in STAT_KEYS], dtype=np.int64)
+    mstats, mrows = merge_arrays(stats, rows, device, group=group)
+    u = mrows.view(np.uint64)
+    return {"stats": {s: int(mstats[j]) for j, s in enumerate(STAT_KEYS)},
+            "rows": {(int(u[i, 0]), int(u[i, 1])): int(u[i, 2]) for i in range(len(u))}}
