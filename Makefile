@@ -44,11 +44,11 @@ oracle/_build/liboracle.so: oracle/oracle.c oracle/oracle.h
 ref:
 	bash oracle/build_ref.sh
 
-VARIANT_BLOCKS ?= 3 5
-# tuning builds (not shipped): make variants; MMANNOT_B200_LIB=mmannot_b200/lib/variants/f3.so python bench.py ...
+# tuning builds (not shipped): make variants V="t128b6:-DMMA_FAST_THREADS=128,-DMMA_FAST_BLOCKS_PER_SM=6 ..." ;
+# MMANNOT_B200_LIB=mmannot_b200/lib/variants/t128b6.so python bench.py ...
 variants: $(CU_SRC) $(CU_HDR)
 	@mkdir -p mmannot_b200/lib/variants
-	for b in $(VARIANT_BLOCKS); do $(NVCC) $(NVFLAGS) -DMMA_FAST_BLOCKS_PER_SM=$$b $(VARIANT_DEFS) -shared -o mmannot_b200/lib/variants/f$${b}$(VARIANT_TAG).so mmannot_b200/csrc/mma_api.cu & done; wait
+	for v in $(V); do name=$${v%%:*}; defs=$$(echo $${v#*:} | tr ',' ' '); $(NVCC) $(NVFLAGS) $$defs -shared -o mmannot_b200/lib/variants/$$name.so mmannot_b200/csrc/mma_api.cu & done; wait
 
 clean:
 	rm -rf mmannot_b200/lib mmannot_b200/bin oracle/_build

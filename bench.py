@@ -277,7 +277,7 @@ def run_product_arm(args):
             ann.reset(0)
             for b in dev_batches:
                 ann.submit_device(0, b)
-            return merge(ann.finish_arrays(0))
+            return merge(ann.finish_arrays(0, sort=False))
 
         def step_e2e():
             ann.reset(0)
@@ -287,13 +287,13 @@ def run_product_arm(args):
             else:
                 for b in host_batches:
                     ann.submit_batch(0, b)
-            return merge(ann.finish_arrays(0))
+            return merge(ann.finish_arrays(0, sort=False))
 
         def step_e2e_wide():
             ann.reset(0)
             for b in host_batches:
                 ann.submit_batch(0, b)
-            return merge(ann.finish_arrays(0))
+            return merge(ann.finish_arrays(0, sort=False))
 
         def barrier():
             torch.cuda.synchronize()
@@ -337,7 +337,7 @@ def run_product_arm(args):
         ann.timing_enable(False)
         _, wall_e2e, res_e2e = timed(step_e2e, args.steps, False)
         _, wall_e2e_wide, res_e2e_wide = timed(step_e2e_wide, max(1, args.steps // 2), False)
-        same = lambda x, y: np.array_equal(x[0], y[0]) and np.array_equal(x[1], y[1])
+        same = lambda x, y: np.array_equal(x[0], y[0]) and np.array_equal(device.sort_rows(x[1]), device.sort_rows(y[1]))
         assert same(res_e2e_wide, res_e2e), "packed and wide host-buffer passes disagree"
         clocks = sampler.stop() if rank == 0 else None
 

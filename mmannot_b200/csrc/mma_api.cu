@@ -104,7 +104,8 @@ struct mma_ctx {
   u32 maxGrid = 0;           // MMANNOT_B200_MAX_GRID=n: cap on k_batch blocks, so that small test inputs still give every warp a multi-tile chunk (testing only)
   bool legacyBatch = false;  // MMANNOT_B200_LEGACY_BATCH=1: A/B runs of the general k_batch against k_batch_fast (tuning only)
   std::vector<uint32_t> intervalIds;  // result of the last mma_annotate_intervals
-  u64 *hostTable = nullptr;  // pinned, 2 x tableCap: keys then values of the sample being read back
+  u64 *hostTable = nullptr;  // pinned: [TableDump | rows] of the sample being read back
+  DevBuf dumpBuf;            // device side of the same
 
   int fail(int code, const std::string &msg) {
     error = msg;
@@ -251,10 +252,10 @@ void launchBatchKernels(mma_ctx *ctx, Sample &s, const HitView &h) {
   bool launched = false;
   if constexpr (useFast) if (!ctx->legacyBatch) {
     launched = true;
-    u32 grid = std::max<u32>(1u, std::min<u32>((nWT + BATCH_WARPS - 1) / BATCH_WARPS, (u32)ctx->nSM * MMA_FAST_BLOCKS_PER_SM));
+    u32 grid = std::max<u32>(1u, std::min<u32>((nWT + FAST_WARPS - 1) / FAST_WARPS, (u32)ctx->nSM * MMA_FAST_BLOCKS_PER_SM));
     if (ctx->maxGrid) grid = std::min(grid, ctx->maxGrid);
     mma_ctx::Timed t(ctx, TC_BATCH);
-    k_batch_fast<MODE, STRAT><<<grid, BATCH_THREADS, 0, ctx->sc>>>(ctx->index, ctx->fast, h, r, table, s.ctl, slow, open);
+    k_batch_fast<MODE, STRAT><<<grid, FAST_THREADS, 0, ctx->sc>>>(ctx->index, ctx->fast, h, r, table, s.ctl, slow, open);
   }
   if (!launched) {
     const u32 perSM = (sizeof(MaskT) == 4) ? MMA_BLOCKS_PER_SM : 2;
@@ -415,6 +416,7 @@ void mma_destroy(mma_ctx *ctx) {
   ctx->dElemLine.release(); ctx->dElemStrand.release(); ctx->dElemVic.release();
   ctx->collectTiming();
   if (ctx->hostTable) cudaFreeHost(ctx->hostTable);
+  ctx->dumpBuf.release();
   for (cudaEvent_t e : ctx->eventPool) cudaEventDestroy(e);
   if (ctx->sc) cudaStreamDestroy(ctx->sc);
   if (ctx->sh) cudaStreamDestroy(ctx->sh);
@@ -633,7 +635,7 @@ int mma_load_features(mma_ctx *ctx, const mma_features *f) {
 
 uint64_t mma_index_bytes(const mma_ctx *ctx) { return ctx ? ctx->indexBytes : 0; }
 uint64_t mma_index_segments(const mma_ctx *ctx) { return ctx ? ctx->nSegments : 0; }
-uint64_t mma_readback_bytes(const mma_ctx *ctx) { return ctx ? (uint64_t)ctx->tableCap * 16 + sizeof(SampleCtl) : 0; }
+uint64_t mma_readback_bytes(const mma_ctx *ctx) { return ctx ? (uint64_t)std::min<u32>(ctx->tableCap, 8192u) * 16 + sizeof(TableDump) : 0; }
 const char *mma_dominant_kernel(void) { return "k_batch_fast"; }
 
 static int submitCommon(mma_ctx *ctx, uint32_t sample, const mma_hit_batch *b, bool onDevice) {
@@ -896,8 +898,7 @@ int mma_reset_sample(mma_ctx *ctx, uint32_t sample) {
     k_fill_u32<<<gridFor(s.openCap, 256), 256, 0, ctx->sc>>>(s.openSeq.as<u32>(), 0xFFFFFFFFu, s.openCap);
     ctx->launches += 2;
   }
-  s.openMaybeUsed = false;
-  CK(cudaStreamSynchronize(ctx->sc));
+  s.openMaybeUsed = false;  // (stream-ordered: the next batch kernels of this sample run after these fills)
   s.cumHits = 0; s.knownCount = 0; s.knownCum = 0; s.seq = 0; s.touched = false;
   for (int i = 0; i < 4; ++i) s.ringUsed[i] = false;
   return MMA_OK;
@@ -995,33 +996,53 @@ int mma_finish_sample(mma_ctx *ctx, uint32_t sample, mma_sample_result *out) {
     k_flush_carry<<<1, 1, 0, ctx->sc>>>(s.ctl, slowView(s));
     ctx->launches++;
   }
-  CK(cudaStreamSynchronize(ctx->sc));
-  SampleCtl hc;
-  CK(cudaMemcpy(&hc, s.ctl, sizeof(hc), cudaMemcpyDeviceToHost));
+  // compact the table on the device and bring back [control block | row count | rows] with one copy and one
+  // synchronisation for the usual few thousand rows (a second copy only when the table holds more than the first chunk)
+  const size_t headBytes = sizeof(TableDump);
+  const u32 firstRows = std::min<u32>(ctx->tableCap, 8192u);
+  if (!ctx->hostTable) CK(cudaHostAlloc(&ctx->hostTable, headBytes + (size_t)ctx->tableCap * 16, cudaHostAllocDefault));
+  CK(ctx->dumpBuf.ensure(headBytes + (size_t)ctx->tableCap * 16));
+  const TableDump *hHead = reinterpret_cast<const TableDump *>(ctx->hostTable);
+  auto dump = [&]() -> int {
+    TableDump *dHead = ctx->dumpBuf.as<TableDump>();
+    ulonglong2 *dRows = reinterpret_cast<ulonglong2 *>(ctx->dumpBuf.as<char>() + headBytes);
+    CK(cudaMemsetAsync(&dHead->nRows, 0, sizeof(u64), ctx->sc));
+    k_table_compact<<<gridFor(ctx->tableCap, 256), 256, 0, ctx->sc>>>(tableView(s.tableKeys, s.tableVals, ctx->tableCap, s.ctl), s.ctl, dHead, dRows, ctx->tableCap);
+    ctx->launches++;
+    CK(cudaMemcpyAsync(ctx->hostTable, ctx->dumpBuf.p, headBytes + (size_t)firstRows * 16, cudaMemcpyDeviceToHost, ctx->sc));
+    CK(cudaStreamSynchronize(ctx->sc));
+    if (hHead->nRows > firstRows) {
+      const size_t off = headBytes + (size_t)firstRows * 16;
+      CK(cudaMemcpyAsync(reinterpret_cast<char *>(ctx->hostTable) + off, ctx->dumpBuf.as<char>() + off, (size_t)(hHead->nRows - firstRows) * 16,
+                         cudaMemcpyDeviceToHost, ctx->sc));
+      CK(cudaStreamSynchronize(ctx->sc));
+    }
+    return MMA_OK;
+  };
+  int rc = dump();
+  if (rc) return rc;
+  SampleCtl hc = hHead->ctl;
   if (hc.overflow) return ctx->fail(MMA_ERR_CAPACITY, "a device table overflowed (combination table, deferred list or NH range under -y ratio)");
   s.openMaybeUsed = hc.openCount != 0;
   if (hc.slowCount > 0) {
-    int rc = finishDeferred(ctx, s, hc.slowCount);
-    if (rc) return rc;
+    if ((rc = finishDeferred(ctx, s, hc.slowCount))) return rc;
     // the deferred records are consumed: a later finish must not count them twice
     CK(cudaMemsetAsync(&s.ctl->slowCount, 0, sizeof(u32), ctx->sc));
-    CK(cudaStreamSynchronize(ctx->sc));
-    CK(cudaMemcpy(&hc, s.ctl, sizeof(hc), cudaMemcpyDeviceToHost));
+    if ((rc = dump())) return rc;
+    hc = hHead->ctl;
     if (hc.overflow) return ctx->fail(MMA_ERR_CAPACITY, "the combination table overflowed");
     s.knownCount = 0; s.knownCum = s.cumHits;
   }
-  if (!ctx->hostTable) CK(cudaHostAlloc(&ctx->hostTable, (size_t)ctx->tableCap * 16, cudaHostAllocDefault));
-  const u64 *keys = ctx->hostTable, *vals = ctx->hostTable + ctx->tableCap;
-  CK(cudaMemcpyAsync(ctx->hostTable, s.tableKeys.p, (size_t)ctx->tableCap * 8, cudaMemcpyDeviceToHost, ctx->sc));
-  CK(cudaMemcpyAsync(ctx->hostTable + ctx->tableCap, s.tableVals.p, (size_t)ctx->tableCap * 8, cudaMemcpyDeviceToHost, ctx->sc));
-  CK(cudaStreamSynchronize(ctx->sc));
+  const u64 nRows = hHead->nRows;
   const bool ratio = ctx->rules.strategy == MMA_STRATEGY_RATIO;
   const u64 lowMask = (1ull << NH_SHIFT) - 1;
-  for (u32 i = 0; i < ctx->tableCap; ++i) {
-    if (!keys[i] || !vals[i]) continue;  // a count taken back by k_batch_close can leave an empty row
-    s.rowMask.push_back(ratio ? (keys[i] & lowMask) : keys[i]);
-    s.rowNh.push_back(ratio ? (uint32_t)(keys[i] >> NH_SHIFT) : 0u);
-    s.rowCount.push_back(vals[i]);
+  const u64 *hRows = reinterpret_cast<const u64 *>(reinterpret_cast<const char *>(ctx->hostTable) + headBytes);
+  s.rowMask.reserve(nRows); s.rowNh.reserve(nRows); s.rowCount.reserve(nRows);
+  for (u64 i = 0; i < nRows; ++i) {
+    const u64 key = hRows[2 * i], val = hRows[2 * i + 1];
+    s.rowMask.push_back(ratio ? (key & lowMask) : key);
+    s.rowNh.push_back(ratio ? (uint32_t)(key >> NH_SHIFT) : 0u);
+    s.rowCount.push_back(val);
   }
   out->stats.n_hits = hc.stats[ST_HITS];
   out->stats.n_reads = hc.stats[ST_READS];

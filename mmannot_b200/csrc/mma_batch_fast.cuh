@@ -20,9 +20,14 @@
 
 namespace mma {
 
+#ifndef MMA_FAST_THREADS
+#define MMA_FAST_THREADS 256
+#endif
 #ifndef MMA_FAST_BLOCKS_PER_SM
 #define MMA_FAST_BLOCKS_PER_SM 3
 #endif
+#define FAST_THREADS MMA_FAST_THREADS
+#define FAST_WARPS (FAST_THREADS / 32)
 
 #ifdef MMA_DIAG
 // tuning builds only: why hits leave the table fast path.  0 degenerate, 3 start beyond the looked-up segment (coarse granules),
@@ -88,11 +93,11 @@ template <int SLOTS> struct BlockTableOf<true, SLOTS> { typedef BlockTable32<SLO
 template <bool HIST, int SLOTS>
 struct FastSmem {
   typename BlockTableOf<HIST, SLOTS>::type bt;
-  unsigned short hist[HIST ? HIST_ROWS : 1][BATCH_THREADS];
-  u32 walkQ[4][BATCH_THREADS];
+  unsigned short hist[HIST ? HIST_ROWS : 1][FAST_THREADS];
+  u32 walkQ[4][FAST_THREADS];
   uint2 chrInfo[CHR_SMEM];
-  u32 slowRes[BATCH_WARPS][WT_HITS];
-  unsigned char slowQ[BATCH_WARPS][WT_HITS];
+  u32 slowRes[FAST_WARPS][WT_HITS];
+  unsigned char slowQ[FAST_WARPS][WT_HITS];
   u32 stat[ST_N];
 };
 
@@ -114,7 +119,7 @@ struct FastCount {  // one read counted for an element set, from divergent code 
 };
 
 template <int MODE, int STRAT>
-__global__ void __launch_bounds__(BATCH_THREADS, MMA_FAST_BLOCKS_PER_SM)
+__global__ void __launch_bounds__(FAST_THREADS, MMA_FAST_BLOCKS_PER_SM)
 k_batch_fast(const __grid_constant__ IndexView ix, const __grid_constant__ FastView fx, const __grid_constant__ HitView h, const __grid_constant__ Rules r,
              const __grid_constant__ TableView table, SampleCtl *ctl, const __grid_constant__ SlowView slow, const __grid_constant__ KeySetView open) {
   constexpr bool HIST = (STRAT != 3);
@@ -129,7 +134,7 @@ k_batch_fast(const __grid_constant__ IndexView ix, const __grid_constant__ FastV
   }
   if (tid < ST_N) sm.stat[tid] = 0;
   const bool chrInSmem = fx.nChr <= CHR_SMEM;
-  if (chrInSmem) for (u32 c = tid; c < fx.nChr; c += BATCH_THREADS) sm.chrInfo[c] = fx.chrInfo[c];
+  if (chrInSmem) for (u32 c = tid; c < fx.nChr; c += FAST_THREADS) sm.chrInfo[c] = fx.chrInfo[c];
   __syncthreads();
   const Annotator<MODE, true> annot{ix, fx, r.overlap};
   const u32 seq = ctl->batchSeq;
@@ -141,9 +146,9 @@ k_batch_fast(const __grid_constant__ IndexView ix, const __grid_constant__ FastV
   RunWalker<MODE, true, FastCount<HIST, SLOTS>> w{h, r, annot, ctl, slow, open, count, seq, 0u, 0u};
 
   const u32 nWT = (h.n + WT_HITS - 1) / WT_HITS;
-  const u32 nWarps = gridDim.x * BATCH_WARPS;
+  const u32 nWarps = gridDim.x * FAST_WARPS;
   const u32 per = (nWT + nWarps - 1) / nWarps;
-  const u32 t0 = min(nWT, (blockIdx.x * BATCH_WARPS + warp) * per), t1 = min(nWT, t0 + per);
+  const u32 t0 = min(nWT, (blockIdx.x * FAST_WARPS + warp) * per), t1 = min(nWT, t0 + per);
 
   bool cValid = false, cCont = false;  // cCont: the run open at the end of the tile continues in the next tile
   u32 cStart = 0, cTot = 0, cNh = 0;
@@ -257,7 +262,13 @@ k_batch_fast(const __grid_constant__ IndexView ix, const __grid_constant__ FastV
       const bool fwd = (meta[j] >> 31) != 0;
       const u32 i = look ? en[j].y + __popc(en[j].x & pm[j]) : 0u;
       uint4 tt, xx;
+#ifdef MMA_HOTCOLD
+      tt = __ldg(&fx.seg[2u * i]);
+      xx = make_uint4(ANS_GENERAL, ANS_GENERAL, 0u, 0u);
+      if (look && (re[j] > tt.x || ((fwd ? tt.y : tt.z) & ANS_VICPAIR))) xx = __ldg(&fx.seg[2u * i + 1u]);
+#else
       ldRecord(&fx.seg[2u * i], tt, xx);
+#endif
       tEnd[j] = tt.x; tAns[j] = fwd ? tt.y : tt.z; tEnd2[j] = tt.w;
       xAns[j] = fwd ? xx.x : xx.y; tie[j] = fwd ? xx.z : xx.w;
     }
@@ -451,10 +462,10 @@ k_batch_fast(const __grid_constant__ IndexView ix, const __grid_constant__ FastV
   __syncthreads();
   sm.bt.flush(table);
   if (HIST) {
-    for (u32 e = warp; e < HIST_ROWS; e += BATCH_WARPS) {
+    for (u32 e = warp; e < HIST_ROWS; e += FAST_WARPS) {
       u32 v = 0;
 #pragma unroll
-      for (int q = 0; q < BATCH_WARPS; ++q) v += sm.hist[e][lane + 32 * q];
+      for (int q = 0; q < FAST_WARPS; ++q) v += sm.hist[e][lane + 32 * q];
       v = __reduce_add_sync(FULL, v);
       if (lane == 0 && v) tableAdd(table, 1ull << e, v);
     }

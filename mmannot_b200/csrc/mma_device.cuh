@@ -1129,6 +1129,22 @@ __global__ void k_fill_u32(u32 *dst, u32 v, u64 n) {
   if (p < n) dst[p] = v;
 }
 
+// end of sample: the non-empty rows of the combination table, compacted (any order), with the control block in front:
+// one small device->host copy instead of the whole table.  out = [SampleCtl | row count | rows {key, count}]
+struct TableDump {
+  SampleCtl ctl;
+  u64 nRows;
+};
+__global__ void k_table_compact(TableView t, const SampleCtl *ctl, TableDump *head, ulonglong2 *rows, u32 cap) {
+  const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i == 0) head->ctl = *ctl;
+  if (i > t.capMask) return;
+  const u64 k = t.keys[i], v = t.vals[i];
+  if (k == 0 || v == 0) return;  // a count taken back by k_batch_close can leave an empty row
+  const u32 at = (u32)atomicAdd(&head->nRows, 1ull);
+  if (at < cap) rows[at] = make_ulonglong2(k, v);
+}
+
 // dense read-out for the cross-GPU sum: out[i] = count of key ckey[i]
 __global__ void k_dense_counts(TableView t, const u64 *__restrict__ ckey, u64 n, u64 *out) {
   const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;

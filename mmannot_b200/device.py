@@ -285,9 +285,10 @@ class Annotator:
     def reset(self, sample):
         self._check(lib().mma_reset_sample(self._h, sample))
 
-    def finish_arrays(self, sample=0):
-        """-> (stats int64[7] in SampleStats order, rows int64[n, 3] = (mask, nh, count) sorted by (mask, nh)): the result
-        of mma_finish_sample as arrays, for callers that merge or compare tables without building dictionaries."""
+    def finish_arrays(self, sample=0, sort=True):
+        """-> (stats int64[7] in SampleStats order, rows int64[n, 3] = (mask, nh, count), sorted by (mask, nh) unless
+        sort=False): the result of mma_finish_sample as arrays, for callers that merge or compare tables without building
+        dictionaries."""
         r = SampleResult()
         self._check(lib().mma_finish_sample(self._h, sample, C.byref(r)))
         stats = np.array([int(getattr(r.stats, k)) for k, _ in SampleStats._fields_], dtype=np.int64)
@@ -297,7 +298,8 @@ class Annotator:
             rows[:, 0] = np.ctypeslib.as_array(r.row_mask, shape=(n,)).view(np.int64)
             rows[:, 1] = np.ctypeslib.as_array(r.row_nh, shape=(n,))
             rows[:, 2] = np.ctypeslib.as_array(r.row_count, shape=(n,)).view(np.int64)
-            rows = rows[np.lexsort((rows[:, 1], rows[:, 0].view(np.uint64)))]
+            if sort:
+                rows = sort_rows(rows)
         return stats, rows
 
     def finish(self, sample=0):
@@ -358,6 +360,11 @@ class Annotator:
             self.close()
         except Exception:
             pass
+
+
+def sort_rows(rows):
+    """rows int64[n, 3] = (mask, nh, count) ordered by (mask as unsigned, nh)."""
+    return rows[np.lexsort((rows[:, 1], rows[:, 0].view(np.uint64)))] if len(rows) else rows
 
 
 def values_by_mask(rows):
