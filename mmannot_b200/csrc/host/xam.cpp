@@ -1,7 +1,9 @@
 #include "xam.hpp"
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
+#include <thread>
 
 namespace mmb {
 
@@ -83,12 +85,19 @@ bool XamReader::open(std::string &err) {
     sam_.open(fileName_.c_str());
     return true;
   }
-  gz_ = gzopen(fileName_.c_str(), "rb");
-  if (!gz_) {
-    err = "Cannot open file '" + fileName_ + "'.";
-    return false;
+  {
+    unsigned threads = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+    if (const char *e = std::getenv("MMANNOT_B200_DECODE_THREADS")) threads = static_cast<unsigned>(std::max(1, std::atoi(e)));
+    useBgzf_ = bgzf_.open(fileName_, threads);
   }
-  gzbuffer(gz_, 1 << 20);
+  if (!useBgzf_) {  // plain gzip (or uncompressed): the reference's own route, gzread
+    gz_ = gzopen(fileName_.c_str(), "rb");
+    if (!gz_) {
+      err = "Cannot open file '" + fileName_ + "'.";
+      return false;
+    }
+    gzbuffer(gz_, 1 << 20);
+  }
   raw_.resize(8 << 20);
   if (!fillRaw(12) || std::memcmp(&raw_[rawPos_], "BAM\1", 4) != 0) {
     err = "Problem with file '" + fileName_ + "': file does not look like a BAM file (missing magic string).";
@@ -116,6 +125,11 @@ bool XamReader::open(std::string &err) {
   return true;
 }
 
+long XamReader::readRaw(unsigned char *dst, size_t cap) {
+  if (useBgzf_) return bgzf_.read(dst, cap);
+  return gzread(gz_, dst, static_cast<unsigned>(cap));
+}
+
 bool XamReader::fillRaw(size_t need) {
   if (rawEnd_ - rawPos_ >= need) return true;
   if (rawPos_ > 0) {
@@ -125,13 +139,13 @@ bool XamReader::fillRaw(size_t need) {
   }
   if (raw_.size() < need) raw_.resize(std::max(need, raw_.size() * 2));
   while (rawEnd_ < need) {
-    int got = gzread(gz_, &raw_[rawEnd_], static_cast<unsigned>(std::min<size_t>(raw_.size() - rawEnd_, 1u << 30)));
+    long got = readRaw(&raw_[rawEnd_], std::min<size_t>(raw_.size() - rawEnd_, 1u << 30));
     if (got <= 0) return false;
     rawEnd_ += static_cast<size_t>(got);
   }
   // opportunistically top the buffer up so that most records need no further call
   if (rawEnd_ < raw_.size()) {
-    int got = gzread(gz_, &raw_[rawEnd_], static_cast<unsigned>(std::min<size_t>(raw_.size() - rawEnd_, 1u << 30)));
+    long got = readRaw(&raw_[rawEnd_], std::min<size_t>(raw_.size() - rawEnd_, 1u << 30));
     if (got > 0) rawEnd_ += static_cast<size_t>(got);
   }
   return true;
@@ -231,11 +245,12 @@ bool XamReader::decodeBamRecord() {
   uint32_t lSeq = le32(p + 16);
   const unsigned char *q = p + 32;
   if (q + lReadName + 4ull * nCigar + (lSeq + 1ull) / 2 + lSeq > recEnd) return true;  // malformed, skip
-  std::string name(reinterpret_cast<const char *>(q), lReadName);
-  name = name.c_str();
+  // (buffers reused from record to record: no allocation on the hot path)
+  std::string &name = nameBuf_;
+  name.assign(reinterpret_cast<const char *>(q), strnlen(reinterpret_cast<const char *>(q), lReadName));  // up to the first NUL (mm:1545)
   q += lReadName;
-  std::vector<std::pair<char, int> > cigar;
-  cigar.reserve(nCigar);
+  std::vector<std::pair<char, int> > &cigar = cigarBuf_;
+  cigar.clear();
   for (uint32_t i = 0; i < nCigar; ++i, q += 4) {
     uint32_t v = le32(q);
     uint32_t op = v & 15;
@@ -250,7 +265,8 @@ bool XamReader::decodeBamRecord() {
   }
   uint32_t nHits = 1;
   alts_.clear();
-  std::string lastZ;
+  std::string &lastZ = lastZBuf_;
+  lastZ.clear();
   while (q + 3 <= recEnd) {  // aux fields (mm:1563-1648); unsigned integer types only feed NH / NM (mm:1596-1618)
     char t0 = static_cast<char>(q[0]), t1 = static_cast<char>(q[1]), ty = static_cast<char>(q[2]);
     q += 3;

@@ -13,6 +13,7 @@
 #include <vector>
 
 #include "annotation.hpp"
+#include "bgzf.hpp"
 
 namespace mmb {
 
@@ -69,6 +70,9 @@ class XamReader {
   std::vector<std::string> unknownChr_;
   bool bam_ = false, over_ = false;
   gzFile gz_ = nullptr;
+  BgzfSource bgzf_;        // multi-threaded inflate when the file is BGZF (every BAM is); gz_ otherwise
+  bool useBgzf_ = false;
+  long readRaw(unsigned char *dst, size_t cap);
   std::ifstream sam_;
   std::vector<unsigned char> raw_;
   size_t rawPos_ = 0, rawEnd_ = 0;
@@ -76,6 +80,8 @@ class XamReader {
   std::vector<std::string> bamChrName_;
   uint32_t nMismatches_ = 0;          // persists across records like XamRecord::nMismatches (mm:596)
   std::vector<Alt> alts_;
+  std::string nameBuf_, lastZBuf_;                  // per-record scratch, reused
+  std::vector<std::pair<char, int> > cigarBuf_;
   std::vector<Hit> pending_;          // decoded but not yet handed out
   std::vector<std::string> pendingNames_;
   size_t pendingPos_ = 0;
