@@ -161,6 +161,7 @@ typedef struct mma_timing {
   uint64_t fast_miss; /* hits the segment table could not answer (since the sample was reset) */
 } mma_timing;
 
+int mma_device_count(void); /* number of CUDA devices visible to the process (0 when there is none) */
 int mma_create(mma_ctx **out, const mma_params *params);
 void mma_destroy(mma_ctx *ctx);
 const char *mma_last_error(const mma_ctx *ctx); /* ctx may be NULL: error of the last failed mma_create */

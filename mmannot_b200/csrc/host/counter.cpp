@@ -141,8 +141,8 @@ void Counter::dump(std::ostream &log) const {
   printStats(log, stats_.n_unassigned, "# unassigned hits:             ", stats_.n_hits);
 }
 
-void TableCount::addCounter(const Counter &counter) {
-  for (const auto &kv : counter.getCounts()) {
+void TableCount::addCounts(const std::map<uint64_t, double> &counts) {
+  for (const auto &kv : counts) {
     std::vector<size_t> elements;
     for (size_t i = 0; i < 64; ++i) if ((kv.first >> i) & 1) elements.push_back(i);
     std::vector<unsigned int> &row = rows_[elements];

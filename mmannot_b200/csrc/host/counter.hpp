@@ -63,7 +63,8 @@ class Counter {
 class TableCount {
  public:
   TableCount(const Config &config, uint32_t nInputs) : config_(config), nInputs_(nInputs), nColumns_(0) {}
-  void addCounter(const Counter &counter);                                     // mm:1861-1876
+  void addCounter(const Counter &counter) { addCounts(counter.getCounts()); }   // mm:1861-1876
+  void addCounts(const std::map<uint64_t, double> &counts);
   void dump(std::ostream &out, const std::vector<std::string> &samples) const;  // mm:1877-1900
 
  private:

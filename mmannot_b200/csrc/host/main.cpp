@@ -2,9 +2,14 @@
 // Flags, defaults, messages and exit codes follow main() of the reference
 // (mmannot.cpp:1903-2149); the annotation itself runs on the GPU through the C ABI
 // (include/mmannot_b200.h).  There is no CPU fallback.
+#include <algorithm>
 #include <cstdlib>
 #include <fstream>
 #include <iostream>
+#include <map>
+#include <mutex>
+#include <sstream>
+#include <thread>
 #include <string>
 #include <vector>
 
@@ -57,7 +62,7 @@ int main(int argc, char **argv) {
   AnnotationOptions annOpt;
   std::string gtfFileName, outputFileName, configFileName = "config.txt", readStatsFile, intervalStatsFile;
   std::vector<std::string> readsFileNames, names;
-  int device = 0;
+  int device = 0, nThreads = 1;
   if (argc == 1) {
     printUsage();
     return EXIT_SUCCESS;
@@ -96,7 +101,7 @@ int main(int argc, char **argv) {
       }
     }
     else if (s == "-p") opt.progress = true;
-    else if (s == "-t") (void)std::stoi(value(i));  // one GPU stream replaces the per-file thread pool
+    else if (s == "-t") nThreads = std::max(1, std::stoi(value(i)));  // workers, one input file at a time each, spread over the GPUs
     else if (s == "-g") device = std::stoi(value(i));
     else if (s == "-m") { readStatsFile = value(i); opt.readStats = true; }
     else if (s == "-M") { intervalStatsFile = value(i); opt.intervalStats = true; }
@@ -192,33 +197,71 @@ int main(int argc, char **argv) {
   params.n_samples = nInputs;
   params.max_batch_hits = opt.batchHits;
   params.rand_seed = 1;
-  mma_ctx *ctx = nullptr;
-  if (mma_create(&ctx, &params) != MMA_OK) return fail(std::string("Error: ") + mma_last_error(nullptr));
   mma_features f;
   f.n = static_cast<uint32_t>(features.size());
   f.n_chr = static_cast<uint32_t>(features.chromosomes.size());
   f.chr = features.chr.data(); f.start = features.start.data(); f.end = features.end.data();
   f.type = features.type.data(); f.strand = features.strand.data();
-  if (mma_load_features(ctx, &f) != MMA_OK) { std::string m = mma_last_error(ctx); mma_destroy(ctx); return fail("Error: " + m); }
 
+  // -t n: n workers take the input files in turn (the reference's pool, mm:2117-2141: one thread per file); worker w drives its
+  // own context on GPU (device + w) mod #GPUs, with the feature index replicated.  Reports and table columns keep file order.
+  const int nDevices = std::max(1, mma_device_count());
+  const uint32_t nWorkers = (opt.readStats || opt.intervalStats) ? 1u : std::min<uint32_t>(static_cast<uint32_t>(nThreads), nInputs);
+  struct FileResult { bool ok = false; std::string err, log; std::map<uint64_t, double> counts; };
+  std::vector<FileResult> results(nInputs);
+  std::ofstream readStatsStream, intervalStatsStream;
+  if (opt.readStats) readStatsStream.open(readStatsFile.c_str());            // mm:2000
+  if (opt.intervalStats) intervalStatsStream.open(intervalStatsFile.c_str());  // mm:2005
+  StatsWriters writers(config, features, opt.strategy, opt.rescueThreshold, opt.readStats ? &readStatsStream : nullptr, opt.intervalStats);
+  std::string fatal;
+  std::mutex fatalMutex;
+  auto worker = [&](uint32_t w) {
+    mma_params p = params;
+    p.device = (device + static_cast<int>(w)) % nDevices;
+    mma_ctx *ctx = nullptr;
+    if (mma_create(&ctx, &p) != MMA_OK) { std::lock_guard<std::mutex> g(fatalMutex); fatal = std::string("Error: ") + mma_last_error(nullptr); return; }
+    if (mma_load_features(ctx, &f) != MMA_OK) {
+      std::lock_guard<std::mutex> g(fatalMutex);
+      fatal = std::string("Error: ") + mma_last_error(ctx);
+      mma_destroy(ctx);
+      return;
+    }
+    {
+      Counter counter(ctx, features, config, opt);
+      if (opt.readStats || opt.intervalStats) counter.setStatsWriters(&writers);
+      for (uint32_t i = w; i < nInputs; i += nWorkers) {
+        FileResult &r = results[i];
+        std::ostringstream log;
+        std::ostream &lg = (nWorkers == 1) ? static_cast<std::ostream &>(std::cerr) : static_cast<std::ostream &>(log);
+        r.ok = counter.read(readsFileNames[i], i, r.err, lg);
+        if (r.ok) {
+          counter.dump(lg);
+          if (opt.intervalStats) writers.dumpIntervals(intervalStatsStream);
+          r.counts = counter.getCounts();
+        }
+        r.log = log.str();
+        if (!r.ok) break;
+      }
+    }
+    mma_destroy(ctx);
+  };
+  if (nWorkers == 1) worker(0);
+  else {
+    std::vector<std::thread> pool;
+    for (uint32_t w = 0; w < nWorkers; ++w) pool.emplace_back(worker, w);
+    for (std::thread &t : pool) t.join();
+  }
+  if (!fatal.empty()) return fail(fatal);
   int rc = 0;
   {
     TableCount table(config, nInputs);
-    Counter counter(ctx, features, config, opt);
-    std::ofstream readStatsStream, intervalStatsStream;
-    if (opt.readStats) readStatsStream.open(readStatsFile.c_str());            // mm:2000
-    if (opt.intervalStats) intervalStatsStream.open(intervalStatsFile.c_str());  // mm:2005
-    StatsWriters writers(config, features, opt.strategy, opt.rescueThreshold, opt.readStats ? &readStatsStream : nullptr, opt.intervalStats);
-    if (opt.readStats || opt.intervalStats) counter.setStatsWriters(&writers);
-    for (uint32_t i = 0; i < nInputs; i++) {
-      if (!counter.read(readsFileNames[i], i, err, std::cerr)) { std::cerr << err << std::endl; rc = EXIT_FAILURE; break; }
-      counter.dump(std::cerr);
-      if (opt.intervalStats) writers.dumpIntervals(intervalStatsStream);
-      table.addCounter(counter);
+    for (uint32_t i = 0; i < nInputs && rc == 0; i++) {
+      std::cerr << results[i].log;
+      if (!results[i].ok) { std::cerr << results[i].err << std::endl; rc = EXIT_FAILURE; break; }
+      table.addCounts(results[i].counts);
     }
     if (rc == 0) table.dump(outputFile, names);
   }
-  mma_destroy(ctx);
   if (rc == 0) std::cerr << "Successfully done." << std::endl;
   return rc;
 }

@@ -331,6 +331,11 @@ const char *mma_version(void) { return "mmannot_b200 0.1 (sm_100a)"; }
 
 const char *mma_last_error(const mma_ctx *ctx) { return ctx ? ctx->error.c_str() : g_createError.c_str(); }
 
+int mma_device_count(void) {
+  int n = 0;
+  return cudaGetDeviceCount(&n) == cudaSuccess ? n : 0;
+}
+
 int mma_create(mma_ctx **out, const mma_params *p) {
   if (!out || !p) { g_createError = "null argument"; return MMA_ERR_INVALID; }
   *out = nullptr;

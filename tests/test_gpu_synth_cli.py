@@ -130,3 +130,25 @@ def test_cli_read_and_interval_statistics(workload, args, sorted_input):
     assert out["b200"][3] == out["ref"][3], "-M differs"
     assert out["b200"][2] == out["ref"][2], "-m differs"
     assert len(out["ref"][2]) > 1000 and len(out["ref"][3]) > 1000
+
+
+@pytest.mark.skipif(pyoracle.ref_binary("fixed") is None or not os.path.exists(CLI), reason="needs oracle/_ref and the CLI binary")
+def test_cli_threads_spread_files_over_contexts(workload):
+    """-t n: n workers, one context each (on as many GPUs as there are), files in turn; same table and per-file reports,
+    in file order, as the reference run one file after the other."""
+    w = workload
+    bams = []
+    for i in range(3):
+        b = str(w["tmp"] / ("t%d.bam" % i))
+        if not os.path.exists(b):
+            w["synth"].write_bam(b, 100000 + i * 7000, 7000)
+        bams.append(b)
+    common_args = ["-a", w["gtf"], "-c", w["cfg_path"], "-r"] + bams + ["-s", "F", "-y", "ratio"]
+    rc, ref_out, ref_err = pyoracle.run_reference(common_args, kind="fixed")
+    assert rc == 0, ref_err
+    for t in ("2", "3", "8"):
+        pr = subprocess.run([CLI] + common_args + ["-t", t], capture_output=True, text=True, timeout=300)
+        assert pr.returncode == 0, pr.stderr
+        assert pr.stdout == ref_out
+        pick = lambda txt: [l for l in txt.split("\n") if l.startswith("\t#") or l.startswith("Results for")]
+        assert pick(pr.stderr) == pick(ref_err)
