@@ -250,7 +250,7 @@ void launchBatchKernels(mma_ctx *ctx, Sample &s, const HitView &h) {
   const u32 nWT = (h.n + WT_HITS - 1) / WT_HITS;
   constexpr bool useFast = FAST && sizeof(MaskT) == 4 && STRAT != 2;  // k_batch_fast (mma_batch_fast.cuh)
   bool launched = false;
-  if constexpr (useFast) if (!ctx->legacyBatch) {
+  if constexpr (useFast) if (!ctx->legacyBatch && ctx->fast.nChr <= CHR_SMEM) {
     launched = true;
     u32 grid = std::max<u32>(1u, std::min<u32>((nWT + FAST_WARPS - 1) / FAST_WARPS, (u32)ctx->nSM * MMA_FAST_BLOCKS_PER_SM));
     if (ctx->maxGrid) grid = std::min(grid, ctx->maxGrid);

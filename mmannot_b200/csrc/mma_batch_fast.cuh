@@ -50,7 +50,7 @@ __device__ __forceinline__ void ldRecord(const uint4 *p, uint4 &lo, uint4 &hi) {
                : "=r"(lo.x), "=r"(lo.y), "=r"(lo.z), "=r"(lo.w), "=r"(hi.x), "=r"(hi.y), "=r"(hi.z), "=r"(hi.w)
                : "l"(p));
 }
-#define CHR_SMEM 512  // chromosome table staged in shared memory up to this many chromosomes
+#define CHR_SMEM 512  // the chromosome table lives in shared memory: annotations with more chromosomes take the general k_batch
 
 template <int MODE>
 __device__ __noinline__ u32 slowAnnotate(const FastView &fx, const IndexView &ix, u32 rs, u32 re, u32 meta, float ovl) {
@@ -133,14 +133,17 @@ k_batch_fast(const __grid_constant__ IndexView ix, const __grid_constant__ FastV
     for (int e = 0; e < HIST_ROWS; ++e) sm.hist[e][tid] = 0;
   }
   if (tid < ST_N) sm.stat[tid] = 0;
-  const bool chrInSmem = fx.nChr <= CHR_SMEM;
-  if (chrInSmem) for (u32 c = tid; c < fx.nChr; c += FAST_THREADS) sm.chrInfo[c] = fx.chrInfo[c];
+  for (u32 c = tid; c < fx.nChr; c += FAST_THREADS) sm.chrInfo[c] = fx.chrInfo[c];  // launched only when nChr <= CHR_SMEM
   __syncthreads();
   const Annotator<MODE, true> annot{ix, fx, r.overlap};
   const u32 seq = ctl->batchSeq;
   // every run takes the serial walker when rescue() needs multiplicities or some read name is known as unfinished
   const bool forceWalk = (STRAT == 0) && (r.rescue || __shfl_sync(FULL, ctl->openCount, 0) != 0);
-  u32 pUnasAmbi = 0, pUniqMult = 0, pHitsMiss = 0, pClosResc = 0;  // packed 16-bit counters, see k_batch
+  // per-thread counters, two 16-bit fields per register (a thread sees < 2^15 hits of one batch, see k_batch)
+  u32 pAsgUniq = 0;   // assigned hits | hits with NH = 1 and exactly one element << 16        (mm:1666, 1668)
+  u32 pMultAmbi = 0;  // hits joining the by-name countdown | ambiguous hits << 16               (mm:1670, 1667)
+  u32 pHitsMiss = 0;  // hits looked at | segment-table misses << 16
+  u32 pClosResc = 0;  // multi-mapping reads closed by the parallel countdown | of which rescued << 16
 
   FastCount<HIST, SLOTS> count{sm, table, tid};
   RunWalker<MODE, true, FastCount<HIST, SLOTS>> w{h, r, annot, ctl, slow, open, count, seq, 0u, 0u};
@@ -180,7 +183,13 @@ k_batch_fast(const __grid_constant__ IndexView ix, const __grid_constant__ FastV
       if (STRAT == 0) {
         const ulonglong2 k0 = __ldcs(reinterpret_cast<const ulonglong2 *>(h.key + base));
         const ulonglong2 k1 = __ldcs(reinterpret_cast<const ulonglong2 *>(h.key + base + 2));
-        key[0] = normKey(k0.x); key[1] = normKey(k0.y); key[2] = normKey(k1.x); key[3] = normKey(k1.y);
+        key[0] = k0.x; key[1] = k0.y; key[2] = k1.x; key[3] = k1.y;
+        // the all-ones key is reserved (normKey): only a tile that holds a key with all-ones upper half needs the fix-up
+        const u32 hiMax = max(max((u32)(k0.x >> 32), (u32)(k0.y >> 32)), max((u32)(k1.x >> 32), (u32)(k1.y >> 32)));
+        if (__any_sync(FULL, hiMax == 0xFFFFFFFFu)) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) key[j] = normKey(key[j]);
+        }
       }
       validBits = 15u;
     } else {
@@ -215,9 +224,8 @@ k_batch_fast(const __grid_constant__ IndexView ix, const __grid_constant__ FastV
           if (c.valid) { carryIn = &c; prev = c.key; }
         } else prev = normKey(h.key[base - 1]);
       }
-      const u32 inv = ~validBits;
-      hbits = ((key[0] != prev || (inv & 1u)) ? 1u : 0u) | ((key[1] != key[0] || (inv & 2u)) ? 2u : 0u) |
-              ((key[2] != key[1] || (inv & 4u)) ? 4u : 0u) | ((key[3] != key[2] || (inv & 8u)) ? 8u : 0u);
+      hbits = ((key[0] != prev) ? 1u : 0u) | ((key[1] != key[0]) ? 2u : 0u) | ((key[2] != key[1]) ? 4u : 0u) | ((key[3] != key[2]) ? 8u : 0u);
+      hbits |= ~validBits & 15u;  // (slots past the end of the batch count as run starts)
       F = __ballot_sync(FULL, hbits != 0);
       nextKey = __shfl_sync(FULL, key[3], 31);
     }
@@ -248,14 +256,14 @@ k_batch_fast(const __grid_constant__ IndexView ix, const __grid_constant__ FastV
       const bool look = vis && !degen && pass;
       if (look) lookBits |= 1u << j;
       const u32 chrSafe = look ? chr : 0u;
-      const uint2 ci = chrInSmem ? sm.chrInfo[chrSafe] : __ldg(&fx.chrInfo[chrSafe]);
+      const uint2 ci = sm.chrInfo[chrSafe];
       const u32 bRaw = rs[j] >> shift;
       en[j] = __ldg(&fx.bm[ci.x + min(bRaw, ci.y - 1u)]);
       const u32 p = (bRaw < ci.y) ? ((rs[j] >> gshift) & 31u) : 31u;
       pm[j] = (gshift == 0) ? (0xFFFFFFFFu >> (31u - p)) : ((1u << p) - 1u);
     }
     // ---- phase B: the 32-byte record of the segment holding the read start
-    u32 tEnd[4], tEnd2[4], tAns[4], xAns[4], tie[4];
+    u32 tEnd[4], tEnd2[4], tAns[4], xAns[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const bool look = (lookBits >> j) & 1u;
@@ -270,18 +278,15 @@ k_batch_fast(const __grid_constant__ IndexView ix, const __grid_constant__ FastV
       ldRecord(&fx.seg[2u * i], tt, xx);
 #endif
       tEnd[j] = tt.x; tAns[j] = fwd ? tt.y : tt.z; tEnd2[j] = tt.w;
-      xAns[j] = fwd ? xx.x : xx.y; tie[j] = fwd ? xx.z : xx.w;
+      xAns[j] = fwd ? xx.x : xx.y;
     }
-    // ---- phase C: in-segment answer (with the upstream/downstream tie settled from the tie point) or cross-segment answer
+    // ---- phase C: in-segment or cross-segment answer
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const bool look = (lookBits >> j) & 1u;
       const bool inT = re[j] <= tEnd[j];
       const bool inX = (MODE == 0) && re[j] <= tEnd2[j];
-      u32 a = inT ? tAns[j] : xAns[j];
-      const u64 sum = (u64)rs[j] + (u64)re[j];
-      const u32 keep = (sum > (u64)tie[j]) ? fx.upMask : (sum < (u64)tie[j]) ? fx.downMask : 0xFFFFFFFFu;
-      if (inT && (a & ANS_VICPAIR)) a = (a & ~ANS_VICPAIR) & keep;
+      const u32 a = inT ? tAns[j] : xAns[j];  // (an upstream/downstream tie, < 1 % of the hits, is settled out of line)
       const bool ok = rs[j] <= tEnd[j] && (inT || inX) && !(a & (ANS_VICPAIR | ANS_GENERAL));
       if (look && ok) m[j] = a;
       if (look && !ok) slowBits |= 1u << j;
@@ -317,19 +322,31 @@ k_batch_fast(const __grid_constant__ IndexView ix, const __grid_constant__ FastV
       __syncwarp();
     }
     // ---- per-hit counters (mm:1666-1668); a visited hit that does not join the by-name countdown is a read of its own
+    //      Slots that are not visited (past the end of the batch, NH != 1 under -y unique) hold m = 0 and, past the end, NH = 1.
+    //      Counted here: hits, ASSIGNED hits (unassigned = hits - assigned at the end), hits with NH = 1 and an element
+    //      (unique, corrected below for the rare ambiguous hit), hits joining the by-name countdown.
     u32 ev[4];  // the element set counted at this hit slot (0 = none)
+    u32 ambOr = 0;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const bool vis = (visBits >> j) & 1u;
-      const int nreg = __popc(m[j]);
-      const bool multi = vis && STRAT == 0 && nh[j] > 1;
-      pHitsMiss += vis ? 1u : 0u;
-      pUnasAmbi += (vis && nreg == 0 ? 1u : 0u) | (vis && nreg > 1 ? 0x10000u : 0u);
-      pUniqMult += (vis && nreg == 1 && nh[j] == 1 ? 1u : 0u) | (multi ? 0x10000u : 0u);
-      ev[j] = (vis && !multi) ? m[j] : 0u;
+      const u32 a1 = min(m[j], 1u);
+      const bool multi = STRAT == 0 && nh[j] > 1;
+      pAsgUniq += a1 + ((nh[j] == 1 ? a1 : 0u) << 16);
+      pMultAmbi += multi ? 1u : 0u;
+      ambOr |= m[j] & (m[j] - 1u);
+      ev[j] = multi ? 0u : m[j];
       if (r.rescue) ev[j] = (u32)rescueSingle(r, (u64)ev[j]);
     }
-    u32 nWalk = 0;
+    pHitsMiss += __popc(visBits);
+    if (ambOr) {  // some hit of this lane matched several elements (mm:1667): it is ambiguous, and not "unique"
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (m[j] & (m[j] - 1u)) {
+          pMultAmbi += 0x10000u;
+          if (nh[j] == 1) pAsgUniq -= 0x10000u;
+        }
+    }
+    u32 nWalk = 0, closeBits = 0;
     u32 inc = 0, lastHeadPos = 0;
     if (STRAT == 0) {
       // ---- per-read countdown (mm:1669-1702)
@@ -389,20 +406,20 @@ k_batch_fast(const __grid_constant__ IndexView ix, const __grid_constant__ FastV
         const bool irregular = flagged || (nh[j] > 1 && nh[j] != base + j + 1 - runStart);
         if (last && mine && irregular) sm.walkQ[nWalk++][tid] = runStart;
         if (last && mine && !irregular && nh[j] > 1) {
-          const u32 gm = tot & 0x7FFFFFFFu;
-          ev[j] = gm;
-          pClosResc += 1u | (__popc(gm) == 1 ? 0x10000u : 0u);
+          ev[j] = tot & 0x7FFFFFFFu;
+          closeBits |= 1u << j;
         }
       }
     }
     // ---- counting: single-element sets into the lane's histogram column, the rest into the block table
     {
-      u32 pend = 0;
+      u32 pend = 0, rescBits = 0;
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const u32 c = ev[j];
+        const bool single = c != 0 && (c & (c - 1)) == 0;
+        if (single && ((closeBits >> j) & 1u)) rescBits |= 1u << j;  // a multi-mapping read resolved to one element (mm:1691)
         if (HIST) {
-          const bool single = c != 0 && (c & (c - 1)) == 0;
           const u32 row = single ? (u32)(__ffs(c) - 1) : (u32)(HIST_ROWS - 1);  // E <= 30: the last row only ever receives zeros
           sm.hist[row][tid] += single ? 1 : 0;
           if (c != 0 && !single) pend |= 1u << j;
@@ -410,6 +427,7 @@ k_batch_fast(const __grid_constant__ IndexView ix, const __grid_constant__ FastV
           if (c != 0) pend |= 1u << j;
         }
       }
+      pClosResc += __popc(closeBits) | (__popc(rescBits) << 16);
       while (__any_sync(FULL, pend != 0)) {
         if (pend) {
           const int j = __ffs(pend) - 1;
@@ -445,8 +463,8 @@ k_batch_fast(const __grid_constant__ IndexView ix, const __grid_constant__ FastV
   // ---- a read open at the end of the chunk that continues in another warp's chunk: finished by the serial walk.  (A run
   //      ending exactly at the chunk's last record was closed above, like the last run of the batch.)
   if (STRAT == 0 && cValid && cCont && t1 > t0 && lane == 0) w.walk(cStart, cKey, nullptr);
-  u32 cHits = pHitsMiss & 0xFFFFu, cMiss = pHitsMiss >> 16, cUnassigned = pUnasAmbi & 0xFFFFu, cAmbiguous = pUnasAmbi >> 16;
-  u32 cUnique = pUniqMult & 0xFFFFu, cMultiple = pUniqMult >> 16;
+  u32 cHits = pHitsMiss & 0xFFFFu, cMiss = pHitsMiss >> 16, cUnassigned = cHits - (pAsgUniq & 0xFFFFu), cAmbiguous = pMultAmbi >> 16;
+  u32 cUnique = pAsgUniq >> 16, cMultiple = pMultAmbi & 0xFFFFu;
   u32 cReads = cHits - cMultiple + (pClosResc & 0xFFFFu) + w.nReads, cRescued = (pClosResc >> 16) + w.nRescued;
 
   // ---- block epilogue: counters, the private histogram columns and the private table
