@@ -38,6 +38,9 @@ WORKLOADS = {
     "tair10_srna": dict(shape="tair10", config="configTAIR10", seed=20261018 + 2, reads=50_000_000,
                         spec=dict(max_nh=20), strand="F", strategy="default", overlap=-1.0,
                         describe="synthetic sRNA-Seq single-end, NH<=20, TAIR10-shaped GFF3, configTAIR10.txt, -s F, -y default, -l -1"),
+    "flybase6_paired": dict(shape="flybase6", config="configFlybase6", seed=20261018 + 5, reads=25_000_000,
+                            spec=dict(max_nh=8, paired=True, rna_seq=True, flip_mate2=True), strand="F", strategy="default", overlap=-1.0,
+                            describe="synthetic paired-end RNA-Seq (mate 2 strand-flipped: -s FR as -s F), NH<=8, Flybase6-shaped GFF, configFlybase6.txt"),
     "hs38_multi": dict(shape="hs38", config="configHS38", seed=20261018 + 3, reads=20_000_000,
                        spec=dict(max_nh=100), strand="F", strategy="default", overlap=-1.0,
                        describe="synthetic heavy multi-mapping reads, NH<=100, GRCh38-shaped GTF, configHS38.txt"),
@@ -352,7 +355,8 @@ def run_product_arm(args):
         # counted must be the reads generated and the hits counted the hits submitted, over all ranks
         if w["strategy"] == "default":
             assert stats_dev["n_hits"] == total_hits, "hits counted %d != hits submitted %d" % (stats_dev["n_hits"], total_hits)
-            assert stats_dev["n_reads"] == reads * world, "reads counted %d != reads generated %d" % (stats_dev["n_reads"], reads * world)
+            per_name = 2 if w["spec"].get("paired") else 1  # both mates carry the name and the NH: two countdowns per name
+            assert stats_dev["n_reads"] == per_name * reads * world, "reads counted %d != reads generated %d" % (stats_dev["n_reads"], per_name * reads * world)
         ms_per_step = ms_dev / args.steps
         value = total_hits / (ms_per_step * 1e-3)
         e2e_value = total_hits / (wall_e2e / args.steps * 1e-3)
