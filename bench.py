@@ -374,7 +374,21 @@ def run_product_arm(args):
             bytes_per_launch = 24.0 * n_hits * args.steps / n_batches
             avg_ms = k_ms / n_batches
             achieved = bytes_per_launch / (avg_ms * 1e-3) / 1e9
-            roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+            # dram bytes of the dominant kernel per launch, from the committed ncu --set full capture (bytes per hit there x
+            # the hits of an average launch here); null when no capture of this kernel is on file
+            traffic, traffic_src = None, None
+            try:
+                import glob
+                for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "*_traffic.json")), reverse=True):
+                    tj = json.load(open(path))
+                    if tj.get("kernel") == ann.dominant_kernel() and tj.get("dram_bytes_per_hit"):
+                        traffic = tj["dram_bytes_per_hit"] * n_hits * args.steps / n_batches
+                        traffic_src = os.path.relpath(path, ROOT)
+                        break
+            except Exception:  # noqa: BLE001
+                pass
+            roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                        "traffic_source": traffic_src,
                         "kernel": ann.dominant_kernel(), "bytes_per_launch": bytes_per_launch, "avg_launch_ms": avg_ms,
                         "launches_timed": n_batches, "peak_source": peak_src,
                         "kernel_ms_per_step": {k: tm[k] / args.steps for k in ("ms_batch", "ms_close", "ms_finish")},
