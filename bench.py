@@ -273,14 +273,14 @@ def run_product_arm(args):
                 packed_batches.append(device.PackedHits(*[pinned.arrays[k][a:a + n] for k in ("start", "end", "meta", "nh", "read_key")]))
         stream = torch.cuda.ExternalStream(ann.stream_ptr(), device=dev)
 
-        def merge(res):  # res = (stats int64[7], rows int64[n, 3]); one all-gather when there is more than one GPU
-            return multi.merge_arrays(res[0], res[1], dev) if world > 1 else res
+        def finish():  # (stats int64[7], rows int64[n, 3]); with several GPUs: device-side merge around one all-gather
+            return multi.merge_on_device(ann, 0, dev) if world > 1 else ann.finish_arrays(0, sort=False)
 
         def step_device():
             ann.reset(0)
             for b in dev_batches:
                 ann.submit_device(0, b)
-            return merge(ann.finish_arrays(0, sort=False))
+            return finish()
 
         def step_e2e():
             ann.reset(0)
@@ -290,13 +290,13 @@ def run_product_arm(args):
             else:
                 for b in host_batches:
                     ann.submit_batch(0, b)
-            return merge(ann.finish_arrays(0, sort=False))
+            return finish()
 
         def step_e2e_wide():
             ann.reset(0)
             for b in host_batches:
                 ann.submit_batch(0, b)
-            return merge(ann.finish_arrays(0, sort=False))
+            return finish()
 
         def barrier():
             torch.cuda.synchronize()

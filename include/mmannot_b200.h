@@ -218,6 +218,18 @@ int mma_reset_sample(mma_ctx *ctx, uint32_t sample);
  * issued by whoever owns the communicator (torch.distributed / NCCL). */
 int mma_dense_counts(mma_ctx *ctx, uint32_t sample, const uint64_t *mask, const uint32_t *nh, uint64_t n, uint64_t *out_dev);
 
+/* Multi-GPU merge of a sample on the devices (the sum TableCount::addCounter forms column by column, mmannot.cpp:1861-1876):
+ *   1. every rank:  mma_export_table(ctx, sample, dev_buf)   end-of-file flush, then the compacted table and the counters
+ *                   into dev_buf (device memory of ctx's GPU, mma_export_bytes(ctx) bytes), enqueued on mma_stream(ctx)
+ *   2. the caller all-gathers the buffers (NCCL over NVLink; the communicator belongs to the caller)
+ *   3. every rank:  mma_import_tables(ctx, sample, gathered, n_ranks)   replaces the sample's table and counters by the
+ *                   sum over the n_ranks buffers (mma_export_bytes apart), on mma_stream(ctx)
+ *   4. mma_finish_sample as usual: the merged result, identical on every rank.
+ * Only the control block crosses PCIe before step 4. */
+uint64_t mma_export_bytes(const mma_ctx *ctx);
+int mma_export_table(mma_ctx *ctx, uint32_t sample, void *dev_dst);
+int mma_import_tables(mma_ctx *ctx, uint32_t sample, const void *dev_src, uint32_t n_tables);
+
 int mma_sync(mma_ctx *ctx);
 void *mma_stream(mma_ctx *ctx); /* cudaStream_t of the compute stream */
 

@@ -987,24 +987,17 @@ static int finishDeferred(mma_ctx *ctx, Sample &s, u32 nSlow) {
   return MMA_OK;
 }
 
-int mma_finish_sample(mma_ctx *ctx, uint32_t sample, mma_sample_result *out) {
-  if (!ctx) return MMA_ERR_INVALID;
-  if (!out) return ctx->fail(MMA_ERR_INVALID, "null result");
-  if (sample >= ctx->samples.size()) return ctx->fail(MMA_ERR_INVALID, "sample index out of range");
-  CK(cudaSetDevice(ctx->device));
-  Sample &s = ctx->samples[sample];
-  std::memset(out, 0, sizeof(*out));
-  s.rowMask.clear(); s.rowNh.clear(); s.rowCount.clear();
-  if (!s.ctl) return MMA_OK;  // nothing was ever submitted
+// End-of-file flush of a sample (mm:1783-1792) and compaction of its table on the device: afterwards ctx->dumpBuf holds
+// [TableDump | rows] and ctx->hostTable its head and (rows == true) rows.  One copy and one synchronisation in the usual
+// case (no deferred records, a few thousand rows); `hc` receives the control block.
+static int flushAndDump(mma_ctx *ctx, Sample &s, bool rows, SampleCtl &hc) {
   CK(cudaStreamSynchronize(ctx->sh));
   if (ctx->rules.strategy == MMA_STRATEGY_DEFAULT && s.slowCap) {
     k_flush_carry<<<1, 1, 0, ctx->sc>>>(s.ctl, slowView(s));
     ctx->launches++;
   }
-  // compact the table on the device and bring back [control block | row count | rows] with one copy and one
-  // synchronisation for the usual few thousand rows (a second copy only when the table holds more than the first chunk)
   const size_t headBytes = sizeof(TableDump);
-  const u32 firstRows = std::min<u32>(ctx->tableCap, 8192u);
+  const u32 firstRows = rows ? std::min<u32>(ctx->tableCap, 8192u) : 0u;
   if (!ctx->hostTable) CK(cudaHostAlloc(&ctx->hostTable, headBytes + (size_t)ctx->tableCap * 16, cudaHostAllocDefault));
   CK(ctx->dumpBuf.ensure(headBytes + (size_t)ctx->tableCap * 16));
   const TableDump *hHead = reinterpret_cast<const TableDump *>(ctx->hostTable);
@@ -1016,7 +1009,7 @@ int mma_finish_sample(mma_ctx *ctx, uint32_t sample, mma_sample_result *out) {
     ctx->launches++;
     CK(cudaMemcpyAsync(ctx->hostTable, ctx->dumpBuf.p, headBytes + (size_t)firstRows * 16, cudaMemcpyDeviceToHost, ctx->sc));
     CK(cudaStreamSynchronize(ctx->sc));
-    if (hHead->nRows > firstRows) {
+    if (rows && hHead->nRows > firstRows) {
       const size_t off = headBytes + (size_t)firstRows * 16;
       CK(cudaMemcpyAsync(reinterpret_cast<char *>(ctx->hostTable) + off, ctx->dumpBuf.as<char>() + off, (size_t)(hHead->nRows - firstRows) * 16,
                          cudaMemcpyDeviceToHost, ctx->sc));
@@ -1026,7 +1019,7 @@ int mma_finish_sample(mma_ctx *ctx, uint32_t sample, mma_sample_result *out) {
   };
   int rc = dump();
   if (rc) return rc;
-  SampleCtl hc = hHead->ctl;
+  hc = hHead->ctl;
   if (hc.overflow) return ctx->fail(MMA_ERR_CAPACITY, "a device table overflowed (combination table, deferred list or NH range under -y ratio)");
   s.openMaybeUsed = hc.openCount != 0;
   if (hc.slowCount > 0) {
@@ -1038,6 +1031,60 @@ int mma_finish_sample(mma_ctx *ctx, uint32_t sample, mma_sample_result *out) {
     if (hc.overflow) return ctx->fail(MMA_ERR_CAPACITY, "the combination table overflowed");
     s.knownCount = 0; s.knownCum = s.cumHits;
   }
+  return MMA_OK;
+}
+
+uint64_t mma_export_bytes(const mma_ctx *ctx) { return ctx ? sizeof(TableDump) + (uint64_t)ctx->tableCap * 16 : 0; }
+
+int mma_export_table(mma_ctx *ctx, uint32_t sample, void *dev_dst) {
+  if (!ctx) return MMA_ERR_INVALID;
+  if (!dev_dst) return ctx->fail(MMA_ERR_INVALID, "null destination");
+  if (sample >= ctx->samples.size()) return ctx->fail(MMA_ERR_INVALID, "sample index out of range");
+  CK(cudaSetDevice(ctx->device));
+  Sample &s = ctx->samples[sample];
+  int rc = initSample(ctx, s);
+  if (rc) return rc;
+  SampleCtl hc;
+  if ((rc = flushAndDump(ctx, s, false, hc))) return rc;
+  const u64 nRows = reinterpret_cast<const TableDump *>(ctx->hostTable)->nRows;
+  CK(cudaMemcpyAsync(dev_dst, ctx->dumpBuf.p, sizeof(TableDump) + (size_t)nRows * 16, cudaMemcpyDeviceToDevice, ctx->sc));
+  return MMA_OK;
+}
+
+int mma_import_tables(mma_ctx *ctx, uint32_t sample, const void *dev_src, uint32_t n_tables) {
+  if (!ctx) return MMA_ERR_INVALID;
+  if (!dev_src || n_tables == 0) return ctx->fail(MMA_ERR_INVALID, "null source");
+  if (sample >= ctx->samples.size()) return ctx->fail(MMA_ERR_INVALID, "sample index out of range");
+  CK(cudaSetDevice(ctx->device));
+  Sample &s = ctx->samples[sample];
+  int rc = initSample(ctx, s);
+  if (rc) return rc;
+  const size_t tb = (size_t)ctx->tableCap * sizeof(u64);
+  CK(cudaMemsetAsync(s.tableKeys.p, 0, tb, ctx->sc)); CK(cudaMemsetAsync(s.tableVals.p, 0, tb, ctx->sc));
+  CK(cudaMemsetAsync(s.ctl->stats, 0, sizeof(u64) * ST_N, ctx->sc));
+  const u64 total = (u64)n_tables * ctx->tableCap;
+  k_table_import<<<gridFor(total, 256), 256, 0, ctx->sc>>>(tableView(s.tableKeys, s.tableVals, ctx->tableCap, s.ctl), s.ctl,
+                                                          reinterpret_cast<const char *>(dev_src), n_tables, (size_t)mma_export_bytes(ctx), ctx->tableCap);
+  ctx->launches++;
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return ctx->fail(MMA_ERR_CUDA, std::string("kernel launch: ") + cudaGetErrorString(e));
+  return MMA_OK;
+}
+
+int mma_finish_sample(mma_ctx *ctx, uint32_t sample, mma_sample_result *out) {
+  if (!ctx) return MMA_ERR_INVALID;
+  if (!out) return ctx->fail(MMA_ERR_INVALID, "null result");
+  if (sample >= ctx->samples.size()) return ctx->fail(MMA_ERR_INVALID, "sample index out of range");
+  CK(cudaSetDevice(ctx->device));
+  Sample &s = ctx->samples[sample];
+  std::memset(out, 0, sizeof(*out));
+  s.rowMask.clear(); s.rowNh.clear(); s.rowCount.clear();
+  if (!s.ctl) return MMA_OK;  // nothing was ever submitted
+  SampleCtl hc;
+  int rc = flushAndDump(ctx, s, true, hc);
+  if (rc) return rc;
+  const size_t headBytes = sizeof(TableDump);
+  const TableDump *hHead = reinterpret_cast<const TableDump *>(ctx->hostTable);
   const u64 nRows = hHead->nRows;
   const bool ratio = ctx->rules.strategy == MMA_STRATEGY_RATIO;
   const u64 lowMask = (1ull << NH_SHIFT) - 1;

@@ -1145,6 +1145,19 @@ __global__ void k_table_compact(TableView t, const SampleCtl *ctl, TableDump *he
   if (at < cap) rows[at] = make_ulonglong2(k, v);
 }
 
+// multi-GPU merge on the device: the compacted tables of all ranks ([TableDump | rows] each, `stride` bytes apart, as left by
+// an all-gather) are added into this sample's (cleared) table and counters
+__global__ void k_table_import(TableView t, SampleCtl *ctl, const char *bufs, u32 nBufs, size_t stride, u32 cap) {
+  const u64 idx = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  const u32 b = (u32)(idx / cap), i = (u32)(idx % cap);
+  if (b >= nBufs) return;
+  const TableDump *head = reinterpret_cast<const TableDump *>(bufs + (size_t)b * stride);
+  const ulonglong2 *rows = reinterpret_cast<const ulonglong2 *>(bufs + (size_t)b * stride + sizeof(TableDump));
+  if (i < ST_N && head->ctl.stats[i]) atomicAdd(&ctl->stats[i], head->ctl.stats[i]);
+  if (i == 0 && head->ctl.overflow) atomicExch(&ctl->overflow, 1u);
+  if (i < head->nRows) { const ulonglong2 r = rows[i]; tableAdd(t, r.x, r.y); }
+}
+
 // dense read-out for the cross-GPU sum: out[i] = count of key ckey[i]
 __global__ void k_dense_counts(TableView t, const u64 *__restrict__ ckey, u64 n, u64 *out) {
   const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;

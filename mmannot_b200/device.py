@@ -20,7 +20,7 @@ FAST_OFF = 0xFFFFFFFF  # fast_bin_shift=None: no segment answer table
 EXPORTS = [
     "mma_create", "mma_destroy", "mma_last_error", "mma_load_features", "mma_alloc_pinned", "mma_free_pinned",
     "mma_submit_hits", "mma_submit_hits_device", "mma_finish_sample", "mma_reset_sample", "mma_dense_counts",
-    "mma_sync", "mma_stream", "mma_timing_enable", "mma_timing_reset", "mma_timing_get", "mma_index_bytes", "mma_version", "mma_readback_bytes", "mma_dominant_kernel", "mma_index_segments", "mma_annotate_hits", "mma_annotate_intervals", "mma_pack_hits", "mma_submit_hits_packed", "mma_device_count",
+    "mma_sync", "mma_stream", "mma_timing_enable", "mma_timing_reset", "mma_timing_get", "mma_index_bytes", "mma_version", "mma_readback_bytes", "mma_dominant_kernel", "mma_index_segments", "mma_annotate_hits", "mma_annotate_intervals", "mma_pack_hits", "mma_submit_hits_packed", "mma_device_count", "mma_export_bytes", "mma_export_table", "mma_import_tables",
 ]
 
 
@@ -117,6 +117,10 @@ def lib():
         L.mma_free_pinned.argtypes = [C.c_void_p]
         L.mma_pack_hits.argtypes = [C.POINTER(HitBatch)] + [C.c_void_p] * 6 + [C.c_uint64, C.POINTER(PackedBatch)]
         L.mma_submit_hits_packed.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(PackedBatch)]
+        L.mma_export_bytes.argtypes = [C.c_void_p]
+        L.mma_export_bytes.restype = C.c_uint64
+        L.mma_export_table.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p]
+        L.mma_import_tables.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32]
         L.mma_annotate_intervals.argtypes = [C.c_void_p, C.POINTER(HitBatch), C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]
         _lib = L
     return _lib
@@ -316,6 +320,17 @@ class Annotator:
         else:
             rows = {}
         return {"stats": stats, "rows": rows}
+
+    def export_bytes(self):
+        return int(lib().mma_export_bytes(self._h))
+
+    def export_table(self, sample, dev_ptr):
+        """End-of-file flush, then the compacted table + counters into device memory (mma_export_bytes bytes); asynchronous."""
+        self._check(lib().mma_export_table(self._h, sample, dev_ptr))
+
+    def import_tables(self, sample, dev_ptr, n_tables):
+        """Replace the sample's table and counters by the sum of n_tables exported buffers laid out back to back."""
+        self._check(lib().mma_import_tables(self._h, sample, dev_ptr, n_tables))
 
     def dense_counts(self, sample, masks, nhs, out_dev_ptr):
         m = np.ascontiguousarray(masks, np.uint64)

@@ -28,6 +28,29 @@ def read_range(rank, world, n_reads):
     return first, min(per, n_reads - first)
 
 
+def merge_on_device(ann, sample, device, group=None):
+    """The merge as the GPUs do it: every rank exports its compacted table and counters into device memory
+    (mma_export_table), ONE NCCL all-gather over NVLink moves them, every rank adds all of them into its own table with one
+    kernel (mma_import_tables); the usual mma_finish_sample then returns the merged result.  Nothing but the control block
+    crosses PCIe before that, and the host does no arithmetic.  -> (stats int64[7], rows int64[n, 3]) like finish_arrays."""
+    import torch
+    import torch.distributed as dist
+
+    world = dist.get_world_size(group)
+    nbytes = ann.export_bytes()
+    cache = getattr(ann, "_merge_buffers", None)
+    if cache is None or cache[0].numel() != nbytes or cache[1].numel() != world * nbytes:
+        cache = (torch.empty(nbytes, dtype=torch.uint8, device=device), torch.empty(world * nbytes, dtype=torch.uint8, device=device))
+        ann._merge_buffers = cache
+    mine, gathered = cache
+    stream = torch.cuda.ExternalStream(ann.stream_ptr(), device=device)
+    with torch.cuda.stream(stream):  # the library's own compute stream: export -> all-gather -> import stay ordered on it
+        ann.export_table(sample, mine.data_ptr())
+        dist.all_gather_into_tensor(gathered, mine, group=group)
+        ann.import_tables(sample, gathered.data_ptr(), world)
+    return ann.finish_arrays(sample, sort=False)
+
+
 def merge_arrays(stats, rows, device, group=None, capacity=4096):
     """Sum of the per-rank results over the process group with ONE collective: an all-gather of the compact rows.
 

@@ -257,3 +257,35 @@ def test_packed_refuses_what_does_not_fit():
     meta = np.zeros(n, np.uint32); nh = np.ones(n, np.uint32); key = np.arange(n, dtype=np.uint64)
     with pytest.raises(device.MmaError):
         device.PackedHits(start, end, meta, nh, key, esc_capacity=10)
+
+
+def test_export_import_tables_on_device():
+    """The device-side merge used across GPUs, on one GPU: a sample's exported table imported twice must give every count
+    and counter doubled; imported once, the table itself."""
+    import torch
+    from mmannot_b200 import device
+    rng = np.random.default_rng(31337)
+    et = fuzz.make_elements(rng)
+    feats = fuzz.make_features(rng, et, n_feat=300)
+    hits = fuzz.make_hits(rng, feats, n_reads=20000, max_nh=5, messy=0.1)
+    ref = oracle_run(et, feats, hits)
+    a = device.Annotator(et, max_batch_hits=1 << 20)
+    try:
+        a.load_features(feats)
+        a.submit(0, hits)
+        nb = a.export_bytes()
+        buf = torch.empty(2 * nb, dtype=torch.uint8, device="cuda")
+        a.export_table(0, buf.data_ptr())
+        a.sync()
+        buf[nb:] = buf[:nb]
+        torch.cuda.synchronize()
+        a.import_tables(0, buf.data_ptr(), 1)
+        once = a.finish(0)
+        a.import_tables(0, buf.data_ptr(), 2)
+        twice = a.finish(0)
+    finally:
+        a.close()
+    once["values"] = device.values_by_mask(once["rows"])
+    check(once, ref)
+    assert {k: 2 * v for k, v in once["rows"].items()} == twice["rows"]
+    assert {k: 2 * v for k, v in once["stats"].items()} == twice["stats"]
