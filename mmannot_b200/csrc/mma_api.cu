@@ -57,7 +57,7 @@ struct Sample {
   DevBuf slowKey, slowOrd, slowMask, slowNh, openKeys, openSeq;
   u32 slowCap = 0, openCap = 0;
   // host-side bound on the number of deferred records (see ensureDeferred)
-  u32 *countRing = nullptr;  // pinned, 4 entries
+  u32 *countRing = nullptr;  // pinned, 4 entries of slowCount followed by 4 entries of walkCount
   cudaEvent_t ringEv[4] = {nullptr, nullptr, nullptr, nullptr};
   uint64_t ringCum[4] = {0, 0, 0, 0};
   bool ringUsed[4] = {false, false, false, false};
@@ -102,6 +102,8 @@ struct mma_ctx {
   uint64_t launches = 0, hitsSubmitted = 0, batches = 0;
   int nSM = 148;
   u32 maxGrid = 0;           // MMANNOT_B200_MAX_GRID=n: cap on k_batch blocks, so that small test inputs still give every warp a multi-tile chunk (testing only)
+  int forceGroups = -1;      // MMANNOT_B200_GROUPS=0/1: pin the variant (testing only)
+  bool useGroups = false;    // k_batch_fast variant for runs of k x NH records, chosen from the walk counters of earlier batches
   bool legacyBatch = false;  // MMANNOT_B200_LEGACY_BATCH=1: A/B runs of the general k_batch against k_batch_fast (tuning only)
   std::vector<uint32_t> intervalIds;  // result of the last mma_annotate_intervals
   u64 *hostTable = nullptr;  // pinned: [TableDump | rows] of the sample being read back
@@ -163,7 +165,7 @@ int initSample(mma_ctx *ctx, Sample &s) {
   const size_t tb = (size_t)ctx->tableCap * sizeof(u64);
   CK(s.tableKeys.ensure(tb)); CK(s.tableVals.ensure(tb));
   CK(cudaMemsetAsync(s.tableKeys.p, 0, tb, ctx->sc)); CK(cudaMemsetAsync(s.tableVals.p, 0, tb, ctx->sc));
-  CK(cudaHostAlloc(&s.countRing, 4 * sizeof(u32), cudaHostAllocDefault));
+  CK(cudaHostAlloc(&s.countRing, 8 * sizeof(u32), cudaHostAllocDefault));
   for (int i = 0; i < 4; ++i) CK(cudaEventCreateWithFlags(&s.ringEv[i], cudaEventDisableTiming));
   return MMA_OK;
 }
@@ -195,6 +197,13 @@ int ensureDeferred(mma_ctx *ctx, Sample &s, uint64_t n) {
     if (!s.ringUsed[slot]) continue;
     if (cudaEventQuery(s.ringEv[slot]) == cudaSuccess) {
       if (s.ringCum[slot] >= s.knownCum) { s.knownCount = s.countRing[slot]; s.knownCum = s.ringCum[slot]; }
+      // many serial walks (or, in the GROUPS variant, many groups beyond the first of their run) per hit so far: paired-end
+      // like input, keep / switch to the GROUPS variant; hardly any: the plain variant (hysteresis in between)
+      const uint64_t walks = s.countRing[4 + slot], hitsSoFar = std::max<uint64_t>(s.ringCum[slot], 1);
+      if (ctx->forceGroups < 0) {
+        if (walks * 32 > hitsSoFar) ctx->useGroups = true;
+        else if (walks * 256 < hitsSoFar) ctx->useGroups = false;
+      }
       break;
     }
   }
@@ -255,7 +264,9 @@ void launchBatchKernels(mma_ctx *ctx, Sample &s, const HitView &h) {
     u32 grid = std::max<u32>(1u, std::min<u32>((nWT + FAST_WARPS - 1) / FAST_WARPS, (u32)ctx->nSM * MMA_FAST_BLOCKS_PER_SM));
     if (ctx->maxGrid) grid = std::min(grid, ctx->maxGrid);
     mma_ctx::Timed t(ctx, TC_BATCH);
-    k_batch_fast<MODE, STRAT><<<grid, FAST_THREADS, 0, ctx->sc>>>(ctx->index, ctx->fast, h, r, table, s.ctl, slow, open);
+    // runs of k x NH records (paired-end data): the GROUPS variant once a batch has shown many of them (see afterBatch)
+    if (STRAT == 0 && ctx->useGroups) k_batch_fast<MODE, STRAT, (STRAT == 0)><<<grid, FAST_THREADS, 0, ctx->sc>>>(ctx->index, ctx->fast, h, r, table, s.ctl, slow, open);
+    else k_batch_fast<MODE, STRAT, false><<<grid, FAST_THREADS, 0, ctx->sc>>>(ctx->index, ctx->fast, h, r, table, s.ctl, slow, open);
   }
   if (!launched) {
     const u32 perSM = (sizeof(MaskT) == 4) ? MMA_BLOCKS_PER_SM : 2;
@@ -306,6 +317,7 @@ int afterBatch(mma_ctx *ctx, Sample &s, uint64_t n) {
   ctx->hitsSubmitted += n;
   const int slot = (int)(s.seq & 3);
   CK(cudaMemcpyAsync(&s.countRing[slot], &s.ctl->slowCount, sizeof(u32), cudaMemcpyDeviceToHost, ctx->sc));
+  CK(cudaMemcpyAsync(&s.countRing[4 + slot], &s.ctl->walkCount, sizeof(u32), cudaMemcpyDeviceToHost, ctx->sc));
   CK(cudaEventRecord(s.ringEv[slot], ctx->sc));
   s.ringCum[slot] = s.cumHits;
   s.ringUsed[slot] = true;
@@ -391,6 +403,7 @@ int mma_create(mma_ctx **out, const mma_params *p) {
     if ((e = cudaEventCreateWithFlags(&ctx->stage[k].done, cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
   }
   { const char *lg = getenv("MMANNOT_B200_LEGACY_BATCH"); ctx->legacyBatch = lg && lg[0] == '1';
+    const char *fg = getenv("MMANNOT_B200_GROUPS"); if (fg && (fg[0] == '0' || fg[0] == '1')) { ctx->forceGroups = fg[0] - '0'; ctx->useGroups = fg[0] == '1'; }
     const char *mg = getenv("MMANNOT_B200_MAX_GRID"); ctx->maxGrid = mg ? (u32)std::max(0, atoi(mg)) : 0u; }
   ctx->samples.resize(p->n_samples);
   *out = ctx;

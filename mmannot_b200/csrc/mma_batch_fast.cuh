@@ -118,7 +118,9 @@ struct FastCount {  // one read counted for an element set, from divergent code 
   }
 };
 
-template <int MODE, int STRAT>
+// GROUPS: runs of k x NH records (paired-end data) are resolved in parallel as k reads; costs registers, so the host only
+// switches to this variant when a batch has sent many runs to the serial walker (walk counter of the control block)
+template <int MODE, int STRAT, bool GROUPS>
 __global__ void __launch_bounds__(FAST_THREADS, MMA_FAST_BLOCKS_PER_SM)
 k_batch_fast(const __grid_constant__ IndexView ix, const __grid_constant__ FastView fx, const __grid_constant__ HitView h, const __grid_constant__ Rules r,
              const __grid_constant__ TableView table, SampleCtl *ctl, const __grid_constant__ SlowView slow, const __grid_constant__ KeySetView open) {
@@ -144,6 +146,7 @@ k_batch_fast(const __grid_constant__ IndexView ix, const __grid_constant__ FastV
   u32 pMultAmbi = 0;  // hits joining the by-name countdown | ambiguous hits << 16               (mm:1670, 1667)
   u32 pHitsMiss = 0;  // hits looked at | segment-table misses << 16
   u32 pClosResc = 0;  // multi-mapping reads closed by the parallel countdown | of which rescued << 16
+  u32 pWalks = 0;     // serial walks started (feeds the host's choice between the two variants of this kernel)
 
   FastCount<HIST, SLOTS> count{sm, table, tid};
   RunWalker<MODE, true, FastCount<HIST, SLOTS>> w{h, r, annot, ctl, slow, open, count, seq, 0u, 0u};
@@ -347,67 +350,167 @@ k_batch_fast(const __grid_constant__ IndexView ix, const __grid_constant__ FastV
         }
     }
     u32 nWalk = 0, closeBits = 0;
-    u32 inc = 0, lastHeadPos = 0;
-    if (STRAT == 0) {
-      // ---- per-read countdown (mm:1669-1702)
-      if (carryIn) {  // lane 0 of the batch's first tile: the read carried into this batch
-        if (!(hbits & 1u)) w.walk(0, carryIn->key, carryIn);
-        else {  // its name does not continue: unfinished
-          --w.nReads;
-          slowAppend(slow, ctl, carryIn->key, carryIn->ord, carryIn->gm, carryIn->remaining + 1);
-          keySetInsert(open, carryIn->key, seq, ctl);
-          ctl->dirty = 1;
+    u32 inc = 0, lastHeadPos = 0, F2 = 0;
+    bool serialTile = false;
+    if (GROUPS) {
+      if (STRAT == 0) {
+        // ---- per-read countdown (mm:1669-1702)
+        if (carryIn) {  // lane 0 of the batch's first tile: the read carried into this batch
+          if (!(hbits & 1u)) w.walk(0, carryIn->key, carryIn);
+          else {  // its name does not continue: unfinished
+            --w.nReads;
+            slowAppend(slow, ctl, carryIn->key, carryIn->ord, carryIn->gm, carryIn->remaining + 1);
+            keySetInsert(open, carryIn->key, seq, ctl);
+            ctl->dirty = 1;
+          }
+        }
+        // A read opens at a record with NH = n > 1 and takes the n - 1 records of its name that follow, so a run of records
+        // sharing a read key and carrying the same NH = n is a sequence of GROUPS of n records, one read each (one group for
+        // single-end data, two -- the two mates -- for paired-end data, mm:1673-1681).  The element set of a read is the
+        // union over its group: a segmented OR scan over the 128 hits of the warp tile, segments starting at run starts and
+        // at every n-th record of a run, seeded with the state carried from the previous tile; the lane owning the LAST
+        // record of a group counts the read.  A run that ends inside a group leaves an unfinished read: serial walk
+        // (RunWalker) from the start of that group.  A tile in which NH changes inside a run -- or any tile while rescue() needs
+        // multiplicities or some read name is known as unfinished -- is resolved serially: one walk per run (serialTile).
+        u32 prevNh = __shfl_up_sync(FULL, nh[3], 1);
+        if (lane == 0) prevNh = cNh;
+        const u32 badBits = ((!(hbits & 1u) && nh[0] != prevNh) ? 1u : 0u) | ((!(hbits & 2u) && nh[1] != nh[0]) ? 2u : 0u) |
+                            ((!(hbits & 4u) && nh[2] != nh[1]) ? 4u : 0u) | ((!(hbits & 8u) && nh[3] != nh[2]) ? 8u : 0u);
+        serialTile = forceWalk || __any_sync(FULL, (badBits & validBits) != 0);
+        const u32 before = F & ((1u << lane) - 1u);
+        lastHeadPos = base + (31 - __clz(hbits | 1u));
+        const u32 sPrev = __shfl_sync(FULL, lastHeadPos, before ? (31 - __clz(before)) : 0);
+        // a run that starts before this lane's hits: its first record, and whether this warp owns it at all
+        const u32 inStart = before ? sPrev : cStart;
+        const bool inMine = before || cValid;  // else the run starts in another warp's chunk: that warp finishes it
+        if (!serialTile) {
+          const u32 nextHead0 = __shfl_down_sync(FULL, hbits & 1u, 1);
+          // bit j: the next record starts another run, i.e. this record ends its run (the tile's last record: from the peek)
+          const u32 lastBits = ((hbits >> 1) | ((lane < 31u ? nextHead0 : tileEndsRun) << 3)) & validBits;
+          u32 off[4];           // position of the record inside its group
+          u32 hb2 = hbits, endBits = 0, tailBits = 0;
+          bool longRun = false;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const u32 hbLe = hbits & ((2u << j) - 1u);
+            const u32 runStart = hbLe ? base + (31 - __clz(hbLe)) : inStart;
+            const bool mine = (hbLe || inMine) && ((validBits >> j) & 1u) && nh[j] > 1;
+            u32 o = base + j - runStart;
+            if (o >= nh[j]) o -= nh[j];
+            if (mine && o >= nh[j]) longRun = true;  // third group or later: exact remainder below
+            off[j] = o;
+          }
+          if (__any_sync(FULL, longRun)) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              if (nh[j] > 1) off[j] %= nh[j];
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const u32 hbLe = hbits & ((2u << j) - 1u);
+            const bool mine = (hbLe || inMine) && ((validBits >> j) & 1u) && nh[j] > 1;
+            if (mine && off[j] == 0) hb2 |= 1u << j;                                  // first record of a group
+            if (mine && off[j] + 1 == nh[j]) endBits |= 1u << j;                      // last record of a group
+            else if (mine && ((lastBits >> j) & 1u)) tailBits |= 1u << j;             // the run ends inside a group
+          }
+          F2 = __ballot_sync(FULL, hb2 != 0);
+        pWalks += __popc(hb2 & ~hbits);  // groups beyond the first of their run: what the other variant would walk serially
+          u32 pre[4], acc = 0;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            acc = ((hb2 >> j) & 1u) ? m[j] : (acc | m[j]);
+            pre[j] = acc;
+          }
+          inc = acc;  // inclusive scan over lanes: OR of `acc` from the nearest lane with a group start up to this lane
+#pragma unroll
+          for (int d = 1; d < 32; d <<= 1) {
+            const u32 tt = __shfl_up_sync(FULL, inc, d);
+            if (lane >= (u32)d && ((F2 >> (lane - d + 1)) & ((1u << d) - 1u)) == 0) inc |= tt;
+          }
+          u32 X = __shfl_up_sync(FULL, inc, 1);
+          if (lane == 0) X = 0;
+          const u32 inTot = (F2 & ((1u << lane) - 1u)) ? X : (cTot | X);  // union so far of a group that starts before this lane's hits
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            if ((endBits >> j) & 1u) {
+              ev[j] = (hb2 & ((2u << j) - 1u)) ? pre[j] : (inTot | pre[j]);
+              closeBits |= 1u << j;
+            }
+            if ((tailBits >> j) & 1u) sm.walkQ[nWalk++][tid] = base + j - off[j];
+          }
+        } else {
+          // serial tile: the run carried into the tile (from the start of its open group) and every run that starts in it
+          if (lane == 0 && cValid && !(hbits & 1u) && (validBits & 1u)) {
+            const u32 o = base - cStart;
+            sm.walkQ[nWalk++][tid] = base - ((cNh > 1) ? o % cNh : 0u);
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if (((hbits & validBits) >> j) & 1u) sm.walkQ[nWalk++][tid] = base + j;
         }
       }
-      // A run of n records that all carry NH = n (> 1) is one read; its element set is the union over the run: a
-      // segmented OR scan over the 128 hits of the warp tile (bit 31 of the scanned word = "irregular": NH changes inside
-      // the run, or every run has to be walked), seeded with the state carried from the previous tile.  The lane owning
-      // the run's LAST record closes it; irregular runs take the serial walk (RunWalker), started by the same lane.
-      u32 prevNh = __shfl_up_sync(FULL, nh[3], 1);
-      if (lane == 0) prevNh = cNh;
-      u32 pre[4], acc = 0;
-      const u32 force = forceWalk ? 0x80000000u : 0u;
+    } else {
+      if (STRAT == 0) {
+        // ---- per-read countdown (mm:1669-1702)
+        if (carryIn) {  // lane 0 of the batch's first tile: the read carried into this batch
+          if (!(hbits & 1u)) w.walk(0, carryIn->key, carryIn);
+          else {  // its name does not continue: unfinished
+            --w.nReads;
+            slowAppend(slow, ctl, carryIn->key, carryIn->ord, carryIn->gm, carryIn->remaining + 1);
+            keySetInsert(open, carryIn->key, seq, ctl);
+            ctl->dirty = 1;
+          }
+        }
+        // A run of n records that all carry NH = n (> 1) is one read; its element set is the union over the run: a
+        // segmented OR scan over the 128 hits of the warp tile (bit 31 of the scanned word = "irregular": NH changes inside
+        // the run, or every run has to be walked), seeded with the state carried from the previous tile.  The lane owning
+        // the run's LAST record closes it; irregular runs take the serial walk (RunWalker), started by the same lane.
+        u32 prevNh = __shfl_up_sync(FULL, nh[3], 1);
+        if (lane == 0) prevNh = cNh;
+        u32 pre[4], acc = 0;
+        const u32 force = forceWalk ? 0x80000000u : 0u;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const bool isHead = (hbits >> j) & 1u;
-        const bool bad = !isHead && nh[j] != (j ? nh[j > 0 ? j - 1 : 0] : prevNh);
-        const u32 x = m[j] | (bad ? 0x80000000u : 0u) | force;
-        acc = isHead ? x : (acc | x);
-        pre[j] = acc;
-      }
-      inc = acc;  // inclusive scan over lanes: OR of `acc` from the nearest lane with a run start up to this lane
+        for (int j = 0; j < 4; ++j) {
+          const bool isHead = (hbits >> j) & 1u;
+          const bool bad = !isHead && nh[j] != (j ? nh[j > 0 ? j - 1 : 0] : prevNh);
+          const u32 x = m[j] | (bad ? 0x80000000u : 0u) | force;
+          acc = isHead ? x : (acc | x);
+          pre[j] = acc;
+        }
+        inc = acc;  // inclusive scan over lanes: OR of `acc` from the nearest lane with a run start up to this lane
 #pragma unroll
-      for (int d = 1; d < 32; d <<= 1) {
-        const u32 tt = __shfl_up_sync(FULL, inc, d);
-        if (lane >= (u32)d && ((F >> (lane - d + 1)) & ((1u << d) - 1u)) == 0) inc |= tt;
-      }
-      u32 X = __shfl_up_sync(FULL, inc, 1);
-      if (lane == 0) X = 0;
-      const u32 before = F & ((1u << lane) - 1u);
-      lastHeadPos = base + (31 - __clz(hbits | 1u));
-      const u32 sPrev = __shfl_sync(FULL, lastHeadPos, before ? (31 - __clz(before)) : 0);
-      const u32 nextHead0 = __shfl_down_sync(FULL, hbits & 1u, 1);
-      // bit j: the next record starts another run, i.e. this record ends its run (the tile's last record: from the peek)
-      const u32 lastBits = ((hbits >> 1) | ((lane < 31u ? nextHead0 : tileEndsRun) << 3)) & validBits;
-      // a run that starts before this lane's hits: union so far, first record, and whether this warp owns it at all
-      const u32 inTot = before ? X : (cTot | X);
-      const u32 inStart = before ? sPrev : cStart;
-      const bool inMine = before || cValid;  // else the run starts in another warp's chunk: that warp finishes it
+        for (int d = 1; d < 32; d <<= 1) {
+          const u32 tt = __shfl_up_sync(FULL, inc, d);
+          if (lane >= (u32)d && ((F >> (lane - d + 1)) & ((1u << d) - 1u)) == 0) inc |= tt;
+        }
+        u32 X = __shfl_up_sync(FULL, inc, 1);
+        if (lane == 0) X = 0;
+        const u32 before = F & ((1u << lane) - 1u);
+        lastHeadPos = base + (31 - __clz(hbits | 1u));
+        const u32 sPrev = __shfl_sync(FULL, lastHeadPos, before ? (31 - __clz(before)) : 0);
+        const u32 nextHead0 = __shfl_down_sync(FULL, hbits & 1u, 1);
+        // bit j: the next record starts another run, i.e. this record ends its run (the tile's last record: from the peek)
+        const u32 lastBits = ((hbits >> 1) | ((lane < 31u ? nextHead0 : tileEndsRun) << 3)) & validBits;
+        // a run that starts before this lane's hits: union so far, first record, and whether this warp owns it at all
+        const u32 inTot = before ? X : (cTot | X);
+        const u32 inStart = before ? sPrev : cStart;
+        const bool inMine = before || cValid;  // else the run starts in another warp's chunk: that warp finishes it
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const bool last = (lastBits >> j) & 1u;
-        const u32 hbLe = hbits & ((2u << j) - 1u);
-        // union of the run's element sets and its first record, wherever the run starts
-        const u32 tot = hbLe ? pre[j] : (inTot | pre[j]);
-        const u32 runStart = hbLe ? base + (31 - __clz(hbLe)) : inStart;
-        const bool mine = hbLe || inMine;
-        const bool flagged = (tot & 0x80000000u) != 0;
-        // a run of reads that are their own group (NH <= 1 throughout) has nothing to close
-        const bool irregular = flagged || (nh[j] > 1 && nh[j] != base + j + 1 - runStart);
-        if (last && mine && irregular) sm.walkQ[nWalk++][tid] = runStart;
-        if (last && mine && !irregular && nh[j] > 1) {
-          ev[j] = tot & 0x7FFFFFFFu;
-          closeBits |= 1u << j;
+        for (int j = 0; j < 4; ++j) {
+          const bool last = (lastBits >> j) & 1u;
+          const u32 hbLe = hbits & ((2u << j) - 1u);
+          // union of the run's element sets and its first record, wherever the run starts
+          const u32 tot = hbLe ? pre[j] : (inTot | pre[j]);
+          const u32 runStart = hbLe ? base + (31 - __clz(hbLe)) : inStart;
+          const bool mine = hbLe || inMine;
+          const bool flagged = (tot & 0x80000000u) != 0;
+          // a run of reads that are their own group (NH <= 1 throughout) has nothing to close
+          const bool irregular = flagged || (nh[j] > 1 && nh[j] != base + j + 1 - runStart);
+          if (last && mine && irregular) sm.walkQ[nWalk++][tid] = runStart;
+          if (last && mine && !irregular && nh[j] > 1) {
+            ev[j] = tot & 0x7FFFFFFFu;
+            closeBits |= 1u << j;
+          }
         }
       }
     }
@@ -444,25 +547,52 @@ k_batch_fast(const __grid_constant__ IndexView ix, const __grid_constant__ FastV
       }
     }
     if (STRAT == 0) {
+      pWalks += nWalk;
 #pragma unroll 1
       for (u32 q = 0; q < nWalk; ++q) { const u32 i0 = sm.walkQ[q][tid]; w.walk(i0, normKey(h.key[i0]), nullptr); }
-      // the run still open at the end of the tile
-      const u32 incLast = __shfl_sync(FULL, inc, 31);
-      if (F) {
-        cTot = incLast;
-        cStart = __shfl_sync(FULL, lastHeadPos, 31 - __clz(F));
-        cValid = true;
-      } else if (cValid) {
-        cTot |= incLast;
+      if (GROUPS) {
+        // the run (and, inside it, the group) still open at the end of the tile
+        if (!serialTile) {
+          const u32 incLast = __shfl_sync(FULL, inc, 31);
+          if (F2) cTot = incLast;
+          else cTot |= incLast;
+          if (F) {
+            cStart = __shfl_sync(FULL, lastHeadPos, 31 - __clz(F));
+            cValid = true;
+          }
+        } else {
+          cValid = false;  // every run reaching into or starting in the tile has been walked to its end
+          cTot = 0;
+        }
+      } else {
+        // the run still open at the end of the tile
+        const u32 incLast = __shfl_sync(FULL, inc, 31);
+        if (F) {
+          cTot = incLast;
+          cStart = __shfl_sync(FULL, lastHeadPos, 31 - __clz(F));
+          cValid = true;
+        } else if (cValid) {
+          cTot |= incLast;
+        }
       }
       cNh = __shfl_sync(FULL, nh[3], 31);
       cKey = nextKey;
       cCont = __shfl_sync(FULL, tileEndsRun, 31) == 0;
     }
   }
-  // ---- a read open at the end of the chunk that continues in another warp's chunk: finished by the serial walk.  (A run
-  //      ending exactly at the chunk's last record was closed above, like the last run of the batch.)
-  if (STRAT == 0 && cValid && cCont && t1 > t0 && lane == 0) w.walk(cStart, cKey, nullptr);
+  if (GROUPS) {
+    // ---- a run open at the end of the chunk continues in another warp's chunk: its remaining reads, from the group that is
+    //      open there (or starts there), are finished by the serial walk.  (A run ending exactly at the chunk's last record
+    //      was closed above, like the last run of the batch.)
+    if (STRAT == 0 && cValid && cCont && t1 > t0 && lane == 0) {
+      const u32 next = t1 * WT_HITS, o = next - cStart;
+      w.walk(next - ((cNh > 1) ? o % cNh : 0u), cKey, nullptr);
+    }
+  } else {
+    // ---- a read open at the end of the chunk that continues in another warp's chunk: finished by the serial walk.  (A run
+    //      ending exactly at the chunk's last record was closed above, like the last run of the batch.)
+    if (STRAT == 0 && cValid && cCont && t1 > t0 && lane == 0) w.walk(cStart, cKey, nullptr);
+  }
   u32 cHits = pHitsMiss & 0xFFFFu, cMiss = pHitsMiss >> 16, cUnassigned = cHits - (pAsgUniq & 0xFFFFu), cAmbiguous = pMultAmbi >> 16;
   u32 cUnique = pAsgUniq >> 16, cMultiple = pMultAmbi & 0xFFFFu;
   u32 cReads = cHits - cMultiple + (pClosResc & 0xFFFFu) + w.nReads, cRescued = (pClosResc >> 16) + w.nRescued;
@@ -472,6 +602,10 @@ k_batch_fast(const __grid_constant__ IndexView ix, const __grid_constant__ FastV
   cAmbiguous = __reduce_add_sync(FULL, cAmbiguous); cUnique = __reduce_add_sync(FULL, cUnique);
   cMultiple = __reduce_add_sync(FULL, cMultiple); cReads = __reduce_add_sync(FULL, cReads);
   cRescued = __reduce_add_sync(FULL, cRescued); cMiss = __reduce_add_sync(FULL, cMiss);
+  if (STRAT == 0 && !forceWalk) {
+    pWalks = __reduce_add_sync(FULL, pWalks);
+    if (lane == 0 && pWalks) atomicAdd(&ctl->walkCount, pWalks);
+  }
   if (lane == 0) {
     atomicAdd(&sm.stat[ST_HITS], cHits); atomicAdd(&sm.stat[ST_UNASSIGNED], cUnassigned); atomicAdd(&sm.stat[ST_AMBIGUOUS], cAmbiguous);
     atomicAdd(&sm.stat[ST_UNIQUE], cUnique); atomicAdd(&sm.stat[ST_MULTIPLE], cMultiple); atomicAdd(&sm.stat[ST_READS], cReads);

@@ -111,7 +111,7 @@ struct SampleCtl {
   u32 overflow;      // any capacity problem (tables, deferred list, key set)
   u32 closeCount;    // blocks of k_batch_close that are done
   u32 fastMiss;      // hits the segment table could not answer (diagnostics)
-  u32 pad;
+  u32 walkCount;     // k_batch_fast: runs that needed the serial walker, or (GROUPS variant) groups beyond the first of a run
 };
 
 struct SlowView {  // deferred records: resolved after a (key, ordinal) sort at end of sample

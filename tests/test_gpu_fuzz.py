@@ -289,3 +289,32 @@ def test_export_import_tables_on_device():
     check(once, ref)
     assert {k: 2 * v for k, v in once["rows"].items()} == twice["rows"]
     assert {k: 2 * v for k, v in once["stats"].items()} == twice["stats"]
+
+
+@pytest.mark.parametrize("groups", ["0", "1"])
+@pytest.mark.parametrize("seed", range(3))
+def test_runs_of_k_times_nh_records(seed, groups, monkeypatch):
+    """Paired-end shaped input: every name is a run of 2 x NH (sometimes 3 x NH) records carrying NH, i.e. two (three) reads
+    back to back (mmannot.cpp:1673-1698).  Both variants of k_batch_fast (runs resolved group by group in parallel /
+    serial walker), natural and capped grids, cut batches, plus some irregular names."""
+    monkeypatch.setenv("MMANNOT_B200_GROUPS", groups)
+    if seed == 2:
+        monkeypatch.setenv("MMANNOT_B200_MAX_GRID", "2")
+    rng = np.random.default_rng(5100 + seed)
+    et = fuzz.make_elements(rng)
+    feats = fuzz.make_features(rng, et, n_feat=400)
+    base = fuzz.make_hits(rng, feats, n_reads=30000, max_nh=(4, 9, 40)[seed], messy=(0.0, 0.03, 0.0)[seed])
+    # every name k times in a row
+    heads = np.nonzero(np.concatenate([[True], base.read_key[1:] != base.read_key[:-1]]))[0]
+    ends = np.concatenate([heads[1:], [base.n]])
+    idx = []
+    for a, b in zip(heads, ends):
+        k = 3 if (a % 11 == 0) else 2
+        for _ in range(k):
+            idx.extend(range(a, b))
+    idx = np.array(idx)
+    from mmannot_b200 import host
+    hits = host.Hits(base.start[idx], base.end[idx], base.meta[idx], base.nh[idx], base.read_key[idx])
+    ref = oracle_run(et, feats, hits)
+    for batch in (1 << 21, 20011):
+        check(device_run(et, feats, hits, max_batch=batch), ref)
