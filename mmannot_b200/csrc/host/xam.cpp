@@ -3,6 +3,7 @@
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
+#include <memory>
 #include <thread>
 
 namespace mmb {
@@ -54,6 +55,13 @@ std::string XamReader::takeWarnings() {
 uint32_t XamReader::chrMetaOf(const std::string &name) {
   auto it = chrByName_.find(name);
   if (it != chrByName_.end()) return it->second;
+  if (clone_) {  // the owning reader decides, in record order, whether the name is new (decodeBamChunkParallel)
+    if (std::find(unknownChr_.begin(), unknownChr_.end(), name) == unknownChr_.end()) {
+      warnings_ += '\x01' + name + "\n";
+      unknownChr_.push_back(name);
+    }
+    return HIT_CHR_NONE;
+  }
   if (std::find(unknownChr_.begin(), unknownChr_.end(), name) == unknownChr_.end()) {
     if (name != "*")
       warnings_ += "\t\tWarning!  Chromosome '" + name + "' (found in your reads) is not present in your annotation file.\n";
@@ -89,6 +97,7 @@ bool XamReader::open(std::string &err) {
     unsigned threads = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
     if (const char *e = std::getenv("MMANNOT_B200_DECODE_THREADS")) threads = static_cast<unsigned>(std::max(1, std::atoi(e)));
     useBgzf_ = bgzf_.open(fileName_, threads);
+    parseThreads_ = threads;
   }
   if (!useBgzf_) {  // plain gzip (or uncompressed): the reference's own route, gzread
     gz_ = gzopen(fileName_.c_str(), "rb");
@@ -227,6 +236,7 @@ void XamReader::pushRecordHits(const std::string &name, uint32_t chrMeta, uint64
 }
 
 bool XamReader::decodeBamRecord() {
+  if (decodeBamChunkParallel() > 0) return true;
   if (!fillRaw(4)) return false;
   uint32_t blockSize = le32(&raw_[rawPos_]);
   if (!fillRaw(static_cast<size_t>(blockSize) + 4)) {
@@ -234,9 +244,17 @@ bool XamReader::decodeBamRecord() {
     return false;
   }
   const unsigned char *p = &raw_[rawPos_ + 4];
-  const unsigned char *recEnd = p + blockSize;
   rawPos_ += static_cast<size_t>(blockSize) + 4;
-  if (blockSize < 32) return true;  // malformed, skip
+  parseBamRecord(p, blockSize);
+  return true;
+}
+
+// One BAM alignment record (the bytes after its block_size field) -> hits.  Touches only the parser state of `this`
+// (scratch buffers, NM carried from record to record, chromosome cache, pending hits, warnings), so that the records of a
+// chunk can be parsed by several parser clones side by side (decodeBamChunkParallel).
+void XamReader::parseBamRecord(const unsigned char *p, uint32_t blockSize) {
+  const unsigned char *recEnd = p + blockSize;
+  if (blockSize < 32) return;  // malformed, skip
   int32_t refId = static_cast<int32_t>(le32(p));
   int32_t pos = static_cast<int32_t>(le32(p + 4));
   uint32_t lReadName = le32(p + 8) & 0xff;
@@ -244,7 +262,7 @@ bool XamReader::decodeBamRecord() {
   uint32_t flag = flagNc >> 16, nCigar = flagNc & 0xffff;
   uint32_t lSeq = le32(p + 16);
   const unsigned char *q = p + 32;
-  if (q + lReadName + 4ull * nCigar + (lSeq + 1ull) / 2 + lSeq > recEnd) return true;  // malformed, skip
+  if (q + lReadName + 4ull * nCigar + (lSeq + 1ull) / 2 + lSeq > recEnd) return;  // malformed, skip
   // (buffers reused from record to record: no allocation on the hot path)
   std::string &name = nameBuf_;
   name.assign(reinterpret_cast<const char *>(q), strnlen(reinterpret_cast<const char *>(q), lReadName));  // up to the first NUL (mm:1545)
@@ -307,8 +325,113 @@ bool XamReader::decodeBamRecord() {
   }
   uint64_t start = static_cast<uint64_t>(static_cast<int64_t>(pos) + 1);  // ++pos then widened (mm:1536-1537)
   pushRecordHits(name, chrMeta, start, (flag & 0x10) == 0, cigar, false, nHits);
-  return true;
 }
+
+namespace {
+// NM as the record parser leaves it after this record (mm:1596-1618: only the unsigned integer types carry a value, any
+// other type of an NM tag gives 0); false when the record has no NM tag
+bool lastNmOfRecord(const unsigned char *p, uint32_t blockSize, uint32_t &nm) {
+  if (blockSize < 32) return false;
+  const unsigned char *recEnd = p + blockSize;
+  const uint32_t lReadName = le32(p + 8) & 0xff, nCigar = le32(p + 12) & 0xffff, lSeq = le32(p + 16);
+  const unsigned char *q = p + 32;
+  if (q + lReadName + 4ull * nCigar + (lSeq + 1ull) / 2 + lSeq > recEnd) return false;
+  q += lReadName + 4ull * nCigar + (lSeq + 1ull) / 2 + lSeq;
+  bool found = false;
+  while (q + 3 <= recEnd) {
+    const char t0 = static_cast<char>(q[0]), t1 = static_cast<char>(q[1]), ty = static_cast<char>(q[2]);
+    q += 3;
+    uint32_t vU = 0;
+    bool bad = false;
+    switch (ty) {
+      case 'A': case 'c': q += 1; break;
+      case 'C': if (q + 1 <= recEnd) vU = q[0]; q += 1; break;
+      case 's': q += 2; break;
+      case 'S': if (q + 2 <= recEnd) vU = le16(q); q += 2; break;
+      case 'i': case 'f': q += 4; break;
+      case 'I': if (q + 4 <= recEnd) vU = le32(q); q += 4; break;
+      case 'Z': case 'H': { while (q < recEnd && *q) ++q; ++q; break; }
+      case 'B': {
+        if (q + 5 > recEnd) { bad = true; break; }
+        const char sub = static_cast<char>(q[0]);
+        const uint64_t cnt = le32(q + 1), width = (sub == 'c' || sub == 'C') ? 1 : (sub == 's' || sub == 'S') ? 2 : 4;
+        q += 5 + cnt * width;
+        break;
+      }
+      default: bad = true;
+    }
+    if (bad || q > recEnd) break;
+    if (t0 == 'N' && t1 == 'M') { nm = vU; found = true; }
+  }
+  return found;
+}
+}  // namespace
+
+// Parses every complete record currently in the raw buffer with several parser clones, each on a contiguous range of
+// records, and appends their hits, warnings and counters in record order.  Returns the number of records consumed (0: not
+// enough data for this to pay off, the caller parses one record the usual way).
+size_t XamReader::decodeBamChunkParallel() {
+  if (parseThreads_ < 2 || keepNames_) return 0;
+  if (raw_.size() < (32u << 20)) raw_.resize(32u << 20);
+  fillRaw(std::min<size_t>(raw_.size(), 4));  // tops the buffer up (no-op at end of input)
+  // index the complete records
+  recOff_.clear();
+  size_t pos = rawPos_;
+  while (pos + 4 <= rawEnd_) {
+    const size_t bs = le32(&raw_[pos]);
+    if (pos + 4 + bs > rawEnd_) break;
+    recOff_.push_back(pos);
+    pos += 4 + bs;
+  }
+  const size_t nRec = recOff_.size();
+  if (nRec < 4096) return 0;
+  const unsigned nT = static_cast<unsigned>(std::min<size_t>(parseThreads_, nRec / 1024));
+  std::vector<std::unique_ptr<XamReader> > clones;
+  for (unsigned t = 0; t < nT; ++t) clones.emplace_back(new XamReader(*this, 0));
+  auto work = [&](unsigned t) {
+    XamReader &c = *clones[t];
+    const size_t lo = nRec * t / nT, hi = nRec * (t + 1) / nT;
+    // NM carried into the range: from the nearest earlier record of the chunk that has the tag, else the reader's own
+    c.nMismatches_ = nMismatches_;
+    for (size_t k = lo; k-- > 0;) {
+      uint32_t nm;
+      if (lastNmOfRecord(&raw_[recOff_[k] + 4], le32(&raw_[recOff_[k]]), nm)) { c.nMismatches_ = nm; break; }
+    }
+    c.pending_.reserve((hi - lo) + (hi - lo) / 8);
+    for (size_t k = lo; k < hi; ++k) c.parseBamRecord(&raw_[recOff_[k] + 4], le32(&raw_[recOff_[k]]));
+  };
+  {
+    std::vector<std::thread> pool;
+    for (unsigned t = 1; t < nT; ++t) pool.emplace_back(work, t);
+    work(0);
+    for (std::thread &th : pool) th.join();
+  }
+  for (unsigned t = 0; t < nT; ++t) {  // merge in record order
+    XamReader &c = *clones[t];
+    pending_.insert(pending_.end(), c.pending_.begin(), c.pending_.end());
+    nRecords_ += c.nRecords_;
+    // warnings: lines starting with \x01 announce a chromosome the clone did not know
+    size_t a = 0;
+    while (a < c.warnings_.size()) {
+      size_t b = c.warnings_.find('\n', a);
+      if (b == std::string::npos) b = c.warnings_.size() - 1;
+      if (c.warnings_[a] == '\x01') (void)chrMetaOf(c.warnings_.substr(a + 1, b - a - 1));
+      else warnings_.append(c.warnings_, a, b - a + 1);
+      a = b + 1;
+    }
+    for (size_t r = 0; r < bamChrMeta_.size(); ++r)
+      if (bamChrMeta_[r] == 0xFFFFFFFFu && c.bamChrMeta_[r] != 0xFFFFFFFFu) bamChrMeta_[r] = c.bamChrMeta_[r];
+  }
+  nMismatches_ = clones[nT - 1]->nMismatches_;
+  rawPos_ = pos;
+  return nRec;
+}
+
+// parser clone: the read-only tables of `parent`, fresh parser state
+XamReader::XamReader(const XamReader &parent, int)
+    : fileName_(parent.fileName_), format_(parent.format_), strandedness_(parent.strandedness_), features_(parent.features_),
+      chrByName_(parent.chrByName_), unknownChr_(), bam_(true), bamChrMeta_(parent.bamChrMeta_), bamChrName_(parent.bamChrName_),
+      clone_(true) {}
 
 bool XamReader::decodeSamRecord() {
   std::string line;

@@ -54,7 +54,10 @@ class XamReader {
   struct Alt { uint32_t chrMeta; bool strand; uint64_t start; std::vector<std::pair<char, int> > cigar; };
 
   bool fillRaw(size_t need);  // make `need` bytes available at rawPos_ (BAM)
+  XamReader(const XamReader &parent, int);  // parser clone (decodeBamChunkParallel)
   bool decodeBamRecord();
+  void parseBamRecord(const unsigned char *p, uint32_t blockSize);
+  size_t decodeBamChunkParallel();
   bool decodeSamRecord();
   void pushRecordHits(const std::string &name, uint32_t chrMeta, uint64_t start, bool strand,
                       const std::vector<std::pair<char, int> > &cigar, bool cigarIsStar, uint32_t nHits);
@@ -87,6 +90,9 @@ class XamReader {
   size_t pendingPos_ = 0;
   bool keepNames_ = false;
   uint64_t nRecords_ = 0;
+  unsigned parseThreads_ = 1;   // record parsers working side by side on a chunk (BAM)
+  bool clone_ = false;
+  std::vector<size_t> recOff_;
   std::string warnings_;
 };
 
