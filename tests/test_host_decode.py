@@ -35,3 +35,4 @@ def test_parallel_decode_equals_sequential(tmp_path, monkeypatch, shape, cfg_key
             assert np.array_equal(getattr(out["1"][0], k), getattr(out[threads][0], k)), (threads, k)
         assert out["1"][1] == out[threads][1]
     assert out["1"][0].n > 40000
+    assert "is not present in your annotation file" in out["1"][1]
