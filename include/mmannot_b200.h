@@ -162,6 +162,8 @@ typedef struct mma_timing {
 } mma_timing;
 
 int mma_device_count(void); /* number of CUDA devices visible to the process (0 when there is none) */
+int mma_warmup(int device); /* creates the CUDA context of `device` (a few 100 ms); callable from any thread, e.g. while the
+                               annotation is being parsed */
 int mma_create(mma_ctx **out, const mma_params *params);
 void mma_destroy(mma_ctx *ctx);
 const char *mma_last_error(const mma_ctx *ctx); /* ctx may be NULL: error of the last failed mma_create */

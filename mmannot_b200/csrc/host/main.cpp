@@ -163,6 +163,12 @@ int main(int argc, char **argv) {
     printUsage();
     return EXIT_FAILURE;
   }
+  // the CUDA context comes up on a side thread while the configuration and the annotation are parsed
+  std::thread warm([device, nThreads]() {
+    const int nDev = std::max(1, mma_device_count());
+    for (int w = 0; w < std::min(nThreads, nDev); ++w) mma_warmup((device + w) % nDev);
+  });
+  struct Joiner { std::thread &t; ~Joiner() { if (t.joinable()) t.join(); } } joinWarm{warm};
   std::string err, warnings;
   Config config;
   if (!config.parse(configFileName, err)) return fail(err);

@@ -348,6 +348,11 @@ int mma_device_count(void) {
   return cudaGetDeviceCount(&n) == cudaSuccess ? n : 0;
 }
 
+int mma_warmup(int device) {
+  if (cudaSetDevice(device) != cudaSuccess) return MMA_ERR_CUDA;
+  return cudaFree(nullptr) == cudaSuccess ? MMA_OK : MMA_ERR_CUDA;
+}
+
 int mma_create(mma_ctx **out, const mma_params *p) {
   if (!out || !p) { g_createError = "null argument"; return MMA_ERR_INVALID; }
   *out = nullptr;

@@ -20,7 +20,7 @@ FAST_OFF = 0xFFFFFFFF  # fast_bin_shift=None: no segment answer table
 EXPORTS = [
     "mma_create", "mma_destroy", "mma_last_error", "mma_load_features", "mma_alloc_pinned", "mma_free_pinned",
     "mma_submit_hits", "mma_submit_hits_device", "mma_finish_sample", "mma_reset_sample", "mma_dense_counts",
-    "mma_sync", "mma_stream", "mma_timing_enable", "mma_timing_reset", "mma_timing_get", "mma_index_bytes", "mma_version", "mma_readback_bytes", "mma_dominant_kernel", "mma_index_segments", "mma_annotate_hits", "mma_annotate_intervals", "mma_pack_hits", "mma_submit_hits_packed", "mma_device_count", "mma_export_bytes", "mma_export_table", "mma_import_tables",
+    "mma_sync", "mma_stream", "mma_timing_enable", "mma_timing_reset", "mma_timing_get", "mma_index_bytes", "mma_version", "mma_readback_bytes", "mma_dominant_kernel", "mma_index_segments", "mma_annotate_hits", "mma_annotate_intervals", "mma_pack_hits", "mma_submit_hits_packed", "mma_device_count", "mma_warmup", "mma_export_bytes", "mma_export_table", "mma_import_tables",
 ]
 
 
