@@ -245,8 +245,9 @@ def run_product_arm(args):
         pinned, n_hits = wl.fill_pinned(rank * reads, reads, threads)
         log("[rank %d] workload %s: %d features, %d reads -> %d hits generated in %.1fs (%d threads)" % (
             rank, args.workload, wl.annotation.n, reads, n_hits, time.time() - t0, threads))
-        batch = args.batch
-        ann = device.Annotator(wl.config, strategy=w["strategy"], overlap=w["overlap"], n_samples=1, max_batch_hits=batch,
+        batch = args.batch                                  # hits per call, host-buffer passes (copies overlap the kernels)
+        dev_batch = max(args.device_batch, batch)           # hits per call, device-resident pass
+        ann = device.Annotator(wl.config, strategy=w["strategy"], overlap=w["overlap"], n_samples=1, max_batch_hits=dev_batch,
                                device=local_rank, table_log2=args.table_log2, fast_bin_shift=args.fast_shift, bin_shift=args.bin_shift)
         ann.load_features(wl.annotation)
         index_bytes = ann.index_bytes()
@@ -256,15 +257,15 @@ def run_product_arm(args):
         torch.cuda.synchronize()
         isz = {"start": 4, "end": 4, "meta": 4, "nh": 4, "read_key": 8}
 
-        def batches(ptr_of):
+        def batches(ptr_of, size):
             out = []
-            for a in range(0, n_hits, batch):
-                n = min(batch, n_hits - a)
+            for a in range(0, n_hits, size):
+                n = min(size, n_hits - a)
                 out.append(device.HitBatch(n, *[ptr_of(k) + a * isz[k] for k in ("start", "end", "meta", "nh", "read_key")]))
             return out
 
-        dev_batches = batches(lambda k: dev_arrays[k].data_ptr())
-        host_batches = batches(lambda k: pinned.arrays[k].ctypes.data)
+        dev_batches = batches(lambda k: dev_arrays[k].data_ptr(), dev_batch)
+        host_batches = batches(lambda k: pinned.arrays[k].ctypes.data, batch)
         # the same batches in the compact transfer format the host decoder produces (mma_pack_hits): 8 B/hit + 8 B/run
         packed_batches = []
         if not args.e2e_wide:
@@ -407,7 +408,7 @@ def run_product_arm(args):
                     "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                     "dtype": "u32", "data": "synthetic",
                     "config": {"workload": w["describe"], "name": args.workload, "reads_per_gpu": reads, "hits_per_gpu": n_hits,
-                               "features": int(wl.annotation.n), "elements": int(wl.config.n_elements), "batch_hits": batch,
+                               "features": int(wl.annotation.n), "elements": int(wl.config.n_elements), "batch_hits": dev_batch, "batch_hits_e2e": batch,
                                "index_bytes": index_bytes, "segments": ann.index_segments(),
                                "sharding": "read-name ranges, index replicated, tables merged by one allreduce" if world > 1 else "single GPU",
                                "l2": "inputs (%.2f GB per pass) larger than L2; no explicit flush" % (24e-9 * n_hits),
@@ -458,7 +459,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="tair10_srna", choices=sorted(WORKLOADS))
     ap.add_argument("--reads", type=int, default=0, help="reads per GPU (default: the workload's full size)")
-    ap.add_argument("--batch", type=int, default=1 << 25, help="hits per mma_submit_hits call")
+    ap.add_argument("--batch", type=int, default=1 << 25, help="hits per mma_submit_hits* call of the host-buffer (e2e) passes")
+    ap.add_argument("--device-batch", type=int, default=1 << 27, help="hits per mma_submit_hits_device call of the device-resident pass")
     ap.add_argument("--table-log2", type=int, default=0)
     ap.add_argument("--fast-shift", type=int, default=0, help="log2 bin width of the segment answer table (0 = auto, -1 = no table)")
     ap.add_argument("--bin-shift", type=int, default=0)

@@ -10,8 +10,8 @@ if [ "${NCU:-1}" = "1" ]; then
 timeout 300 python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/plain1.log 2>&1 && \
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_a.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu1.log 2>&1
 echo "ncu list rc=$?"
-timeout 300 python bench.py --reads 16000000 --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/plain2.log 2>&1 && \
-ncu --set full --clock-control none --import-source on -k regex:"^k_batch" -s 0 -c 1 -o gpurun_out/prof_a python bench.py --reads 16000000 --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/ncu2.log 2>&1
+timeout 300 python bench.py --reads 16000000 --steps 1 --warmup 1 --no-cpu-baseline --device-batch 33554432 > gpurun_out/plain2.log 2>&1 && \
+ncu --set full --clock-control none --import-source on -k regex:"^k_batch" -s 0 -c 1 -o gpurun_out/prof_a python bench.py --reads 16000000 --steps 1 --warmup 1 --no-cpu-baseline --device-batch 33554432 > gpurun_out/ncu2.log 2>&1
 echo "ncu full rc=$?"
 fi
 timeout 600 python scripts/cli_compare.py 5000000 2>&1 | tail -1
