@@ -3,18 +3,20 @@
 // contiguous chunk of 128-hit warp tiles, 4 consecutive hits per lane, no block-wide barrier in the loop.  What differs
 // is the shape of the per-tile code, written so that the warp stays converged and its memory requests overlap:
 //
-//   phase A   4 independent gathers per lane: the bin entries of the segment table (unconditional, dummy address for
-//             hits that need no lookup)
-//   phase B   4 independent gathers of the 32-byte segment record for the hits the bin entry did not answer
-//   phase C   pick the in-segment / cross-segment answer; whatever is left (position-dependent picks, reads over three
-//             or more segments, degenerate intervals: a few % of the hits) is COMPACTED over the warp through shared
-//             memory and evaluated out of line, one hit per lane, instead of diverging hit by hit
-//   counting  every hit slot yields at most one count event (a read that is its own group, or the read whose run ends
+//   phase A   4 independent gathers per lane: the position-map entries {bitmap, rank} of the read starts (unconditional,
+//             dummy address for hits that need no lookup) -> rank + popc = index of the segment holding the start
+//   phase B   4 independent 256-bit gathers: the 32-byte records of those segments
+//   phase C   pick the in-segment / cross-segment answer; whatever is left (upstream/downstream ties, other position-
+//             dependent picks, reads over three or more segments, degenerate intervals: < 1 % of the hits) is COMPACTED
+//             over the warp through shared memory and evaluated out of line, one hit per lane
+//   counting  every hit slot yields at most one count event (a read that is its own group, or the read whose group ends
 //             at this record); single-element sets go to the lane's private histogram column with one unconditional
 //             read-modify-write, the others to the block table in a loop the whole warp runs in lockstep
 //
-// Reads whose run is not the clean "n records carrying NH = n" shape, -m rescue and batches following one that left
-// unfinished read names take the serial RunWalker of mma_device.cuh, exactly as in k_batch.
+// Two variants of the per-read step (template flag GROUPS): the plain one closes a run of n records carrying NH = n as one
+// read; the GROUPS one cuts a run of k x n records into k reads inside the scan (paired-end data) and resolves a tile in
+// which NH changes inside a run serially.  Whatever does not fit (-m rescue, batches following one that left unfinished read
+// names, runs ending inside a group) takes the serial RunWalker of mma_device.cuh, exactly as in k_batch.
 #pragma once
 #include "mma_device.cuh"
 
@@ -39,11 +41,6 @@ __device__ unsigned long long g_diag[16];
 #define DIAG(i, c) do { } while (0)
 #endif
 
-#ifndef MMA_PF_DIST
-#define MMA_PF_DIST 1000000  // L2 prefetch of later tiles: measured slightly slower than none on B200 (kept for tuning builds)
-#endif
-#define PF_DIST MMA_PF_DIST
-__device__ __forceinline__ void prefetchL2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 // one 256-bit read-only gather of a 32-byte segment record (LDG.E.256, sm_100+)
 __device__ __forceinline__ void ldRecord(const uint4 *p, uint4 &lo, uint4 &hi) {
   asm volatile("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
@@ -169,11 +166,6 @@ k_batch_fast(const __grid_constant__ IndexView ix, const __grid_constant__ FastV
     u32 rs[4], re[4], meta[4], nh[4];
     u64 key[4];
     u32 validBits;
-    if (h.vec && (t + 1 + PF_DIST) * WT_HITS <= h.n && t + PF_DIST < t1) {  // pull a later tile of the chunk into L2
-      const u32 pb = base + PF_DIST * WT_HITS;
-      prefetchL2(h.start + pb); prefetchL2(h.end + pb); prefetchL2(h.meta + pb); prefetchL2(h.nh + pb);
-      if (STRAT == 0) { prefetchL2(h.key + pb); prefetchL2(h.key + pb + 2); }
-    }
     if (h.vec && (t + 1) * WT_HITS <= h.n) {
       const uint4 a = __ldcs(reinterpret_cast<const uint4 *>(h.start + base));
       const uint4 b = __ldcs(reinterpret_cast<const uint4 *>(h.end + base));
@@ -273,13 +265,7 @@ k_batch_fast(const __grid_constant__ IndexView ix, const __grid_constant__ FastV
       const bool fwd = (meta[j] >> 31) != 0;
       const u32 i = look ? en[j].y + __popc(en[j].x & pm[j]) : 0u;
       uint4 tt, xx;
-#ifdef MMA_HOTCOLD
-      tt = __ldg(&fx.seg[2u * i]);
-      xx = make_uint4(ANS_GENERAL, ANS_GENERAL, 0u, 0u);
-      if (look && (re[j] > tt.x || ((fwd ? tt.y : tt.z) & ANS_VICPAIR))) xx = __ldg(&fx.seg[2u * i + 1u]);
-#else
       ldRecord(&fx.seg[2u * i], tt, xx);
-#endif
       tEnd[j] = tt.x; tAns[j] = fwd ? tt.y : tt.z; tEnd2[j] = tt.w;
       xAns[j] = fwd ? xx.x : xx.y;
     }
