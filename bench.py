@@ -92,6 +92,32 @@ class Workload:
         return pinned, total
 
 
+def bind_to_gpu_numa_node(gpu_index):
+    """Runs this rank on the CPUs of the NUMA node its GPU hangs off, BEFORE the page-locked buffers are allocated, so that
+    they are local to the GPU's PCIe root (with 8 ranks on a two-socket box half of the host->device traffic would
+    otherwise cross the socket interconnect).  Best effort: silently does nothing when the topology cannot be read."""
+    try:
+        exe = shutil.which("nvidia-smi")
+        out = subprocess.run([exe, "-i", str(gpu_index), "--query-gpu=pci.bus_id", "--format=csv,noheader"], capture_output=True, text=True, timeout=20).stdout.strip()
+        bus = out.lower()
+        if bus.startswith("00000000:"):
+            bus = bus[4:]  # sysfs uses a 4-digit PCI domain
+        node = int(open("/sys/bus/pci/devices/%s/numa_node" % bus).read().strip())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return node
+    except Exception:  # noqa: BLE001
+        pass
+    return None
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
     Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
@@ -229,12 +255,13 @@ def run_product_arm(args):
     rank, local_rank, world = dist_env()
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback")
+    numa_node = bind_to_gpu_numa_node(local_rank)
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     cores = os.cpu_count() or 1
-    threads = max(1, min(64, cores // max(1, world)))
+    threads = max(1, min(64, cores // max(1, world), len(os.sched_getaffinity(0))))
     tmp = tempfile.mkdtemp(prefix="mmannot_bench_%d_" % rank)
     try:
         t0 = time.time()
@@ -418,7 +445,7 @@ def run_product_arm(args):
                             "format": "compact (mma_submit_hits_packed: 8 B/hit + 8 B/run, expanded on the device)" if packed_batches else "wide (24 B/hit)",
                             "wide_format_value": total_hits / (wall_e2e_wide / max(1, args.steps // 2) * 1e-3), "wide_h2d_bytes_per_step": 24 * n_hits},
                     "gpu_launches": int(tm["launches"]),
-                    "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks, "host_cores": cores,
+                    "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks, "host_cores": cores, "numa_node": numa_node,
                     "wall_ms_per_step_device_resident": wall_dev / args.steps,
                     "stats": stats_dev, "table_rows": int(len(res_dev[1]))}
             emit(line)
