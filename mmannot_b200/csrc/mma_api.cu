@@ -102,6 +102,7 @@ struct mma_ctx {
   uint64_t launches = 0, hitsSubmitted = 0, batches = 0;
   int nSM = 148;
   u32 maxGrid = 0;           // MMANNOT_B200_MAX_GRID=n: cap on k_batch blocks, so that small test inputs still give every warp a multi-tile chunk (testing only)
+  size_t randDrawsUsed = 0;  // -y random: rand() draws consumed by the samples finished so far
   int forceGroups = -1;      // MMANNOT_B200_GROUPS=0/1: pin the variant (testing only)
   bool useGroups = false;    // k_batch_fast variant for runs of k x NH records, chosen from the walk counters of earlier batches
   bool legacyBatch = false;  // MMANNOT_B200_LEGACY_BATCH=1: A/B runs of the general k_batch against k_batch_fast (tuning only)
@@ -975,7 +976,10 @@ static int finishDeferred(mma_ctx *ctx, Sample &s, u32 nSlow) {
     if ((e = tmp2.ensure(tb2 ? tb2 : 1)) != cudaSuccess) { cleanup2(); cleanup(); return ctx->fail(MMA_ERR_CUDA, cudaGetErrorString(e)); }
     cub::DeviceRadixSort::SortKeys(tmp2.p, tb2, headOrd.as<u64>(), headSorted.as<u64>(), (int)nHeads, 0, 64, st);
     // the reference's rand() stream (glibc TYPE_3 additive feedback generator, mm:1711; never seeded => seed 1)
-    std::vector<u32> stream((size_t)nHeads + 344);
+    // the draws of this sample follow those of the samples finished before it on this context: the reference never
+    // reseeds between input files (mm:1711)
+    const size_t skip = ctx->randDrawsUsed;
+    std::vector<u32> stream((size_t)nHeads + skip + 344);
     {
       u32 seed = ctx->params.rand_seed ? ctx->params.rand_seed : 1u;
       std::vector<u32> &q = stream;
@@ -988,7 +992,8 @@ static int finishDeferred(mma_ctx *ctx, Sample &s, u32 nSlow) {
       }
       for (int i = 31; i < 34; ++i) q[i] = q[i - 31];
       for (size_t i = 34; i < q.size(); ++i) q[i] = q[i - 31] + q[i - 3];
-      for (size_t i = 0; i < nHeads; ++i) q[i] = q[i + 344] >> 1;
+      for (size_t i = 0; i < nHeads; ++i) q[i] = q[i + skip + 344] >> 1;
+      ctx->randDrawsUsed += nHeads;
     }
     if ((e = randDev.ensure((size_t)std::max<u32>(nHeads, 1) * 4)) != cudaSuccess) { tmp2.release(); cleanup2(); cleanup(); return ctx->fail(MMA_ERR_CUDA, cudaGetErrorString(e)); }
     cudaMemcpyAsync(randDev.p, stream.data(), (size_t)nHeads * 4, cudaMemcpyHostToDevice, st);

@@ -76,7 +76,8 @@ def test_coordinate_sorted_variant(workload):
 
 
 @pytest.mark.skipif(pyoracle.ref_binary("fixed") is None or not os.path.exists(CLI), reason="needs oracle/_ref and the CLI binary")
-@pytest.mark.parametrize("args", [["-s", "F"], ["-s", "U", "-l", "1"], ["-s", "R", "-y", "ratio"], ["-s", "F", "-y", "unique", "-l", "0.5"]],
+@pytest.mark.parametrize("args", [["-s", "F"], ["-s", "U", "-l", "1"], ["-s", "R", "-y", "ratio"], ["-s", "F", "-y", "unique", "-l", "0.5"],
+                                  ["-s", "F", "-y", "random"]],  # two files: the rand() stream runs on from the first into the second
                          ids=lambda a: " ".join(a))
 def test_cli_equals_reference(workload, args):
     w = workload
