@@ -14,4 +14,4 @@ timeout 300 python bench.py --reads 16000000 --steps 1 --warmup 1 --no-cpu-basel
 ncu --set full --clock-control none --import-source on -k regex:"^k_batch" -s 0 -c 1 -o gpurun_out/prof_a python bench.py --reads 16000000 --steps 1 --warmup 1 --no-cpu-baseline --device-batch 33554432 > gpurun_out/ncu2.log 2>&1
 echo "ncu full rc=$?"
 fi
-timeout 600 python scripts/cli_compare.py 5000000 2>&1 | tail -1
+timeout 600 python tests/tools/cli_compare.py 5000000 2>&1 | tail -1

@@ -1,7 +1,7 @@
 """File -> table wall clock of the drop-in command line against the reference binary on the same synthetic BAM/GFF
 (GPU box).  Writes gpurun_out/cli_compare.json."""
 import json, os, subprocess, sys, tempfile, time
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 from tests import common
 from oracle import pyoracle

@@ -1,6 +1,6 @@
 """GPU debugging aid: device vs oracle on a synthetic benchmark shape; per-hit masks first, then the smallest failing prefix."""
 import sys, os, json, tempfile
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np
 from tests import common
 from oracle import pyoracle
