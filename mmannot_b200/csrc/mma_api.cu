@@ -86,7 +86,7 @@ struct mma_ctx {
   // index
   bool haveIndex = false;
   DevBuf feat, chrInfo, bins, spanIdx, dElemLine, dElemStrand, dElemVic;
-  DevBuf fastBin, fastSeg, fastChrInfo;
+  DevBuf fastBin, fastSeg, fastTie, fastChrInfo;
   IndexView index;
   FastView fast;
   uint64_t nSegments = 0;
@@ -436,7 +436,7 @@ void mma_destroy(mma_ctx *ctx) {
     if (g.done) cudaEventDestroy(g.done);
   }
   ctx->feat.release(); ctx->chrInfo.release(); ctx->bins.release(); ctx->spanIdx.release();
-  ctx->fastBin.release(); ctx->fastSeg.release(); ctx->fastChrInfo.release();
+  ctx->fastBin.release(); ctx->fastSeg.release(); ctx->fastTie.release(); ctx->fastChrInfo.release();
   ctx->dElemLine.release(); ctx->dElemStrand.release(); ctx->dElemVic.release();
   ctx->collectTiming();
   if (ctx->hostTable) cudaFreeHost(ctx->hostTable);
@@ -608,6 +608,7 @@ int mma_load_features(mma_ctx *ctx, const mma_features *f) {
     if (fEntries <= 0x7FFFFFFFull && nSeg < (1u << 30)) {
       CKS(segKey.ensure((size_t)nSeg * 8));
       CKS(ctx->fastSeg.ensure(((size_t)nSeg + 16) * 2 * sizeof(uint4)));
+      CKS(ctx->fastTie.ensure(((size_t)nSeg + 16) * 2 * sizeof(u32)));
       u32 upMask = 0, downMask = 0;
       for (uint32_t q = 0; q < ctx->params.n_elements; ++q) {
         if (ctx->elemVic[q] == MMA_VICINITY_UP) upMask |= 1u << q;
@@ -622,7 +623,7 @@ int mma_load_features(mma_ctx *ctx, const mma_features *f) {
       {
         mma_ctx::Timed t(ctx, TC_INDEX);
         k_seg_scatter<<<gridFor(nKeys, 256), 256, 0, st>>>(kB.as<u64>(), flag.as<u32>(), pos.as<u32>(), (u32)nKeys, segKey.as<u64>());
-        k_seg_eval<<<gridFor(nSeg, 128), 128, 0, st>>>(ctx->index, segKey.as<u64>(), nSeg, upMask, downMask, ctx->fastSeg.as<uint4>());
+        k_seg_eval<<<gridFor(nSeg, 128), 128, 0, st>>>(ctx->index, segKey.as<u64>(), nSeg, upMask, downMask, ctx->fastSeg.as<uint4>(), ctx->fastTie.as<u32>());
         k_fast_bitmap<<<gridFor(fEntries, 256), 256, 0, st>>>(segKey.as<u64>(), nSeg, fChrBinBase.as<u32>(), nChr, fshift, gshift, (u32)fEntries,
                                                               ctx->fastBin.as<uint2>());
         ctx->launches += 3;
@@ -631,6 +632,7 @@ int mma_load_features(mma_ctx *ctx, const mma_features *f) {
       CKS(cudaGetLastError());
       ctx->fast.bm = ctx->fastBin.as<uint2>();
       ctx->fast.seg = ctx->fastSeg.as<uint4>();
+      ctx->fast.tie = ctx->fastTie.as<u32>();
       ctx->fast.upMask = upMask;
       ctx->fast.downMask = downMask;
       ctx->fast.chrInfo = ctx->fastChrInfo.as<uint2>();
@@ -639,7 +641,7 @@ int mma_load_features(mma_ctx *ctx, const mma_features *f) {
       ctx->fast.gshift = gshift;
       ctx->fast.enabled = 1;
       ctx->nSegments = nSeg;
-      fastBytes = (uint64_t)nSeg * 2 * sizeof(uint4) + fEntries * sizeof(uint2) + (uint64_t)nChr * sizeof(uint2);
+      fastBytes = (uint64_t)nSeg * (2 * sizeof(uint4) + 2 * sizeof(u32)) + fEntries * sizeof(uint2) + (uint64_t)nChr * sizeof(uint2);
     }
 #undef CKS
     cleanupFast();

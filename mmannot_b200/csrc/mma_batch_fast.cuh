@@ -258,7 +258,7 @@ k_batch_fast(const __grid_constant__ IndexView ix, const __grid_constant__ FastV
       pm[j] = (gshift == 0) ? (0xFFFFFFFFu >> (31u - p)) : ((1u << p) - 1u);
     }
     // ---- phase B: the 32-byte record of the segment holding the read start
-    u32 tEnd[4], tEnd2[4], tAns[4], xAns[4];
+    u32 tEnd[4], tLens[4], tAns[4], xAns[4], yAns[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const bool look = (lookBits >> j) & 1u;
@@ -266,16 +266,17 @@ k_batch_fast(const __grid_constant__ IndexView ix, const __grid_constant__ FastV
       const u32 i = look ? en[j].y + __popc(en[j].x & pm[j]) : 0u;
       uint4 tt, xx;
       ldRecord(&fx.seg[2u * i], tt, xx);
-      tEnd[j] = tt.x; tAns[j] = fwd ? tt.y : tt.z; tEnd2[j] = tt.w;
-      xAns[j] = fwd ? xx.x : xx.y;
+      tEnd[j] = tt.x; tAns[j] = fwd ? tt.y : tt.z; tLens[j] = tt.w;
+      xAns[j] = fwd ? xx.x : xx.y; yAns[j] = fwd ? xx.z : xx.w;
     }
     // ---- phase C: in-segment or cross-segment answer
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const bool look = (lookBits >> j) & 1u;
       const bool inT = re[j] <= tEnd[j];
-      const bool inX = (MODE == 0) && re[j] <= tEnd2[j];
-      const u32 a = inT ? tAns[j] : xAns[j];  // (an upstream/downstream tie, < 1 % of the hits, is settled out of line)
+      const int ahead = (MODE == 0 && !inT) ? segmentsAhead(re[j] - tEnd[j], tLens[j]) : 0;  // read over two / three segments
+      const bool inX = ahead != 0;
+      const u32 a = inT ? tAns[j] : (ahead == 2) ? yAns[j] : xAns[j];  // (an upstream/downstream tie, < 1 % of the hits, is settled out of line)
       const bool ok = rs[j] <= tEnd[j] && (inT || inX) && !(a & (ANS_VICPAIR | ANS_GENERAL));
       if (look && ok) m[j] = a;
       if (look && !ok) slowBits |= 1u << j;

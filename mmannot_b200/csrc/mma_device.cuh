@@ -53,21 +53,26 @@ struct IndexView {
 //               per bit: annotations up to ~128 Mb) the segment holding position x is EXACTLY rank + popc(bits up to x's bit);
 //               with coarser granules it is a lower bound, corrected by stepping right (a boundary in x's own granule, or two in
 //               one granule).
-//   segment i   seg[2i]   = {end_i, answer F, answer R, end_{i+1}}                            read inside the segment
-//               seg[2i+1] = {cross answer F, cross answer R, tie point F, tie point R}          read = tail of i + head of i+1
+//   segment i   seg[2i]   = {end_i, answer F, answer R, len_{i+1} | len_{i+2} << 16}        read inside the segment
+//               seg[2i+1] = {cross answer F, cross answer R, triple answer F, triple answer R}
+//               (inclusion mode) cross: read = tail of i + head of i+1; triple: tail of i + all of i+1 + head of i+2.
+//               len = length of the segment, saturated at 65535 (a saturated length only vouches for reads ending within
+//               65534 positions of the previous boundary); 0 when the chromosome has no such segment.
+//               tie[2i + {0 F, 1 R}] = tie point of an ANS_VICPAIR in-segment answer
 // "answer F" is for a read whose strand bit is set (MMA_HIT_STRAND_BIT), "answer R" for the other one.
 // An answer word is the element set (E <= 30), or carries one of two flags:
 //   ANS_VICPAIR  the winning Order line matched exactly one upstream and one downstream element (bits 0..29 hold both): the
 //                pick goes to the nearer one (mm:1066-1075).  With U = end of the upstream feature and D = start of the
 //                downstream one, the read [s, e] is at distance U - e from the first and s - D from the second, so the pick
 //                is upstream iff s + e > U + D, downstream iff s + e < U + D, both on a tie: "tie point" = U + D.  Only
-//                in-segment answers carry the flag (a cross answer of that kind is stored as ANS_GENERAL).
+//                in-segment answers carry the flag (a cross / triple answer of that kind is stored as ANS_GENERAL).
 //   ANS_GENERAL  any other position-dependent pick: the table cannot answer
 #define ANS_VICPAIR 0x80000000u
 #define ANS_GENERAL 0x40000000u
 struct FastView {
   const uint2 *bm;
   const uint4 *seg;
+  const u32 *tie;
   const uint2 *chrInfo;  // per chromosome {first entry of bm, number of bins}
   u32 nChr, shift, gshift, enabled;
   u32 upMask, downMask;  // upstream / downstream elements (Config::isUpstream / isDownstream, mm:463-470)
@@ -350,6 +355,17 @@ __device__ __forceinline__ u32 fastSegIndex(const FastView &fx, uint2 ci, u32 rs
   return en.y + __popc(en.x & m);
 }
 
+// A read ends d >= 1 positions after the end of its start segment; lens = len_{i+1} | len_{i+2} << 16 (saturated at 65535).
+// 1: it ends inside the next segment, 2: inside the one after, 0: further away or unknown
+__device__ __forceinline__ int segmentsAhead(u32 d, u32 lens) {
+  const u32 len1 = lens & 0xFFFFu, len2 = lens >> 16;
+  if (d <= len1 && (len1 != 65535u || d <= 65534u)) return 1;
+  if (len1 == 65535u) return 0;
+  const u32 d2 = d - len1;  // > 0 here
+  if (d2 <= len2 && (len2 != 65535u || d2 <= 65534u)) return 2;
+  return 0;
+}
+
 // the pick of an ANS_VICPAIR answer for the read [rs, re]
 __device__ __forceinline__ u32 vicPick(const FastView &fx, u32 a, u32 tie, u32 rs, u32 re) {
   const u64 sum = (u64)rs + (u64)re;
@@ -387,13 +403,12 @@ __device__ __forceinline__ u32 fastAnnotate(const FastView &fx, const IndexView 
   u32 a;
   if (re <= t.x) {
     a = fwd ? t.y : t.z;
-    if (a & ANS_VICPAIR) {
-      const uint4 x = __ldg(&fx.seg[2u * i + 1u]);
-      a = vicPick(fx, a, fwd ? x.z : x.w, rs, re);
-    }
-  } else if (MODE == 0 && re <= t.w) {
-    const uint4 x = __ldg(&fx.seg[2u * i + 1u]);  // {cross answer F, cross answer R, tie F, tie R}
-    a = fwd ? x.x : x.y;
+    if (a & ANS_VICPAIR) a = vicPick(fx, a, __ldg(&fx.tie[2u * i + (fwd ? 0u : 1u)]), rs, re);
+  } else if (MODE == 0) {
+    const int which = segmentsAhead(re - t.x, t.w);  // 1: ends in the next segment, 2: in the one after, 0: further
+    if (which == 0) return fastMissEval<MODE>(ix, rs, re, meta, ovl);
+    const uint4 x = __ldg(&fx.seg[2u * i + 1u]);  // {cross answer F, cross answer R, triple answer F, triple answer R}
+    a = (which == 1) ? (fwd ? x.x : x.y) : (fwd ? x.z : x.w);
   } else {
     return fastMissEval<MODE>(ix, rs, re, meta, ovl);
   }
@@ -1323,34 +1338,41 @@ __device__ __forceinline__ u32 answerWord(u64 chosen, const EvalTrack &tr, u32 u
 // one thread per segment: the answers of a read inside it and of a read over it and its right neighbour, per
 // strand, evaluated with the SAME candidate walk as any hit (inclusion scoring; see fastAnnotate for why that
 // also serves the overlap modes)
-__global__ void k_seg_eval(IndexView ix, const u64 *__restrict__ segKey, u32 nSeg, u32 upMask, u32 downMask, uint4 *seg) {
+__global__ void k_seg_eval(IndexView ix, const u64 *__restrict__ segKey, u32 nSeg, u32 upMask, u32 downMask, uint4 *seg, u32 *tieOut) {
   const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= nSeg) return;
   const u64 k = segKey[i];
   const u32 chr = (u32)(k >> 32), start = (u32)k;
   const bool hasNext = (i + 1 < nSeg) && (u32)(segKey[i + 1] >> 32) == chr;
+  const bool hasNext2 = hasNext && (i + 2 < nSeg) && (u32)(segKey[i + 2] >> 32) == chr;
+  const bool hasNext3 = hasNext2 && (i + 3 < nSeg) && (u32)(segKey[i + 3] >> 32) == chr;
   const u32 end = hasNext ? (u32)segKey[i + 1] - 1u : 0xFFFFFFFEu;
-  u32 end2 = 0;
-  if (hasNext) {
-    const bool hasNext2 = (i + 2 < nSeg) && (u32)(segKey[i + 2] >> 32) == chr;
-    end2 = hasNext2 ? (u32)segKey[i + 2] - 1u : 0xFFFFFFFEu;
-  }
-  u32 in[2], cross[2], tie[2];  // index 0: strand bit set ("F"), 1: not set
+  const u32 end1 = hasNext ? (hasNext2 ? (u32)segKey[i + 2] - 1u : 0xFFFFFFFEu) : 0u;   // end of segment i+1
+  const u32 end2 = hasNext2 ? (hasNext3 ? (u32)segKey[i + 3] - 1u : 0xFFFFFFFEu) : 0u;  // end of segment i+2
+  const u32 len1 = hasNext ? min(end1 - end, 65535u) : 0u, len2 = hasNext2 ? min(end2 - end1, 65535u) : 0u;
+  u32 in[2], cross[2], triple[2], tie[2];  // index 0: strand bit set ("F"), 1: not set
   for (u32 s = 0; s < 2; ++s) {
     const u32 meta = chr | (s == 0 ? 0x80000000u : 0u);
     EvalTrack tr;
+    u32 otherTie;
     u64 a = annotateEval<0, true>(ix, start, start, meta, -1.0f, &tr);
     in[s] = answerWord(a, tr, upMask, downMask, &tie[s]);
-    cross[s] = ANS_GENERAL;
+    cross[s] = triple[s] = ANS_GENERAL;
     if (hasNext) {
-      u32 crossTie;
       a = annotateEval<0, true>(ix, end, end + 1u, meta, -1.0f, &tr);
-      cross[s] = answerWord(a, tr, upMask, downMask, &crossTie);
-      if (cross[s] & ANS_VICPAIR) cross[s] = ANS_GENERAL;  // no room for a second tie point: left to the index walk
+      cross[s] = answerWord(a, tr, upMask, downMask, &otherTie);
+      if (cross[s] & ANS_VICPAIR) cross[s] = ANS_GENERAL;  // only in-segment answers have a tie point: left to the index walk
+    }
+    if (hasNext2) {
+      a = annotateEval<0, true>(ix, end, end1 + 1u, meta, -1.0f, &tr);
+      triple[s] = answerWord(a, tr, upMask, downMask, &otherTie);
+      if (triple[s] & ANS_VICPAIR) triple[s] = ANS_GENERAL;
     }
   }
-  seg[2 * i] = make_uint4(end, in[0], in[1], end2);
-  seg[2 * i + 1] = make_uint4(cross[0], cross[1], tie[0], tie[1]);
+  seg[2 * i] = make_uint4(end, in[0], in[1], len1 | (len2 << 16));
+  seg[2 * i + 1] = make_uint4(cross[0], cross[1], triple[0], triple[1]);
+  tieOut[2 * i] = tie[0];
+  tieOut[2 * i + 1] = tie[1];
 }
 
 // one thread per entry of the position map
