@@ -88,30 +88,36 @@ struct GtfLine {
 
 // Column 9 grammar of the reference (mm:533-567): `tag value;` or `tag=value;`, value quoted or not.
 void parseAttributes(const std::string &col, GtfLine &out) {
-  std::string rest = trimmed(col);
-  while (!rest.empty()) {
-    size_t pSpace = rest.find(' '), pEq = rest.find('=');
-    size_t cut = (pEq == std::string::npos) ? pSpace : (pSpace == std::string::npos) ? pEq : std::min(pSpace, pEq);
-    std::string tag = rest.substr(0, cut), value;
-    rtrim_inplace(tag);
-    rest = (cut == std::string::npos) ? rest : rest.substr(cut + 1);
-    ltrim_inplace(rest);
-    if (!rest.empty() && rest[0] == '"') {
-      rest.erase(0, 1);
-      size_t q = rest.find('"');
-      value = rest.substr(0, q);
-      if (q != std::string::npos) rest.erase(0, q + 1);
+  // cursor version of: rest = trimmed(col); repeatedly cut `tag`, `value`, skip to after the next ';' (no string erases)
+  const char *p = col.data(), *e = p + col.size();
+  while (p < e && is_space(*p)) ++p;
+  while (e > p && is_space(e[-1])) --e;
+  auto findc = [](const char *a, const char *z, char c) { while (a < z && *a != c) ++a; return a; };  // z when absent
+  while (p < e) {
+    const char *pSpace = findc(p, e, ' '), *pEq = findc(p, e, '=');
+    const char *cut = std::min(pSpace, pEq);  // e when neither is present
+    const char *tagEnd = cut;
+    while (tagEnd > p && is_space(tagEnd[-1])) --tagEnd;
+    const char *tagBegin = p;
+    if (cut != e) p = cut + 1;  // (without a separator the tag is the whole rest, which is then read again as the value)
+    while (p < e && is_space(*p)) ++p;
+    const char *vb, *ve;
+    if (p < e && *p == '"') {
+      ++p;
+      vb = p;
+      ve = findc(p, e, '"');
+      if (ve != e) p = ve + 1;
     } else {
-      size_t q = rest.find(';');
-      value = rest.substr(0, q);
-      rtrim_inplace(value);
+      vb = p;
+      ve = findc(p, e, ';');
+      while (ve > vb && is_space(ve[-1])) --ve;
     }
-    size_t comma = value.find(',');
-    std::string first = (comma == std::string::npos) ? value : value.substr(0, comma);
-    out.tags.push_back(std::make_pair(tag, first));
-    size_t semi = rest.find(';');
-    if (semi == std::string::npos) rest.clear();
-    else { rest.erase(0, semi + 1); ltrim_inplace(rest); }
+    const char *comma = findc(vb, ve, ',');
+    out.tags.emplace_back(std::string(tagBegin, tagEnd), std::string(vb, comma));
+    const char *semi = findc(p, e, ';');
+    if (semi == e) break;
+    p = semi + 1;
+    while (p < e && is_space(*p)) ++p;
   }
 }
 

@@ -130,18 +130,32 @@ bool Config::parse(const std::string &fileName, std::string &err) {
   return true;
 }
 
+// Both lookups run std::regex_match per configuration entry; an annotation asks for the same few (source, type) strings
+// hundreds of thousands of times, so the answers are memoised (the annotation is built by one thread).
 std::string Config::translate(const std::string &s) const {
+  auto hit = translateCache_.find(s);
+  if (hit != translateCache_.end()) return hit->second;
+  std::string out = s;
   for (const Synonym &syn : synonyms_)
-    if (std::regex_match(s, syn.matcher)) return syn.value;
-  return s;
+    if (std::regex_match(s, syn.matcher)) { out = syn.value; break; }
+  if (translateCache_.size() < 65536) translateCache_.emplace(s, out);
+  return out;
 }
 
 size_t Config::getOrder(const std::string &source, const std::string &type) const {
+  std::string key;
+  key.reserve(source.size() + type.size() + 1);
+  key.append(source).push_back('\t');
+  key.append(type);
+  auto hit = orderCache_.find(key);
+  if (hit != orderCache_.end()) return hit->second;
+  size_t out = NO_ID;
   for (size_t i = 0; i < elements_.size(); ++i) {
     const OrderElement &e = elements_[i];
-    if (std::regex_match(source, e.matcher) && (e.type.empty() || e.type == type)) return i;
+    if (std::regex_match(source, e.matcher) && (e.type.empty() || e.type == type)) { out = i; break; }
   }
-  return NO_ID;
+  if (orderCache_.size() < 65536) orderCache_.emplace(std::move(key), out);
+  return out;
 }
 
 size_t Config::checkIntrons(const std::string &source, const std::string &type) const {

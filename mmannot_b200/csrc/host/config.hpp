@@ -4,6 +4,7 @@
 #pragma once
 #include <regex>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include "common.hpp"
@@ -52,6 +53,8 @@ class Config {
   struct Synonym { std::regex matcher; std::string value; };
   struct IntronRule { std::string source, type; size_t element; };
   struct VicinityRule { std::string source, type; size_t up, down; };
+  mutable std::unordered_map<std::string, std::string> translateCache_;  // memoised regex lookups (see config.cpp)
+  mutable std::unordered_map<std::string, size_t> orderCache_;
   std::vector<Synonym>      synonyms_;
   std::vector<IntronRule>   introns_;
   std::vector<VicinityRule> vicinity_;
