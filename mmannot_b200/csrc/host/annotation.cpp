@@ -122,9 +122,17 @@ void parseAttributes(const std::string &col, GtfLine &out) {
 }
 
 bool parseGtfLine(const std::string &line, GtfLine &out, std::string &err) {
-  std::vector<std::string> f;
-  split_getline(line, '\t', f);
-  if (f.size() != 9) {
+  // getline()-style split on tabs into pieces that keep their storage from line to line (a trailing empty piece is dropped)
+  static thread_local std::vector<std::string> f(12);
+  size_t nf = 0;
+  for (size_t pos = 0; pos < line.size();) {
+    size_t q = line.find('\t', pos);
+    if (q == std::string::npos) q = line.size();
+    if (nf < f.size()) f[nf].assign(line, pos, q - pos);
+    ++nf;
+    pos = q + 1;
+  }
+  if (nf != 9) {
     err = "Error, annotation line does not have 9 tab-separated fields: '" + line + "'";
     return false;
   }
