@@ -202,6 +202,7 @@ int main(int argc, char **argv) {
   params.elem_vicinity = elemVic.data();
   params.n_samples = nInputs;
   params.max_batch_hits = opt.batchHits;
+  params.table_log2 = 20;  // 2^20 combination slots per input file (16 MB): heavy multi-mapping can produce many distinct sets
   params.rand_seed = 1;
   mma_features f;
   f.n = static_cast<uint32_t>(features.size());
