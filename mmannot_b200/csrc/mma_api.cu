@@ -15,6 +15,7 @@
 
 #include "mma_device.cuh"
 #include "mma_batch_fast.cuh"
+#include "mma_batch_lean.cuh"
 
 using namespace mma;
 
@@ -27,6 +28,10 @@ thread_local std::string g_createError;
     cudaError_t _e = (call);                                                                       \
     if (_e != cudaSuccess) return ctx->fail(MMA_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(_e)); \
   } while (0)
+
+// bin entries (FastView::ent) are built for annotations of up to this many 64-position bins (83 MB of entries: they have to
+// stay L2-resident next to the segment records)
+#define MMA_MAX_BIN_ENTRIES 2600000ull
 
 enum TimeCat { TC_INDEX = 0, TC_BATCH, TC_CLOSE, TC_FINISH, TC_N };
 
@@ -86,7 +91,7 @@ struct mma_ctx {
   // index
   bool haveIndex = false;
   DevBuf feat, chrInfo, bins, spanIdx, dElemLine, dElemStrand, dElemVic;
-  DevBuf fastBin, fastSeg, fastTie, fastChrInfo;
+  DevBuf fastBin, fastSeg, fastTie, fastChrInfo, fastEnt;
   IndexView index;
   FastView fast;
   uint64_t nSegments = 0;
@@ -258,16 +263,29 @@ void launchBatchKernels(mma_ctx *ctx, Sample &s, const HitView &h) {
   KeySetView open = openView(s);
   // one contiguous chunk of 128-hit warp tiles per warp; enough warps to fill the GPU, chunks of >= 8 tiles when possible
   const u32 nWT = (h.n + WT_HITS - 1) / WT_HITS;
-  constexpr bool useFast = FAST && sizeof(MaskT) == 4 && STRAT != 2;  // k_batch_fast (mma_batch_fast.cuh)
+  constexpr bool useFast = FAST && sizeof(MaskT) == 4 && STRAT != 2;  // k_batch_lean / k_batch_fast
   bool launched = false;
   if constexpr (useFast) if (!ctx->legacyBatch && ctx->fast.nChr <= CHR_SMEM) {
-    launched = true;
-    u32 grid = std::max<u32>(1u, std::min<u32>((nWT + FAST_WARPS - 1) / FAST_WARPS, (u32)ctx->nSM * MMA_FAST_BLOCKS_PER_SM));
-    if (ctx->maxGrid) grid = std::min(grid, ctx->maxGrid);
-    mma_ctx::Timed t(ctx, TC_BATCH);
     // runs of k x NH records (paired-end data): the GROUPS variant once a batch has shown many of them (see afterBatch)
-    if (STRAT == 0 && ctx->useGroups) k_batch_fast<MODE, STRAT, (STRAT == 0)><<<grid, FAST_THREADS, 0, ctx->sc>>>(ctx->index, ctx->fast, h, r, table, s.ctl, slow, open);
-    else k_batch_fast<MODE, STRAT, false><<<grid, FAST_THREADS, 0, ctx->sc>>>(ctx->index, ctx->fast, h, r, table, s.ctl, slow, open);
+    const bool groups = STRAT == 0 && ctx->useGroups;
+    if (ctx->fast.ent && h.vec) {  // bin entries: the hit arrays go through the TMA ring (needs 16-byte aligned arrays)
+      launched = true;
+      u32 grid = std::max<u32>(1u, std::min<u32>((nWT + LEAN_WARPS - 1) / LEAN_WARPS, (u32)ctx->nSM * MMA_LEAN_BLOCKS_PER_SM));
+      if (ctx->maxGrid) grid = std::min(grid, ctx->maxGrid);
+      constexpr size_t smem = sizeof(LeanSmem<STRAT != 3>);
+      auto kPlain = k_batch_lean<MODE, STRAT, false>;
+      auto kGroups = k_batch_lean<MODE, STRAT, (STRAT == 0)>;
+      cudaFuncSetAttribute(groups ? kGroups : kPlain, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);  // (per device: cheap enough per launch)
+      mma_ctx::Timed t(ctx, TC_BATCH);
+      (groups ? kGroups : kPlain)<<<grid, LEAN_THREADS, smem, ctx->sc>>>(ctx->index, ctx->fast, h, r, table, s.ctl, slow, open);
+    } else if (ctx->fast.bm) {
+      launched = true;
+      u32 grid = std::max<u32>(1u, std::min<u32>((nWT + FAST_WARPS - 1) / FAST_WARPS, (u32)ctx->nSM * MMA_FAST_BLOCKS_PER_SM));
+      if (ctx->maxGrid) grid = std::min(grid, ctx->maxGrid);
+      mma_ctx::Timed t(ctx, TC_BATCH);
+      if (groups) k_batch_fast<MODE, STRAT, (STRAT == 0)><<<grid, FAST_THREADS, 0, ctx->sc>>>(ctx->index, ctx->fast, h, r, table, s.ctl, slow, open);
+      else k_batch_fast<MODE, STRAT, false><<<grid, FAST_THREADS, 0, ctx->sc>>>(ctx->index, ctx->fast, h, r, table, s.ctl, slow, open);
+    }
   }
   if (!launched) {
     const u32 perSM = (sizeof(MaskT) == 4) ? MMA_BLOCKS_PER_SM : 2;
@@ -436,7 +454,7 @@ void mma_destroy(mma_ctx *ctx) {
     if (g.done) cudaEventDestroy(g.done);
   }
   ctx->feat.release(); ctx->chrInfo.release(); ctx->bins.release(); ctx->spanIdx.release();
-  ctx->fastBin.release(); ctx->fastSeg.release(); ctx->fastTie.release(); ctx->fastChrInfo.release();
+  ctx->fastBin.release(); ctx->fastSeg.release(); ctx->fastTie.release(); ctx->fastChrInfo.release(); ctx->fastEnt.release();
   ctx->dElemLine.release(); ctx->dElemStrand.release(); ctx->dElemVic.release();
   ctx->collectTiming();
   if (ctx->hostTable) cudaFreeHost(ctx->hostTable);
@@ -584,27 +602,32 @@ int mma_load_features(mma_ctx *ctx, const mma_features *f) {
     CKS(cudaMemcpyAsync(&lastPos, pos.as<u32>() + (nKeys - 1), 4, cudaMemcpyDeviceToHost, st));
     CKS(cudaStreamSynchronize(st));
     const u32 nSeg = lastPos + lastFlag;
-    // position map: 32 granules per entry; one position per granule when the map stays within 2^22 entries (32 MB),
-    // coarser granules for larger annotations
+    // Annotations up to ~160 Mb (auto mode only): BIN ENTRIES, one 32-byte entry per 64 positions that answers the common read
+    // with a single gather (k_batch_lean).  Otherwise the position map: 32 granules per entry; one position per granule when the
+    // map stays within 2^22 entries (32 MB), coarser granules for larger annotations.
     uint32_t fshift = ctx->params.fast_bin_shift;
+    uint64_t totalExtent = 0;
+    for (uint32_t c = 0; c < nChr; ++c) totalExtent += extent[c];
+    const bool useEnt = fshift == 0 && (totalExtent >> 6) + 3ull * nChr <= MMA_MAX_BIN_ENTRIES && !getenv("MMANNOT_B200_NO_BINS");
+    if (useEnt) fshift = 6;
     if (fshift == 0) {
-      uint64_t totalExtent = 0;
-      for (uint32_t c = 0; c < nChr; ++c) totalExtent += extent[c];
       fshift = 5;
       while (fshift < 24 && (totalExtent >> fshift) > (1ull << 22)) ++fshift;
     }
     fshift = std::min<uint32_t>(std::max<uint32_t>(fshift, 5), 24);
-    const uint32_t gshift = fshift - 5;
+    const uint32_t gshift = useEnt ? 0 : fshift - 5;
     std::vector<u32> fBase(nChr + 1, 0);
-    std::vector<uint2> fInfo(nChr);
+    std::vector<uint2> fInfo(nChr + 1);
     uint64_t fEntries = 0;
     for (uint32_t c = 0; c < nChr; ++c) {
-      const uint64_t nb = (chrStart[c + 1] > chrStart[c]) ? (extent[c] >> fshift) + 2 : 1;
+      // (bin entries: one more bin, so that the last bin of a chromosome never holds a boundary)
+      const uint64_t nb = (chrStart[c + 1] > chrStart[c]) ? (extent[c] >> fshift) + (useEnt ? 3 : 2) : 1;
       fBase[c] = (u32)fEntries;
       fInfo[c] = make_uint2((u32)fEntries, (u32)nb);
       fEntries += nb;
     }
     fBase[nChr] = (u32)fEntries;
+    fInfo[nChr] = make_uint2((u32)fEntries, 1u);  // bin entries: the dummy bin of unknown chromosomes
     if (fEntries <= 0x7FFFFFFFull && nSeg < (1u << 30)) {
       CKS(segKey.ensure((size_t)nSeg * 8));
       CKS(ctx->fastSeg.ensure(((size_t)nSeg + 16) * 2 * sizeof(uint4)));
@@ -614,23 +637,29 @@ int mma_load_features(mma_ctx *ctx, const mma_features *f) {
         if (ctx->elemVic[q] == MMA_VICINITY_UP) upMask |= 1u << q;
         if (ctx->elemVic[q] == MMA_VICINITY_DOWN) downMask |= 1u << q;
       }
-      CKS(ctx->fastBin.ensure((size_t)fEntries * sizeof(uint2)));
-      CKS(ctx->fastChrInfo.ensure((size_t)nChr * sizeof(uint2)));
+      if (useEnt) CKS(ctx->fastEnt.ensure(((size_t)fEntries + 1) * 2 * sizeof(uint4)));
+      else CKS(ctx->fastBin.ensure((size_t)fEntries * sizeof(uint2)));
+      CKS(ctx->fastChrInfo.ensure((size_t)(nChr + 1) * sizeof(uint2)));
       CKS(fChrBinBase.ensure((size_t)(nChr + 1) * 4));
       CKS(cudaMemsetAsync(ctx->fastSeg.p, 0, ((size_t)nSeg + 16) * 2 * sizeof(uint4), st));
-      CKS(cudaMemcpyAsync(ctx->fastChrInfo.p, fInfo.data(), (size_t)nChr * sizeof(uint2), cudaMemcpyHostToDevice, st));
+      CKS(cudaMemcpyAsync(ctx->fastChrInfo.p, fInfo.data(), (size_t)(nChr + 1) * sizeof(uint2), cudaMemcpyHostToDevice, st));
       CKS(cudaMemcpyAsync(fChrBinBase.p, fBase.data(), (size_t)(nChr + 1) * 4, cudaMemcpyHostToDevice, st));
       {
         mma_ctx::Timed t(ctx, TC_INDEX);
         k_seg_scatter<<<gridFor(nKeys, 256), 256, 0, st>>>(kB.as<u64>(), flag.as<u32>(), pos.as<u32>(), (u32)nKeys, segKey.as<u64>());
         k_seg_eval<<<gridFor(nSeg, 128), 128, 0, st>>>(ctx->index, segKey.as<u64>(), nSeg, upMask, downMask, ctx->fastSeg.as<uint4>(), ctx->fastTie.as<u32>());
-        k_fast_bitmap<<<gridFor(fEntries, 256), 256, 0, st>>>(segKey.as<u64>(), nSeg, fChrBinBase.as<u32>(), nChr, fshift, gshift, (u32)fEntries,
-                                                              ctx->fastBin.as<uint2>());
+        if (useEnt)
+          k_bin_entries<<<gridFor(fEntries + 1, 256), 256, 0, st>>>(segKey.as<u64>(), nSeg, fChrBinBase.as<u32>(), nChr, (u32)fEntries, ctx->fastSeg.as<uint4>(),
+                                                                   ctx->params.n_elements, ctx->fastEnt.as<uint4>());
+        else
+          k_fast_bitmap<<<gridFor(fEntries, 256), 256, 0, st>>>(segKey.as<u64>(), nSeg, fChrBinBase.as<u32>(), nChr, fshift, gshift, (u32)fEntries,
+                                                                ctx->fastBin.as<uint2>());
         ctx->launches += 3;
       }
       CKS(cudaStreamSynchronize(st));
       CKS(cudaGetLastError());
-      ctx->fast.bm = ctx->fastBin.as<uint2>();
+      ctx->fast.bm = useEnt ? nullptr : ctx->fastBin.as<uint2>();
+      ctx->fast.ent = useEnt ? ctx->fastEnt.as<uint4>() : nullptr;
       ctx->fast.seg = ctx->fastSeg.as<uint4>();
       ctx->fast.tie = ctx->fastTie.as<u32>();
       ctx->fast.upMask = upMask;
@@ -641,7 +670,7 @@ int mma_load_features(mma_ctx *ctx, const mma_features *f) {
       ctx->fast.gshift = gshift;
       ctx->fast.enabled = 1;
       ctx->nSegments = nSeg;
-      fastBytes = (uint64_t)nSeg * (2 * sizeof(uint4) + 2 * sizeof(u32)) + fEntries * sizeof(uint2) + (uint64_t)nChr * sizeof(uint2);
+      fastBytes = (uint64_t)nSeg * (2 * sizeof(uint4) + 2 * sizeof(u32)) + fEntries * (useEnt ? 2 * sizeof(uint4) : sizeof(uint2)) + (uint64_t)nChr * sizeof(uint2);
     }
 #undef CKS
     cleanupFast();

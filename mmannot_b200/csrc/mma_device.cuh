@@ -69,6 +69,21 @@ struct IndexView {
 //   ANS_GENERAL  any other position-dependent pick: the table cannot answer
 #define ANS_VICPAIR 0x80000000u
 #define ANS_GENERAL 0x40000000u
+//   bin entries   (annotations up to ~160 Mb: TAIR10, FlyBase) replace the position map: ONE 32-byte gather answers the common read.
+//               ent[2e], ent[2e+1] describe the 64 positions [64b, 64b + 63] of a chromosome (e = chromosome base + b):
+//                 ent[2e]   = {bits lo, bits hi, rank, endZ}    bit p (1..63) = "a segment starts at 64b + p"; rank = index of the
+//                             segment holding position 64b; Z = rank + popc(bits) = the segment holding the bin's LAST position;
+//                             endZ = its end
+//                 ent[2e+1] = {answer F of Z, answer R of Z, cross answer F of (Z, Z+1), cross answer R}
+//               A read [s, e] with no boundary after s inside its start bin starts in Z; it lies inside Z when e <= endZ, and
+//               over Z and Z+1 when e - endZ <= length of Z+1.  That length, saturated at 255, sits in the top nibbles of the
+//               two cross words (low nibble in F, high nibble in R; the cross answers are only stored for E <= 28, else the
+//               length is 0).  An answer the entry cannot give (position dependent pick, flagged) is stored as all ones
+//               (ENT_NONE / ENT_XNONE): the read then takes the segment record like every read that starts before a boundary of
+//               its bin (segment index = rank + popc(bits up to s): exact).  The last bin of a chromosome is always empty, so
+//               a read starting beyond the annotated extent finds the last segment there.
+#define ENT_NONE 0xFFFFFFFFu
+#define ENT_XNONE 0x0FFFFFFFu
 struct FastView {
   const uint2 *bm;
   const uint4 *seg;
@@ -76,6 +91,8 @@ struct FastView {
   const uint2 *chrInfo;  // per chromosome {first entry of bm, number of bins}
   u32 nChr, shift, gshift, enabled;
   u32 upMask, downMask;  // upstream / downstream elements (Config::isUpstream / isDownstream, mm:463-470)
+  const uint4 *ent;      // bin entries (null: position map `bm` instead); then chrInfo = {first entry, number of 64-position bins},
+                         // chrInfo[nChr] = an empty dummy bin whose answers are 0, shift = 6, gshift = 0
 };
 
 struct HitView {
@@ -348,6 +365,11 @@ __device__ __noinline__ u64 annotateHit(const IndexView &ix, u32 rs, u32 re, u32
 
 // segment index (lower bound, exact when gshift == 0) of position rs on chromosome info ci
 __device__ __forceinline__ u32 fastSegIndex(const FastView &fx, uint2 ci, u32 rs) {
+  if (fx.ent) {  // bin entries: exact
+    const uint4 e = __ldg(&fx.ent[2u * (ci.x + min(rs >> 6, ci.y - 1u))]);
+    const u64 bits = ((u64)e.y << 32) | e.x;
+    return e.z + __popcll(bits & ((2ull << (rs & 63u)) - 1ull));  // (the clamped last bin is empty)
+  }
   const u32 bRaw = rs >> fx.shift;
   const uint2 en = __ldg(&fx.bm[ci.x + min(bRaw, ci.y - 1u)]);
   const u32 p = (bRaw < ci.y) ? ((rs >> fx.gshift) & 31u) : 31u;
@@ -1397,6 +1419,42 @@ __global__ void k_fast_bitmap(const u64 *__restrict__ segKey, u32 nSeg, const u3
     bits |= 1u << (u32)((sp - pos) >> gshift);
   }
   bm[e] = make_uint2(bits, lo);
+}
+
+// one thread per bin entry (see FastView): needs the segment records
+__global__ void k_bin_entries(const u64 *__restrict__ segKey, u32 nSeg, const u32 *__restrict__ chrBinBase, u32 nChr, u32 nEntries,
+                              const uint4 *__restrict__ seg, u32 nElements, uint4 *ent) {
+  const u32 e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e > nEntries) return;
+  if (e == nEntries) {  // the dummy bin of hits on a chromosome the annotation does not know: no element
+    ent[2 * e] = make_uint4(0u, 0u, 0u, 0xFFFFFFFFu);
+    ent[2 * e + 1] = make_uint4(0u, 0u, ENT_XNONE, ENT_XNONE);
+    return;
+  }
+  const u32 c = chrOfEntry(chrBinBase, nChr, e);
+  const u64 pos = (u64)(e - chrBinBase[c]) << 6;
+  const u64 cap = 0xFFFFFFFEull;
+  const u64 want = ((u64)c << 32) | (pos > cap ? cap : pos);
+  u32 lo = 0, hi = nSeg;  // last segment whose key <= want (every chromosome has a segment starting at 0)
+  while (hi - lo > 1) { const u32 mid = (lo + hi) >> 1; if (segKey[mid] <= want) lo = mid; else hi = mid; }
+  u64 bits = 0;
+  u32 z = lo;
+  for (u32 k = lo + 1; k < nSeg; ++k) {
+    const u64 sk = segKey[k];
+    if ((u32)(sk >> 32) != c) break;
+    const u64 sp = sk & 0xFFFFFFFFull;
+    if (sp >= pos + 64ull) break;
+    bits |= 1ull << (u32)(sp - pos);
+    z = k;
+  }
+  const uint4 t = seg[2 * z], x = seg[2 * z + 1];
+  const u32 flags = ANS_VICPAIR | ANS_GENERAL;
+  const u32 zf = (t.y & flags) ? ENT_NONE : t.y, zr = (t.z & flags) ? ENT_NONE : t.z;
+  u32 len = min(t.w & 0xFFFFu, 255u);  // (a saturated 16-bit length vouches for 65534 positions: more than 255)
+  if (nElements > 28) len = 0;
+  const u32 xf = ((x.x & flags) || nElements > 28) ? ENT_XNONE : x.x, xr = ((x.y & flags) || nElements > 28) ? ENT_XNONE : x.y;
+  ent[2 * e] = make_uint4((u32)bits, (u32)(bits >> 32), lo, t.x);
+  ent[2 * e + 1] = make_uint4(zf, zr, xf | ((len & 15u) << 28), xr | ((len >> 4) << 28));
 }
 
 // adjacent-duplicate removal of the sorted boundary keys: flags, then a scatter through their prefix sums
