@@ -91,7 +91,7 @@ struct mma_ctx {
   // index
   bool haveIndex = false;
   DevBuf feat, chrInfo, bins, spanIdx, dElemLine, dElemStrand, dElemVic;
-  DevBuf fastBin, fastSeg, fastTie, fastChrInfo, fastEnt;
+  DevBuf fastBin, fastSeg, fastTie, fastChrInfo, fastEnt, fastRank, fastDict;
   IndexView index;
   FastView fast;
   uint64_t nSegments = 0;
@@ -255,8 +255,28 @@ int ensureDeferred(mma_ctx *ctx, Sample &s, uint64_t n) {
   return MMA_OK;
 }
 
+// The batch kernels keep per-thread counters in 16-bit fields (and 16-bit histogram columns): a warp must not see more than
+// 2^14 tiles of 128 hits in one launch.  With the usual grids that is far away (2^32 hits per batch); a capped grid
+// (MMANNOT_B200_MAX_GRID, small GPUs) reaches it earlier, so longer batches are cut into several launches -- a cut is just a
+// batch border, which the kernels handle anyway.
+#define MMA_MAX_TILES_PER_WARP 16000ull
+
 template <int MODE, int STRAT, bool FAST, typename MaskT>
-void launchBatchKernels(mma_ctx *ctx, Sample &s, const HitView &h) {
+void launchBatchKernels(mma_ctx *ctx, Sample &s, const HitView &hAll) {
+  {
+    const u32 minGrid = ctx->maxGrid ? std::min<u32>(ctx->maxGrid, (u32)ctx->nSM) : (u32)ctx->nSM;
+    const uint64_t maxHits = MMA_MAX_TILES_PER_WARP * WT_HITS * (uint64_t)minGrid * 8ull;
+    if (hAll.n > maxHits) {
+      const u32 n1 = (u32)(maxHits);  // (a multiple of 128: the second part keeps the alignment of the arrays)
+      HitView a = hAll, b = hAll;
+      a.n = n1;
+      b.n = hAll.n - n1; b.start += n1; b.end += n1; b.meta += n1; b.nh += n1; b.key += n1;
+      launchBatchKernels<MODE, STRAT, FAST, MaskT>(ctx, s, a);
+      launchBatchKernels<MODE, STRAT, FAST, MaskT>(ctx, s, b);
+      return;
+    }
+  }
+  const HitView &h = hAll;
   const Rules &r = ctx->rules;
   TableView table = tableView(s.tableKeys, s.tableVals, ctx->tableCap, s.ctl);
   SlowView slow = slowView(s);
@@ -454,7 +474,7 @@ void mma_destroy(mma_ctx *ctx) {
     if (g.done) cudaEventDestroy(g.done);
   }
   ctx->feat.release(); ctx->chrInfo.release(); ctx->bins.release(); ctx->spanIdx.release();
-  ctx->fastBin.release(); ctx->fastSeg.release(); ctx->fastTie.release(); ctx->fastChrInfo.release(); ctx->fastEnt.release();
+  ctx->fastBin.release(); ctx->fastSeg.release(); ctx->fastTie.release(); ctx->fastChrInfo.release(); ctx->fastEnt.release(); ctx->fastRank.release(); ctx->fastDict.release();
   ctx->dElemLine.release(); ctx->dElemStrand.release(); ctx->dElemVic.release();
   ctx->collectTiming();
   if (ctx->hostTable) cudaFreeHost(ctx->hostTable);
@@ -577,8 +597,8 @@ int mma_load_features(mma_ctx *ctx, const mma_features *f) {
   uint64_t fastBytes = 0;
   if (ctx->params.n_elements <= 30 && ctx->params.fast_bin_shift != MMA_FAST_OFF) {
     const uint64_t nKeys = 2ull * n + nChr;
-    DevBuf kA, kB, flag, pos, tmp, segKey, fChrBinBase;
-    auto cleanupFast = [&]() { kA.release(); kB.release(); flag.release(); pos.release(); tmp.release(); segKey.release(); fChrBinBase.release(); };
+    DevBuf kA, kB, flag, pos, tmp, segKey, fChrBinBase, dictHash;
+    auto cleanupFast = [&]() { kA.release(); kB.release(); flag.release(); pos.release(); tmp.release(); segKey.release(); fChrBinBase.release(); dictHash.release(); };
 #define CKS(call)                                                                                  \
   do {                                                                                             \
     cudaError_t _e = (call);                                                                       \
@@ -637,7 +657,7 @@ int mma_load_features(mma_ctx *ctx, const mma_features *f) {
         if (ctx->elemVic[q] == MMA_VICINITY_UP) upMask |= 1u << q;
         if (ctx->elemVic[q] == MMA_VICINITY_DOWN) downMask |= 1u << q;
       }
-      if (useEnt) CKS(ctx->fastEnt.ensure(((size_t)fEntries + 1) * 2 * sizeof(uint4)));
+      if (useEnt) { CKS(ctx->fastEnt.ensure(((size_t)fEntries + 1) * sizeof(uint4))); CKS(ctx->fastRank.ensure(((size_t)fEntries + 1) * 4)); CKS(ctx->fastDict.ensure(ENT_DICT * sizeof(uint2))); }
       else CKS(ctx->fastBin.ensure((size_t)fEntries * sizeof(uint2)));
       CKS(ctx->fastChrInfo.ensure((size_t)(nChr + 1) * sizeof(uint2)));
       CKS(fChrBinBase.ensure((size_t)(nChr + 1) * 4));
@@ -648,10 +668,18 @@ int mma_load_features(mma_ctx *ctx, const mma_features *f) {
         mma_ctx::Timed t(ctx, TC_INDEX);
         k_seg_scatter<<<gridFor(nKeys, 256), 256, 0, st>>>(kB.as<u64>(), flag.as<u32>(), pos.as<u32>(), (u32)nKeys, segKey.as<u64>());
         k_seg_eval<<<gridFor(nSeg, 128), 128, 0, st>>>(ctx->index, segKey.as<u64>(), nSeg, upMask, downMask, ctx->fastSeg.as<uint4>(), ctx->fastTie.as<u32>());
-        if (useEnt)
-          k_bin_entries<<<gridFor(fEntries + 1, 256), 256, 0, st>>>(segKey.as<u64>(), nSeg, fChrBinBase.as<u32>(), nChr, (u32)fEntries, ctx->fastSeg.as<uint4>(),
-                                                                   ctx->params.n_elements, ctx->fastEnt.as<uint4>());
-        else
+        if (useEnt) {
+          CKS(dictHash.ensure(DICT_SLOTS * 12));
+          CKS(cudaMemsetAsync(dictHash.p, 0, DICT_SLOTS * 12, st));
+          BinBuild bb;
+          bb.segKey = segKey.as<u64>(); bb.chrBinBase = fChrBinBase.as<u32>(); bb.seg = ctx->fastSeg.as<uint4>();
+          bb.nSeg = nSeg; bb.nChr = nChr; bb.nEntries = (u32)fEntries; bb.nElements = ctx->params.n_elements;
+          bb.hashKey = dictHash.as<u64>(); bb.hashId = reinterpret_cast<u32 *>(dictHash.as<u64>() + DICT_SLOTS);
+          k_bin_entries<<<gridFor(fEntries + 1, 256), 256, 0, st>>>(bb, 0, ctx->fastEnt.as<uint4>(), ctx->fastRank.as<u32>());
+          k_dict_number<<<1, 1024, 0, st>>>(bb.hashKey, bb.hashId, ctx->fastDict.as<uint2>());
+          k_bin_entries<<<gridFor(fEntries + 1, 256), 256, 0, st>>>(bb, 1, ctx->fastEnt.as<uint4>(), ctx->fastRank.as<u32>());
+          ctx->launches += 2;
+        } else
           k_fast_bitmap<<<gridFor(fEntries, 256), 256, 0, st>>>(segKey.as<u64>(), nSeg, fChrBinBase.as<u32>(), nChr, fshift, gshift, (u32)fEntries,
                                                                 ctx->fastBin.as<uint2>());
         ctx->launches += 3;
@@ -660,6 +688,8 @@ int mma_load_features(mma_ctx *ctx, const mma_features *f) {
       CKS(cudaGetLastError());
       ctx->fast.bm = useEnt ? nullptr : ctx->fastBin.as<uint2>();
       ctx->fast.ent = useEnt ? ctx->fastEnt.as<uint4>() : nullptr;
+      ctx->fast.rank = useEnt ? ctx->fastRank.as<u32>() : nullptr;
+      ctx->fast.dict = useEnt ? ctx->fastDict.as<uint2>() : nullptr;
       ctx->fast.seg = ctx->fastSeg.as<uint4>();
       ctx->fast.tie = ctx->fastTie.as<u32>();
       ctx->fast.upMask = upMask;
@@ -670,7 +700,7 @@ int mma_load_features(mma_ctx *ctx, const mma_features *f) {
       ctx->fast.gshift = gshift;
       ctx->fast.enabled = 1;
       ctx->nSegments = nSeg;
-      fastBytes = (uint64_t)nSeg * (2 * sizeof(uint4) + 2 * sizeof(u32)) + fEntries * (useEnt ? 2 * sizeof(uint4) : sizeof(uint2)) + (uint64_t)nChr * sizeof(uint2);
+      fastBytes = (uint64_t)nSeg * (2 * sizeof(uint4) + 2 * sizeof(u32)) + fEntries * (useEnt ? sizeof(uint4) + 4 : sizeof(uint2)) + (uint64_t)nChr * sizeof(uint2);
     }
 #undef CKS
     cleanupFast();

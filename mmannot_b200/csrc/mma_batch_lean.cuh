@@ -5,14 +5,16 @@
 //
 //   stream    the five hit arrays of a tile are brought into a per-warp shared-memory ring by the TMA unit: one elected lane
 //             issues five 1-D bulk copies (cp.async.bulk ... mbarrier::complete_tx, L2 evict-first) for the tile TWO tiles
-//             ahead, the warp waits on the stage's mbarrier and reads its hits with conflict-free 128-bit shared loads.  No
-//             global load of the stream goes through the LSU, and the first key of the next tile (needed to close a run that
-//             ends on the tile border) is simply read from the next stage.
-//   lookup    ONE 32-byte gather per hit: the bin entry of the read start holds the answers of the segment that covers the end
-//             of the bin (in-segment and over the next boundary).  Reads that start before a boundary of their bin, or need an
-//             answer the entry does not hold (~10 %), are compacted over the warp and take the segment record, one hit per lane.
+//             ahead, the warp waits on the stage's mbarrier and reads its hits with conflict-free 128-bit shared loads, each
+//             array only when it is needed (registers).  No global load of the stream goes through the LSU, and the first key
+//             of the next tile (needed to close a run that ends on the tile border) is simply read from the next stage.
+//   lookup    ONE 16-byte gather per hit: the bin entry of the read start names, in a dictionary of answer pairs kept in shared
+//             memory, the answers of the segment that covers the end of the bin (in-segment and over the next boundary) and of
+//             the one that covers its start.  Reads the entry cannot answer (5-10 %) are compacted over the warp and take the
+//             segment record, one hit per lane.
 //   per read  the segmented OR scan over the runs of a tile tests "distance to the nearest run start <= d" per round instead of
-//             re-deriving it from the ballot; counters are kept per lane in plain 32-bit registers.
+//             re-deriving it from the ballot; slots past the end of the batch are padding (no special cases in the loop);
+//             rescued reads are counted from the histogram columns at the end instead of per record.
 //
 // Everything that is not the regular shape (-m rescue, unfinished read names, runs whose NH disagrees with their length, runs cut
 // by a chunk border) takes the serial RunWalker of mma_device.cuh exactly as in k_batch: results are identical by construction
@@ -23,7 +25,10 @@
 namespace mma {
 
 #ifndef MMA_LEAN_THREADS
-#define MMA_LEAN_THREADS 352
+#define MMA_LEAN_THREADS 288
+#endif
+#ifndef MMA_LEAN_MAXREG
+#define MMA_LEAN_MAXREG 112  // 2 blocks of 288 threads per SM
 #endif
 #ifndef MMA_LEAN_BLOCKS_PER_SM
 #define MMA_LEAN_BLOCKS_PER_SM 2
@@ -62,22 +67,37 @@ __device__ __forceinline__ void bulkLoad(u32 dst, const void *src, u32 bytes, u3
                "r"(bytes), "r"(bar), "l"(pol)
                : "memory");
 }
-__device__ __forceinline__ void ldEntry(const uint4 *p, uint4 &lo, uint4 &hi) {
-  asm volatile("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-               : "=r"(lo.x), "=r"(lo.y), "=r"(lo.z), "=r"(lo.w), "=r"(hi.x), "=r"(hi.y), "=r"(hi.z), "=r"(hi.w)
-               : "l"(p));
+__device__ __forceinline__ uint4 lds128(u32 addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ u64 lds64(u32 addr) {
+  u64 v;
+  asm volatile("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ uint2 lds64x2(u32 addr) {
+  uint2 v;
+  asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
+  return v;
 }
 
+struct LeanWarp {  // private to one warp
+  alignas(128) unsigned char ring[LEAN_STAGES][LEAN_STAGE_BYTES];
+  u64 bar[LEAN_STAGES];
+  u32 scratch[WT_HITS];          // answers of the compacted hits; then the first records of the runs to walk
+  unsigned char slowQ[WT_HITS];
+};
+#define LEAN_BAR_OFF (LEAN_STAGES * LEAN_STAGE_BYTES)
 template <bool HIST>
 struct LeanSmem {
-  alignas(128) unsigned char ring[LEAN_WARPS][LEAN_STAGES][LEAN_STAGE_BYTES];
-  alignas(8) u64 bar[LEAN_WARPS][LEAN_STAGES];
+  LeanWarp w[LEAN_WARPS];
+  uint2 dict[ENT_DICT];
+  uint2 chrInfo[CHR_SMEM + 1];
   typename BlockTableOf<HIST, LEAN_BT_SLOTS>::type bt;
   unsigned short hist[HIST ? HIST_ROWS : 1][LEAN_THREADS];
-  uint2 chrInfo[CHR_SMEM + 1];
-  u32 scratch[LEAN_WARPS][WT_HITS];  // answers of the compacted hits; then the first records of the runs to walk
-  unsigned char slowQ[LEAN_WARPS][WT_HITS];
-  u32 stat[ST_N];
+  u32 stat[ST_N + 1];  // [ST_N]: reads of their own counted for a single element (see the epilogue)
 };
 
 template <bool HIST>
@@ -97,9 +117,37 @@ struct LeanCount {  // one read counted for an element set, from divergent code 
   }
 };
 
+// A hit the bin entry could not answer: the record of its segment (index = rank of the bin + boundaries up to the read start),
+// then like fastAnnotate (which this replaces on the hot path: no chromosome check, no stepping).
+template <int MODE>
+__device__ __forceinline__ u32 recordAnnotate(const FastView &fx, const IndexView &ix, uint2 ci, u32 rs, u32 re, u32 meta, float ovl) {
+  if (re < rs || re >= 0xFFFFFFF0u) return fastMissEval<MODE>(ix, rs, re, meta, ovl);
+  const u32 at = ci.x + min(rs >> 6, ci.y - 1u);
+  const uint4 e = __ldg(&fx.ent[at]);
+  const u32 rank = __ldg(&fx.rank[at]);
+  const u64 bits = ((u64)e.y << 32) | e.x;
+  const u32 i = rank + __popcll(bits & ((2ull << (rs & 63u)) - 1ull));
+  uint4 t, x;
+  ldRecord(&fx.seg[2u * i], t, x);
+  const bool fwd = (int)meta < 0;
+  u32 a;
+  if (re <= t.x) {
+    a = fwd ? t.y : t.z;
+    if (a & ANS_VICPAIR) a = vicPick(fx, a, __ldg(&fx.tie[2u * i + (fwd ? 0u : 1u)]), rs, re);
+  } else if (MODE == 0) {
+    const int which = segmentsAhead(re - t.x, t.w);
+    if (which == 0) return fastMissEval<MODE>(ix, rs, re, meta, ovl);
+    a = (which == 1) ? (fwd ? x.x : x.y) : (fwd ? x.z : x.w);
+  } else {
+    return fastMissEval<MODE>(ix, rs, re, meta, ovl);
+  }
+  if (a & ANS_GENERAL) return fastMissEval<MODE>(ix, rs, re, meta, ovl);
+  return a;
+}
+
 // GROUPS: runs of k x NH records (paired-end data) are resolved in parallel as k reads (see k_batch_fast)
 template <int MODE, int STRAT, bool GROUPS>
-__global__ void __launch_bounds__(LEAN_THREADS, MMA_LEAN_BLOCKS_PER_SM)
+__global__ void __maxnreg__(MMA_LEAN_MAXREG)
 k_batch_lean(const __grid_constant__ IndexView ix, const __grid_constant__ FastView fx, const __grid_constant__ HitView h, const __grid_constant__ Rules r,
              const __grid_constant__ TableView table, SampleCtl *ctl, const __grid_constant__ SlowView slow, const __grid_constant__ KeySetView open) {
   constexpr bool HIST = (STRAT != 3);
@@ -112,12 +160,15 @@ k_batch_lean(const __grid_constant__ IndexView ix, const __grid_constant__ FastV
 #pragma unroll
     for (int e = 0; e < HIST_ROWS; ++e) sm.hist[e][tid] = 0;
   }
-  if (tid < ST_N) sm.stat[tid] = 0;
+  if (tid <= ST_N) sm.stat[tid] = 0;
   for (u32 c = tid; c <= fx.nChr; c += LEAN_THREADS) sm.chrInfo[c] = fx.chrInfo[c];  // launched only when nChr <= CHR_SMEM
-  const u32 bar0 = smemAddr(&sm.bar[warp][0]), ring0 = smemAddr(&sm.ring[warp][0][0]);
+  for (u32 c = tid; c < ENT_DICT; c += LEAN_THREADS) sm.dict[c] = fx.dict[c];
+  const u32 wbase = smemAddr(&sm.w[warp]);  // ring stage s at wbase + s * LEAN_STAGE_BYTES, its barrier at wbase + LEAN_BAR_OFF + 8 s
+  const u32 dict0 = smemAddr(&sm.dict[0]);  // (the chromosome table follows the dictionary)
+  LeanWarp &mine = sm.w[warp];
   if (lane == 0) {
-    mbarInit(bar0, 1);
-    mbarInit(bar0 + 8, 1);
+    mbarInit(wbase + LEAN_BAR_OFF, 1);
+    mbarInit(wbase + LEAN_BAR_OFF + 8, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
@@ -125,7 +176,13 @@ k_batch_lean(const __grid_constant__ IndexView ix, const __grid_constant__ FastV
   const u32 seq = ctl->batchSeq;
   // every run takes the serial walker when rescue() needs multiplicities or some read name is known as unfinished
   const bool forceWalk = (STRAT == 0) && (r.rescue || __shfl_sync(FULL, ctl->openCount, 0) != 0);
-  u32 cAsg = 0, cUniq = 0, cMulti = 0, cAmbi = 0, cHits = 0, cMiss = 0, cClosed = 0, cResc = 0, pWalks = 0;
+  // per-lane counters, two 16-bit fields per register (a lane sees at most 4 hits per tile and the host keeps a warp's chunk
+  // below 2^14 tiles, see launchBatchKernels):
+  u32 pAsgUniq = 0;   // assigned hits | hits of NH = 1 with an element (corrected for ambiguous ones) << 16        (mm:1666, 1668)
+  u32 pMultAmbi = 0;  // hits joining the by-name countdown | ambiguous hits << 16                                 (mm:1670, 1667)
+  u32 pOwnClos = 0;   // reads of their own counted for one element | multi-mapping reads closed by the scan << 16
+  u32 pMissResc = 0;  // segment-table misses | (rescue() active only) closed reads resolved to one element << 16
+  u32 pWalks = 0, cVis = 0;
 
   LeanCount<HIST> count{sm, table, tid};
   RunWalker<MODE, true, LeanCount<HIST>> w{h, r, annot, ctl, slow, open, count, seq, 0u, 0u};
@@ -134,18 +191,15 @@ k_batch_lean(const __grid_constant__ IndexView ix, const __grid_constant__ FastV
   const u32 nWarps = gridDim.x * LEAN_WARPS;
   const u32 per = (nWT + nWarps - 1) / nWarps;
   const u32 t0 = min(nWT, (blockIdx.x * LEAN_WARPS + warp) * per), t1 = min(nWT, t0 + per);
-  const u32 nMax = fx.nChr;
-  const u64 pol = policyEvictFirst();
 
-  // ---- staging: tile t of the chunk goes to stage (t - t0) & 1.  Full tiles by bulk copies, the (one) partial tile at the end
-  //      of the batch by the warp itself.
-  auto stage = [&](u32 t) {
-    const u32 s = (t - t0) & 1u;
-    const u32 dst = ring0 + s * LEAN_STAGE_BYTES;
+  // ---- staging: the i-th tile of the chunk goes to stage i & 1.  Full tiles by bulk copies; the (one) partial tile at the end
+  //      of the batch by the warp itself, padded with hits that count for nothing (unknown chromosome, NH = 1, the reserved key).
+  auto stage = [&](u32 t, u32 s) {
     const size_t base = (size_t)t * WT_HITS;
     if ((t + 1) * WT_HITS <= h.n) {
       if (lane == 0) {
-        const u32 bar = bar0 + s * 8;
+        const u32 dst = wbase + s * LEAN_STAGE_BYTES, bar = wbase + LEAN_BAR_OFF + s * 8;
+        const u64 pol = policyEvictFirst();
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // the warp's reads of the stage come before the unit's writes
         mbarExpectTx(bar, (STRAT == 0) ? LEAN_STAGE_BYTES : 2048u);
         bulkLoad(dst, h.start + base, 512, bar, pol);
@@ -155,8 +209,8 @@ k_batch_lean(const __grid_constant__ IndexView ix, const __grid_constant__ FastV
         if (STRAT == 0) bulkLoad(dst + 2048, h.key + base, 1024, bar, pol);
       }
     } else {
-      u32 *d32 = reinterpret_cast<u32 *>(&sm.ring[warp][s][0]);
-      u64 *d64 = reinterpret_cast<u64 *>(&sm.ring[warp][s][2048]);
+      u32 *d32 = reinterpret_cast<u32 *>(&mine.ring[s][0]);
+      u64 *d64 = reinterpret_cast<u64 *>(&mine.ring[s][2048]);
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const u32 o = lane * 4 + j;
@@ -166,112 +220,107 @@ k_batch_lean(const __grid_constant__ IndexView ix, const __grid_constant__ FastV
         d32[128 + o] = v ? h.end[i] : 0u;
         d32[256 + o] = v ? h.meta[i] : 0x00FFFFFFu;
         d32[384 + o] = v ? h.nh[i] : 1u;
-        if (STRAT == 0) d64[o] = v ? h.key[i] : KEY_EMPTY;
+        if (STRAT == 0) d64[o] = v ? normKey(h.key[i]) : KEY_EMPTY;
       }
     }
   };
 
   bool cValid = false, cCont = false;  // cCont: the run open at the end of the tile continues in the next tile
   u32 cStart = 0, cTot = 0, cNh = 0;
-  u64 cKey = KEY_EMPTY;
-  u64 chunkPeek = KEY_EMPTY;  // first key after the chunk
-  if (STRAT == 0 && t1 > t0 && (size_t)t1 * WT_HITS < h.n) chunkPeek = __ldg(&h.key[(size_t)t1 * WT_HITS]);
-  if (t0 < t1) stage(t0);
-  if (t0 + 1 < t1) stage(t0 + 1);
+  // lane 0: does the chunk's first record start a run?  (The state carried into the batch counts as the record before it.)
+  bool headFirst = true;
+  const Carry *carryIn = nullptr;
+  if (STRAT == 0 && lane == 0 && t0 < t1) {
+    const u64 first = normKey(__ldg(&h.key[(size_t)t0 * WT_HITS]));
+    if (t0 == 0) {
+      const Carry &c = ctl->carry[seq & 1];
+      if (c.valid) { carryIn = &c; headFirst = c.key != first; }
+    } else {
+      headFirst = normKey(__ldg(&h.key[(size_t)t0 * WT_HITS - 1])) != first;
+    }
+  }
+  if (t0 < t1) stage(t0, 0);
+  if (t0 + 1 < t1) stage(t0 + 1, 1);
   __syncwarp();
 
-  for (u32 t = t0; t < t1; ++t) {
-    const u32 s = (t - t0) & 1u, use = (t - t0) >> 1;
+  for (u32 t = t0, it = 0; t < t1; ++t, ++it) {
+    const u32 s = it & 1u;
     const u32 base = t * WT_HITS + lane * 4;
     const bool fullTile = (t + 1) * WT_HITS <= h.n;
-    if (fullTile) mbarWait(bar0 + s * 8, use & 1u);
-    u32 rs[4], re[4], meta[4], nh[4];
-    u64 key[4];
-    u32 validBits = 15u;
-    {
-      const unsigned char *st = &sm.ring[warp][s][0];
-      const uint4 a = *reinterpret_cast<const uint4 *>(st + lane * 16);
-      const uint4 b = *reinterpret_cast<const uint4 *>(st + 512 + lane * 16);
-      const uint4 c = *reinterpret_cast<const uint4 *>(st + 1024 + lane * 16);
-      const uint4 d = *reinterpret_cast<const uint4 *>(st + 1536 + lane * 16);
-      rs[0] = a.x; rs[1] = a.y; rs[2] = a.z; rs[3] = a.w;
-      re[0] = b.x; re[1] = b.y; re[2] = b.z; re[3] = b.w;
-      meta[0] = c.x; meta[1] = c.y; meta[2] = c.z; meta[3] = c.w;
-      nh[0] = d.x; nh[1] = d.y; nh[2] = d.z; nh[3] = d.w;
-      if (STRAT == 0) {
-        const ulonglong2 k0 = *reinterpret_cast<const ulonglong2 *>(st + 2048 + lane * 32);
-        const ulonglong2 k1 = *reinterpret_cast<const ulonglong2 *>(st + 2048 + lane * 32 + 16);
-        key[0] = k0.x; key[1] = k0.y; key[2] = k1.x; key[3] = k1.y;
-        // the all-ones key is reserved (normKey): only a tile that holds a key with all-ones upper half needs the fix-up
-        const u32 hiMax = max(max((u32)(k0.x >> 32), (u32)(k0.y >> 32)), max((u32)(k1.x >> 32), (u32)(k1.y >> 32)));
-        if (__any_sync(FULL, hiMax == 0xFFFFFFFFu)) {
-#pragma unroll
-          for (int j = 0; j < 4; ++j) key[j] = normKey(key[j]);
-        }
-      }
-      if (!fullTile) {
-        const u32 left = (h.n > base) ? min(h.n - base, 4u) : 0u;
-        validBits = (1u << left) - 1u;
-      }
-    }
+    const u32 st = wbase + s * LEAN_STAGE_BYTES + lane * 16;
+    if (fullTile) mbarWait(wbase + LEAN_BAR_OFF + s * 8, (it >> 1) & 1u);
     // ---- run starts
     u32 hbits = 0, F = 0;
-    const Carry *carryIn = nullptr;
     u64 nextKey = KEY_EMPTY;
     if (STRAT == 0) {
-      u64 prev = __shfl_up_sync(FULL, key[3], 1);
-      if (lane == 0) {
-        if (t != t0) prev = cKey;
-        else if (base == 0) {
-          const Carry &c = ctl->carry[seq & 1];
-          prev = KEY_EMPTY;
-          if (c.valid) { carryIn = &c; prev = c.key; }
-        } else prev = normKey(h.key[base - 1]);
+      u64 key[4];
+      const uint4 k0 = lds128(st + 2048 + lane * 16), k1 = lds128(st + 2048 + lane * 16 + 16);
+      key[0] = ((u64)k0.y << 32) | k0.x; key[1] = ((u64)k0.w << 32) | k0.z; key[2] = ((u64)k1.y << 32) | k1.x; key[3] = ((u64)k1.w << 32) | k1.z;
+      // the all-ones key is reserved (normKey): only a tile that holds a key with all-ones upper half needs the fix-up (the
+      // partial tile was normalised when it was staged: its padding keeps the reserved key)
+      const u32 hiMax = max(max(k0.y, k0.w), max(k1.y, k1.w));
+      if (fullTile && __any_sync(FULL, hiMax == 0xFFFFFFFFu)) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) key[j] = normKey(key[j]);
       }
-      hbits = ((key[0] != prev) ? 1u : 0u) | ((key[1] != key[0]) ? 2u : 0u) | ((key[2] != key[1]) ? 4u : 0u) | ((key[3] != key[2]) ? 8u : 0u);
-      hbits |= ~validBits & 15u;  // (slots past the end of the batch count as run starts)
+      const u64 prev = __shfl_up_sync(FULL, key[3], 1);
+      // lane 0: the tile's first record starts a run unless the previous tile's last run continues (first tile: see headFirst)
+      const bool head0 = (lane == 0) ? (it == 0 ? headFirst : !cCont) : (key[0] != prev);
+      hbits = (head0 ? 1u : 0u) | ((key[1] != key[0]) ? 2u : 0u) | ((key[2] != key[1]) ? 4u : 0u) | ((key[3] != key[2]) ? 8u : 0u);
       F = __ballot_sync(FULL, hbits != 0);
       nextKey = __shfl_sync(FULL, key[3], 31);
     }
-    // ---- which hits are looked at (unique: only NH == 1, mm:1773)
-    u32 visBits = validBits;
-    if (STRAT == 1) {
-#pragma unroll
-      for (int j = 0; j < 4; ++j) if (nh[j] != 1) visBits &= ~(1u << j);
-    }
-    // ---- lookup: the bin entry of the read start
+    // ---- lookup: the bin entries of the read starts
     u32 m[4];
     u32 slowBits = 0;
     {
-      uint4 e0[4], e1[4];
+      u32 rs[4], meta[4];
+      uint4 en[4];
+      const uint4 a = lds128(st), c = lds128(st + 1024);
+      rs[0] = a.x; rs[1] = a.y; rs[2] = a.z; rs[3] = a.w;
+      meta[0] = c.x; meta[1] = c.y; meta[2] = c.z; meta[3] = c.w;
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const uint2 ci = sm.chrInfo[min(meta[j] & 0x00FFFFFFu, nMax)];
-        ldEntry(&fx.ent[2u * (ci.x + min(rs[j] >> 6, ci.y - 1u))], e0[j], e1[j]);
+        const uint2 ci = lds64x2(dict0 + 8u * ENT_DICT + 8u * min(meta[j] & 0x00FFFFFFu, fx.nChr));
+        en[j] = __ldg(&fx.ent[ci.x + min(rs[j] >> 6, ci.y - 1u)]);
       }
+      const uint4 b = lds128(st + 512);
+      const u32 re[4] = {b.x, b.y, b.z, b.w};
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const bool fwd = (int)meta[j] < 0;
-        const u64 bits = ((u64)e0[j].y << 32) | e0[j].x;
+        const u64 bits = ((u64)en[j].y << 32) | en[j].x;
         const bool inZ = ((bits >> (rs[j] & 63u)) >> 1) == 0;  // no boundary after the read start inside its bin
-        u32 a = fwd ? e1[j].x : e1[j].y;
-        if (re[j] > e0[j].w) {  // over the end of Z: the cross answer, when the read ends inside the next segment
-          const u32 len = (e1[j].z >> 28) | ((e1[j].w >> 28) << 4);
-          const u32 x = (fwd ? e1[j].z : e1[j].w) & ENT_XNONE;
-          a = (MODE == 0 && re[j] - e0[j].w <= len && x != ENT_XNONE) ? x : ENT_NONE;
-        }
+        const u32 binEnd = rs[j] | 63u;
+        const u32 x = max(re[j], binEnd) - binEnd;               // how far the read reaches beyond its bin
+        const u32 lenZ = en[j].z & 0xFFFFu, lenZ1 = en[j].z >> 16;
+        const bool inside = x <= lenZ;
+        const bool cross = MODE == 0 && !inside && x - lenZ <= lenZ1;
+        const u32 id = inside ? (en[j].w & 1023u) : ((en[j].w >> 10) & 1023u);
+        const uint2 pair = lds64x2(dict0 + 8u * id);
+        const u32 a = ((int)meta[j] < 0) ? pair.x : pair.y;
+        bool ok = inZ && (inside || cross) && a != ENT_NONE && re[j] >= rs[j];
         bool pass = true;
         if (MODE != 0) {  // no feature can overlap the read by more than end - start
           const u32 o = re[j] - rs[j];
           if (MODE == 1) pass = (o != 0) && (__fmul_rn((float)(o + 1u), r.overlap) <= (float)o);
           else pass = (o != 0) && ((float)o >= r.overlap);
+          if (re[j] < rs[j]) pass = true;  // (an empty interval, end = start - 1: left to the index walk)
         }
-        const bool degen = re[j] < rs[j] || re[j] >= 0xFFFFFFF0u;
-        const bool vis = (visBits >> j) & 1u;
-        const bool ok = inZ && a != ENT_NONE && !degen;
-        m[j] = (vis && pass && ok) ? a : 0u;
-        if (vis && !ok && (pass || degen)) slowBits |= 1u << j;
+        m[j] = (ok && pass) ? a : 0u;
+        if (!ok && pass) slowBits |= 1u << j;
       }
+    }
+    u32 nh[4];
+    {
+      const uint4 d = lds128(st + 1536);
+      nh[0] = d.x; nh[1] = d.y; nh[2] = d.z; nh[3] = d.w;
+    }
+    if (STRAT == 1) {  // unique: only NH == 1 is looked at (mm:1773)
+      const u32 skip = (nh[0] != 1 ? 1u : 0u) | (nh[1] != 1 ? 2u : 0u) | (nh[2] != 1 ? 4u : 0u) | (nh[3] != 1 ? 8u : 0u);
+      slowBits &= ~skip;
+      cVis += 4u - __popc(skip);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) if ((skip >> j) & 1u) m[j] = 0;
     }
     // ---- the rest, compacted over the warp: one hit per lane against the segment record (and, behind it, the feature index)
     if (__any_sync(FULL, slowBits != 0)) {
@@ -284,56 +333,67 @@ k_batch_lean(const __grid_constant__ IndexView ix, const __grid_constant__ FastV
       }
 #pragma unroll
       for (int j = 0; j < 4; ++j)
-        if ((slowBits >> j) & 1u) sm.slowQ[warp][off[j]] = (unsigned char)(lane * 4 + j);
+        if ((slowBits >> j) & 1u) mine.slowQ[off[j]] = (unsigned char)(lane * 4 + j);
       __syncwarp();
-      const u32 *st32 = reinterpret_cast<const u32 *>(&sm.ring[warp][s][0]);
+      const u32 *st32 = reinterpret_cast<const u32 *>(&mine.ring[s][0]);
       for (u32 k = lane; k < total; k += 32) {
-        const u32 id = sm.slowQ[warp][k];
-        sm.scratch[warp][id] = slowAnnotate<MODE>(fx, ix, st32[id], st32[128 + id], st32[256 + id], r.overlap);
+        const u32 id = mine.slowQ[k];
+        const u32 qs = st32[id], qe = st32[128 + id], qm = st32[256 + id];
+        const u32 chr = qm & 0x00FFFFFFu;
+        mine.scratch[id] = (chr < fx.nChr) ? recordAnnotate<MODE>(fx, ix, sm.chrInfo[chr], qs, qe, qm, r.overlap) : 0u;
       }
       __syncwarp();
 #pragma unroll
       for (int j = 0; j < 4; ++j)
         if ((slowBits >> j) & 1u) {
-          const u32 a = sm.scratch[warp][lane * 4 + j];
+          const u32 a = mine.scratch[lane * 4 + j];
           m[j] = a & ~FAST_MISS;
-          cMiss += a >> 31;
+          pMissResc += a >> 31;
         }
     }
     __syncwarp();
     // the stage is free: bring in the tile two tiles ahead
-    if (t + 2 < t1) stage(t + 2);
-    // ---- per-hit counters (mm:1666-1668); a visited hit that does not join the by-name countdown is a read of its own
+    if (t + 2 < t1) stage(t + 2, s);
+    // ---- per-hit counters (mm:1666-1668); a hit that does not join the by-name countdown is a read of its own.  (Padding
+    //      slots -- and, under -y unique, the hits that are not looked at -- hold m = 0; what the padding adds to the hit count is
+    //      taken back after the loop.)
     u32 ev[4];  // the element set counted at this hit slot (0 = none)
+    u32 ambOr = 0;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
+      const u32 a1 = min(m[j], 1u);
       const bool multi = STRAT == 0 && nh[j] > 1;
-      const bool amb = (m[j] & (m[j] - 1u)) != 0;
-      cAsg += m[j] != 0 ? 1u : 0u;
-      cUniq += (m[j] != 0 && !amb && nh[j] == 1) ? 1u : 0u;
-      cMulti += multi ? 1u : 0u;
-      cAmbi += amb ? 1u : 0u;
+      pAsgUniq += a1 + ((nh[j] == 1 ? a1 : 0u) << 16);
+      pMultAmbi += multi ? 1u : 0u;
+      ambOr |= m[j] & (m[j] - 1u);
       ev[j] = multi ? 0u : m[j];
       if (r.rescue) ev[j] = (u32)rescueSingle(r, (u64)ev[j]);
     }
-    cHits += __popc(visBits);
+    if (ambOr) {  // some hit of this lane matched several elements (mm:1667): it is ambiguous, and not "unique"
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (m[j] & (m[j] - 1u)) {
+          pMultAmbi += 0x10000u;
+          if (nh[j] == 1) pAsgUniq -= 0x10000u;
+        }
+    }
     u32 nWalk = 0, closeBits = 0;
     u32 inc = 0, lastHeadPos = 0, F2 = 0;
     bool serialTile = false;
     u32 tileEndsRun = 1;  // the record after the tile's last one starts another run (or the batch ends there)
     if (STRAT == 0) {
-      // first key of the next tile: from the next stage of the ring, or (last tile of the chunk) fetched when the chunk began
-      const u32 nextTile = (t + 1) * WT_HITS;
-      if (nextTile < h.n) {
-        u64 pk = chunkPeek;
-        if (t + 1 < t1) {
-          if ((t + 2) * WT_HITS <= h.n) mbarWait(bar0 + (s ^ 1u) * 8, ((t + 1 - t0) >> 1) & 1u);
-          pk = *reinterpret_cast<const u64 *>(&sm.ring[warp][s ^ 1u][2048]);
-        }
-        tileEndsRun = (normKey(pk) != nextKey) ? 1u : 0u;
+      // first key of the next tile: from the next stage of the ring, or (last tile of the chunk) from global memory
+      if (t + 1 < t1) {
+        const bool nextFull = (t + 2) * WT_HITS <= h.n;
+        if (nextFull) mbarWait(wbase + LEAN_BAR_OFF + (s ^ 1u) * 8, ((it + 1) >> 1) & 1u);
+        u64 pk = lds64(wbase + (s ^ 1u) * LEAN_STAGE_BYTES + 2048);
+        if (nextFull) pk = normKey(pk);
+        tileEndsRun = (pk != nextKey) ? 1u : 0u;
+      } else if ((size_t)t1 * WT_HITS < h.n) {
+        tileEndsRun = (normKey(__ldg(&h.key[(size_t)t1 * WT_HITS])) != nextKey) ? 1u : 0u;
       }
       // ---- per-read countdown (mm:1669-1702)
-      if (carryIn) {  // lane 0 of the batch's first tile: the read carried into this batch
+      if (it == 0 && carryIn) {  // lane 0 of the batch's first tile: the read carried into this batch
         if (!(hbits & 1u)) w.walk(0, carryIn->key, carryIn);
         else {  // its name does not continue: unfinished
           --w.nReads;
@@ -343,18 +403,18 @@ k_batch_lean(const __grid_constant__ IndexView ix, const __grid_constant__ FastV
         }
       }
       const u32 before = F & ((1u << lane) - 1u);
-      // distance (in lanes) to the nearest lane, this one included, in which a run starts
-      const u32 upTo = F & (0xFFFFFFFFu >> (31u - lane));
       u32 prevNh = __shfl_up_sync(FULL, nh[3], 1);
       if (lane == 0) prevNh = cNh;
       lastHeadPos = base + (31 - __clz(hbits | 1u));
       const u32 sPrev = __shfl_sync(FULL, lastHeadPos, before ? (31 - __clz(before)) : 0);
       const u32 nextHead0 = __shfl_down_sync(FULL, hbits & 1u, 1);
       // bit j: the next record starts another run, i.e. this record ends its run (the tile's last record: from the peek)
-      const u32 lastBits = ((hbits >> 1) | ((lane < 31u ? nextHead0 : tileEndsRun) << 3)) & validBits;
+      const u32 lastBits = (hbits >> 1) | ((lane < 31u ? nextHead0 : tileEndsRun) << 3);
       // a run that starts before this lane's hits: its first record, and whether this warp owns it at all
       const u32 inStart = before ? sPrev : cStart;
       const bool inMine = before || cValid;  // else the run starts in another warp's chunk: that warp finishes it
+      u32 walkBits = 0;  // slots whose run (GROUPS: whose group) has to be walked serially
+      u32 off[4];        // GROUPS: position of the record inside its group
       if (GROUPS) {
         // A read opens at a record with NH = n > 1 and takes the n - 1 records of its name that follow, so a run of records
         // sharing a read key and carrying the same NH = n is a sequence of GROUPS of n records, one read each (one group for
@@ -366,19 +426,18 @@ k_batch_lean(const __grid_constant__ IndexView ix, const __grid_constant__ FastV
         // multiplicities or some read name is known as unfinished -- is resolved serially: one walk per run (serialTile).
         const u32 badBits = ((!(hbits & 1u) && nh[0] != prevNh) ? 1u : 0u) | ((!(hbits & 2u) && nh[1] != nh[0]) ? 2u : 0u) |
                             ((!(hbits & 4u) && nh[2] != nh[1]) ? 4u : 0u) | ((!(hbits & 8u) && nh[3] != nh[2]) ? 8u : 0u);
-        serialTile = forceWalk || __any_sync(FULL, (badBits & validBits) != 0);
+        serialTile = forceWalk || __any_sync(FULL, badBits != 0);
         if (!serialTile) {
-          u32 off[4];  // position of the record inside its group
-          u32 hb2 = hbits, endBits = 0, tailBits = 0;
+          u32 hb2 = hbits, endBits = 0;
           bool longRun = false;
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             const u32 hbLe = hbits & ((2u << j) - 1u);
             const u32 runStart = hbLe ? base + (31 - __clz(hbLe)) : inStart;
-            const bool mine = (hbLe || inMine) && ((validBits >> j) & 1u) && nh[j] > 1;
+            const bool own = (hbLe || inMine) && nh[j] > 1;
             u32 o = base + j - runStart;
             if (o >= nh[j]) o -= nh[j];
-            if (mine && o >= nh[j]) longRun = true;  // third group or later: exact remainder below
+            if (own && o >= nh[j]) longRun = true;  // third group or later: exact remainder below
             off[j] = o;
           }
           if (__any_sync(FULL, longRun)) {
@@ -389,10 +448,10 @@ k_batch_lean(const __grid_constant__ IndexView ix, const __grid_constant__ FastV
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             const u32 hbLe = hbits & ((2u << j) - 1u);
-            const bool mine = (hbLe || inMine) && ((validBits >> j) & 1u) && nh[j] > 1;
-            if (mine && off[j] == 0) hb2 |= 1u << j;                                  // first record of a group
-            if (mine && off[j] + 1 == nh[j]) endBits |= 1u << j;                      // last record of a group
-            else if (mine && ((lastBits >> j) & 1u)) tailBits |= 1u << j;             // the run ends inside a group
+            const bool own = (hbLe || inMine) && nh[j] > 1;
+            if (own && off[j] == 0) hb2 |= 1u << j;                                  // first record of a group
+            if (own && off[j] + 1 == nh[j]) endBits |= 1u << j;                      // last record of a group
+            else if (own && ((lastBits >> j) & 1u)) walkBits |= 1u << j;             // the run ends inside a group
           }
           F2 = __ballot_sync(FULL, hb2 != 0);
           pWalks += __popc(hb2 & ~hbits);  // groups beyond the first of their run: what the other variant would walk serially
@@ -414,22 +473,25 @@ k_batch_lean(const __grid_constant__ IndexView ix, const __grid_constant__ FastV
           if (lane == 0) X = 0;
           const u32 inTot = (F2 & ((1u << lane) - 1u)) ? X : (cTot | X);  // union so far of a group that starts before this lane's hits
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
+          for (int j = 0; j < 4; ++j)
             if ((endBits >> j) & 1u) {
               ev[j] = (hb2 & ((2u << j) - 1u)) ? pre[j] : (inTot | pre[j]);
               closeBits |= 1u << j;
             }
-            if ((tailBits >> j) & 1u) sm.scratch[warp][lane * 4 + nWalk++] = base + j - off[j];
+          if (walkBits) {  // rare
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              if ((walkBits >> j) & 1u) mine.scratch[lane * 4 + nWalk++] = base + j - off[j];
           }
         } else {
           // serial tile: the run carried into the tile (from the start of its open group) and every run that starts in it
-          if (lane == 0 && cValid && !(hbits & 1u) && (validBits & 1u)) {
+          if (lane == 0 && cValid && !(hbits & 1u)) {
             const u32 o = base - cStart;
-            sm.scratch[warp][lane * 4 + nWalk++] = base - ((cNh > 1) ? o % cNh : 0u);
+            mine.scratch[lane * 4 + nWalk++] = base - ((cNh > 1) ? o % cNh : 0u);
           }
 #pragma unroll
           for (int j = 0; j < 4; ++j)
-            if (((hbits & validBits) >> j) & 1u) sm.scratch[warp][lane * 4 + nWalk++] = base + j;
+            if ((hbits >> j) & 1u) mine.scratch[lane * 4 + nWalk++] = base + j;
         }
       } else {
         // A run of n records that all carry NH = n (> 1) is one read; its element set is the union over the run: a
@@ -447,7 +509,8 @@ k_batch_lean(const __grid_constant__ IndexView ix, const __grid_constant__ FastV
           pre[j] = acc;
         }
         inc = acc;  // inclusive scan over lanes: OR of `acc` from the nearest lane with a run start up to this lane
-        const u32 hd = upTo ? (u32)__clz(upTo) - (31u - lane) : 64u;
+        const u32 upTo = F & (0xFFFFFFFFu >> (31u - lane));
+        const u32 hd = upTo ? (u32)__clz(upTo) - (31u - lane) : 64u;  // lanes back to the nearest one in which a run starts
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
           const u32 tt = __shfl_up_sync(FULL, inc, d);
@@ -463,15 +526,19 @@ k_batch_lean(const __grid_constant__ IndexView ix, const __grid_constant__ FastV
           // union of the run's element sets and its first record, wherever the run starts
           const u32 tot = hbLe ? pre[j] : (inTot | pre[j]);
           const u32 runStart = hbLe ? base + (31 - __clz(hbLe)) : inStart;
-          const bool mine = hbLe || inMine;
-          const bool flagged = (tot & 0x80000000u) != 0;
+          const bool own = hbLe || inMine;
           // a run of reads that are their own group (NH <= 1 throughout) has nothing to close
-          const bool irregular = flagged || (nh[j] > 1 && nh[j] != base + j + 1 - runStart);
-          if (last && mine && irregular) sm.scratch[warp][lane * 4 + nWalk++] = runStart;
-          if (last && mine && !irregular && nh[j] > 1) {
-            ev[j] = tot & 0x7FFFFFFFu;
-            closeBits |= 1u << j;
-          }
+          const bool irregular = (int)tot < 0 || nh[j] != base + j + 1 - runStart;
+          if (last && own && nh[j] > 1 && !irregular) { ev[j] = tot; closeBits |= 1u << j; }
+          else if (last && own && ((int)tot < 0 || nh[j] > 1)) walkBits |= 1u << j;
+        }
+        if (walkBits) {  // rare
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if ((walkBits >> j) & 1u) {
+              const u32 hbLe = hbits & ((2u << j) - 1u);
+              mine.scratch[lane * 4 + nWalk++] = hbLe ? base + (31 - __clz(hbLe)) : inStart;
+            }
         }
       }
     }
@@ -482,16 +549,17 @@ k_batch_lean(const __grid_constant__ IndexView ix, const __grid_constant__ FastV
       for (int j = 0; j < 4; ++j) {
         const u32 c = ev[j];
         const bool single = c != 0 && (c & (c - 1)) == 0;
-        if (single && ((closeBits >> j) & 1u)) ++cResc;  // a multi-mapping read resolved to one element (mm:1691)
         if (HIST) {
-          const u32 row = single ? (u32)(__ffs(c) - 1) : (u32)(HIST_ROWS - 1);  // E <= 30: the last row only ever receives zeros
+          const u32 row = single ? (u32)(31 - __clz(c)) : (u32)(HIST_ROWS - 1);  // E <= 30: the last row only ever receives zeros
           sm.hist[row][tid] += single ? 1 : 0;
           if (c != 0 && !single) pend |= 1u << j;
+          if (r.rescue) { if (single && ((closeBits >> j) & 1u)) pMissResc += 0x10000u; }  // (else: from the histogram columns, see the epilogue)
+          else if (single && !((closeBits >> j) & 1u)) pOwnClos += 1u;
         } else {
           if (c != 0) pend |= 1u << j;
         }
       }
-      cClosed += __popc(closeBits);
+      pOwnClos += __popc(closeBits) << 16;
       while (__any_sync(FULL, pend != 0)) {
         if (pend) {
           const int j = __ffs(pend) - 1;
@@ -510,7 +578,10 @@ k_batch_lean(const __grid_constant__ IndexView ix, const __grid_constant__ FastV
     if (STRAT == 0) {
       pWalks += nWalk;
 #pragma unroll 1
-      for (u32 q = 0; q < nWalk; ++q) { const u32 i0 = sm.scratch[warp][lane * 4 + q]; w.walk(i0, normKey(h.key[i0]), nullptr); }
+      for (u32 q = 0; q < nWalk; ++q) {
+        const u32 i0 = mine.scratch[lane * 4 + q];
+        if (i0 < h.n) w.walk(i0, normKey(h.key[i0]), nullptr);  // (a run of padding slots has nothing to walk)
+      }
       const u32 incLast = __shfl_sync(FULL, inc, 31);
       if (GROUPS) {
         // the run (and, inside it, the group) still open at the end of the tile
@@ -536,7 +607,6 @@ k_batch_lean(const __grid_constant__ IndexView ix, const __grid_constant__ FastV
         }
       }
       cNh = __shfl_sync(FULL, nh[3], 31);
-      cKey = nextKey;
       cCont = tileEndsRun == 0;
     }
   }
@@ -544,21 +614,36 @@ k_batch_lean(const __grid_constant__ IndexView ix, const __grid_constant__ FastV
   //      open there, or starts there) are finished by the serial walk.  (A run ending exactly at the chunk's last record was
   //      closed above, like the last run of the batch.)
   if (STRAT == 0 && cValid && cCont && t1 > t0 && lane == 0) {
+    const u32 next = t1 * WT_HITS;
+    const u64 k = normKey(h.key[next]);
     if (GROUPS) {
-      const u32 next = t1 * WT_HITS, o = next - cStart;
-      w.walk(next - ((cNh > 1) ? o % cNh : 0u), cKey, nullptr);
+      const u32 o = next - cStart;
+      w.walk(next - ((cNh > 1) ? o % cNh : 0u), k, nullptr);
     } else {
-      w.walk(cStart, cKey, nullptr);
+      w.walk(cStart, k, nullptr);
+    }
+  }
+  const u32 cAsg = pAsgUniq & 0xFFFFu, cClosed = pOwnClos >> 16, cResc = pMissResc >> 16;
+  u32 cMulti = pMultAmbi & 0xFFFFu, cUniq = pAsgUniq >> 16, cAmbi = pMultAmbi >> 16, cOwn1 = pOwnClos & 0xFFFFu, cMiss = pMissResc & 0xFFFFu;
+  // hits looked at: 4 per lane and tile (-y unique: those with NH = 1), minus the padding of the batch's last tile
+  u32 cHits = 0;
+  if (t1 > t0) {
+    cHits = (STRAT == 1) ? cVis : 4u * (t1 - t0);
+    if (t1 == nWT) {
+      const u32 b = (nWT - 1) * WT_HITS + lane * 4;
+      const u32 real = (h.n > b) ? min(h.n - b, 4u) : 0u;
+      cHits -= 4u - real;
     }
   }
   u32 cUnassigned = cHits - cAsg;
-  u32 cReads = cHits - cMulti + cClosed + w.nReads, cRescued = cResc + w.nRescued;
+  u32 cReads = cHits - cMulti + cClosed + w.nReads, cRescued = cResc + (r.rescue ? w.nRescued : 0u);
 
   // ---- block epilogue: counters, the private histogram columns and the private table
   cHits = __reduce_add_sync(FULL, cHits); cUnassigned = __reduce_add_sync(FULL, cUnassigned);
   cAmbi = __reduce_add_sync(FULL, cAmbi); cUniq = __reduce_add_sync(FULL, cUniq);
   cMulti = __reduce_add_sync(FULL, cMulti); cReads = __reduce_add_sync(FULL, cReads);
   cRescued = __reduce_add_sync(FULL, cRescued); cMiss = __reduce_add_sync(FULL, cMiss);
+  cOwn1 = __reduce_add_sync(FULL, cOwn1);
   if (STRAT == 0 && !forceWalk) {
     pWalks = __reduce_add_sync(FULL, pWalks);
     if (lane == 0 && pWalks) atomicAdd(&ctl->walkCount, pWalks);
@@ -566,21 +651,27 @@ k_batch_lean(const __grid_constant__ IndexView ix, const __grid_constant__ FastV
   if (lane == 0) {
     atomicAdd(&sm.stat[ST_HITS], cHits); atomicAdd(&sm.stat[ST_UNASSIGNED], cUnassigned); atomicAdd(&sm.stat[ST_AMBIGUOUS], cAmbi);
     atomicAdd(&sm.stat[ST_UNIQUE], cUniq); atomicAdd(&sm.stat[ST_MULTIPLE], cMulti); atomicAdd(&sm.stat[ST_READS], cReads);
-    atomicAdd(&sm.stat[ST_RESCUED], cRescued); atomicAdd(&sm.stat[7], cMiss);
+    atomicAdd(&sm.stat[ST_RESCUED], cRescued); atomicAdd(&sm.stat[7], cMiss); atomicAdd(&sm.stat[ST_N], cOwn1);
   }
   __syncthreads();
   sm.bt.flush(table);
   if (HIST) {
+    u32 singles = 0;
     for (u32 e = warp; e < HIST_ROWS; e += LEAN_WARPS) {
       u32 v = 0;
 #pragma unroll
       for (int q = 0; q < LEAN_WARPS; ++q) v += sm.hist[e][lane + 32 * q];
       v = __reduce_add_sync(FULL, v);
       if (lane == 0 && v) tableAdd(table, 1ull << e, v);
+      singles += v;
     }
+    // multi-mapping reads resolved to one element (mm:1691) = reads counted for a single element - those that were a read of
+    // their own (with rescue() active they are counted one by one instead: a rescued single hit is neither)
+    if (STRAT == 0 && !r.rescue && lane == 0 && singles) atomicAdd(&ctl->stats[ST_RESCUED], (u64)singles);
   }
   if (tid < 7) {
-    const int sv = (int)sm.stat[tid];  // reads / rescued can be negative within a block (unfinished reads)
+    int sv = (int)sm.stat[tid];  // reads / rescued can be negative within a block (unfinished reads)
+    if (tid == ST_RESCUED && STRAT == 0 && !r.rescue) sv -= (int)sm.stat[ST_N];
     if (sv) atomicAdd(&ctl->stats[tid], (u64)(long long)sv);
   }
   if (tid == 7 && sm.stat[7]) atomicAdd(&ctl->fastMiss, sm.stat[7]);

@@ -69,21 +69,25 @@ struct IndexView {
 //   ANS_GENERAL  any other position-dependent pick: the table cannot answer
 #define ANS_VICPAIR 0x80000000u
 #define ANS_GENERAL 0x40000000u
-//   bin entries   (annotations up to ~160 Mb: TAIR10, FlyBase) replace the position map: ONE 32-byte gather answers the common read.
-//               ent[2e], ent[2e+1] describe the 64 positions [64b, 64b + 63] of a chromosome (e = chromosome base + b):
-//                 ent[2e]   = {bits lo, bits hi, rank, endZ}    bit p (1..63) = "a segment starts at 64b + p"; rank = index of the
-//                             segment holding position 64b; Z = rank + popc(bits) = the segment holding the bin's LAST position;
-//                             endZ = its end
-//                 ent[2e+1] = {answer F of Z, answer R of Z, cross answer F of (Z, Z+1), cross answer R}
-//               A read [s, e] with no boundary after s inside its start bin starts in Z; it lies inside Z when e <= endZ, and
-//               over Z and Z+1 when e - endZ <= length of Z+1.  That length, saturated at 255, sits in the top nibbles of the
-//               two cross words (low nibble in F, high nibble in R; the cross answers are only stored for E <= 28, else the
-//               length is 0).  An answer the entry cannot give (position dependent pick, flagged) is stored as all ones
-//               (ENT_NONE / ENT_XNONE): the read then takes the segment record like every read that starts before a boundary of
-//               its bin (segment index = rank + popc(bits up to s): exact).  The last bin of a chromosome is always empty, so
-//               a read starting beyond the annotated extent finds the last segment there.
+//   bin entries   (annotations up to ~160 Mb: TAIR10, FlyBase) replace the position map: ONE 16-byte gather answers the common read.
+//               ent[e] describes the 64 positions [64b, 64b + 63] of a chromosome (e = chromosome base + b):
+//                 x, y   bits: bit p (1..63) = "a segment starts at 64b + p"
+//                 z      lenZ (16 bits) | lenZ1 (8 bits) << 16      Z = the segment holding the bin's LAST position; lenZ = how far
+//                        Z reaches beyond the bin (saturated at 65535), lenZ1 = length of the segment after Z (saturated at 255;
+//                        0 when lenZ is saturated or there is no such segment)
+//                 w      idZ (10 bits) | idZX << 10 | idA << 20      indices into the PAIR DICTIONARY dict[] = {answer F, answer R}:
+//                        idZ the answers of a read inside Z, idZX of a read over Z and Z+1 (inclusion mode), idA of a read inside
+//                        A = the segment holding the bin's FIRST position
+//               rank[e] = index of A (the segment table index of a position p of the bin is rank + popc(bits up to p): exact).
+//               A read [s, e] with no boundary after s inside its start bin starts in Z; with x = e - (s | 63) it lies inside Z
+//               when x <= lenZ and over Z and Z+1 when 0 < x - lenZ <= lenZ1.  A read with no boundary up to s in its bin starts in
+//               A and lies inside A when e stays before the bin's first boundary.  An answer the dictionary cannot give (position
+//               dependent pick, or more than ENT_DICT distinct pairs) is ENT_NONE: the read then takes the segment record like
+//               every other read.  The last bin of a chromosome is always empty, so a read starting beyond the annotated extent
+//               finds the last segment there.  dict[0] = {0, 0} (also the answer of the dummy bin of unknown chromosomes),
+//               dict[ENT_DICT - 1] = {ENT_NONE, ENT_NONE}.
 #define ENT_NONE 0xFFFFFFFFu
-#define ENT_XNONE 0x0FFFFFFFu
+#define ENT_DICT 1024u
 struct FastView {
   const uint2 *bm;
   const uint4 *seg;
@@ -93,6 +97,8 @@ struct FastView {
   u32 upMask, downMask;  // upstream / downstream elements (Config::isUpstream / isDownstream, mm:463-470)
   const uint4 *ent;      // bin entries (null: position map `bm` instead); then chrInfo = {first entry, number of 64-position bins},
                          // chrInfo[nChr] = an empty dummy bin whose answers are 0, shift = 6, gshift = 0
+  const u32 *rank;       // bin entries: segment index of the first position of each bin
+  const uint2 *dict;     // bin entries: ENT_DICT answer pairs
 };
 
 struct HitView {
@@ -366,9 +372,10 @@ __device__ __noinline__ u64 annotateHit(const IndexView &ix, u32 rs, u32 re, u32
 // segment index (lower bound, exact when gshift == 0) of position rs on chromosome info ci
 __device__ __forceinline__ u32 fastSegIndex(const FastView &fx, uint2 ci, u32 rs) {
   if (fx.ent) {  // bin entries: exact
-    const uint4 e = __ldg(&fx.ent[2u * (ci.x + min(rs >> 6, ci.y - 1u))]);
+    const u32 at = ci.x + min(rs >> 6, ci.y - 1u);
+    const uint4 e = __ldg(&fx.ent[at]);
     const u64 bits = ((u64)e.y << 32) | e.x;
-    return e.z + __popcll(bits & ((2ull << (rs & 63u)) - 1ull));  // (the clamped last bin is empty)
+    return __ldg(&fx.rank[at]) + __popcll(bits & ((2ull << (rs & 63u)) - 1ull));  // (the clamped last bin is empty)
   }
   const u32 bRaw = rs >> fx.shift;
   const uint2 en = __ldg(&fx.bm[ci.x + min(bRaw, ci.y - 1u)]);
@@ -1421,40 +1428,89 @@ __global__ void k_fast_bitmap(const u64 *__restrict__ segKey, u32 nSeg, const u3
   bm[e] = make_uint2(bits, lo);
 }
 
-// one thread per bin entry (see FastView): needs the segment records
-__global__ void k_bin_entries(const u64 *__restrict__ segKey, u32 nSeg, const u32 *__restrict__ chrBinBase, u32 nChr, u32 nEntries,
-                              const uint4 *__restrict__ seg, u32 nElements, uint4 *ent) {
+// ---- bin entries (see FastView): one thread per bin, two passes around the numbering of the pair dictionary
+#define DICT_SLOTS 4096u
+struct BinBuild {
+  const u64 *segKey;
+  const u32 *chrBinBase;
+  const uint4 *seg;
+  u32 nSeg, nChr, nEntries, nElements;
+  u64 *hashKey;  // [DICT_SLOTS] answer pair + 1 (0 = empty)
+  u32 *hashId;   // [DICT_SLOTS] dictionary index of the slot's pair
+};
+__device__ __forceinline__ u32 dictSlot(u64 pair) { return (u32)(mix64(pair) & (DICT_SLOTS - 1)); }
+// pass 0: registers the pair; pass 1: its dictionary index (ENT_DICT - 1 when it has none)
+__device__ __forceinline__ u32 dictPair(const BinBuild &b, u32 f, u32 r, int pass) {
+  const u32 flags = ANS_VICPAIR | ANS_GENERAL;
+  if (f & flags) f = ENT_NONE;
+  if (r & flags) r = ENT_NONE;
+  const u64 pair = (((u64)r << 32) | f) + 1ull;
+  if (pair == 1ull) return 0;                       // {0, 0}
+  if (pair == 0ull) return ENT_DICT - 1;            // {none, none}
+  u32 slot = dictSlot(pair);
+  for (u32 probe = 0; probe < 64; ++probe) {
+    u64 k = b.hashKey[slot];
+    if (k == 0 && pass == 0) k = atomicCAS(&b.hashKey[slot], 0ull, pair), k = k ? k : pair;
+    if (k == pair) return pass ? b.hashId[slot] : 0u;
+    if (k == 0) break;
+    slot = (slot + 1) & (DICT_SLOTS - 1);
+  }
+  return ENT_DICT - 1;
+}
+__global__ void k_bin_entries(BinBuild b, int pass, uint4 *ent, u32 *rank) {
   const u32 e = blockIdx.x * blockDim.x + threadIdx.x;
-  if (e > nEntries) return;
-  if (e == nEntries) {  // the dummy bin of hits on a chromosome the annotation does not know: no element
-    ent[2 * e] = make_uint4(0u, 0u, 0u, 0xFFFFFFFFu);
-    ent[2 * e + 1] = make_uint4(0u, 0u, ENT_XNONE, ENT_XNONE);
+  if (e > b.nEntries) return;
+  if (e == b.nEntries) {  // the dummy bin of hits on a chromosome the annotation does not know: no element
+    if (pass) { ent[e] = make_uint4(0u, 0u, 65535u, 0u); rank[e] = 0; }
     return;
   }
-  const u32 c = chrOfEntry(chrBinBase, nChr, e);
-  const u64 pos = (u64)(e - chrBinBase[c]) << 6;
+  const u32 c = chrOfEntry(b.chrBinBase, b.nChr, e);
+  const u64 pos = (u64)(e - b.chrBinBase[c]) << 6;
   const u64 cap = 0xFFFFFFFEull;
   const u64 want = ((u64)c << 32) | (pos > cap ? cap : pos);
-  u32 lo = 0, hi = nSeg;  // last segment whose key <= want (every chromosome has a segment starting at 0)
-  while (hi - lo > 1) { const u32 mid = (lo + hi) >> 1; if (segKey[mid] <= want) lo = mid; else hi = mid; }
+  u32 lo = 0, hi = b.nSeg;  // last segment whose key <= want (every chromosome has a segment starting at 0)
+  while (hi - lo > 1) { const u32 mid = (lo + hi) >> 1; if (b.segKey[mid] <= want) lo = mid; else hi = mid; }
   u64 bits = 0;
   u32 z = lo;
-  for (u32 k = lo + 1; k < nSeg; ++k) {
-    const u64 sk = segKey[k];
+  for (u32 k = lo + 1; k < b.nSeg; ++k) {
+    const u64 sk = b.segKey[k];
     if ((u32)(sk >> 32) != c) break;
     const u64 sp = sk & 0xFFFFFFFFull;
     if (sp >= pos + 64ull) break;
     bits |= 1ull << (u32)(sp - pos);
     z = k;
   }
-  const uint4 t = seg[2 * z], x = seg[2 * z + 1];
-  const u32 flags = ANS_VICPAIR | ANS_GENERAL;
-  const u32 zf = (t.y & flags) ? ENT_NONE : t.y, zr = (t.z & flags) ? ENT_NONE : t.z;
-  u32 len = min(t.w & 0xFFFFu, 255u);  // (a saturated 16-bit length vouches for 65534 positions: more than 255)
-  if (nElements > 28) len = 0;
-  const u32 xf = ((x.x & flags) || nElements > 28) ? ENT_XNONE : x.x, xr = ((x.y & flags) || nElements > 28) ? ENT_XNONE : x.y;
-  ent[2 * e] = make_uint4((u32)bits, (u32)(bits >> 32), lo, t.x);
-  ent[2 * e + 1] = make_uint4(zf, zr, xf | ((len & 15u) << 28), xr | ((len >> 4) << 28));
+  const uint4 tz = b.seg[2 * z], xz = b.seg[2 * z + 1], ta = b.seg[2 * lo];
+  const u64 binEnd = pos + 63ull;
+  const u64 beyond = (u64)tz.x > binEnd ? (u64)tz.x - binEnd : 0ull;  // (Z holds the bin's last position: its end is not before it)
+  const u32 lenZ = (u32)(beyond < 65535ull ? beyond : 65535ull);
+  u32 lenZ1 = (lenZ < 65535u) ? min(tz.w & 0xFFFFu, 255u) : 0u;  // (a saturated 16-bit length vouches for 65534 positions: more than 255)
+  const u32 idZ = dictPair(b, tz.y, tz.z, pass), idA = dictPair(b, ta.y, ta.z, pass);
+  u32 idZX = ENT_DICT - 1;
+  if (lenZ1) idZX = dictPair(b, xz.x, xz.y, pass);
+  if (pass) {
+    ent[e] = make_uint4((u32)bits, (u32)(bits >> 32), lenZ | (lenZ1 << 16), idZ | (idZX << 10) | (idA << 20));
+    rank[e] = lo;
+  }
+}
+// numbers the registered pairs (single block of DICT_SLOTS / 4 threads; index 0 and ENT_DICT - 1 are reserved)
+__global__ void k_dict_number(u64 *hashKey, u32 *hashId, uint2 *dict) {
+  __shared__ u32 next;
+  if (threadIdx.x == 0) next = 1;
+  for (u32 i = threadIdx.x; i < ENT_DICT; i += blockDim.x) dict[i] = (i == 0) ? make_uint2(0u, 0u) : make_uint2(ENT_NONE, ENT_NONE);
+  __syncthreads();
+  for (u32 sIdx = threadIdx.x; sIdx < DICT_SLOTS; sIdx += blockDim.x) {
+    const u64 k = hashKey[sIdx];
+    if (k == 0) continue;
+    const u32 id = atomicAdd(&next, 1u);
+    if (id < ENT_DICT - 1) {
+      const u64 pair = k - 1ull;
+      hashId[sIdx] = id;
+      dict[id] = make_uint2((u32)pair, (u32)(pair >> 32));
+    } else {
+      hashId[sIdx] = ENT_DICT - 1;
+    }
+  }
 }
 
 // adjacent-duplicate removal of the sorted boundary keys: flags, then a scatter through their prefix sums
