@@ -296,6 +296,7 @@ void launchBatchKernels(mma_ctx *ctx, Sample &s, const HitView &hAll) {
       auto kPlain = k_batch_lean<MODE, STRAT, false>;
       auto kGroups = k_batch_lean<MODE, STRAT, (STRAT == 0)>;
       cudaFuncSetAttribute(groups ? kGroups : kPlain, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);  // (per device: cheap enough per launch)
+      cudaFuncSetAttribute(groups ? kGroups : kPlain, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
       mma_ctx::Timed t(ctx, TC_BATCH);
       (groups ? kGroups : kPlain)<<<grid, LEAN_THREADS, smem, ctx->sc>>>(ctx->index, ctx->fast, h, r, table, s.ctl, slow, open);
     } else if (ctx->fast.bm) {

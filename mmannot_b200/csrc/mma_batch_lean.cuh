@@ -25,10 +25,10 @@
 namespace mma {
 
 #ifndef MMA_LEAN_THREADS
-#define MMA_LEAN_THREADS 288
+#define MMA_LEAN_THREADS 256
 #endif
 #ifndef MMA_LEAN_MAXREG
-#define MMA_LEAN_MAXREG 112  // 2 blocks of 288 threads per SM
+#define MMA_LEAN_MAXREG 128  // 2 blocks of 256 threads per SM (registers are handed out per SM quarter: warps per block in fours)
 #endif
 #ifndef MMA_LEAN_BLOCKS_PER_SM
 #define MMA_LEAN_BLOCKS_PER_SM 2
@@ -361,9 +361,8 @@ k_batch_lean(const __grid_constant__ IndexView ix, const __grid_constant__ FastV
     u32 ambOr = 0;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const u32 a1 = min(m[j], 1u);
       const bool multi = STRAT == 0 && nh[j] > 1;
-      pAsgUniq += a1 + ((nh[j] == 1 ? a1 : 0u) << 16);
+      if (m[j] != 0) pAsgUniq += (nh[j] == 1) ? 0x10001u : 1u;
       pMultAmbi += multi ? 1u : 0u;
       ambOr |= m[j] & (m[j] - 1u);
       ev[j] = multi ? 0u : m[j];
@@ -518,19 +517,20 @@ k_batch_lean(const __grid_constant__ IndexView ix, const __grid_constant__ FastV
         }
         u32 X = __shfl_up_sync(FULL, inc, 1);
         if (lane == 0) X = 0;
-        const u32 inTot = before ? X : (cTot | X);  // union so far of a run that starts before this lane's hits
+        u32 carryTot = before ? X : (cTot | X);  // union so far of a run that starts before this lane's hits ...
+        u32 runLen = base - inStart;             // ... and its length so far
+        bool own = inMine;                       // ... and whether this warp owns it
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const bool last = (lastBits >> j) & 1u;
-          const u32 hbLe = hbits & ((2u << j) - 1u);
-          // union of the run's element sets and its first record, wherever the run starts
-          const u32 tot = hbLe ? pre[j] : (inTot | pre[j]);
-          const u32 runStart = hbLe ? base + (31 - __clz(hbLe)) : inStart;
-          const bool own = hbLe || inMine;
-          // a run of reads that are their own group (NH <= 1 throughout) has nothing to close
-          const bool irregular = (int)tot < 0 || nh[j] != base + j + 1 - runStart;
-          if (last && own && nh[j] > 1 && !irregular) { ev[j] = tot; closeBits |= 1u << j; }
-          else if (last && own && ((int)tot < 0 || nh[j] > 1)) walkBits |= 1u << j;
+          const bool isHead = (hbits >> j) & 1u;
+          if (isHead) { carryTot = 0; own = true; }
+          runLen = isHead ? 1u : runLen + 1u;
+          const u32 tot = carryTot | pre[j];  // union of the run's element sets up to this record, wherever the run starts
+          if (((lastBits >> j) & 1u) && own) {
+            // a run of reads that are their own group (NH <= 1 throughout) has nothing to close
+            if ((int)tot >= 0 && nh[j] > 1 && nh[j] == runLen) { ev[j] = tot; closeBits |= 1u << j; }
+            else if ((int)tot < 0 || nh[j] > 1) walkBits |= 1u << j;
+          }
         }
         if (walkBits) {  // rare
 #pragma unroll
@@ -544,7 +544,7 @@ k_batch_lean(const __grid_constant__ IndexView ix, const __grid_constant__ FastV
     }
     // ---- counting: single-element sets into the lane's histogram column, the rest into the block table
     {
-      u32 pend = 0;
+      u32 pend = 0, singleBits = 0;
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const u32 c = ev[j];
@@ -552,26 +552,29 @@ k_batch_lean(const __grid_constant__ IndexView ix, const __grid_constant__ FastV
         if (HIST) {
           const u32 row = single ? (u32)(31 - __clz(c)) : (u32)(HIST_ROWS - 1);  // E <= 30: the last row only ever receives zeros
           sm.hist[row][tid] += single ? 1 : 0;
-          if (c != 0 && !single) pend |= 1u << j;
-          if (r.rescue) { if (single && ((closeBits >> j) & 1u)) pMissResc += 0x10000u; }  // (else: from the histogram columns, see the epilogue)
-          else if (single && !((closeBits >> j) & 1u)) pOwnClos += 1u;
+          if (single) singleBits |= 1u << j;
+          else if (c != 0) pend |= 1u << j;
         } else {
           if (c != 0) pend |= 1u << j;
         }
       }
+      // rescue() active: closed reads resolved to one element, one by one; else: reads of their own counted for one element
+      // (the closed ones then follow from the histogram columns, see the epilogue)
+      if (r.rescue) pMissResc += __popc(singleBits & closeBits) << 16;
+      else pOwnClos += __popc(singleBits & ~closeBits);
       pOwnClos += __popc(closeBits) << 16;
-      while (__any_sync(FULL, pend != 0)) {
-        if (pend) {
-          const int j = __ffs(pend) - 1;
-          pend &= pend - 1;
-          const u32 c = (j == 0) ? ev[0] : (j == 1) ? ev[1] : (j == 2) ? ev[2] : ev[3];
-          u64 ckey = c;
-          if (STRAT == 3) {
-            const u32 n = (j == 0) ? nh[0] : (j == 1) ? nh[1] : (j == 2) ? nh[2] : nh[3];
-            if (n >= (1u << (64 - NH_SHIFT))) atomicExch(&ctl->overflow, 1u);
-            ckey |= (u64)n << NH_SHIFT;
+      if (__any_sync(FULL, pend != 0)) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (!__any_sync(FULL, (pend >> j) & 1u)) continue;
+          if ((pend >> j) & 1u) {
+            u64 ckey = ev[j];
+            if (STRAT == 3) {
+              if (nh[j] >= (1u << (64 - NH_SHIFT))) atomicExch(&ctl->overflow, 1u);
+              ckey |= (u64)nh[j] << NH_SHIFT;
+            }
+            sm.bt.add(ckey, 1, table);
           }
-          sm.bt.add(ckey, 1, table);
         }
       }
     }
