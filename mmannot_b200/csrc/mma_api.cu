@@ -110,6 +110,7 @@ struct mma_ctx {
   size_t randDrawsUsed = 0;  // -y random: rand() draws consumed by the samples finished so far
   int forceGroups = -1;      // MMANNOT_B200_GROUPS=0/1: pin the variant (testing only)
   bool useGroups = false;    // k_batch_fast variant for runs of k x NH records, chosen from the walk counters of earlier batches
+  int carveout = -1;         // MMANNOT_B200_CARVEOUT=percent: shared-memory carveout of k_batch_lean (tuning only)
   bool legacyBatch = false;  // MMANNOT_B200_LEGACY_BATCH=1: A/B runs of the general k_batch against k_batch_fast (tuning only)
   std::vector<uint32_t> intervalIds;  // result of the last mma_annotate_intervals
   u64 *hostTable = nullptr;  // pinned: [TableDump | rows] of the sample being read back
@@ -296,7 +297,12 @@ void launchBatchKernels(mma_ctx *ctx, Sample &s, const HitView &hAll) {
       auto kPlain = k_batch_lean<MODE, STRAT, false>;
       auto kGroups = k_batch_lean<MODE, STRAT, (STRAT == 0)>;
       cudaFuncSetAttribute(groups ? kGroups : kPlain, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);  // (per device: cheap enough per launch)
-      cudaFuncSetAttribute(groups ? kGroups : kPlain, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+      {  // shared memory for the blocks one SM can hold, the rest of the 228 KB stays L1 (the bin entries of neighbouring hits hit there)
+        const size_t perSM = (size_t)MMA_LEAN_BLOCKS_PER_SM * (smem + 1024);
+        int pct = (int)std::min<size_t>(100, (perSM * 100 + 228 * 1024 - 1) / (228 * 1024));
+        if (ctx->carveout >= 0) pct = ctx->carveout;
+        cudaFuncSetAttribute(groups ? kGroups : kPlain, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+      }
       mma_ctx::Timed t(ctx, TC_BATCH);
       (groups ? kGroups : kPlain)<<<grid, LEAN_THREADS, smem, ctx->sc>>>(ctx->index, ctx->fast, h, r, table, s.ctl, slow, open);
     } else if (ctx->fast.bm) {
@@ -449,6 +455,7 @@ int mma_create(mma_ctx **out, const mma_params *p) {
   }
   { const char *lg = getenv("MMANNOT_B200_LEGACY_BATCH"); ctx->legacyBatch = lg && lg[0] == '1';
     const char *fg = getenv("MMANNOT_B200_GROUPS"); if (fg && (fg[0] == '0' || fg[0] == '1')) { ctx->forceGroups = fg[0] - '0'; ctx->useGroups = fg[0] == '1'; }
+    const char *cv = getenv("MMANNOT_B200_CARVEOUT"); if (cv) ctx->carveout = atoi(cv);
     const char *mg = getenv("MMANNOT_B200_MAX_GRID"); ctx->maxGrid = mg ? (u32)std::max(0, atoi(mg)) : 0u; }
   ctx->samples.resize(p->n_samples);
   *out = ctx;

@@ -563,18 +563,18 @@ k_batch_lean(const __grid_constant__ IndexView ix, const __grid_constant__ FastV
       if (r.rescue) pMissResc += __popc(singleBits & closeBits) << 16;
       else pOwnClos += __popc(singleBits & ~closeBits);
       pOwnClos += __popc(closeBits) << 16;
-      if (__any_sync(FULL, pend != 0)) {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          if (!__any_sync(FULL, (pend >> j) & 1u)) continue;
-          if ((pend >> j) & 1u) {
-            u64 ckey = ev[j];
-            if (STRAT == 3) {
-              if (nh[j] >= (1u << (64 - NH_SHIFT))) atomicExch(&ctl->overflow, 1u);
-              ckey |= (u64)nh[j] << NH_SHIFT;
-            }
-            sm.bt.add(ckey, 1, table);
+      while (__any_sync(FULL, pend != 0)) {
+        if (pend) {
+          const int j = __ffs(pend) - 1;
+          pend &= pend - 1;
+          const u32 c = (j == 0) ? ev[0] : (j == 1) ? ev[1] : (j == 2) ? ev[2] : ev[3];
+          u64 ckey = c;
+          if (STRAT == 3) {
+            const u32 n = (j == 0) ? nh[0] : (j == 1) ? nh[1] : (j == 2) ? nh[2] : nh[3];
+            if (n >= (1u << (64 - NH_SHIFT))) atomicExch(&ctl->overflow, 1u);
+            ckey |= (u64)n << NH_SHIFT;
           }
+          sm.bt.add(ckey, 1, table);
         }
       }
     }
