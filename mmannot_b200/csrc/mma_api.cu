@@ -293,7 +293,7 @@ void launchBatchKernels(mma_ctx *ctx, Sample &s, const HitView &hAll) {
       launched = true;
       u32 grid = std::max<u32>(1u, std::min<u32>((nWT + LEAN_WARPS - 1) / LEAN_WARPS, (u32)ctx->nSM * MMA_LEAN_BLOCKS_PER_SM));
       if (ctx->maxGrid) grid = std::min(grid, ctx->maxGrid);
-      constexpr size_t smem = sizeof(LeanSmem<STRAT != 3>);
+      const size_t smem = leanSmemBytes<STRAT != 3>(ctx->fast.nDict, ctx->fast.nChr, r.nElements);
       auto kPlain = k_batch_lean<MODE, STRAT, false>;
       auto kGroups = k_batch_lean<MODE, STRAT, (STRAT == 0)>;
       cudaFuncSetAttribute(groups ? kGroups : kPlain, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);  // (per device: cheap enough per launch)
@@ -606,6 +606,7 @@ int mma_load_features(mma_ctx *ctx, const mma_features *f) {
   if (ctx->params.n_elements <= 30 && ctx->params.fast_bin_shift != MMA_FAST_OFF) {
     const uint64_t nKeys = 2ull * n + nChr;
     DevBuf kA, kB, flag, pos, tmp, segKey, fChrBinBase, dictHash;
+    u32 nDictUsed = 2;
     auto cleanupFast = [&]() { kA.release(); kB.release(); flag.release(); pos.release(); tmp.release(); segKey.release(); fChrBinBase.release(); dictHash.release(); };
 #define CKS(call)                                                                                  \
   do {                                                                                             \
@@ -677,16 +678,17 @@ int mma_load_features(mma_ctx *ctx, const mma_features *f) {
         k_seg_scatter<<<gridFor(nKeys, 256), 256, 0, st>>>(kB.as<u64>(), flag.as<u32>(), pos.as<u32>(), (u32)nKeys, segKey.as<u64>());
         k_seg_eval<<<gridFor(nSeg, 128), 128, 0, st>>>(ctx->index, segKey.as<u64>(), nSeg, upMask, downMask, ctx->fastSeg.as<uint4>(), ctx->fastTie.as<u32>());
         if (useEnt) {
-          CKS(dictHash.ensure(DICT_SLOTS * 12));
-          CKS(cudaMemsetAsync(dictHash.p, 0, DICT_SLOTS * 12, st));
+          CKS(dictHash.ensure(DICT_SLOTS * 12 + 4));
+          CKS(cudaMemsetAsync(dictHash.p, 0, DICT_SLOTS * 12 + 4, st));
           BinBuild bb;
           bb.segKey = segKey.as<u64>(); bb.chrBinBase = fChrBinBase.as<u32>(); bb.seg = ctx->fastSeg.as<uint4>();
           bb.nSeg = nSeg; bb.nChr = nChr; bb.nEntries = (u32)fEntries; bb.nElements = ctx->params.n_elements;
           bb.hashKey = dictHash.as<u64>(); bb.hashId = reinterpret_cast<u32 *>(dictHash.as<u64>() + DICT_SLOTS);
           k_bin_entries<<<gridFor(fEntries + 1, 256), 256, 0, st>>>(bb, 0, ctx->fastEnt.as<uint4>(), ctx->fastRank.as<u32>());
-          k_dict_number<<<1, 1024, 0, st>>>(bb.hashKey, bb.hashId, ctx->fastDict.as<uint2>());
+          k_dict_number<<<1, 1024, 0, st>>>(bb.hashKey, bb.hashId, ctx->fastDict.as<uint2>(), bb.hashId + DICT_SLOTS);
           k_bin_entries<<<gridFor(fEntries + 1, 256), 256, 0, st>>>(bb, 1, ctx->fastEnt.as<uint4>(), ctx->fastRank.as<u32>());
           ctx->launches += 2;
+          CKS(cudaMemcpyAsync(&nDictUsed, bb.hashId + DICT_SLOTS, 4, cudaMemcpyDeviceToHost, st));
         } else
           k_fast_bitmap<<<gridFor(fEntries, 256), 256, 0, st>>>(segKey.as<u64>(), nSeg, fChrBinBase.as<u32>(), nChr, fshift, gshift, (u32)fEntries,
                                                                 ctx->fastBin.as<uint2>());
@@ -698,6 +700,7 @@ int mma_load_features(mma_ctx *ctx, const mma_features *f) {
       ctx->fast.ent = useEnt ? ctx->fastEnt.as<uint4>() : nullptr;
       ctx->fast.rank = useEnt ? ctx->fastRank.as<u32>() : nullptr;
       ctx->fast.dict = useEnt ? ctx->fastDict.as<uint2>() : nullptr;
+      ctx->fast.nDict = useEnt ? std::max<u32>(2u, std::min<u32>(nDictUsed, ENT_DICT)) : 0u;
       ctx->fast.seg = ctx->fastSeg.as<uint4>();
       ctx->fast.tie = ctx->fastTie.as<u32>();
       ctx->fast.upMask = upMask;

@@ -25,13 +25,13 @@
 namespace mma {
 
 #ifndef MMA_LEAN_THREADS
-#define MMA_LEAN_THREADS 256
+#define MMA_LEAN_THREADS 512
 #endif
 #ifndef MMA_LEAN_MAXREG
-#define MMA_LEAN_MAXREG 128  // 2 blocks of 256 threads per SM (registers are handed out per SM quarter: warps per block in fours)
+#define MMA_LEAN_MAXREG 128  // 16 warps per SM (registers are handed out per SM quarter: warps per block in fours)
 #endif
 #ifndef MMA_LEAN_BLOCKS_PER_SM
-#define MMA_LEAN_BLOCKS_PER_SM 2
+#define MMA_LEAN_BLOCKS_PER_SM 1  // one block per SM: the block-wide tables exist once, the shared memory they do not take stays L1
 #endif
 #define LEAN_THREADS MMA_LEAN_THREADS
 #define LEAN_WARPS (LEAN_THREADS / 32)
@@ -90,27 +90,31 @@ struct LeanWarp {  // private to one warp
   unsigned char slowQ[WT_HITS];
 };
 #define LEAN_BAR_OFF (LEAN_STAGES * LEAN_STAGE_BYTES)
+// Shared memory of a block: this fixed part, then (sized at launch, so that what the block does not need stays L1 cache)
+//   uint2 dict[nDict] | uint2 chrInfo[nChr + 1] | unsigned short hist[nElements + 1][LEAN_THREADS]   (histogram only when HIST)
 template <bool HIST>
 struct LeanSmem {
   LeanWarp w[LEAN_WARPS];
-  uint2 dict[ENT_DICT];
-  uint2 chrInfo[CHR_SMEM + 1];
   typename BlockTableOf<HIST, LEAN_BT_SLOTS>::type bt;
-  unsigned short hist[HIST ? HIST_ROWS : 1][LEAN_THREADS];
   u32 stat[ST_N + 1];  // [ST_N]: reads of their own counted for a single element (see the epilogue)
+  alignas(16) unsigned char var[16];
 };
+template <bool HIST>
+inline size_t leanSmemBytes(u32 nDict, u32 nChr, u32 nElements) {
+  return offsetof(LeanSmem<HIST>, var) + 8ull * nDict + 8ull * (nChr + 1) + (HIST ? 2ull * (nElements + 1) * LEAN_THREADS : 0ull) + 16;
+}
 
 template <bool HIST>
 struct LeanCount {  // one read counted for an element set, from divergent code (the serial walker)
   LeanSmem<HIST> &sm;
+  unsigned short *hist;  // this thread's column
   const TableView &table;
-  u32 tid;
   __device__ __forceinline__ void operator()(u64 ckey) const {
     if (HIST) {
       const u32 c = (u32)ckey;
       if (c == 0) return;
       if (c & (c - 1)) sm.bt.add(ckey, 1, table);
-      else sm.hist[__ffs(c) - 1][tid] += 1;
+      else hist[(__ffs(c) - 1) * LEAN_THREADS] += 1;
     } else if (ckey) {
       sm.bt.add(ckey, 1, table);
     }
@@ -155,16 +159,19 @@ k_batch_lean(const __grid_constant__ IndexView ix, const __grid_constant__ FastV
   extern __shared__ __align__(128) unsigned char leanSmemRaw[];
   LeanSmem<HIST> &sm = *reinterpret_cast<LeanSmem<HIST> *>(leanSmemRaw);
   const u32 tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+  uint2 *const smDict = reinterpret_cast<uint2 *>(sm.var);
+  uint2 *const smChr = smDict + fx.nDict;
+  unsigned short *const myHist = reinterpret_cast<unsigned short *>(smChr + fx.nChr + 1) + tid;  // this thread's column: row e at e * LEAN_THREADS
+  const u32 nRows = r.nElements + 1;  // the last row only ever receives zeros
   sm.bt.init();
   if (HIST) {
-#pragma unroll
-    for (int e = 0; e < HIST_ROWS; ++e) sm.hist[e][tid] = 0;
+    for (u32 e = 0; e < nRows; ++e) myHist[e * LEAN_THREADS] = 0;
   }
   if (tid <= ST_N) sm.stat[tid] = 0;
-  for (u32 c = tid; c <= fx.nChr; c += LEAN_THREADS) sm.chrInfo[c] = fx.chrInfo[c];  // launched only when nChr <= CHR_SMEM
-  for (u32 c = tid; c < ENT_DICT; c += LEAN_THREADS) sm.dict[c] = fx.dict[c];
+  for (u32 c = tid; c <= fx.nChr; c += LEAN_THREADS) smChr[c] = fx.chrInfo[c];  // launched only when nChr <= CHR_SMEM
+  for (u32 c = tid; c < fx.nDict; c += LEAN_THREADS) smDict[c] = fx.dict[c];
   const u32 wbase = smemAddr(&sm.w[warp]);  // ring stage s at wbase + s * LEAN_STAGE_BYTES, its barrier at wbase + LEAN_BAR_OFF + 8 s
-  const u32 dict0 = smemAddr(&sm.dict[0]);  // (the chromosome table follows the dictionary)
+  const u32 dict0 = smemAddr(smDict);  // (the chromosome table follows the dictionary)
   LeanWarp &mine = sm.w[warp];
   if (lane == 0) {
     mbarInit(wbase + LEAN_BAR_OFF, 1);
@@ -184,7 +191,7 @@ k_batch_lean(const __grid_constant__ IndexView ix, const __grid_constant__ FastV
   u32 pMissResc = 0;  // segment-table misses | (rescue() active only) closed reads resolved to one element << 16
   u32 pWalks = 0, cVis = 0;
 
-  LeanCount<HIST> count{sm, table, tid};
+  LeanCount<HIST> count{sm, myHist, table};
   RunWalker<MODE, true, LeanCount<HIST>> w{h, r, annot, ctl, slow, open, count, seq, 0u, 0u};
 
   const u32 nWT = (h.n + WT_HITS - 1) / WT_HITS;
@@ -281,7 +288,7 @@ k_batch_lean(const __grid_constant__ IndexView ix, const __grid_constant__ FastV
       meta[0] = c.x; meta[1] = c.y; meta[2] = c.z; meta[3] = c.w;
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const uint2 ci = lds64x2(dict0 + 8u * ENT_DICT + 8u * min(meta[j] & 0x00FFFFFFu, fx.nChr));
+        const uint2 ci = lds64x2(dict0 + 8u * fx.nDict + 8u * min(meta[j] & 0x00FFFFFFu, fx.nChr));
         en[j] = __ldg(&fx.ent[ci.x + min(rs[j] >> 6, ci.y - 1u)]);
       }
       const uint4 b = lds128(st + 512);
@@ -340,7 +347,7 @@ k_batch_lean(const __grid_constant__ IndexView ix, const __grid_constant__ FastV
         const u32 id = mine.slowQ[k];
         const u32 qs = st32[id], qe = st32[128 + id], qm = st32[256 + id];
         const u32 chr = qm & 0x00FFFFFFu;
-        mine.scratch[id] = (chr < fx.nChr) ? recordAnnotate<MODE>(fx, ix, sm.chrInfo[chr], qs, qe, qm, r.overlap) : 0u;
+        mine.scratch[id] = (chr < fx.nChr) ? recordAnnotate<MODE>(fx, ix, smChr[chr], qs, qe, qm, r.overlap) : 0u;
       }
       __syncwarp();
 #pragma unroll
@@ -550,8 +557,8 @@ k_batch_lean(const __grid_constant__ IndexView ix, const __grid_constant__ FastV
         const u32 c = ev[j];
         const bool single = c != 0 && (c & (c - 1)) == 0;
         if (HIST) {
-          const u32 row = single ? (u32)(31 - __clz(c)) : (u32)(HIST_ROWS - 1);  // E <= 30: the last row only ever receives zeros
-          sm.hist[row][tid] += single ? 1 : 0;
+          const u32 row = single ? (u32)(31 - __clz(c)) : r.nElements;  // (the last row only ever receives zeros)
+          myHist[row * LEAN_THREADS] += single ? 1 : 0;
           if (single) singleBits |= 1u << j;
           else if (c != 0) pend |= 1u << j;
         } else {
@@ -660,10 +667,10 @@ k_batch_lean(const __grid_constant__ IndexView ix, const __grid_constant__ FastV
   sm.bt.flush(table);
   if (HIST) {
     u32 singles = 0;
-    for (u32 e = warp; e < HIST_ROWS; e += LEAN_WARPS) {
+    for (u32 e = warp; e < r.nElements; e += LEAN_WARPS) {
       u32 v = 0;
 #pragma unroll
-      for (int q = 0; q < LEAN_WARPS; ++q) v += sm.hist[e][lane + 32 * q];
+      for (int q = 0; q < LEAN_WARPS; ++q) v += (myHist - tid)[e * LEAN_THREADS + lane + 32 * q];
       v = __reduce_add_sync(FULL, v);
       if (lane == 0 && v) tableAdd(table, 1ull << e, v);
       singles += v;

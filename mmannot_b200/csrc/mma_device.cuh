@@ -85,7 +85,7 @@ struct IndexView {
 //               dependent pick, or more than ENT_DICT distinct pairs) is ENT_NONE: the read then takes the segment record like
 //               every other read.  The last bin of a chromosome is always empty, so a read starting beyond the annotated extent
 //               finds the last segment there.  dict[0] = {0, 0} (also the answer of the dummy bin of unknown chromosomes),
-//               dict[ENT_DICT - 1] = {ENT_NONE, ENT_NONE}.
+//               dict[1] = {ENT_NONE, ENT_NONE}; nDict entries are in use.
 #define ENT_NONE 0xFFFFFFFFu
 #define ENT_DICT 1024u
 struct FastView {
@@ -98,7 +98,8 @@ struct FastView {
   const uint4 *ent;      // bin entries (null: position map `bm` instead); then chrInfo = {first entry, number of 64-position bins},
                          // chrInfo[nChr] = an empty dummy bin whose answers are 0, shift = 6, gshift = 0
   const u32 *rank;       // bin entries: segment index of the first position of each bin
-  const uint2 *dict;     // bin entries: ENT_DICT answer pairs
+  const uint2 *dict;     // bin entries: answer pairs
+  u32 nDict;             // bin entries: pairs in use (<= ENT_DICT)
 };
 
 struct HitView {
@@ -1446,7 +1447,7 @@ __device__ __forceinline__ u32 dictPair(const BinBuild &b, u32 f, u32 r, int pas
   if (r & flags) r = ENT_NONE;
   const u64 pair = (((u64)r << 32) | f) + 1ull;
   if (pair == 1ull) return 0;                       // {0, 0}
-  if (pair == 0ull) return ENT_DICT - 1;            // {none, none}
+  if (pair == 0ull) return 1;                       // {none, none}
   u32 slot = dictSlot(pair);
   for (u32 probe = 0; probe < 64; ++probe) {
     u64 k = b.hashKey[slot];
@@ -1455,7 +1456,7 @@ __device__ __forceinline__ u32 dictPair(const BinBuild &b, u32 f, u32 r, int pas
     if (k == 0) break;
     slot = (slot + 1) & (DICT_SLOTS - 1);
   }
-  return ENT_DICT - 1;
+  return 1;
 }
 __global__ void k_bin_entries(BinBuild b, int pass, uint4 *ent, u32 *rank) {
   const u32 e = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1486,31 +1487,33 @@ __global__ void k_bin_entries(BinBuild b, int pass, uint4 *ent, u32 *rank) {
   const u32 lenZ = (u32)(beyond < 65535ull ? beyond : 65535ull);
   u32 lenZ1 = (lenZ < 65535u) ? min(tz.w & 0xFFFFu, 255u) : 0u;  // (a saturated 16-bit length vouches for 65534 positions: more than 255)
   const u32 idZ = dictPair(b, tz.y, tz.z, pass), idA = dictPair(b, ta.y, ta.z, pass);
-  u32 idZX = ENT_DICT - 1;
+  u32 idZX = 1;
   if (lenZ1) idZX = dictPair(b, xz.x, xz.y, pass);
   if (pass) {
     ent[e] = make_uint4((u32)bits, (u32)(bits >> 32), lenZ | (lenZ1 << 16), idZ | (idZX << 10) | (idA << 20));
     rank[e] = lo;
   }
 }
-// numbers the registered pairs (single block of DICT_SLOTS / 4 threads; index 0 and ENT_DICT - 1 are reserved)
-__global__ void k_dict_number(u64 *hashKey, u32 *hashId, uint2 *dict) {
+// numbers the registered pairs (single block; indices 0 and 1 are reserved); *nUsed = entries of the dictionary in use
+__global__ void k_dict_number(u64 *hashKey, u32 *hashId, uint2 *dict, u32 *nUsed) {
   __shared__ u32 next;
-  if (threadIdx.x == 0) next = 1;
+  if (threadIdx.x == 0) next = 2;
   for (u32 i = threadIdx.x; i < ENT_DICT; i += blockDim.x) dict[i] = (i == 0) ? make_uint2(0u, 0u) : make_uint2(ENT_NONE, ENT_NONE);
   __syncthreads();
   for (u32 sIdx = threadIdx.x; sIdx < DICT_SLOTS; sIdx += blockDim.x) {
     const u64 k = hashKey[sIdx];
     if (k == 0) continue;
     const u32 id = atomicAdd(&next, 1u);
-    if (id < ENT_DICT - 1) {
+    if (id < ENT_DICT) {
       const u64 pair = k - 1ull;
       hashId[sIdx] = id;
       dict[id] = make_uint2((u32)pair, (u32)(pair >> 32));
     } else {
-      hashId[sIdx] = ENT_DICT - 1;
+      hashId[sIdx] = 1;
     }
   }
+  __syncthreads();
+  if (threadIdx.x == 0) *nUsed = min(next, ENT_DICT);
 }
 
 // adjacent-duplicate removal of the sorted boundary keys: flags, then a scatter through their prefix sums
