@@ -72,6 +72,7 @@ class Workload:
         self.synth.write_annotation(self.gtf_path)
         self.config = host.Config(self.config_path)
         self.annotation = host.Annotation(self.config, self.gtf_path)
+        self.first_read = 0
 
     def fill_pinned(self, first_read, n_reads, threads):
         """Packed hits of the read range, generated straight into page-locked buffers."""
@@ -232,7 +233,7 @@ def run_reference_arm(args):
         line = {"impl": "reference", "metric": "alignment_records_per_sec", "value": v, "unit": "records/s", "n_gpus": args.gpus,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * records / v, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
-                "config": {"workload": wl.w["describe"], "name": args.workload},
+                "config": bench_config(wl, args, extra={"sample_reads_per_file": args.ref_reads, "files": n_files}),
                 "cpu_baseline": {"value": v, "unit": "records/s", "cores": used, "kind": "reference", "sample": desc},
                 "e2e": {"value": v, "unit": "records/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0, "host_cores": cores}
@@ -244,9 +245,62 @@ def run_reference_arm(args):
 
 # ------------------------------------------------------------------------------------------ product arm
 
-def run_product_arm(args):
-    import ctypes as C
+class HitSet:
+    """One rank's hits of a workload: page-locked host arrays, a device-resident copy, and the batch descriptors of both."""
+    ISZ = {"start": 4, "end": 4, "meta": 4, "nh": 4, "read_key": 8}
+    KEYS = ("start", "end", "meta", "nh", "read_key")
 
+    def __init__(self, pinned, n_hits, dev, own_pinned=True):
+        import torch
+        self.pinned, self.n, self.own = pinned, int(n_hits), own_pinned
+        self.dev = {k: torch.from_numpy(pinned.arrays[k][:max(self.n, 1)].view(np.int32 if k != "read_key" else np.int64)).to(dev)
+                    for k in self.KEYS}
+        torch.cuda.synchronize()
+
+    def batches(self, where, size):
+        from mmannot_b200 import device
+        ptr = (lambda k: self.dev[k].data_ptr()) if where == "device" else (lambda k: self.pinned.arrays[k].ctypes.data)
+        out = []
+        for a in range(0, self.n, size):
+            n = min(size, self.n - a)
+            out.append(device.HitBatch(n, *[ptr(k) + a * self.ISZ[k] for k in self.KEYS]))
+        return out
+
+    def close(self):
+        self.dev = {}
+        if self.own:
+            self.pinned.close()
+
+
+class SortedView:
+    """The first `n` hits of a PinnedHits in another record order (page-locked copy)."""
+
+    def __init__(self, src, n, order):
+        from mmannot_b200 import device
+        self.inner = device.PinnedHits(max(n, 1))
+        for k in HitSet.KEYS:
+            self.inner.arrays[k][:n] = src.arrays[k][:n][order]
+        self.arrays = self.inner.arrays
+
+    def close(self):
+        self.inner.close()
+
+
+def roofline_of(tm, n_hits, steps, peak, peak_src, kernel):
+    """Algorithmic bytes of one launch of the batch kernel: 24 B per hit read once (start, end, meta, nh
+    u32 + read key u64); the 16 B/feature index and the 8 B/row table are per sample, not per launch."""
+    n_batches = max(1, int(tm["batches"]))
+    bytes_per_launch = 24.0 * n_hits * steps / n_batches
+    avg_ms = tm["ms_batch"] / n_batches
+    achieved = bytes_per_launch / (avg_ms * 1e-3) / 1e9 if avg_ms > 0 else 0.0
+    return {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+            "traffic_source": None, "kernel": kernel, "bytes_per_launch": bytes_per_launch, "avg_launch_ms": avg_ms,
+            "launches_timed": n_batches, "peak_source": peak_src,
+            "kernel_ms_per_step": {k: tm[k] / steps for k in ("ms_batch", "ms_close", "ms_finish")},
+            "segment_table_miss_frac": tm["fast_miss"] / max(1, n_hits)}
+
+
+def run_product_arm(args):
     import torch
     import torch.distributed as dist
 
@@ -262,53 +316,186 @@ def run_product_arm(args):
         dist.init_process_group("nccl", device_id=dev)
     cores = os.cpu_count() or 1
     threads = max(1, min(64, cores // max(1, world), len(os.sched_getaffinity(0))))
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, stream):
+        """K passes bracketed by barrier + synchronize; CUDA events on the library's own compute stream, max over ranks."""
+        barrier()
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+        t0 = time.perf_counter()
+        ev[0].record(stream)
+        res = None
+        for _ in range(steps):
+            res = fn()
+        ev[1].record(stream)
+        torch.cuda.synchronize()
+        wall_ms = (time.perf_counter() - t0) * 1e3
+        ms = max(ev[0].elapsed_time(ev[1]), 0.0)
+        if world > 1:
+            t = torch.tensor([ms, wall_ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms, wall_ms = float(t[0]), float(t[1])
+        return ms, wall_ms, res
+
+    def all_sum(v):
+        if world == 1:
+            return int(v)
+        t = torch.tensor([int(v)], device=dev, dtype=torch.int64)
+        dist.all_reduce(t)
+        return int(t[0])
+
+    same = lambda x, y: np.array_equal(x[0], y[0]) and np.array_equal(device.sort_rows(x[1]), device.sort_rows(y[1]))
+
+    def check_merge(ann, step_local, merged, what):
+        """N > 1, outside the timed region: the table the GPUs merged (export / all-gather / import) must be the sum of the
+        per-rank tables, formed here on the host from every rank's own mma_finish_sample."""
+        if world == 1:
+            return True
+        loc = step_local()
+        gathered = [None] * world
+        dist.all_gather_object(gathered, (loc[0], loc[1]))
+        stats = np.sum([g[0] for g in gathered], axis=0)
+        acc = {}
+        for g in gathered:
+            u = g[1].view(np.uint64)
+            for i in range(len(u)):
+                key = (int(u[i, 0]), int(u[i, 1]))
+                acc[key] = acc.get(key, 0) + int(u[i, 2])
+        got = merged[1].view(np.uint64)
+        got_d = {(int(got[i, 0]), int(got[i, 1])): int(got[i, 2]) for i in range(len(got))}
+        acc = {k: v for k, v in acc.items() if v}
+        assert np.array_equal(stats, merged[0]), "%s: merged counters %s != sum of the per-rank counters %s" % (what, merged[0], stats)
+        assert got_d == acc, "%s: device-merged table differs from the host-side sum of the per-rank tables" % what
+        return True
+
+    def check_oracle(wl, ann, hs, n_reads, per_name):
+        """This rank's table on its first reads against the CPU oracle (test infrastructure, here as the checker only)."""
+        from oracle import pyoracle
+        from mmannot_b200 import host
+        first = wl.first_read
+        n = wl.synth.count_hits(first, n_reads)
+        h = host.Hits(*[np.array(hs.pinned.arrays[k][:n]) for k in HitSet.KEYS])
+        ref = pyoracle.run(wl.config.elem_line, wl.config.elem_strand, wl.config.elem_vicinity, wl.annotation, h,
+                           strategy=wl.w["strategy"], overlap=wl.w["overlap"])
+        ann.reset(0)
+        ann.submit(0, h)
+        res = ann.finish(0)
+        got = device.values_by_mask(res["rows"])
+        assert set(got) == set(ref["rows"]), "oracle check: element sets differ on the first %d reads" % n_reads
+        for m, v in ref["rows"].items():
+            assert abs(got[m] - v) <= 1e-9 * max(1.0, abs(v)), "oracle check: count of set %x" % m
+        assert res["stats"] == ref["stats"], "oracle check: counters %s != %s" % (res["stats"], ref["stats"])
+        return n
+
+    def device_resident(wl, hs, strategy=None, merge=True, steps=None, dev_batch=None, what=""):
+        """Device-resident passes of one workload: -> dict for the `workloads` key (and the objects the main workload needs)."""
+        w = wl.w
+        steps = steps or args.steps
+        dev_batch = dev_batch or max(args.device_batch, args.batch)
+        strategy = strategy or w["strategy"]
+        ann = device.Annotator(wl.config, strategy=strategy, overlap=w["overlap"], n_samples=1, max_batch_hits=dev_batch,
+                               device=local_rank, table_log2=args.table_log2, fast_bin_shift=args.fast_shift, bin_shift=args.bin_shift)
+        ann.load_features(wl.annotation)
+        stream = torch.cuda.ExternalStream(ann.stream_ptr(), device=dev)
+        dev_batches = hs.batches("device", dev_batch)
+        merged = world > 1 and merge
+
+        def step_local():
+            ann.reset(0)
+            for b in dev_batches:
+                ann.submit_device(0, b)
+            return ann.finish_arrays(0, sort=False)
+
+        def step():
+            if not merged:
+                return step_local()
+            ann.reset(0)
+            for b in dev_batches:
+                ann.submit_device(0, b)
+            return multi.merge_on_device(ann, 0, dev)
+
+        for _ in range(max(2, min(args.warmup, 3))):
+            step()
+        ann.timing_enable(True)
+        ann.timing_reset()
+        ms, wall, res = timed(step, steps, stream)
+        tm = ann.timing()
+        ann.timing_enable(False)
+        total_hits = all_sum(hs.n)
+        stats = {k: int(v) for k, v in zip(multi.STAT_KEYS, res[0])}
+        if not merged and world > 1:  # one sample per GPU: the counters of the samples, summed for the invariants below
+            t = torch.tensor(res[0], device=dev, dtype=torch.int64)
+            dist.all_reduce(t)
+            stats = {k: int(v) for k, v in zip(multi.STAT_KEYS, t.cpu().numpy())}
+        # size-independent properties of the synthetic workloads: every read is complete (NH records each), so the reads counted
+        # must be the reads generated and the hits counted the hits submitted, over all ranks
+        checks = []
+        if strategy in ("default", "ratio"):
+            assert stats["n_hits"] == total_hits, "%s: hits counted %d != hits submitted %d" % (what, stats["n_hits"], total_hits)
+            checks.append("hits counted == hits submitted")
+        if strategy == "default" and hs.complete_reads:
+            per_name = 2 if w["spec"].get("paired") else 1  # both mates carry the name and the NH: two countdowns per name
+            want = per_name * hs.complete_reads * world
+            assert stats["n_reads"] == want, "%s: reads counted %d != reads generated %d" % (what, stats["n_reads"], want)
+            checks.append("reads counted == reads generated")
+        if merged:
+            check_merge(ann, step_local, res, what)
+            checks.append("device-merged table == host-side sum of the per-rank tables")
+        ms_per_step = ms / steps
+        out = {"value": total_hits / (ms_per_step * 1e-3), "unit": "records/s", "ms_per_step": ms_per_step, "hits_per_gpu": hs.n,
+               "reads_per_gpu": hs.reads, "features": int(wl.annotation.n), "elements": int(wl.config.n_elements), "strategy": strategy,
+               "describe": w["describe"], "roofline": roofline_of(tm, hs.n, steps, peak, peak_src, ann.dominant_kernel()),
+               "gpu_launches": int(tm["launches"]), "table_rows": int(len(res[1])), "stats": stats, "checks": checks,
+               "multi_gpu": ("read-name ranges, index replicated, tables merged on the GPUs around one NCCL all-gather" if merged
+                             else "one sample per GPU, no exchange") if world > 1 else "single GPU"}
+        return out, ann, res, stream, wall / steps, tm
+
+    def make_hitset(wl, reads):
+        """Read-name-range sharding: rank r owns reads [r * reads, (r + 1) * reads) -- every record of a read stays on one GPU."""
+        t0 = time.time()
+        wl.first_read = rank * reads
+        pinned, n_hits = wl.fill_pinned(rank * reads, reads, threads)
+        hs = HitSet(pinned, n_hits, dev)
+        hs.reads, hs.complete_reads = reads, reads
+        log("[rank %d] workload %s: %d features, %d reads -> %d hits generated in %.1fs (%d threads)" % (
+            rank, wl.name, wl.annotation.n, reads, n_hits, time.time() - t0, threads))
+        return hs
+
     tmp = tempfile.mkdtemp(prefix="mmannot_bench_%d_" % rank)
     try:
-        t0 = time.time()
         wl = Workload(args.workload, tmp)
         w = wl.w
         reads = args.reads or w["reads"]
-        # read-name-range sharding: rank r owns reads [r*reads, (r+1)*reads) -- every record of a read stays on one GPU
-        pinned, n_hits = wl.fill_pinned(rank * reads, reads, threads)
-        log("[rank %d] workload %s: %d features, %d reads -> %d hits generated in %.1fs (%d threads)" % (
-            rank, args.workload, wl.annotation.n, reads, n_hits, time.time() - t0, threads))
+        hs = make_hitset(wl, reads)
+        n_hits = hs.n
         batch = args.batch                                  # hits per call, host-buffer passes (copies overlap the kernels)
         dev_batch = max(args.device_batch, batch)           # hits per call, device-resident pass
-        ann = device.Annotator(wl.config, strategy=w["strategy"], overlap=w["overlap"], n_samples=1, max_batch_hits=dev_batch,
-                               device=local_rank, table_log2=args.table_log2, fast_bin_shift=args.fast_shift, bin_shift=args.bin_shift)
-        ann.load_features(wl.annotation)
-        index_bytes = ann.index_bytes()
-        # device-resident copy of the packed hit buffers
-        dev_arrays = {k: torch.from_numpy(pinned.arrays[k][:max(n_hits, 1)].view(np.int32 if k != "read_key" else np.int64)).to(dev)
-                      for k in ("start", "end", "meta", "nh", "read_key")}
-        torch.cuda.synchronize()
-        isz = {"start": 4, "end": 4, "meta": 4, "nh": 4, "read_key": 8}
-
-        def batches(ptr_of, size):
-            out = []
-            for a in range(0, n_hits, size):
-                n = min(size, n_hits - a)
-                out.append(device.HitBatch(n, *[ptr_of(k) + a * isz[k] for k in ("start", "end", "meta", "nh", "read_key")]))
-            return out
-
-        dev_batches = batches(lambda k: dev_arrays[k].data_ptr(), dev_batch)
-        host_batches = batches(lambda k: pinned.arrays[k].ctypes.data, batch)
-        # the same batches in the compact transfer format the host decoder produces (mma_pack_hits): 8 B/hit + 8 B/run
+        sampler = ClockSampler(local_rank)
+        if rank == 0:
+            sampler.start()
+        main, ann, res_dev, stream, wall_dev, tm = device_resident(wl, hs, what=args.workload)
+        index_bytes, segments = ann.index_bytes(), ann.index_segments()
+        # ---- the same sample through the C ABI from HOST buffers (page-locked), copies and table read-back inside the timed
+        #      region: in the compact transfer format the host decoder emits, and in the wide arrays of mma_submit_hits
+        host_batches = hs.batches("host", batch)
         packed_batches = []
         if not args.e2e_wide:
             for a in range(0, n_hits, batch):
                 n = min(batch, n_hits - a)
-                packed_batches.append(device.PackedHits(*[pinned.arrays[k][a:a + n] for k in ("start", "end", "meta", "nh", "read_key")]))
-        stream = torch.cuda.ExternalStream(ann.stream_ptr(), device=dev)
+                packed_batches.append(device.PackedHits(*[hs.pinned.arrays[k][a:a + n] for k in HitSet.KEYS]))
 
-        def finish():  # (stats int64[7], rows int64[n, 3]); with several GPUs: device-side merge around one all-gather
+        def finish():
             return multi.merge_on_device(ann, 0, dev) if world > 1 else ann.finish_arrays(0, sort=False)
-
-        def step_device():
-            ann.reset(0)
-            for b in dev_batches:
-                ann.submit_device(0, b)
-            return finish()
 
         def step_e2e():
             ann.reset(0)
@@ -326,101 +513,78 @@ def run_product_arm(args):
                 ann.submit_batch(0, b)
             return finish()
 
-        def barrier():
-            torch.cuda.synchronize()
-            if world > 1:
-                dist.barrier()
-            torch.cuda.synchronize()
-
-        def timed(fn, steps, with_events):
-            barrier()
-            ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
-            t0 = time.perf_counter()
-            if with_events:
-                ev[0].record(stream)
-            res = None
-            for _ in range(steps):
-                res = fn()
-            if with_events:
-                ev[1].record(stream)
-            torch.cuda.synchronize()
-            wall_ms = (time.perf_counter() - t0) * 1e3
-            ms = ev[0].elapsed_time(ev[1]) if with_events else wall_ms
-            ms = max(ms, 0.0)
-            if world > 1:
-                t = torch.tensor([ms, wall_ms], device=dev, dtype=torch.float64)
-                dist.all_reduce(t, op=dist.ReduceOp.MAX)
-                ms, wall_ms = float(t[0]), float(t[1])
-            return ms, wall_ms, res
-
-        for _ in range(args.warmup):
-            step_device()
         for _ in range(min(args.warmup, 2)):
             step_e2e()
-
-        sampler = ClockSampler(local_rank)
-        if rank == 0:
-            sampler.start()
-        ann.timing_enable(True)
-        ann.timing_reset()
-        ms_dev, wall_dev, res_dev = timed(step_device, args.steps, True)
-        tm = ann.timing()
-        ann.timing_enable(False)
-        _, wall_e2e, res_e2e = timed(step_e2e, args.steps, False)
-        _, wall_e2e_wide, res_e2e_wide = timed(step_e2e_wide, max(1, args.steps // 2), False)
-        same = lambda x, y: np.array_equal(x[0], y[0]) and np.array_equal(device.sort_rows(x[1]), device.sort_rows(y[1]))
-        assert same(res_e2e_wide, res_e2e), "packed and wide host-buffer passes disagree"
+        _, wall_e2e, res_e2e = timed(step_e2e, args.steps, stream)
+        _, wall_e2e_wide, res_e2e_wide = timed(step_e2e_wide, max(1, args.steps // 2), stream)
         clocks = sampler.stop() if rank == 0 else None
-
+        assert same(res_e2e_wide, res_e2e), "packed and wide host-buffer passes disagree"
         assert same(res_dev, res_e2e), "device-resident and host-buffer passes disagree"
-        stats_dev = {k: int(v) for k, v in zip(multi.STAT_KEYS, res_dev[0])}
-        total_hits = n_hits
-        if world > 1:
-            t = torch.tensor([n_hits], device=dev, dtype=torch.int64)
-            dist.all_reduce(t)
-            total_hits = int(t[0])
-        # size-independent properties of the synthetic workload: every read is complete (NH records each), so the reads
-        # counted must be the reads generated and the hits counted the hits submitted, over all ranks
-        if w["strategy"] == "default":
-            assert stats_dev["n_hits"] == total_hits, "hits counted %d != hits submitted %d" % (stats_dev["n_hits"], total_hits)
-            per_name = 2 if w["spec"].get("paired") else 1  # both mates carry the name and the NH: two countdowns per name
-            assert stats_dev["n_reads"] == per_name * reads * world, "reads counted %d != reads generated %d" % (stats_dev["n_reads"], per_name * reads * world)
-        ms_per_step = ms_dev / args.steps
-        value = total_hits / (ms_per_step * 1e-3)
+        main["checks"].append("device-resident pass == compact host pass == wide host pass")
+        if args.oracle_reads:
+            n_checked = check_oracle(wl, ann, hs, min(args.oracle_reads, reads), 1)
+            main["checks"].append("table of this rank's first %d reads (%d hits) == CPU oracle" % (min(args.oracle_reads, reads), n_checked))
+        total_hits = all_sum(n_hits)
         e2e_value = total_hits / (wall_e2e / args.steps * 1e-3)
+        h2d = sum(pb.h2d_bytes for pb in packed_batches) if packed_batches else 24 * n_hits
+        d2h = ann.table_readback_bytes()
+        for pb in packed_batches:
+            pb.close()
+        packed_batches = []
+
+        # ---- the other shapes BASELINE.json names, device-resident (value, ms per step, roofline of the batch kernel)
+        workloads = {}
+        if not args.no_secondary:
+            # config 4: one sample per GPU, -y ratio (-e 80 is inert without -m): this rank's sample is its read range
+            r4, a4, _, _, _, _ = device_resident(wl, hs, strategy="ratio", merge=False, what="ratio_samples")
+            a4.close()
+            r4["describe"] = "BASELINE config 4: one synthetic sRNA sample per GPU (TAIR10 shape), -y ratio -e 80"
+            workloads["ratio_%dsamples" % world] = r4
+            # coordinate-sorted variant of config 2 (deferred path: every multi-mapping read is resolved after a sort by name)
+            n_cs = wl.synth.count_hits(wl.first_read, min(reads, args.coordsorted_reads))
+            order = np.lexsort((hs.pinned.arrays["start"][:n_cs], hs.pinned.arrays["meta"][:n_cs] & 0xFFFFFF))
+            sv = SortedView(hs.pinned, n_cs, order)
+            hcs = HitSet(sv, n_cs, dev)
+            hcs.reads, hcs.complete_reads = min(reads, args.coordsorted_reads), min(reads, args.coordsorted_reads)
+            rcs, acs, _, _, _, _ = device_resident(wl, hcs, what="tair10_coordsorted")
+            acs.close()
+            hcs.close()
+            rcs["describe"] = "config 2 hits in coordinate-sorted order (deferred path)"
+            workloads["tair10_coordsorted"] = rcs
+        ann.close()
+        hs.close()
+        if not args.no_secondary:
+            for name in ("flybase6_paired", "hs38_multi"):
+                if name == args.workload:
+                    continue
+                tmp2 = tempfile.mkdtemp(prefix="mmannot_bench_%d_%s_" % (rank, name))
+                try:
+                    wl2 = Workload(name, tmp2)
+                    hs2 = make_hitset(wl2, args.secondary_reads or wl2.w["reads"])
+                    r2, a2, _, _, _, _ = device_resident(wl2, hs2, what=name)
+                    if args.oracle_reads:
+                        nck = check_oracle(wl2, a2, hs2, min(args.oracle_reads, hs2.reads), 1)
+                        r2["checks"].append("table of this rank's first %d reads (%d hits) == CPU oracle" % (min(args.oracle_reads, hs2.reads), nck))
+                    a2.close()
+                    hs2.close()
+                    workloads[name] = r2
+                finally:
+                    shutil.rmtree(tmp2, ignore_errors=True)
 
         if rank == 0:
-            peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-            if os.path.exists(peaks_path):
-                peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)"
-            else:
-                peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
-            n_batches = int(tm["batches"])
-            k_ms = tm["ms_batch"]
-            # algorithmic bytes of one k_batch launch: 24 B per hit read once (start, end, meta, nh u32 +
-            # read key u64); the 16 B/feature index and the 8 B/row table are per sample, not per launch
-            bytes_per_launch = 24.0 * n_hits * args.steps / n_batches
-            avg_ms = k_ms / n_batches
-            achieved = bytes_per_launch / (avg_ms * 1e-3) / 1e9
+            roofline = main["roofline"]
             # dram bytes of the dominant kernel per launch, from the committed ncu --set full capture (bytes per hit there x
             # the hits of an average launch here); null when no capture of this kernel is on file
-            traffic, traffic_src = None, None
             try:
                 import glob
                 for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "*_traffic.json")), reverse=True):
                     tj = json.load(open(path))
-                    if tj.get("kernel") == ann.dominant_kernel() and tj.get("dram_bytes_per_hit"):
-                        traffic = tj["dram_bytes_per_hit"] * n_hits * args.steps / n_batches
-                        traffic_src = os.path.relpath(path, ROOT)
+                    if tj.get("kernel") == roofline["kernel"] and tj.get("dram_bytes_per_hit"):
+                        roofline["traffic"] = tj["dram_bytes_per_hit"] * n_hits * args.steps / roofline["launches_timed"]
+                        roofline["traffic_source"] = os.path.relpath(path, ROOT)
                         break
             except Exception:  # noqa: BLE001
                 pass
-            roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                        "traffic_source": traffic_src,
-                        "kernel": ann.dominant_kernel(), "bytes_per_launch": bytes_per_launch, "avg_launch_ms": avg_ms,
-                        "launches_timed": n_batches, "peak_source": peak_src,
-                        "kernel_ms_per_step": {k: tm[k] / args.steps for k in ("ms_batch", "ms_close", "ms_finish")},
-                        "segment_table_miss_frac": tm["fast_miss"] / max(1, n_hits)}
             cpu = None
             if not args.no_cpu_baseline:
                 try:
@@ -429,36 +593,85 @@ def run_product_arm(args):
                     cpu = {"value": vals[0], "unit": "records/s", "cores": used, "kind": "reference", "sample": desc}
                 except Exception as e:  # noqa: BLE001
                     cpu = {"value": None, "unit": "records/s", "cores": 0, "kind": "reference", "sample": "unavailable: %s" % e}
-            h2d = sum(pb.h2d_bytes for pb in packed_batches) if packed_batches else 24 * n_hits
-            d2h = ann.table_readback_bytes()
-            line = {"metric": "alignment_records_per_sec", "value": value, "unit": "records/s", "n_gpus": world, "steps": args.steps,
-                    "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            e2e_file = None
+            if not args.no_file:
+                try:
+                    e2e_file = time_cli_file(wl, args.file_reads, threads)
+                except Exception as e:  # noqa: BLE001
+                    e2e_file = {"value": None, "error": str(e)}
+            line = {"metric": "alignment_records_per_sec", "value": main["value"], "unit": "records/s", "n_gpus": world, "steps": args.steps,
+                    "warmup": args.warmup, "ms_per_step": main["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                     "dtype": "u32", "data": "synthetic",
-                    "config": {"workload": w["describe"], "name": args.workload, "reads_per_gpu": reads, "hits_per_gpu": n_hits,
-                               "features": int(wl.annotation.n), "elements": int(wl.config.n_elements), "batch_hits": dev_batch, "batch_hits_e2e": batch,
-                               "index_bytes": index_bytes, "segments": ann.index_segments(),
-                               "sharding": "read-name ranges, index replicated, tables merged by one allreduce" if world > 1 else "single GPU",
-                               "l2": "inputs (%.2f GB per pass) larger than L2; no explicit flush" % (24e-9 * n_hits),
-                               "order": "name-grouped (mapper order)"},
+                    "config": bench_config(wl, args, reads=reads, hits=n_hits, extra={
+                        "features": int(wl.annotation.n), "elements": int(wl.config.n_elements), "batch_hits": dev_batch, "batch_hits_e2e": batch,
+                        "index_bytes": index_bytes, "segments": segments,
+                        "sharding": main["multi_gpu"],
+                        "l2": "inputs (%.2f GB per pass) larger than L2; no explicit flush" % (24e-9 * n_hits),
+                        "order": "name-grouped (mapper order)"}),
                     "e2e": {"value": e2e_value, "unit": "records/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                             "ms_per_step": wall_e2e / args.steps, "timer": "host wall clock around synchronize",
-                            "format": "compact (mma_submit_hits_packed: 8 B/hit + 8 B/run, expanded on the device)" if packed_batches else "wide (24 B/hit)",
+                            "format": "compact transfer format as the host decoder emits it (mma_submit_hits_packed: 8 B/hit + 8 B/run, expanded on the device); "
+                                      "the buffers hold decoded hits -- BAM inflate and record parsing are NOT in this number, see e2e_file"
+                                      if not args.e2e_wide else "wide (24 B/hit)",
                             "wide_format_value": total_hits / (wall_e2e_wide / max(1, args.steps // 2) * 1e-3), "wide_h2d_bytes_per_step": 24 * n_hits},
-                    "gpu_launches": int(tm["launches"]),
+                    "e2e_file": e2e_file,
+                    "gpu_launches": main["gpu_launches"],
                     "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks, "host_cores": cores, "numa_node": numa_node,
-                    "wall_ms_per_step_device_resident": wall_dev / args.steps,
-                    "stats": stats_dev, "table_rows": int(len(res_dev[1]))}
+                    "wall_ms_per_step_device_resident": wall_dev,
+                    "stats": main["stats"], "table_rows": main["table_rows"], "checks": main["checks"], "workloads": workloads}
             emit(line)
-        ann.close()
-        for pb in packed_batches:
-            pb.close()
-        pinned.close()
         if world > 1:
             dist.barrier()
             dist.destroy_process_group()
     finally:
         shutil.rmtree(tmp, ignore_errors=True)
     return 0
+
+
+def bench_config(wl, args, reads=None, hits=None, extra=None):
+    """The `config` object both arms print (same keys, so that the driver can compare them)."""
+    c = {"workload": wl.w["describe"], "name": wl.name, "shape": wl.w["shape"], "strategy": wl.w["strategy"], "strand": wl.w["strand"],
+         "overlap": wl.w["overlap"], "reads_per_gpu": reads if reads is not None else (args.reads or wl.w["reads"])}
+    if hits is not None:
+        c["hits_per_gpu"] = hits
+    c.update(extra or {})
+    return c
+
+
+def time_cli_file(wl, n_reads, threads):
+    """File -> table through the drop-in command line (BGZF inflate, BAM parse, pack, copies, kernels, table): the number that
+    compares like with like with the reference arm.  The BAM is written here (untimed); the command line reports the time of
+    its Counter::read."""
+    exe = os.path.join(ROOT, "mmannot_b200", "bin", "mmannot_b200")
+    bam = os.path.join(wl.tmp, "e2e_file.bam")
+    t0 = time.time()
+    wl.synth.write_bam_parallel(bam, 0, n_reads, threads)
+    records = wl.synth.count_hits(0, n_reads)
+    t_write = time.time() - t0
+    w = wl.w
+    env = dict(os.environ, MMANNOT_B200_TIMING="1")
+    cmd = [exe, "-a", wl.gtf_path, "-c", wl.config_path, "-s", w["strand"], "-y", w["strategy"], "-l", repr(w["overlap"]), "-o", os.devnull, "-r", bam]
+    best = None
+    for _ in range(2):
+        t0 = time.perf_counter()
+        pr = subprocess.run(cmd, capture_output=True, text=True, env=env)
+        wall = time.perf_counter() - t0
+        if pr.returncode != 0:
+            raise RuntimeError("command line failed: " + pr.stderr[-300:])
+        read_ms = None
+        for ln in pr.stderr.splitlines():
+            if ln.startswith("[timing] read_ms="):
+                read_ms = float(ln.split("=")[1].split()[0])
+        if read_ms is not None and (best is None or read_ms < best[0]):
+            best = (read_ms, wall)
+    os.unlink(bam)
+    if best is None:
+        raise RuntimeError("no timing line from the command line")
+    size = None
+    return {"value": records / (best[0] * 1e-3), "unit": "records/s", "records": records, "reads": n_reads, "read_ms": best[0],
+            "process_wall_s": best[1], "bam_write_s": t_write,
+            "what": "one BAM -> count table through mmannot_b200/bin/mmannot_b200 (Counter::read: BGZF inflate + BAM parse on %d host threads, "
+                    "compact format over PCIe, kernels, table read-back); process wall time includes annotation load and CUDA start-up" % threads}
 
 
 _REAL_STDOUT = None
@@ -495,6 +708,12 @@ def main():
     ap.add_argument("--ref-reads", type=int, default=500_000, help="--impl reference: reads per BAM per step")
     ap.add_argument("--ref-threads", type=int, default=0, help="BAM files / threads of the reference run (default: 1 for cpu_baseline, host cores up to 32 for --impl reference)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the `workloads` entries (other BASELINE shapes)")
+    ap.add_argument("--no-file", action="store_true", help="skip e2e_file (BAM -> table through the command line)")
+    ap.add_argument("--secondary-reads", type=int, default=0, help="reads per GPU of the secondary workloads (default: their full size)")
+    ap.add_argument("--coordsorted-reads", type=int, default=10_000_000, help="reads of the coordinate-sorted variant")
+    ap.add_argument("--file-reads", type=int, default=25_000_000, help="reads of the BAM of e2e_file")
+    ap.add_argument("--oracle-reads", type=int, default=200_000, help="reads per rank checked against the CPU oracle outside the timed region (0 = off)")
     ap.add_argument("--e2e-wide", action="store_true", help="e2e through the wide 24 B/hit arrays instead of the compact transfer format")
     args = ap.parse_args()
     if args.fast_shift < 0:

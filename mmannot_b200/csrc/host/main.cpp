@@ -2,6 +2,8 @@
 // Flags, defaults, messages and exit codes follow main() of the reference
 // (mmannot.cpp:1903-2149); the annotation itself runs on the GPU through the C ABI
 // (include/mmannot_b200.h).  There is no CPU fallback.
+#include <chrono>
+#include <cstdlib>
 #include <algorithm>
 #include <cstdlib>
 #include <fstream>
@@ -240,7 +242,10 @@ int main(int argc, char **argv) {
         FileResult &r = results[i];
         std::ostringstream log;
         std::ostream &lg = (nWorkers == 1) ? static_cast<std::ostream &>(std::cerr) : static_cast<std::ostream &>(log);
+        const auto tRead0 = std::chrono::steady_clock::now();
         r.ok = counter.read(readsFileNames[i], i, r.err, lg);
+        if (std::getenv("MMANNOT_B200_TIMING"))  // (bench.py: time of Counter::read alone, without annotation load and CUDA start-up)
+          lg << "[timing] read_ms=" << std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tRead0).count() << " file=" << readsFileNames[i] << std::endl;
         if (r.ok) {
           counter.dump(lg);
           if (opt.intervalStats) writers.dumpIntervals(intervalStatsStream);

@@ -435,10 +435,11 @@ uint64_t SynthGenome::fillHits(const FeatureTable &features, Strandedness s, uin
   return n;
 }
 
-bool SynthGenome::writeBam(const std::string &path, uint64_t first, uint64_t nReads, const SynthReadSpec &spec, bool coordinateSorted) const {
+bool SynthGenome::writeBam(const std::string &path, uint64_t first, uint64_t nReads, const SynthReadSpec &spec, bool coordinateSorted, bool headerless) const {
   BgzfWriter w(path);
   if (!w.ok()) return false;
   std::vector<unsigned char> buf;
+  if (!headerless) {
   std::string text = std::string("@HD\tVN:1.0\tSO:") + (coordinateSorted ? "coordinate" : "unsorted") + "\n";
   for (size_t c = 0; c < chrNames.size(); ++c) text += "@SQ\tSN:" + chrNames[c] + "\tLN:" + std::to_string(chrLen[c]) + "\n";
   buf.insert(buf.end(), {'B', 'A', 'M', 1});
@@ -452,6 +453,7 @@ bool SynthGenome::writeBam(const std::string &path, uint64_t first, uint64_t nRe
     put32(buf, static_cast<uint32_t>(chrLen[c]));
   }
   w.write(buf.data(), buf.size());
+  }
   std::string name;
   std::vector<SynthRecord> recs;
   if (!coordinateSorted) {

@@ -54,7 +54,8 @@ class SynthGenome {
   void readRecords(uint64_t r, const SynthReadSpec &spec, std::string &name, std::vector<SynthRecord> &out) const;
 
   // reads [first, first + nReads): BAM for the reference ...
-  bool writeBam(const std::string &path, uint64_t first, uint64_t nReads, const SynthReadSpec &spec, bool coordinateSorted) const;
+  // (headerless: records only -- BGZF files can be concatenated, so that a large BAM can be written as parts side by side)
+  bool writeBam(const std::string &path, uint64_t first, uint64_t nReads, const SynthReadSpec &spec, bool coordinateSorted, bool headerless = false) const;
   // ... number of hits of the range, and the same hits as packed buffers (chromosome ids of `features`)
   uint64_t countHits(uint64_t first, uint64_t nReads, const SynthReadSpec &spec) const;
   uint64_t fillHits(const FeatureTable &features, Strandedness s, uint64_t first, uint64_t nReads, const SynthReadSpec &spec,

@@ -249,9 +249,25 @@ class Synth:
     def write_annotation(self, path):
         lib().mmh_synth_write_annotation(self._h, os.fsencode(path))
 
-    def write_bam(self, path, first_read, n_reads, coordinate_sorted=False):
-        if lib().mmh_synth_write_bam(self._h, os.fsencode(path), first_read, n_reads, C.byref(self.spec), int(coordinate_sorted)) != 0:
+    def write_bam(self, path, first_read, n_reads, coordinate_sorted=False, headerless=False):
+        if lib().mmh_synth_write_bam(self._h, os.fsencode(path), first_read, n_reads, C.byref(self.spec), int(coordinate_sorted) | (2 if headerless else 0)) != 0:
             raise _err()
+
+    def write_bam_parallel(self, path, first_read, n_reads, threads):
+        """One name-grouped BAM written as `threads` parts side by side (BGZF files concatenate: only the first part has the header)."""
+        from concurrent.futures import ThreadPoolExecutor
+        import shutil
+        threads = max(1, min(threads, n_reads // 100000 or 1))
+        step = (n_reads + threads - 1) // threads
+        parts = [(first_read + t * step, min(step, n_reads - t * step)) for t in range(threads) if t * step < n_reads]
+        names = [path if i == 0 else "%s.part%d" % (path, i) for i in range(len(parts))]
+        with ThreadPoolExecutor(len(parts)) as ex:
+            list(ex.map(lambda i: self.write_bam(names[i], parts[i][0], parts[i][1], headerless=(i > 0)), range(len(parts))))
+        with open(path, "ab") as out:
+            for nm in names[1:]:
+                with open(nm, "rb") as f:
+                    shutil.copyfileobj(f, out, 16 << 20)
+                os.unlink(nm)
 
     def count_hits(self, first_read, n_reads):
         return int(lib().mmh_synth_count_hits(self._h, first_read, n_reads, C.byref(self.spec)))
