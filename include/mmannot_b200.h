@@ -231,6 +231,20 @@ int mma_dense_counts(mma_ctx *ctx, uint32_t sample, const uint64_t *mask, const 
 uint64_t mma_export_bytes(const mma_ctx *ctx);
 int mma_export_table(mma_ctx *ctx, uint32_t sample, void *dev_dst);
 int mma_import_tables(mma_ctx *ctx, uint32_t sample, const void *dev_src, uint32_t n_tables);
+/* Rows of the last mma_export_table of this context, and the import of dumps exchanged at that size only: the dumps lie
+ * stride_bytes apart (a multiple of 16, at least mma_export_head_bytes() + 16 * rows_cap) and hold at most rows_cap rows each,
+ * so that the all-gather moves the live rows (a few thousand) instead of the whole table capacity. */
+uint64_t mma_export_rows(const mma_ctx *ctx);
+uint64_t mma_export_head_bytes(void);
+int mma_import_tables_strided(mma_ctx *ctx, uint32_t sample, const void *dev_src, uint32_t n_tables, uint64_t stride_bytes, uint64_t rows_cap);
+
+/* The same merge for the contexts of ONE process (one per GPU), done by the library: end-of-file flush of every shard, one
+ * ncclAllGather of the live rows over NVLink (single-process clique, ncclCommInitAll, kept for the life of the process), import
+ * on every GPU.  Afterwards mma_finish_sample on any of the contexts returns the sum TableCount::addCounter would form
+ * (mmannot.cpp:1861-1876) had one Counter seen all the shards.  libnccl.so.2 is opened at run time, on the first call with
+ * n_ctx > 1 (MMA_ERR_STATE when it cannot be found).  The contexts must have been created with the same parameters; errors are
+ * reported on ctxs[0]. */
+int mma_allreduce(mma_ctx *const *ctxs, uint32_t n_ctx, uint32_t sample);
 
 int mma_sync(mma_ctx *ctx);
 void *mma_stream(mma_ctx *ctx); /* cudaStream_t of the compute stream */
@@ -249,6 +263,9 @@ uint64_t mma_readback_bytes(const mma_ctx *ctx);
 const char *mma_version(void);
 /* Name of the kernel that dominates a batch (for profiles / the roofline line of bench.py). */
 const char *mma_dominant_kernel(void);
+/* Name of the batch kernel this context launches for its annotation and options ("" before mma_load_features): k_batch_lean with
+ * bin entries (annotations up to ~160 Mb), k_batch_fast with the coarser position map, k_batch otherwise. */
+const char *mma_batch_kernel(const mma_ctx *ctx);
 
 #ifdef __cplusplus
 }

@@ -59,7 +59,36 @@ Counter::Counter(mma_ctx *ctx, const FeatureTable &features, const Config &confi
   }
 }
 
+Counter::Counter(const std::vector<mma_ctx *> &ctxs, const FeatureTable &features, const Config &config, const RunOptions &opt)
+    : Counter(ctxs.empty() ? nullptr : ctxs[0], features, config, opt) {
+  if (ctxs.size() < 2) return;
+  shards_.resize(ctxs.size());
+  for (size_t g = 0; g < ctxs.size(); ++g) {
+    Shard &sh = shards_[g];
+    sh.ctx = ctxs[g];
+    for (int k = 0; k < 2; ++k) {
+      allocPinned(sh.pinned[k], opt.batchHits);
+      PackedBuffers &p = sh.packed[k];
+      const size_t cap = opt.batchHits;
+      p.escCapacity = cap / 64 + 16;
+      p.packed = static_cast<uint32_t *>(mma_alloc_pinned(cap * 4));
+      p.runKey = static_cast<uint64_t *>(mma_alloc_pinned(cap * 8));
+      p.tileRunBase = static_cast<uint32_t *>(mma_alloc_pinned((cap / MMA_PACK_TILE + 1) * 4));
+      p.escIndex = static_cast<uint32_t *>(mma_alloc_pinned(p.escCapacity * 4));
+      p.escEnd = static_cast<uint32_t *>(mma_alloc_pinned(p.escCapacity * 4));
+      p.escNh = static_cast<uint32_t *>(mma_alloc_pinned(p.escCapacity * 4));
+    }
+  }
+}
+
 Counter::~Counter() {
+  for (Shard &sh : shards_)
+    for (int k = 0; k < 2; ++k) {
+      freePinned(sh.pinned[k]);
+      PackedBuffers &p = sh.packed[k];
+      mma_free_pinned(p.packed); mma_free_pinned(p.runKey); mma_free_pinned(p.tileRunBase);
+      mma_free_pinned(p.escIndex); mma_free_pinned(p.escEnd); mma_free_pinned(p.escNh);
+    }
   freePinned(pinned_[0]);
   freePinned(pinned_[1]);
   for (PackedBuffers &p : packedBuf_) {
@@ -76,6 +105,10 @@ bool Counter::read(const std::string &fileName, uint32_t column, std::string &er
   XamReader reader(fileName, opt_.format, opt_.strandedness, features_);
   if (!reader.open(err)) return false;
   log << (reader.isBam() ? "Reading BAM file " : "Reading SAM file ") << fileName << std::endl;
+  if (!shards_.empty()) {
+    if (writers_) { err = "Read / interval statistics need the whole input on one GPU."; return false; }
+    if (!readSharded(reader, column, err, log)) return false;
+  } else {
   if (mma_reset_sample(ctx_, column) != MMA_OK) { err = mma_last_error(ctx_); return false; }
   // decode batch k+1 on the host while batch k is copied and annotated on the device
   std::vector<std::string> names;
@@ -109,6 +142,7 @@ bool Counter::read(const std::string &fileName, uint32_t column, std::string &er
     }
     if (opt_.progress) log << "\t" << withThousands(reader.recordsRead()) << " lines read.\r" << std::flush;
   }
+  }
   log << "\t" << withThousands(reader.recordsRead()) << " lines read, done." << std::endl;
   if (writers_) writers_->endOfFile();
   mma_sample_result res;
@@ -124,6 +158,51 @@ bool Counter::read(const std::string &fileName, uint32_t column, std::string &er
     const double w = res.row_nh[i] ? 1.0 / res.row_nh[i] : 1.0;
     counts_[res.row_mask[i]] += static_cast<double>(res.row_count[i]) * w;
   }
+  return true;
+}
+
+// One input over several GPUs: every decoded batch is dealt out by read name, each GPU gets its share in file order
+bool Counter::readSharded(XamReader &reader, uint32_t column, std::string &err, std::ostream &log) {
+  const size_t nG = shards_.size();
+  for (Shard &sh : shards_)
+    if (mma_reset_sample(sh.ctx, column) != MMA_OK) { err = mma_last_error(sh.ctx); return false; }
+  for (unsigned which = 0;; which ^= 1) {
+    const HitBuffers &buf = pinned_[which & 1];  // (only a staging area here: nothing is copied to a GPU from it)
+    const size_t n = reader.nextBatch(buf, nullptr);
+    std::string w = reader.takeWarnings();
+    if (!w.empty()) log << w;
+    if (n == 0) break;
+    for (Shard &sh : shards_) sh.n = 0;
+    for (size_t i = 0; i < n; ++i) {
+      uint64_t k = buf.key[i];
+      k = (k ^ (k >> 33)) * 0xff51afd7ed558ccdull;
+      k ^= k >> 33;
+      Shard &sh = shards_[k % nG];
+      const HitBuffers &d = sh.pinned[which];
+      const size_t at = sh.n++;
+      d.start[at] = buf.start[i]; d.end[at] = buf.end[i]; d.meta[at] = buf.meta[i]; d.nh[at] = buf.nh[i]; d.key[at] = buf.key[i];
+    }
+    for (Shard &sh : shards_) {
+      const HitBuffers &d = sh.pinned[which];
+      mma_hit_batch b;
+      b.n = sh.n; b.start = d.start; b.end = d.end; b.meta = d.meta; b.nh = d.nh; b.read_key = d.key;
+      if (b.n == 0) {  // nothing for this GPU in this batch: the call still waits for its previous copy, which frees the other slot
+        if (mma_submit_hits(sh.ctx, column, &b) != MMA_OK) { err = mma_last_error(sh.ctx); return false; }
+        continue;
+      }
+      const PackedBuffers &pk = sh.packed[which];
+      mma_packed_batch pb;
+      const bool canPack = pk.packed && pk.runKey && pk.tileRunBase && pk.escIndex && pk.escEnd && pk.escNh &&
+                           mma_pack_hits(&b, pk.packed, pk.runKey, pk.tileRunBase, pk.escIndex, pk.escEnd, pk.escNh, pk.escCapacity, &pb) == MMA_OK;
+      const int rc = canPack ? mma_submit_hits_packed(sh.ctx, column, &pb) : mma_submit_hits(sh.ctx, column, &b);
+      if (rc != MMA_OK) { err = mma_last_error(sh.ctx); return false; }
+    }
+    if (opt_.progress) log << "\t" << withThousands(reader.recordsRead()) << " lines read.\r" << std::flush;
+  }
+  // the sum TableCount::addCounter would form had one Counter seen everything (mm:1861-1876), on the devices
+  std::vector<mma_ctx *> ctxs;
+  for (Shard &sh : shards_) ctxs.push_back(sh.ctx);
+  if (mma_allreduce(ctxs.data(), static_cast<uint32_t>(ctxs.size()), column) != MMA_OK) { err = mma_last_error(ctxs[0]); return false; }
   return true;
 }
 

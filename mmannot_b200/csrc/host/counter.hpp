@@ -32,6 +32,10 @@ std::string withThousands(uint64_t n);  // the comma_numpunct locale of mm:111-1
 class Counter {
  public:
   Counter(mma_ctx *ctx, const FeatureTable &features, const Config &config, const RunOptions &opt);
+  // One input spread over several GPUs (one context each, all created with the same parameters): the hits of a batch are dealt
+  // out by read name (hash of the read key mod #GPUs, so that every record of a name -- both mates, every repeat -- stays on
+  // one GPU in file order), and the tables are summed on the devices at the end of the file (mma_allreduce).  Not with -m / -M.
+  Counter(const std::vector<mma_ctx *> &ctxs, const FeatureTable &features, const Config &config, const RunOptions &opt);
   ~Counter();
   // Annotates one SAM/BAM file as sample `column`; false + message on a fatal problem.
   bool read(const std::string &fileName, uint32_t column, std::string &err, std::ostream &log);
@@ -58,6 +62,15 @@ class Counter {
     uint64_t escCapacity = 0;
   } packedBuf_[2];
   StatsWriters *writers_ = nullptr;
+  // several GPUs: shards_[g] holds GPU g's two page-locked slots (pinned_ / packedBuf_ above are those of GPU 0's reader batch)
+  struct Shard {
+    mma_ctx *ctx = nullptr;
+    HitBuffers pinned[2];
+    PackedBuffers packed[2];
+    size_t n = 0;
+  };
+  std::vector<Shard> shards_;
+  bool readSharded(XamReader &reader, uint32_t column, std::string &err, std::ostream &log);
 };
 
 class TableCount {

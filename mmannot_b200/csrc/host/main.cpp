@@ -48,6 +48,7 @@ void printUsage() {
                "\t\t-M file: print mapping statistics for each interval (slow, only work with 1 input file)\n"
                "\t\t-t integer: # threads (default: 1)\n"
                "\t\t-g integer: CUDA device (default: 0)\n"
+               "\t\t-G integer: # GPUs every input is spread over, by read name (default: 1)\n"
                "\t\t-h: this help"
             << std::endl;
 }
@@ -64,7 +65,7 @@ int main(int argc, char **argv) {
   AnnotationOptions annOpt;
   std::string gtfFileName, outputFileName, configFileName = "config.txt", readStatsFile, intervalStatsFile;
   std::vector<std::string> readsFileNames, names;
-  int device = 0, nThreads = 1;
+  int device = 0, nThreads = 1, gpusPerInput = 1;
   if (argc == 1) {
     printUsage();
     return EXIT_SUCCESS;
@@ -105,6 +106,7 @@ int main(int argc, char **argv) {
     else if (s == "-p") opt.progress = true;
     else if (s == "-t") nThreads = std::max(1, std::stoi(value(i)));  // workers, one input file at a time each, spread over the GPUs
     else if (s == "-g") device = std::stoi(value(i));
+    else if (s == "-G") gpusPerInput = std::max(1, std::stoi(value(i)));
     else if (s == "-m") { readStatsFile = value(i); opt.readStats = true; }
     else if (s == "-M") { intervalStatsFile = value(i); opt.intervalStats = true; }
     else if (s == "-f") {
@@ -166,9 +168,9 @@ int main(int argc, char **argv) {
     return EXIT_FAILURE;
   }
   // the CUDA context comes up on a side thread while the configuration and the annotation are parsed
-  std::thread warm([device, nThreads]() {
+  std::thread warm([device, nThreads, gpusPerInput]() {
     const int nDev = std::max(1, mma_device_count());
-    for (int w = 0; w < std::min(nThreads, nDev); ++w) mma_warmup((device + w) % nDev);
+    for (int w = 0; w < std::min(nThreads * gpusPerInput, nDev); ++w) mma_warmup((device + w) % nDev);
   });
   struct Joiner { std::thread &t; ~Joiner() { if (t.joinable()) t.join(); } } joinWarm{warm};
   std::string err, warnings;
@@ -215,7 +217,12 @@ int main(int argc, char **argv) {
   // -t n: n workers take the input files in turn (the reference's pool, mm:2117-2141: one thread per file); worker w drives its
   // own context on GPU (device + w) mod #GPUs, with the feature index replicated.  Reports and table columns keep file order.
   const int nDevices = std::max(1, mma_device_count());
-  const uint32_t nWorkers = (opt.readStats || opt.intervalStats) ? 1u : std::min<uint32_t>(static_cast<uint32_t>(nThreads), nInputs);
+  // -G n: every input is spread over n GPUs by read name (all the records of a name on one GPU), tables summed on the devices
+  const uint32_t nShards = (opt.readStats || opt.intervalStats) ? 1u : static_cast<uint32_t>(std::min(gpusPerInput, nDevices));
+  const uint32_t nWorkers = (opt.readStats || opt.intervalStats)
+                                ? 1u
+                                : std::max<uint32_t>(1u, std::min<uint32_t>(std::min<uint32_t>(static_cast<uint32_t>(nThreads), nInputs),
+                                                                         nShards > 1 ? static_cast<uint32_t>(nDevices) / nShards : 0xFFFFFFFFu));
   struct FileResult { bool ok = false; std::string err, log; std::map<uint64_t, double> counts; };
   std::vector<FileResult> results(nInputs);
   std::ofstream readStatsStream, intervalStatsStream;
@@ -225,18 +232,28 @@ int main(int argc, char **argv) {
   std::string fatal;
   std::mutex fatalMutex;
   auto worker = [&](uint32_t w) {
-    mma_params p = params;
-    p.device = (device + static_cast<int>(w)) % nDevices;
-    mma_ctx *ctx = nullptr;
-    if (mma_create(&ctx, &p) != MMA_OK) { std::lock_guard<std::mutex> g(fatalMutex); fatal = std::string("Error: ") + mma_last_error(nullptr); return; }
-    if (mma_load_features(ctx, &f) != MMA_OK) {
-      std::lock_guard<std::mutex> g(fatalMutex);
-      fatal = std::string("Error: ") + mma_last_error(ctx);
-      mma_destroy(ctx);
-      return;
+    std::vector<mma_ctx *> ctxs;
+    auto destroyAll = [&ctxs]() { for (mma_ctx *c : ctxs) mma_destroy(c); ctxs.clear(); };
+    for (uint32_t g = 0; g < nShards; ++g) {
+      mma_params p = params;
+      p.device = (device + static_cast<int>(w * nShards + g)) % nDevices;
+      mma_ctx *ctx = nullptr;
+      if (mma_create(&ctx, &p) != MMA_OK) {
+        std::lock_guard<std::mutex> lk(fatalMutex);
+        fatal = std::string("Error: ") + mma_last_error(nullptr);
+        destroyAll();
+        return;
+      }
+      ctxs.push_back(ctx);
+      if (mma_load_features(ctx, &f) != MMA_OK) {
+        std::lock_guard<std::mutex> lk(fatalMutex);
+        fatal = std::string("Error: ") + mma_last_error(ctx);
+        destroyAll();
+        return;
+      }
     }
     {
-      Counter counter(ctx, features, config, opt);
+      Counter counter(ctxs, features, config, opt);
       if (opt.readStats || opt.intervalStats) counter.setStatsWriters(&writers);
       for (uint32_t i = w; i < nInputs; i += nWorkers) {
         FileResult &r = results[i];
@@ -255,7 +272,7 @@ int main(int argc, char **argv) {
         if (!r.ok) break;
       }
     }
-    mma_destroy(ctx);
+    destroyAll();
   };
   if (nWorkers == 1) worker(0);
   else {

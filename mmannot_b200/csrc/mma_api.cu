@@ -6,7 +6,12 @@
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 
+#include <dlfcn.h>
+#include <nccl.h>  // types and prototypes only: the library is opened at run time, by mma_allreduce alone
+
 #include <algorithm>
+#include <map>
+#include <mutex>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -115,6 +120,7 @@ struct mma_ctx {
   std::vector<uint32_t> intervalIds;  // result of the last mma_annotate_intervals
   u64 *hostTable = nullptr;  // pinned: [TableDump | rows] of the sample being read back
   DevBuf dumpBuf;            // device side of the same
+  DevBuf gatherBuf;          // mma_allreduce: the dumps of all the contexts of the group
 
   int fail(int code, const std::string &msg) {
     error = msg;
@@ -487,6 +493,7 @@ void mma_destroy(mma_ctx *ctx) {
   ctx->collectTiming();
   if (ctx->hostTable) cudaFreeHost(ctx->hostTable);
   ctx->dumpBuf.release();
+  ctx->gatherBuf.release();
   for (cudaEvent_t e : ctx->eventPool) cudaEventDestroy(e);
   if (ctx->sc) cudaStreamDestroy(ctx->sc);
   if (ctx->sh) cudaStreamDestroy(ctx->sh);
@@ -732,7 +739,12 @@ int mma_load_features(mma_ctx *ctx, const mma_features *f) {
 uint64_t mma_index_bytes(const mma_ctx *ctx) { return ctx ? ctx->indexBytes : 0; }
 uint64_t mma_index_segments(const mma_ctx *ctx) { return ctx ? ctx->nSegments : 0; }
 uint64_t mma_readback_bytes(const mma_ctx *ctx) { return ctx ? (uint64_t)std::min<u32>(ctx->tableCap, 8192u) * 16 + sizeof(TableDump) : 0; }
-const char *mma_dominant_kernel(void) { return "k_batch_fast"; }
+const char *mma_dominant_kernel(void) { return "k_batch_lean"; }
+const char *mma_batch_kernel(const mma_ctx *ctx) {
+  if (!ctx || !ctx->haveIndex) return "";
+  if (ctx->wideMask || !ctx->fast.enabled || ctx->rules.strategy == MMA_STRATEGY_RANDOM || ctx->legacyBatch || ctx->fast.nChr > CHR_SMEM) return "k_batch";
+  return ctx->fast.ent ? "k_batch_lean" : "k_batch_fast";
+}
 
 static int submitCommon(mma_ctx *ctx, uint32_t sample, const mma_hit_batch *b, bool onDevice) {
   int rc = checkSubmit(ctx, sample, b);
@@ -1146,23 +1158,127 @@ int mma_export_table(mma_ctx *ctx, uint32_t sample, void *dev_dst) {
   return MMA_OK;
 }
 
+// replaces the sample's table and counters by the sum over n_tables dumps ([TableDump | rows], `stride` bytes apart, at most
+// `rowsCap` rows each looked at)
+static int importTables(mma_ctx *ctx, Sample &s, const void *dev_src, uint32_t n_tables, size_t stride, u32 rowsCap) {
+  const size_t tb = (size_t)ctx->tableCap * sizeof(u64);
+  CK(cudaMemsetAsync(s.tableKeys.p, 0, tb, ctx->sc)); CK(cudaMemsetAsync(s.tableVals.p, 0, tb, ctx->sc));
+  CK(cudaMemsetAsync(s.ctl->stats, 0, sizeof(u64) * ST_N, ctx->sc));
+  rowsCap = std::max<u32>(rowsCap, ST_N);  // (the first ST_N threads of each dump also add its counters)
+  const u64 total = (u64)n_tables * rowsCap;
+  k_table_import<<<gridFor(total, 256), 256, 0, ctx->sc>>>(tableView(s.tableKeys, s.tableVals, ctx->tableCap, s.ctl), s.ctl,
+                                                          reinterpret_cast<const char *>(dev_src), n_tables, stride, rowsCap);
+  ctx->launches++;
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return ctx->fail(MMA_ERR_CUDA, std::string("kernel launch: ") + cudaGetErrorString(e));
+  return MMA_OK;
+}
+
 int mma_import_tables(mma_ctx *ctx, uint32_t sample, const void *dev_src, uint32_t n_tables) {
+  return mma_import_tables_strided(ctx, sample, dev_src, n_tables, mma_export_bytes(ctx), ctx ? ctx->tableCap : 0);
+}
+
+int mma_import_tables_strided(mma_ctx *ctx, uint32_t sample, const void *dev_src, uint32_t n_tables, uint64_t stride_bytes, uint64_t rows_cap) {
   if (!ctx) return MMA_ERR_INVALID;
   if (!dev_src || n_tables == 0) return ctx->fail(MMA_ERR_INVALID, "null source");
   if (sample >= ctx->samples.size()) return ctx->fail(MMA_ERR_INVALID, "sample index out of range");
+  if ((stride_bytes & 15) || rows_cap == 0 || rows_cap > ctx->tableCap || stride_bytes < sizeof(TableDump) + rows_cap * 16)
+    return ctx->fail(MMA_ERR_INVALID, "bad stride / row capacity");
   CK(cudaSetDevice(ctx->device));
   Sample &s = ctx->samples[sample];
   int rc = initSample(ctx, s);
   if (rc) return rc;
-  const size_t tb = (size_t)ctx->tableCap * sizeof(u64);
-  CK(cudaMemsetAsync(s.tableKeys.p, 0, tb, ctx->sc)); CK(cudaMemsetAsync(s.tableVals.p, 0, tb, ctx->sc));
-  CK(cudaMemsetAsync(s.ctl->stats, 0, sizeof(u64) * ST_N, ctx->sc));
-  const u64 total = (u64)n_tables * ctx->tableCap;
-  k_table_import<<<gridFor(total, 256), 256, 0, ctx->sc>>>(tableView(s.tableKeys, s.tableVals, ctx->tableCap, s.ctl), s.ctl,
-                                                          reinterpret_cast<const char *>(dev_src), n_tables, (size_t)mma_export_bytes(ctx), ctx->tableCap);
-  ctx->launches++;
-  cudaError_t e = cudaGetLastError();
-  if (e != cudaSuccess) return ctx->fail(MMA_ERR_CUDA, std::string("kernel launch: ") + cudaGetErrorString(e));
+  return importTables(ctx, s, dev_src, n_tables, (size_t)stride_bytes, (u32)rows_cap);
+}
+
+uint64_t mma_export_head_bytes(void) { return sizeof(TableDump); }
+uint64_t mma_export_rows(const mma_ctx *ctx) { return (ctx && ctx->hostTable) ? reinterpret_cast<const TableDump *>(ctx->hostTable)->nRows : 0; }
+
+// ---- NCCL, opened at run time (a process that never merges over several GPUs never loads it; a process that already has a
+//      libnccl.so.2 -- torch's -- gets that one)
+namespace {
+struct NcclApi {
+  void *handle = nullptr;
+  decltype(&ncclCommInitAll) commInitAll = nullptr;
+  decltype(&ncclCommDestroy) commDestroy = nullptr;
+  decltype(&ncclAllGather) allGather = nullptr;
+  decltype(&ncclGroupStart) groupStart = nullptr;
+  decltype(&ncclGroupEnd) groupEnd = nullptr;
+  decltype(&ncclGetErrorString) errorString = nullptr;
+  std::string error;
+  bool load() {
+    if (handle) return true;
+    for (const char *name : {"libnccl.so.2", "libnccl.so"}) {
+      handle = dlopen(name, RTLD_NOW | RTLD_LOCAL);
+      if (handle) break;
+    }
+    if (!handle) { error = std::string("cannot open libnccl.so.2: ") + dlerror(); return false; }
+#define NCCL_SYM(field, sym)                                                          \
+  field = reinterpret_cast<decltype(field)>(dlsym(handle, sym));                      \
+  if (!field) { error = std::string("libnccl lacks ") + sym; handle = nullptr; return false; }
+    NCCL_SYM(commInitAll, "ncclCommInitAll") NCCL_SYM(commDestroy, "ncclCommDestroy") NCCL_SYM(allGather, "ncclAllGather")
+    NCCL_SYM(groupStart, "ncclGroupStart") NCCL_SYM(groupEnd, "ncclGroupEnd") NCCL_SYM(errorString, "ncclGetErrorString")
+#undef NCCL_SYM
+    return true;
+  }
+};
+NcclApi g_nccl;
+std::mutex g_ncclMutex;
+std::map<std::vector<int>, std::vector<ncclComm_t>> g_comms;  // one clique per device list, kept for the life of the process
+}  // namespace
+
+int mma_allreduce(mma_ctx *const *ctxs, uint32_t n_ctx, uint32_t sample) {
+  if (!ctxs || n_ctx == 0 || !ctxs[0]) return MMA_ERR_INVALID;
+  mma_ctx *ctx = ctxs[0];  // (errors are reported on the first context)
+  std::vector<int> devices;
+  for (uint32_t i = 0; i < n_ctx; ++i) {
+    if (!ctxs[i]) return ctx->fail(MMA_ERR_INVALID, "null context");
+    if (sample >= ctxs[i]->samples.size()) return ctx->fail(MMA_ERR_INVALID, "sample index out of range");
+    if (ctxs[i]->tableCap != ctx->tableCap || ctxs[i]->rules.strategy != ctx->rules.strategy) return ctx->fail(MMA_ERR_INVALID, "the contexts of a merge must share table size and strategy");
+    if (std::find(devices.begin(), devices.end(), ctxs[i]->device) != devices.end()) return ctx->fail(MMA_ERR_INVALID, "one context per GPU");
+    devices.push_back(ctxs[i]->device);
+  }
+  if (n_ctx == 1) return MMA_OK;
+  std::lock_guard<std::mutex> lock(g_ncclMutex);
+  if (!g_nccl.load()) return ctx->fail(MMA_ERR_STATE, g_nccl.error);
+  std::vector<ncclComm_t> &comms = g_comms[devices];
+  if (comms.empty()) {
+    comms.resize(n_ctx);
+    ncclResult_t r = g_nccl.commInitAll(comms.data(), (int)n_ctx, devices.data());
+    if (r != ncclSuccess) { comms.clear(); g_comms.erase(devices); return ctx->fail(MMA_ERR_CUDA, std::string("ncclCommInitAll: ") + g_nccl.errorString(r)); }
+  }
+  // 1. end-of-file flush of every shard; its compacted table and counters into the context's dump buffer
+  uint64_t maxRows = ST_N;
+  for (uint32_t i = 0; i < n_ctx; ++i) {
+    mma_ctx *c = ctxs[i];
+    if (cudaSetDevice(c->device) != cudaSuccess) return ctx->fail(MMA_ERR_CUDA, "cudaSetDevice");
+    Sample &s = c->samples[sample];
+    int rc = initSample(c, s);
+    SampleCtl hc;
+    if (!rc) rc = flushAndDump(c, s, false, hc);
+    if (rc) { if (c != ctx) ctx->fail(rc, c->error); return rc; }
+    maxRows = std::max<uint64_t>(maxRows, reinterpret_cast<const TableDump *>(c->hostTable)->nRows);
+  }
+  // 2. ONE all-gather over NVLink of the live rows (padded to the longest shard), every GPU receiving every dump
+  const size_t stride = (sizeof(TableDump) + (size_t)maxRows * 16 + 15) & ~(size_t)15;
+  for (uint32_t i = 0; i < n_ctx; ++i) {
+    mma_ctx *c = ctxs[i];
+    cudaSetDevice(c->device);
+    if (c->gatherBuf.ensure(stride * n_ctx) != cudaSuccess) return ctx->fail(MMA_ERR_CUDA, "cudaMalloc (gather buffer)");
+  }
+  ncclResult_t r = g_nccl.groupStart();
+  for (uint32_t i = 0; i < n_ctx && r == ncclSuccess; ++i)
+    r = g_nccl.allGather(ctxs[i]->dumpBuf.p, ctxs[i]->gatherBuf.p, stride, ncclUint8, comms[i], ctxs[i]->sc);
+  ncclResult_t r2 = g_nccl.groupEnd();
+  if (r == ncclSuccess) r = r2;
+  if (r != ncclSuccess) return ctx->fail(MMA_ERR_CUDA, std::string("ncclAllGather: ") + g_nccl.errorString(r));
+  // 3. every GPU adds the dumps into its own (cleared) table: afterwards mma_finish_sample gives the merged result on any of them
+  for (uint32_t i = 0; i < n_ctx; ++i) {
+    mma_ctx *c = ctxs[i];
+    cudaSetDevice(c->device);
+    int rc = importTables(c, c->samples[sample], c->gatherBuf.p, n_ctx, stride, (u32)maxRows);
+    if (rc) { if (c != ctx) ctx->fail(rc, c->error); return rc; }
+  }
   return MMA_OK;
 }
 

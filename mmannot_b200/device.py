@@ -21,6 +21,7 @@ EXPORTS = [
     "mma_create", "mma_destroy", "mma_last_error", "mma_load_features", "mma_alloc_pinned", "mma_free_pinned",
     "mma_submit_hits", "mma_submit_hits_device", "mma_finish_sample", "mma_reset_sample", "mma_dense_counts",
     "mma_sync", "mma_stream", "mma_timing_enable", "mma_timing_reset", "mma_timing_get", "mma_index_bytes", "mma_version", "mma_readback_bytes", "mma_dominant_kernel", "mma_index_segments", "mma_annotate_hits", "mma_annotate_intervals", "mma_pack_hits", "mma_submit_hits_packed", "mma_device_count", "mma_warmup", "mma_export_bytes", "mma_export_table", "mma_import_tables",
+    "mma_export_rows", "mma_export_head_bytes", "mma_import_tables_strided", "mma_allreduce", "mma_batch_kernel",
 ]
 
 
@@ -121,6 +122,13 @@ def lib():
         L.mma_export_bytes.restype = C.c_uint64
         L.mma_export_table.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p]
         L.mma_import_tables.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32]
+        L.mma_batch_kernel.argtypes = [C.c_void_p]
+        L.mma_batch_kernel.restype = C.c_char_p
+        L.mma_export_rows.argtypes = [C.c_void_p]
+        L.mma_export_rows.restype = C.c_uint64
+        L.mma_export_head_bytes.restype = C.c_uint64
+        L.mma_import_tables_strided.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint64, C.c_uint64]
+        L.mma_allreduce.argtypes = [C.POINTER(C.c_void_p), C.c_uint32, C.c_uint32]
         L.mma_annotate_intervals.argtypes = [C.c_void_p, C.POINTER(HitBatch), C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]
         _lib = L
     return _lib
@@ -328,6 +336,12 @@ class Annotator:
         """End-of-file flush, then the compacted table + counters into device memory (mma_export_bytes bytes); asynchronous."""
         self._check(lib().mma_export_table(self._h, sample, dev_ptr))
 
+    def export_rows(self):
+        return int(lib().mma_export_rows(self._h))
+
+    def import_tables_strided(self, sample, dev_ptr, n_tables, stride_bytes, rows_cap):
+        self._check(lib().mma_import_tables_strided(self._h, sample, C.c_void_p(dev_ptr), n_tables, stride_bytes, rows_cap))
+
     def import_tables(self, sample, dev_ptr, n_tables):
         """Replace the sample's table and counters by the sum of n_tables exported buffers laid out back to back."""
         self._check(lib().mma_import_tables(self._h, sample, dev_ptr, n_tables))
@@ -363,7 +377,8 @@ class Annotator:
         return int(lib().mma_readback_bytes(self._h))
 
     def dominant_kernel(self):
-        return lib().mma_dominant_kernel().decode()
+        """The batch kernel this context launches (k_batch_lean / k_batch_fast / k_batch)."""
+        return lib().mma_batch_kernel(self._h).decode() or lib().mma_dominant_kernel().decode()
 
     def close(self):
         if getattr(self, "_h", None):
@@ -375,6 +390,14 @@ class Annotator:
             self.close()
         except Exception:
             pass
+
+
+def allreduce(annotators, sample=0):
+    """mma_allreduce over the contexts of this process (one per GPU): afterwards finish() of any of them is the merged result."""
+    arr = (C.c_void_p * len(annotators))(*[a._h for a in annotators])
+    rc = lib().mma_allreduce(arr, len(annotators), sample)
+    if rc != 0:
+        raise MmaError(rc, lib().mma_last_error(annotators[0]._h).decode())
 
 
 def sort_rows(rows):

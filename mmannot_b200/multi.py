@@ -36,19 +36,35 @@ def merge_on_device(ann, sample, device, group=None):
     import torch
     import torch.distributed as dist
 
+    from .device import MmaError, lib
+
     world = dist.get_world_size(group)
     nbytes = ann.export_bytes()
+    head = int(lib().mma_export_head_bytes())
+    full_cap = (nbytes - head) // 16
     cache = getattr(ann, "_merge_buffers", None)
     if cache is None or cache[0].numel() != nbytes or cache[1].numel() != world * nbytes:
         cache = (torch.empty(nbytes, dtype=torch.uint8, device=device), torch.empty(world * nbytes, dtype=torch.uint8, device=device))
         ann._merge_buffers = cache
     mine, gathered = cache
     stream = torch.cuda.ExternalStream(ann.stream_ptr(), device=device)
+    # only the live rows cross NVLink: every rank sends `cap` rows (a few thousand are in use; the table capacity is 2^16 and
+    # up).  A rank holding more makes the import flag an overflow on EVERY rank (each one sees every dump's row count), and all
+    # of them repeat the exchange once at full size from the dump they still hold.
+    cap = min(full_cap, getattr(ann, "_merge_cap", 8192))
     with torch.cuda.stream(stream):  # the library's own compute stream: export -> all-gather -> import stay ordered on it
         ann.export_table(sample, mine.data_ptr())
-        dist.all_gather_into_tensor(gathered, mine, group=group)
-        ann.import_tables(sample, gathered.data_ptr(), world)
-    return ann.finish_arrays(sample, sort=False)
+        while True:
+            stride = (head + 16 * cap + 15) & ~15
+            dist.all_gather_into_tensor(gathered[:world * stride], mine[:stride], group=group)
+            ann.import_tables_strided(sample, gathered.data_ptr(), world, stride, cap)
+            try:
+                return ann.finish_arrays(sample, sort=False)
+            except MmaError as e:
+                if e.code != -4 or cap >= full_cap:
+                    raise
+                cap = full_cap
+                ann._merge_cap = full_cap
 
 
 def merge_arrays(stats, rows, device, group=None, capacity=4096):

@@ -63,4 +63,4 @@ def test_no_cpu_fallback_without_a_device():
 def test_version_string():
     from mmannot_b200 import device
     assert b"sm_100a" in device.lib().mma_version()
-    assert device.lib().mma_dominant_kernel() == b"k_batch_fast"
+    assert device.lib().mma_dominant_kernel() in (b"k_batch_lean", b"k_batch_fast")
