@@ -75,6 +75,7 @@ struct Sample {
   uint64_t knownCount = 0, knownCum = 0;
   bool touched = false;
   bool openMaybeUsed = false;  // the open-key set may hold keys (unknown until the control block is read back)
+  bool deferAll = false;       // this sample's multi-mapping records all go to the deferred list (k_batch_lean RUNS = 2); sticky until reset
   // results
   std::vector<uint64_t> rowMask, rowCount;
   std::vector<uint32_t> rowNh;
@@ -114,6 +115,8 @@ struct mma_ctx {
   u32 maxGrid = 0;           // MMANNOT_B200_MAX_GRID=n: cap on k_batch blocks, so that small test inputs still give every warp a multi-tile chunk (testing only)
   size_t randDrawsUsed = 0;  // -y random: rand() draws consumed by the samples finished so far
   int forceGroups = -1;      // MMANNOT_B200_GROUPS=0/1: pin the variant (testing only)
+  bool preferDefer = false;  // the last sample / batch left most multi-mapping reads unfinished: start the next sample in DEFER mode
+  int forceDefer = -1;       // MMANNOT_B200_DEFER=0/1: pin it (testing only)
   bool useGroups = false;    // k_batch_fast variant for runs of k x NH records, chosen from the walk counters of earlier batches
   int carveout = -1;         // MMANNOT_B200_CARVEOUT=percent: shared-memory carveout of k_batch_lean (tuning only)
   bool legacyBatch = false;  // MMANNOT_B200_LEGACY_BATCH=1: A/B runs of the general k_batch against k_batch_fast (tuning only)
@@ -217,6 +220,9 @@ int ensureDeferred(mma_ctx *ctx, Sample &s, uint64_t n) {
         if (walks * 32 > hitsSoFar) ctx->useGroups = true;
         else if (walks * 256 < hitsSoFar) ctx->useGroups = false;
       }
+      // many deferred records per hit: the records of a read are not adjacent (coordinate-sorted file) -- stop running the
+      // countdown in the batch kernel and defer every multi-mapping record of the rest of the sample
+      if (ctx->forceDefer < 0 && !s.deferAll && (uint64_t)s.countRing[slot] * 8 > hitsSoFar) { s.deferAll = true; ctx->preferDefer = true; }
       break;
     }
   }
@@ -232,7 +238,7 @@ int ensureDeferred(mma_ctx *ctx, Sample &s, uint64_t n) {
     if (actual + n <= s.slowCap) return MMA_OK;
   }
   uint64_t want = std::max<uint64_t>(std::max<uint64_t>(2ull * ctx->params.max_batch_hits, 1u << 16), 2 * (actual + n));
-  if (want > 0xFFFFFFF0ull) return ctx->fail(MMA_ERR_CAPACITY, "deferred read list would exceed 2^32 records");
+  if (want > 0x7FFFFFF0ull) return ctx->fail(MMA_ERR_CAPACITY, "deferred read list would exceed 2^31 records");  // (the radix sort takes int counts)
   u32 newCap = (u32)want;
   DevBuf nk, no, nm, nn;
   CK(nk.ensure((size_t)newCap * 8)); CK(no.ensure((size_t)newCap * 8)); CK(nm.ensure((size_t)newCap * 8)); CK(nn.ensure((size_t)newCap * 4));
@@ -295,22 +301,22 @@ void launchBatchKernels(mma_ctx *ctx, Sample &s, const HitView &hAll) {
   if constexpr (useFast) if (!ctx->legacyBatch && ctx->fast.nChr <= CHR_SMEM) {
     // runs of k x NH records (paired-end data): the GROUPS variant once a batch has shown many of them (see afterBatch)
     const bool groups = STRAT == 0 && ctx->useGroups;
+    const bool defer = STRAT == 0 && s.deferAll;
     if (ctx->fast.ent && h.vec) {  // bin entries: the hit arrays go through the TMA ring (needs 16-byte aligned arrays)
       launched = true;
       u32 grid = std::max<u32>(1u, std::min<u32>((nWT + LEAN_WARPS - 1) / LEAN_WARPS, (u32)ctx->nSM * MMA_LEAN_BLOCKS_PER_SM));
       if (ctx->maxGrid) grid = std::min(grid, ctx->maxGrid);
       const size_t smem = leanSmemBytes<STRAT != 3>(ctx->fast.nDict, ctx->fast.nChr, r.nElements);
-      auto kPlain = k_batch_lean<MODE, STRAT, false>;
-      auto kGroups = k_batch_lean<MODE, STRAT, (STRAT == 0)>;
-      cudaFuncSetAttribute(groups ? kGroups : kPlain, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);  // (per device: cheap enough per launch)
+      auto kernel = defer ? k_batch_lean<MODE, STRAT, (STRAT == 0 ? 2 : 0)> : groups ? k_batch_lean<MODE, STRAT, (STRAT == 0 ? 1 : 0)> : k_batch_lean<MODE, STRAT, 0>;
+      cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);  // (per device: cheap enough per launch)
       {  // shared memory for the blocks one SM can hold, the rest of the 228 KB stays L1 (the bin entries of neighbouring hits hit there)
         const size_t perSM = (size_t)MMA_LEAN_BLOCKS_PER_SM * (smem + 1024);
         int pct = (int)std::min<size_t>(100, (perSM * 100 + 228 * 1024 - 1) / (228 * 1024));
         if (ctx->carveout >= 0) pct = ctx->carveout;
-        cudaFuncSetAttribute(groups ? kGroups : kPlain, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+        cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
       }
       mma_ctx::Timed t(ctx, TC_BATCH);
-      (groups ? kGroups : kPlain)<<<grid, LEAN_THREADS, smem, ctx->sc>>>(ctx->index, ctx->fast, h, r, table, s.ctl, slow, open);
+      kernel<<<grid, LEAN_THREADS, smem, ctx->sc>>>(ctx->index, ctx->fast, h, r, table, s.ctl, slow, open);
     } else if (ctx->fast.bm) {
       launched = true;
       u32 grid = std::max<u32>(1u, std::min<u32>((nWT + FAST_WARPS - 1) / FAST_WARPS, (u32)ctx->nSM * MMA_FAST_BLOCKS_PER_SM));
@@ -461,6 +467,7 @@ int mma_create(mma_ctx **out, const mma_params *p) {
   }
   { const char *lg = getenv("MMANNOT_B200_LEGACY_BATCH"); ctx->legacyBatch = lg && lg[0] == '1';
     const char *fg = getenv("MMANNOT_B200_GROUPS"); if (fg && (fg[0] == '0' || fg[0] == '1')) { ctx->forceGroups = fg[0] - '0'; ctx->useGroups = fg[0] == '1'; }
+    const char *fd = getenv("MMANNOT_B200_DEFER"); if (fd && (fd[0] == '0' || fd[0] == '1')) { ctx->forceDefer = fd[0] - '0'; ctx->preferDefer = fd[0] == '1'; }
     const char *cv = getenv("MMANNOT_B200_CARVEOUT"); if (cv) ctx->carveout = atoi(cv);
     const char *mg = getenv("MMANNOT_B200_MAX_GRID"); ctx->maxGrid = mg ? (u32)std::max(0, atoi(mg)) : 0u; }
   ctx->samples.resize(p->n_samples);
@@ -779,6 +786,7 @@ static int submitCommon(mma_ctx *ctx, uint32_t sample, const mma_hit_batch *b, b
     h.start = g.start.as<u32>(); h.end = g.end.as<u32>(); h.meta = g.meta.as<u32>(); h.nh = g.nh.as<u32>(); h.key = g.key.as<u64>();
   }
   h.vec = ((((uintptr_t)h.start | (uintptr_t)h.end | (uintptr_t)h.meta | (uintptr_t)h.nh | (uintptr_t)h.key) & 15u) == 0) ? 1u : 0u;
+  if (!s.touched) s.deferAll = ctx->preferDefer && ctx->rules.strategy == MMA_STRATEGY_DEFAULT;  // (first batch of the sample)
   if ((rc = launchBatch(ctx, s, h))) return rc;
   CK(cudaEventRecord(g.done, ctx->sc));
   if ((rc = afterBatch(ctx, s, n))) return rc;
@@ -867,6 +875,7 @@ int mma_submit_hits_packed(mma_ctx *ctx, uint32_t sample, const mma_packed_batch
   h.n = (u32)n;
   h.start = g.start.as<u32>(); h.end = g.end.as<u32>(); h.meta = g.meta.as<u32>(); h.nh = g.nh.as<u32>(); h.key = g.key.as<u64>();
   h.vec = 1u;
+  if (!s.touched) s.deferAll = ctx->preferDefer && ctx->rules.strategy == MMA_STRATEGY_DEFAULT;  // (first batch of the sample)
   if ((rc = launchBatch(ctx, s, h))) return rc;
   CK(cudaEventRecord(g.done, ctx->sc));
   if ((rc = afterBatch(ctx, s, n))) return rc;
@@ -1007,7 +1016,7 @@ int mma_reset_sample(mma_ctx *ctx, uint32_t sample) {
     ctx->launches += 2;
   }
   s.openMaybeUsed = false;  // (stream-ordered: the next batch kernels of this sample run after these fills)
-  s.cumHits = 0; s.knownCount = 0; s.knownCum = 0; s.seq = 0; s.touched = false;
+  s.cumHits = 0; s.knownCount = 0; s.knownCum = 0; s.seq = 0; s.touched = false; s.deferAll = false;
   for (int i = 0; i < 4; ++i) s.ringUsed[i] = false;
   return MMA_OK;
 }
@@ -1032,6 +1041,30 @@ static int finishDeferred(mma_ctx *ctx, Sample &s, u32 nSlow) {
   CKF(tmp.ensure(tmpBytes));
   mma_ctx::Timed t(ctx, TC_FINISH);
   const u32 g = gridFor(nSlow, 256);
+  if (r.strategy == MMA_STRATEGY_DEFAULT) {
+    // ONE radix sort, by read key: the records of a name become adjacent; each name's few records are then taken in file order
+    // by selection (k_slow_default_byord).  Names with hundreds of records would make that quadratic: then the list is sorted
+    // by (key, ordinal) below like for -y random.
+    DevBuf maxLen;
+    CKF(maxLen.ensure(4));
+    CKF(cudaMemsetAsync(maxLen.p, 0, 4, st));
+    k_iota<<<g, 256, 0, st>>>(permA.as<u32>(), nSlow);
+    CKF(cudaMemcpyAsync(keyA.p, slow.key, (size_t)nSlow * 8, cudaMemcpyDeviceToDevice, st));
+    CKF(cub::DeviceRadixSort::SortPairs(tmp.p, tmpBytes, keyA.as<u64>(), keyB.as<u64>(), permA.as<u32>(), permB.as<u32>(), (int)nSlow, 0, 64, st));
+    k_slow_maxlen<<<g, 256, 0, st>>>(permB.as<u32>(), nSlow, slow, maxLen.as<u32>());
+    u32 hMax = 0;
+    CKF(cudaMemcpyAsync(&hMax, maxLen.p, 4, cudaMemcpyDeviceToHost, st));
+    CKF(cudaStreamSynchronize(st));
+    maxLen.release();
+    ctx->launches += 2;
+    if (hMax <= 512) {
+      k_slow_default_byord<<<g, 256, 0, st>>>(permB.as<u32>(), nSlow, slow, r, table, s.ctl);
+      ctx->launches++;
+      CKF(cudaStreamSynchronize(st));
+      cleanup();
+      return MMA_OK;
+    }
+  }
   k_iota<<<g, 256, 0, st>>>(permA.as<u32>(), nSlow);
   CKF(cudaMemcpyAsync(keyA.p, slow.ord, (size_t)nSlow * 8, cudaMemcpyDeviceToDevice, st));
   CKF(cub::DeviceRadixSort::SortPairs(tmp.p, tmpBytes, keyA.as<u64>(), keyB.as<u64>(), permA.as<u32>(), permB.as<u32>(), (int)nSlow, 0, 64, st));
@@ -1129,6 +1162,14 @@ static int flushAndDump(mma_ctx *ctx, Sample &s, bool rows, SampleCtl &hc) {
   hc = hHead->ctl;
   if (hc.overflow) return ctx->fail(MMA_ERR_CAPACITY, "a device table overflowed (combination table, deferred list or NH range under -y ratio)");
   s.openMaybeUsed = hc.openCount != 0;
+  {  // what this sample says about the next one on this context (a sample of one batch never sees its own counters in time)
+    const uint64_t hits = std::max<uint64_t>(hc.stats[ST_HITS], 1);
+    if (ctx->forceGroups < 0 && ctx->rules.strategy == MMA_STRATEGY_DEFAULT && !s.deferAll) {
+      if ((uint64_t)hc.walkCount * 32 > hits) ctx->useGroups = true;
+      else if ((uint64_t)hc.walkCount * 256 < hits) ctx->useGroups = false;
+    }
+    if (ctx->forceDefer < 0 && ctx->rules.strategy == MMA_STRATEGY_DEFAULT && !s.deferAll && (uint64_t)hc.slowCount * 8 > hits) ctx->preferDefer = true;
+  }
   if (hc.slowCount > 0) {
     if ((rc = finishDeferred(ctx, s, hc.slowCount))) return rc;
     // the deferred records are consumed: a later finish must not count them twice
@@ -1137,6 +1178,8 @@ static int flushAndDump(mma_ctx *ctx, Sample &s, bool rows, SampleCtl &hc) {
     hc = hHead->ctl;
     if (hc.overflow) return ctx->fail(MMA_ERR_CAPACITY, "the combination table overflowed");
     s.knownCount = 0; s.knownCum = s.cumHits;
+    // deferred for nothing: (nearly) every name's records were adjacent in the file -- the next sample runs the countdown again
+    if (ctx->forceDefer < 0 && s.deferAll && (uint64_t)hc.deferContig * 10 >= (uint64_t)hc.deferSegs * 9) ctx->preferDefer = false;
   }
   return MMA_OK;
 }

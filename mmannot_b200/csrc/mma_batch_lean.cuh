@@ -149,12 +149,19 @@ __device__ __forceinline__ u32 recordAnnotate(const FastView &fx, const IndexVie
   return a;
 }
 
-// GROUPS: runs of k x NH records (paired-end data) are resolved in parallel as k reads (see k_batch_fast)
-template <int MODE, int STRAT, bool GROUPS>
+// RUNS: how the records of multi-mapping reads are resolved (-y default)
+//   0  a run of n records carrying NH = n is one read, closed by the scan
+//   1  GROUPS: runs of k x NH records (paired-end data) are resolved in parallel as k reads (see k_batch_fast)
+//   2  DEFER: input in which the records of a read are not adjacent (coordinate-sorted files).  No countdown here at all: every
+//      record with NH > 1 goes to the deferred list with its element set (one reservation per warp tile), and the end-of-sample
+//      pass groups them by read key.  Chosen by the host for a whole sample (sticky) when an earlier batch or sample left most of
+//      its multi-mapping reads unfinished.
+template <int MODE, int STRAT, int RUNS>
 __global__ void __maxnreg__(MMA_LEAN_MAXREG)
 k_batch_lean(const __grid_constant__ IndexView ix, const __grid_constant__ FastView fx, const __grid_constant__ HitView h, const __grid_constant__ Rules r,
              const __grid_constant__ TableView table, SampleCtl *ctl, const __grid_constant__ SlowView slow, const __grid_constant__ KeySetView open) {
   constexpr bool HIST = (STRAT != 3);
+  constexpr bool GROUPS = RUNS == 1, DEFER = (RUNS == 2) && STRAT == 0;
   constexpr u32 FULL = 0xffffffffu;
   extern __shared__ __align__(128) unsigned char leanSmemRaw[];
   LeanSmem<HIST> &sm = *reinterpret_cast<LeanSmem<HIST> *>(leanSmemRaw);
@@ -237,7 +244,9 @@ k_batch_lean(const __grid_constant__ IndexView ix, const __grid_constant__ FastV
   // lane 0: does the chunk's first record start a run?  (The state carried into the batch counts as the record before it.)
   bool headFirst = true;
   const Carry *carryIn = nullptr;
-  if (STRAT == 0 && lane == 0 && t0 < t1) {
+  if (DEFER) {
+    if (lane == 0 && t0 == 0 && t0 < t1 && ctl->carry[seq & 1].valid) carryIn = &ctl->carry[seq & 1];
+  } else if (STRAT == 0 && lane == 0 && t0 < t1) {
     const u64 first = normKey(__ldg(&h.key[(size_t)t0 * WT_HITS]));
     if (t0 == 0) {
       const Carry &c = ctl->carry[seq & 1];
@@ -259,7 +268,7 @@ k_batch_lean(const __grid_constant__ IndexView ix, const __grid_constant__ FastV
     // ---- run starts
     u32 hbits = 0, F = 0;
     u64 nextKey = KEY_EMPTY;
-    if (STRAT == 0) {
+    if (STRAT == 0 && !DEFER) {
       u64 key[4];
       const uint4 k0 = lds128(st + 2048 + lane * 16), k1 = lds128(st + 2048 + lane * 16 + 16);
       key[0] = ((u64)k0.y << 32) | k0.x; key[1] = ((u64)k0.w << 32) | k0.z; key[2] = ((u64)k1.y << 32) | k1.x; key[3] = ((u64)k1.w << 32) | k1.z;
@@ -358,6 +367,38 @@ k_batch_lean(const __grid_constant__ IndexView ix, const __grid_constant__ FastV
           pMissResc += a >> 31;
         }
     }
+    if (DEFER) {
+      // every record with NH > 1 to the deferred list: {key, ordinal, element set, NH}
+      if (it == 0 && carryIn) {  // (a read carried out of a batch that still ran the countdown: it joins the list like its later records)
+        --w.nReads;
+        slowAppend(slow, ctl, carryIn->key, carryIn->ord, carryIn->gm, carryIn->remaining + 1);
+      }
+      const u32 mb = (nh[0] > 1 ? 1u : 0u) | (nh[1] > 1 ? 2u : 0u) | (nh[2] > 1 ? 4u : 0u) | (nh[3] > 1 ? 8u : 0u);
+      u32 mine4 = __popc(mb), incl = mine4;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) { const u32 o = __shfl_up_sync(FULL, incl, d); if (lane >= (u32)d) incl += o; }
+      const u32 total = __shfl_sync(FULL, incl, 31);
+      if (total) {
+        u32 at0 = 0;
+        if (lane == 0) at0 = atomicAdd(&ctl->slowCount, total);
+        at0 = __shfl_sync(FULL, at0, 0);
+        if (at0 + total > slow.cap) {
+          if (lane == 0) atomicExch(&ctl->overflow, 1u);
+        } else if (mb) {
+          u32 at = at0 + incl - mine4;
+          const u64 ord0 = ctl->ordBase + base;
+          const uint4 k0 = lds128(st + 2048 + lane * 16), k1 = lds128(st + 2048 + lane * 16 + 16);
+          const u64 kk[4] = {((u64)k0.y << 32) | k0.x, ((u64)k0.w << 32) | k0.z, ((u64)k1.y << 32) | k1.x, ((u64)k1.w << 32) | k1.z};
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if ((mb >> j) & 1u) {
+              slow.key[at] = fullTile ? normKey(kk[j]) : kk[j];  // (the partial tile was normalised when it was staged)
+              slow.ord[at] = ord0 + j; slow.mask[at] = m[j]; slow.nh[at] = nh[j];
+              ++at;
+            }
+        }
+      }
+    }
     __syncwarp();
     // the stage is free: bring in the tile two tiles ahead
     if (t + 2 < t1) stage(t + 2, s);
@@ -387,7 +428,7 @@ k_batch_lean(const __grid_constant__ IndexView ix, const __grid_constant__ FastV
     u32 inc = 0, lastHeadPos = 0, F2 = 0;
     bool serialTile = false;
     u32 tileEndsRun = 1;  // the record after the tile's last one starts another run (or the batch ends there)
-    if (STRAT == 0) {
+    if (STRAT == 0 && !DEFER) {
       // first key of the next tile: from the next stage of the ring, or (last tile of the chunk) from global memory
       if (t + 1 < t1) {
         const bool nextFull = (t + 2) * WT_HITS <= h.n;
@@ -585,7 +626,7 @@ k_batch_lean(const __grid_constant__ IndexView ix, const __grid_constant__ FastV
         }
       }
     }
-    if (STRAT == 0) {
+    if (STRAT == 0 && !DEFER) {
       pWalks += nWalk;
 #pragma unroll 1
       for (u32 q = 0; q < nWalk; ++q) {
@@ -623,7 +664,7 @@ k_batch_lean(const __grid_constant__ IndexView ix, const __grid_constant__ FastV
   // ---- a run open at the end of the chunk continues in another warp's chunk: its remaining reads (GROUPS: from the group that is
   //      open there, or starts there) are finished by the serial walk.  (A run ending exactly at the chunk's last record was
   //      closed above, like the last run of the batch.)
-  if (STRAT == 0 && cValid && cCont && t1 > t0 && lane == 0) {
+  if (STRAT == 0 && !DEFER && cValid && cCont && t1 > t0 && lane == 0) {
     const u32 next = t1 * WT_HITS;
     const u64 k = normKey(h.key[next]);
     if (GROUPS) {
@@ -654,7 +695,7 @@ k_batch_lean(const __grid_constant__ IndexView ix, const __grid_constant__ FastV
   cMulti = __reduce_add_sync(FULL, cMulti); cReads = __reduce_add_sync(FULL, cReads);
   cRescued = __reduce_add_sync(FULL, cRescued); cMiss = __reduce_add_sync(FULL, cMiss);
   cOwn1 = __reduce_add_sync(FULL, cOwn1);
-  if (STRAT == 0 && !forceWalk) {
+  if (STRAT == 0 && !forceWalk && !DEFER) {
     pWalks = __reduce_add_sync(FULL, pWalks);
     if (lane == 0 && pWalks) atomicAdd(&ctl->walkCount, pWalks);
   }

@@ -141,6 +141,8 @@ struct SampleCtl {
   u32 closeCount;    // blocks of k_batch_close that are done
   u32 fastMiss;      // hits the segment table could not answer (diagnostics)
   u32 walkCount;     // k_batch_fast: runs that needed the serial walker, or (GROUPS variant) groups beyond the first of a run
+  u32 deferSegs;     // deferred pass: read names it resolved ...
+  u32 deferContig;   // ... of which all records were adjacent in the file (name-grouped input that did not need deferring)
 };
 
 struct SlowView {  // deferred records: resolved after a (key, ordinal) sort at end of sample
@@ -1126,6 +1128,77 @@ __global__ void k_slow_default(const u32 *__restrict__ perm, u32 n, SlowView s, 
   }
   if (nReads) atomicAdd(&ctl->stats[ST_READS], (u64)nReads);
   if (nRescued) atomicAdd(&ctl->stats[ST_RESCUED], (u64)nRescued);
+}
+
+// The same for a list sorted by key ONLY (one radix sort instead of two): the records of a name are taken in ordinal order by
+// repeated selection inside the name's segment (a name has at most a few hundred records; k_slow_maxlen tells the host when that
+// does not hold and the fully sorted route has to be taken).
+__global__ void k_slow_maxlen(const u32 *__restrict__ perm, u32 n, SlowView s, u32 *maxLen) {
+  const u32 p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n) return;
+  const u64 k = s.key[perm[p]];
+  if (p > 0 && s.key[perm[p - 1]] == k) return;
+  u32 q = p + 1;
+  while (q < n && s.key[perm[q]] == k) ++q;
+  if (q - p > 64) atomicMax(maxLen, q - p);
+}
+__global__ void k_slow_default_byord(const u32 *__restrict__ perm, u32 n, SlowView s, Rules r, TableView table, SampleCtl *ctl) {
+  const u32 p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n) return;
+  const u64 k = s.key[perm[p]];
+  if (p > 0 && s.key[perm[p - 1]] == k) return;
+  u32 q = p + 1;
+  u64 lo = s.ord[perm[p]], hi = lo;
+  for (; q < n; ++q) {
+    const u32 id = perm[q];
+    if (s.key[id] != k) break;
+    const u64 o = s.ord[id];
+    lo = min(lo, o); hi = max(hi, o);
+  }
+  const u32 len = q - p;
+  bool isOpen = false;
+  u32 remaining = 0, nReads = 0, nRescued = 0;
+  u64 gm = 0, firstOrd = 0, last = 0;
+  auto rescued = [&](u64 g, u64 o0, u64 o1) {  // rescue() over the records of the read: ordinals o0..o1 of this name
+    u32 cnt = 0;
+    for (u32 z = p; z < q; ++z) { const u32 id = perm[z]; const u64 o = s.ord[id]; if (o >= o0 && o <= o1) cnt += __popcll(s.mask[id]); }
+    return rescueFromCounts(r, g, cnt, [&](u64 bit) {
+      u32 c = 0;
+      for (u32 z = p; z < q; ++z) { const u32 id = perm[z]; const u64 o = s.ord[id]; if (o >= o0 && o <= o1 && (s.mask[id] & bit)) ++c; }
+      return c;
+    });
+  };
+  for (u32 step = 0; step < len; ++step) {
+    // the record with the smallest ordinal not taken yet (ordinals are distinct)
+    u32 best = 0;
+    u64 bestOrd = ~0ull;
+    for (u32 z = p; z < q; ++z) {
+      const u32 id = perm[z];
+      const u64 o = s.ord[id];
+      if ((step == 0 || o > last) && o < bestOrd) { bestOrd = o; best = id; }
+    }
+    last = bestOrd;
+    const u64 mq = s.mask[best];
+    if (!isOpen) { isOpen = true; remaining = s.nh[best] - 1; gm = mq; firstOrd = bestOrd; ++nReads; }
+    else { --remaining; gm |= mq; }
+    if (remaining == 0) {
+      if (gm != 0) {
+        if (r.rescue) gm = rescued(gm, firstOrd, bestOrd);
+        tableAdd(table, gm, 1);
+        if (__popcll(gm) == 1) ++nRescued;
+      }
+      isOpen = false;
+    }
+  }
+  if (isOpen && gm != 0) {  // flush at end of file
+    if (r.rescue) gm = rescued(gm, firstOrd, last);
+    tableAdd(table, gm, 1);
+    if (__popcll(gm) == 1) ++nRescued;
+  }
+  if (nReads) atomicAdd(&ctl->stats[ST_READS], (u64)nReads);
+  if (nRescued) atomicAdd(&ctl->stats[ST_RESCUED], (u64)nRescued);
+  atomicAdd(&ctl->deferSegs, 1u);
+  if (hi - lo + 1 == (u64)len) atomicAdd(&ctl->deferContig, 1u);
 }
 
 // random (mm:1706-1726): segment heads publish the ordinal of the name's first annotated hit ...

@@ -318,3 +318,50 @@ def test_runs_of_k_times_nh_records(seed, groups, monkeypatch):
     ref = oracle_run(et, feats, hits)
     for batch in (1 << 21, 20011):
         check(device_run(et, feats, hits, max_batch=batch), ref)
+
+
+@pytest.mark.parametrize("defer", ["0", "1"])
+@pytest.mark.parametrize("seed", range(4))
+def test_defer_mode(seed, defer, monkeypatch):
+    """k_batch_lean's DEFER mode (every record with NH > 1 goes to the deferred list; one sort by read key; the records of a
+    name taken in file order by selection) pinned on and off, on name-grouped, messy and shuffled input, with and without
+    rescue(), batches cut anywhere, natural and capped grids: the table must not depend on the mode."""
+    monkeypatch.setenv("MMANNOT_B200_DEFER", defer)
+    if seed == 3:
+        monkeypatch.setenv("MMANNOT_B200_MAX_GRID", "2")
+    rng = np.random.default_rng(6100 + seed)
+    et = fuzz.make_elements(rng)
+    feats = fuzz.make_features(rng, et, n_feat=400)
+    hits = fuzz.make_hits(rng, feats, n_reads=25000, max_nh=(3, 12, 60, 8)[seed], messy=(0.0, 0.2, 0.05, 0.3)[seed])
+    if seed in (1, 2):
+        hits = fuzz.shuffle_hits(rng, hits, block=int((1, 64)[seed - 1]))
+    ref = oracle_run(et, feats, hits)
+    for batch in (1 << 21, 10007, 129):
+        check(device_run(et, feats, hits, max_batch=batch), ref)
+    ref = oracle_run(et, feats, hits, rescue_threshold=0.5, read_stats=True)
+    check(device_run(et, feats, hits, rescue_threshold=0.5, read_stats=True, max_batch=30011), ref)
+
+
+def test_defer_mode_is_found_without_help():
+    """Coordinate-sorted input with a single batch per sample: the first sample's counters switch the context to DEFER mode for
+    the next one (and name-grouped input switches it back); results are those of the oracle every time."""
+    from mmannot_b200 import device
+    rng = np.random.default_rng(6200)
+    et = fuzz.make_elements(rng)
+    feats = fuzz.make_features(rng, et, n_feat=400)
+    grouped = fuzz.make_hits(rng, feats, n_reads=30000, max_nh=6, messy=0.0)
+    order = np.lexsort((grouped.start, grouped.meta & 0xFFFFFF))
+    from mmannot_b200 import host
+    sorted_hits = host.Hits(*[np.ascontiguousarray(getattr(grouped, k)[order]) for k in ("start", "end", "meta", "nh", "read_key")])
+    a = device.Annotator(et, max_batch_hits=1 << 21)
+    try:
+        a.load_features(feats)
+        for hits in (sorted_hits, sorted_hits, grouped, grouped, sorted_hits):
+            ref = oracle_run(et, feats, hits)
+            a.reset(0)
+            a.submit(0, hits)
+            res = a.finish(0)
+            res["values"] = device.values_by_mask(res["rows"])
+            check(res, ref)
+    finally:
+        a.close()
