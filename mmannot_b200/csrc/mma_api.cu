@@ -1207,6 +1207,7 @@ static int importTables(mma_ctx *ctx, Sample &s, const void *dev_src, uint32_t n
   const size_t tb = (size_t)ctx->tableCap * sizeof(u64);
   CK(cudaMemsetAsync(s.tableKeys.p, 0, tb, ctx->sc)); CK(cudaMemsetAsync(s.tableVals.p, 0, tb, ctx->sc));
   CK(cudaMemsetAsync(s.ctl->stats, 0, sizeof(u64) * ST_N, ctx->sc));
+  CK(cudaMemsetAsync(&s.ctl->overflow, 0, sizeof(u32), ctx->sc));  // (the dumps bring their own flags; an import cut short is repeated)
   rowsCap = std::max<u32>(rowsCap, ST_N);  // (the first ST_N threads of each dump also add its counters)
   const u64 total = (u64)n_tables * rowsCap;
   k_table_import<<<gridFor(total, 256), 256, 0, ctx->sc>>>(tableView(s.tableKeys, s.tableVals, ctx->tableCap, s.ctl), s.ctl,

@@ -1249,10 +1249,11 @@ __global__ void k_fill_u32(u32 *dst, u32 v, u64 n) {
 
 // end of sample: the non-empty rows of the combination table, compacted (any order), with the control block in front:
 // one small device->host copy instead of the whole table.  out = [SampleCtl | row count | rows {key, count}]
-struct TableDump {
+struct alignas(16) TableDump {  // (the rows behind it are read and written 16 bytes at a time)
   SampleCtl ctl;
   u64 nRows;
 };
+static_assert(sizeof(TableDump) % 16 == 0, "rows follow the head at a 16-byte boundary");
 __global__ void k_table_compact(TableView t, const SampleCtl *ctl, TableDump *head, ulonglong2 *rows, u32 cap) {
   const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i == 0) head->ctl = *ctl;
