@@ -36,6 +36,7 @@ extern "C" {
 #define MMA_ERR_STATE (-3)     /* wrong call sequence */
 #define MMA_ERR_CAPACITY (-4)  /* combination table or staging capacity exceeded */
 #define MMA_ERR_NO_DEVICE (-5) /* no CUDA device: the product path has no CPU fallback */
+#define MMA_ERR_RETRY (-6)     /* an optimistic multi-GPU exchange met a shard with deferred records: see mma_export_table_async */
 
 /* -y (Strategy, mmannot.cpp:50, 2033-2045) */
 #define MMA_STRATEGY_DEFAULT 0
@@ -237,6 +238,15 @@ int mma_import_tables(mma_ctx *ctx, uint32_t sample, const void *dev_src, uint32
 uint64_t mma_export_rows(const mma_ctx *ctx);
 uint64_t mma_export_head_bytes(void);
 int mma_import_tables_strided(mma_ctx *ctx, uint32_t sample, const void *dev_src, uint32_t n_tables, uint64_t stride_bytes, uint64_t rows_cap);
+
+/* mma_export_table without any host synchronisation: flush, compaction and the copy of the head and the first rows_cap rows
+ * (stride_bytes in all, see mma_import_tables_strided) are only ENQUEUED on mma_stream(ctx), so that the exchange and the import
+ * can be queued behind the batch kernels while they still run.  The price: a shard that holds deferred records (input whose
+ * reads are not adjacent) cannot resolve them first; the import then marks the merged sample, mma_finish_sample returns
+ * MMA_ERR_RETRY on every rank, and each rank calls mma_restore_export (its own table and counters back from the dump it still
+ * holds) and repeats the exchange with mma_export_table. */
+int mma_export_table_async(mma_ctx *ctx, uint32_t sample, void *dev_dst, uint64_t stride_bytes, uint64_t rows_cap);
+int mma_restore_export(mma_ctx *ctx, uint32_t sample);
 
 /* The same merge for the contexts of ONE process (one per GPU), done by the library: end-of-file flush of every shard, one
  * ncclAllGather of the live rows over NVLink (single-process clique, ncclCommInitAll, kept for the life of the process), import

@@ -1160,7 +1160,8 @@ static int flushAndDump(mma_ctx *ctx, Sample &s, bool rows, SampleCtl &hc) {
   int rc = dump();
   if (rc) return rc;
   hc = hHead->ctl;
-  if (hc.overflow) return ctx->fail(MMA_ERR_CAPACITY, "a device table overflowed (combination table, deferred list or NH range under -y ratio)");
+  if (hc.overflow & 1u) return ctx->fail(MMA_ERR_CAPACITY, "a device table overflowed (combination table, deferred list or NH range under -y ratio)");
+  if (hc.overflow & 2u) return ctx->fail(MMA_ERR_RETRY, "a shard of the exchange held deferred records: mma_restore_export, then the exchange with mma_export_table");
   s.openMaybeUsed = hc.openCount != 0;
   {  // what this sample says about the next one on this context (a sample of one batch never sees its own counters in time)
     const uint64_t hits = std::max<uint64_t>(hc.stats[ST_HITS], 1);
@@ -1216,6 +1217,41 @@ static int importTables(mma_ctx *ctx, Sample &s, const void *dev_src, uint32_t n
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return ctx->fail(MMA_ERR_CUDA, std::string("kernel launch: ") + cudaGetErrorString(e));
   return MMA_OK;
+}
+
+int mma_export_table_async(mma_ctx *ctx, uint32_t sample, void *dev_dst, uint64_t stride_bytes, uint64_t rows_cap) {
+  if (!ctx) return MMA_ERR_INVALID;
+  if (!dev_dst) return ctx->fail(MMA_ERR_INVALID, "null destination");
+  if (sample >= ctx->samples.size()) return ctx->fail(MMA_ERR_INVALID, "sample index out of range");
+  if ((stride_bytes & 15) || rows_cap == 0 || rows_cap > ctx->tableCap || stride_bytes < sizeof(TableDump) + rows_cap * 16) return ctx->fail(MMA_ERR_INVALID, "bad stride / row capacity");
+  CK(cudaSetDevice(ctx->device));
+  Sample &s = ctx->samples[sample];
+  int rc = initSample(ctx, s);
+  if (rc) return rc;
+  CK(cudaStreamSynchronize(ctx->sh));  // (host-side: the copies of the last batch have been handed to the copy engine)
+  if (ctx->rules.strategy == MMA_STRATEGY_DEFAULT && s.slowCap) {
+    k_flush_carry<<<1, 1, 0, ctx->sc>>>(s.ctl, slowView(s));
+    ctx->launches++;
+  }
+  const size_t headBytes = sizeof(TableDump);
+  if (!ctx->hostTable) CK(cudaHostAlloc(&ctx->hostTable, headBytes + (size_t)ctx->tableCap * 16, cudaHostAllocDefault));
+  CK(ctx->dumpBuf.ensure(headBytes + (size_t)ctx->tableCap * 16));
+  TableDump *dHead = ctx->dumpBuf.as<TableDump>();
+  ulonglong2 *dRows = reinterpret_cast<ulonglong2 *>(ctx->dumpBuf.as<char>() + headBytes);
+  CK(cudaMemsetAsync(&dHead->nRows, 0, sizeof(u64), ctx->sc));
+  k_table_compact<<<gridFor(ctx->tableCap, 256), 256, 0, ctx->sc>>>(tableView(s.tableKeys, s.tableVals, ctx->tableCap, s.ctl), s.ctl, dHead, dRows, ctx->tableCap);
+  ctx->launches++;
+  CK(cudaMemcpyAsync(dev_dst, ctx->dumpBuf.p, (size_t)stride_bytes, cudaMemcpyDeviceToDevice, ctx->sc));
+  return MMA_OK;
+}
+
+int mma_restore_export(mma_ctx *ctx, uint32_t sample) {
+  if (!ctx) return MMA_ERR_INVALID;
+  if (sample >= ctx->samples.size() || !ctx->dumpBuf.p) return ctx->fail(MMA_ERR_STATE, "nothing was exported");
+  CK(cudaSetDevice(ctx->device));
+  Sample &s = ctx->samples[sample];
+  if (!s.ctl) return ctx->fail(MMA_ERR_STATE, "nothing was exported");
+  return importTables(ctx, s, ctx->dumpBuf.p, 1, sizeof(TableDump) + (size_t)ctx->tableCap * 16, ctx->tableCap);
 }
 
 int mma_import_tables(mma_ctx *ctx, uint32_t sample, const void *dev_src, uint32_t n_tables) {

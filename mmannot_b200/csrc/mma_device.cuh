@@ -1273,7 +1273,8 @@ __global__ void k_table_import(TableView t, SampleCtl *ctl, const char *bufs, u3
   const TableDump *head = reinterpret_cast<const TableDump *>(bufs + (size_t)b * stride);
   const ulonglong2 *rows = reinterpret_cast<const ulonglong2 *>(bufs + (size_t)b * stride + sizeof(TableDump));
   if (i < ST_N && head->ctl.stats[i]) atomicAdd(&ctl->stats[i], head->ctl.stats[i]);
-  if (i == 0 && (head->ctl.overflow || head->nRows > cap)) atomicExch(&ctl->overflow, 1u);  // (a dump cut short by the exchange counts as an overflow)
+  if (i == 0 && ((head->ctl.overflow & 1u) || head->nRows > cap)) atomicOr(&ctl->overflow, 1u);  // (a dump cut short by the exchange counts as an overflow)
+  if (i == 0 && head->ctl.slowCount) atomicOr(&ctl->overflow, 2u);  // a shard exported without its deferred records resolved (mma_export_table_async)
   if (i < head->nRows) { const ulonglong2 r = rows[i]; tableAdd(t, r.x, r.y); }
 }
 

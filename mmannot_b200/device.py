@@ -21,7 +21,7 @@ EXPORTS = [
     "mma_create", "mma_destroy", "mma_last_error", "mma_load_features", "mma_alloc_pinned", "mma_free_pinned",
     "mma_submit_hits", "mma_submit_hits_device", "mma_finish_sample", "mma_reset_sample", "mma_dense_counts",
     "mma_sync", "mma_stream", "mma_timing_enable", "mma_timing_reset", "mma_timing_get", "mma_index_bytes", "mma_version", "mma_readback_bytes", "mma_dominant_kernel", "mma_index_segments", "mma_annotate_hits", "mma_annotate_intervals", "mma_pack_hits", "mma_submit_hits_packed", "mma_device_count", "mma_warmup", "mma_export_bytes", "mma_export_table", "mma_import_tables",
-    "mma_export_rows", "mma_export_head_bytes", "mma_import_tables_strided", "mma_allreduce", "mma_batch_kernel",
+    "mma_export_rows", "mma_export_head_bytes", "mma_import_tables_strided", "mma_allreduce", "mma_batch_kernel", "mma_export_table_async", "mma_restore_export",
 ]
 
 
@@ -122,6 +122,8 @@ def lib():
         L.mma_export_bytes.restype = C.c_uint64
         L.mma_export_table.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p]
         L.mma_import_tables.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32]
+        L.mma_export_table_async.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint64, C.c_uint64]
+        L.mma_restore_export.argtypes = [C.c_void_p, C.c_uint32]
         L.mma_batch_kernel.argtypes = [C.c_void_p]
         L.mma_batch_kernel.restype = C.c_char_p
         L.mma_export_rows.argtypes = [C.c_void_p]
@@ -335,6 +337,12 @@ class Annotator:
     def export_table(self, sample, dev_ptr):
         """End-of-file flush, then the compacted table + counters into device memory (mma_export_bytes bytes); asynchronous."""
         self._check(lib().mma_export_table(self._h, sample, dev_ptr))
+
+    def export_table_async(self, sample, dev_ptr, stride_bytes, rows_cap):
+        self._check(lib().mma_export_table_async(self._h, sample, C.c_void_p(dev_ptr), stride_bytes, rows_cap))
+
+    def restore_export(self, sample):
+        self._check(lib().mma_restore_export(self._h, sample))
 
     def export_rows(self):
         return int(lib().mma_export_rows(self._h))

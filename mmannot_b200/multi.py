@@ -53,16 +53,31 @@ def merge_on_device(ann, sample, device, group=None):
     # of them repeat the exchange once at full size from the dump they still hold.
     cap = min(full_cap, getattr(ann, "_merge_cap", 8192))
     with torch.cuda.stream(stream):  # the library's own compute stream: export -> all-gather -> import stay ordered on it
-        ann.export_table(sample, mine.data_ptr())
+        optimistic = not getattr(ann, "_merge_sync", False)
+        need_export = True
         while True:
             stride = (head + 16 * cap + 15) & ~15
+            if need_export and optimistic:
+                # nothing here waits for the GPU: flush, compaction, exchange and import queue up behind the batch kernels
+                ann.export_table_async(sample, mine.data_ptr(), stride, cap)
+            elif need_export:
+                ann.export_table(sample, mine.data_ptr())  # (resolves the shard's deferred records first: synchronises; all rows)
             dist.all_gather_into_tensor(gathered[:world * stride], mine[:stride], group=group)
             ann.import_tables_strided(sample, gathered.data_ptr(), world, stride, cap)
             try:
                 return ann.finish_arrays(sample, sort=False)
             except MmaError as e:
+                if e.code == -6 and optimistic:  # some shard held deferred records: own table back, then the careful route
+                    ann.restore_export(sample)
+                    optimistic, need_export = False, True
+                    ann._merge_sync = True
+                    continue
                 if e.code != -4 or cap >= full_cap:
                     raise
+                # some shard holds more rows than were exchanged: once more at full size
+                if optimistic:
+                    ann.restore_export(sample)
+                need_export = optimistic  # (the careful route already left every row in `mine`)
                 cap = full_cap
                 ann._merge_cap = full_cap
 
