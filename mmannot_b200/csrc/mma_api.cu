@@ -124,6 +124,7 @@ struct mma_ctx {
   u64 *hostTable = nullptr;  // pinned: [TableDump | rows] of the sample being read back
   DevBuf dumpBuf;            // device side of the same
   DevBuf gatherBuf;          // mma_allreduce: the dumps of all the contexts of the group
+  DevBuf exportBuf;          // mma_export_table_async: this context's own dump, kept for mma_restore_export (dumpBuf is rewritten by every finish)
 
   int fail(int code, const std::string &msg) {
     error = msg;
@@ -185,6 +186,8 @@ int initSample(mma_ctx *ctx, Sample &s) {
   for (int i = 0; i < 4; ++i) CK(cudaEventCreateWithFlags(&s.ringEv[i], cudaEventDisableTiming));
   return MMA_OK;
 }
+
+__global__ void k_and_u32(u32 *p, u32 mask) { *p &= mask; }
 
 __global__ void k_keyset_rehash(KeySetView from, KeySetView to) {
   const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -501,6 +504,7 @@ void mma_destroy(mma_ctx *ctx) {
   if (ctx->hostTable) cudaFreeHost(ctx->hostTable);
   ctx->dumpBuf.release();
   ctx->gatherBuf.release();
+  ctx->exportBuf.release();
   for (cudaEvent_t e : ctx->eventPool) cudaEventDestroy(e);
   if (ctx->sc) cudaStreamDestroy(ctx->sc);
   if (ctx->sh) cudaStreamDestroy(ctx->sh);
@@ -1234,24 +1238,27 @@ int mma_export_table_async(mma_ctx *ctx, uint32_t sample, void *dev_dst, uint64_
     ctx->launches++;
   }
   const size_t headBytes = sizeof(TableDump);
-  if (!ctx->hostTable) CK(cudaHostAlloc(&ctx->hostTable, headBytes + (size_t)ctx->tableCap * 16, cudaHostAllocDefault));
-  CK(ctx->dumpBuf.ensure(headBytes + (size_t)ctx->tableCap * 16));
-  TableDump *dHead = ctx->dumpBuf.as<TableDump>();
-  ulonglong2 *dRows = reinterpret_cast<ulonglong2 *>(ctx->dumpBuf.as<char>() + headBytes);
+  CK(ctx->exportBuf.ensure(headBytes + (size_t)ctx->tableCap * 16));
+  TableDump *dHead = ctx->exportBuf.as<TableDump>();
+  ulonglong2 *dRows = reinterpret_cast<ulonglong2 *>(ctx->exportBuf.as<char>() + headBytes);
   CK(cudaMemsetAsync(&dHead->nRows, 0, sizeof(u64), ctx->sc));
   k_table_compact<<<gridFor(ctx->tableCap, 256), 256, 0, ctx->sc>>>(tableView(s.tableKeys, s.tableVals, ctx->tableCap, s.ctl), s.ctl, dHead, dRows, ctx->tableCap);
   ctx->launches++;
-  CK(cudaMemcpyAsync(dev_dst, ctx->dumpBuf.p, (size_t)stride_bytes, cudaMemcpyDeviceToDevice, ctx->sc));
+  CK(cudaMemcpyAsync(dev_dst, ctx->exportBuf.p, (size_t)stride_bytes, cudaMemcpyDeviceToDevice, ctx->sc));
   return MMA_OK;
 }
 
 int mma_restore_export(mma_ctx *ctx, uint32_t sample) {
   if (!ctx) return MMA_ERR_INVALID;
-  if (sample >= ctx->samples.size() || !ctx->dumpBuf.p) return ctx->fail(MMA_ERR_STATE, "nothing was exported");
+  if (sample >= ctx->samples.size() || !ctx->exportBuf.p) return ctx->fail(MMA_ERR_STATE, "nothing was exported");
   CK(cudaSetDevice(ctx->device));
   Sample &s = ctx->samples[sample];
   if (!s.ctl) return ctx->fail(MMA_ERR_STATE, "nothing was exported");
-  return importTables(ctx, s, ctx->dumpBuf.p, 1, sizeof(TableDump) + (size_t)ctx->tableCap * 16, ctx->tableCap);
+  int rc = importTables(ctx, s, ctx->exportBuf.p, 1, sizeof(TableDump) + (size_t)ctx->tableCap * 16, ctx->tableCap);
+  if (rc) return rc;
+  k_and_u32<<<1, 1, 0, ctx->sc>>>(&s.ctl->overflow, 1u);  // (the dump's own deferred records are still here: that is not an exchange gone wrong)
+  ctx->launches++;
+  return MMA_OK;
 }
 
 int mma_import_tables(mma_ctx *ctx, uint32_t sample, const void *dev_src, uint32_t n_tables) {

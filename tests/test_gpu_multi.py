@@ -28,6 +28,7 @@ needs2 = pytest.mark.skipif("_n_gpus() < 2", reason="needs two GPUs")
 @needs2
 @pytest.mark.parametrize("strategy,overlap,shuffle", [("default", -1.0, False), ("unique", 1.0, False), ("ratio", -1.0, False), ("default", 0.5, True)])
 def test_allreduce_in_one_process(strategy, overlap, shuffle):
+    import torch  # noqa: F401  (first: a process that loads torch later must not already hold another libnccl.so.2)
     from mmannot_b200 import device, multi
     n = min(_n_gpus(), 4)
     rng = np.random.default_rng(77)
