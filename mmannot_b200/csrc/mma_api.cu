@@ -7,6 +7,7 @@
 #include <cub/device/device_scan.cuh>
 
 #include <dlfcn.h>
+#include <unistd.h>
 #include <nccl.h>  // types and prototypes only: the library is opened at run time, by mma_allreduce alone
 
 #include <algorithm>
@@ -124,6 +125,7 @@ struct mma_ctx {
   u64 *hostTable = nullptr;  // pinned: [TableDump | rows] of the sample being read back
   DevBuf dumpBuf;            // device side of the same
   DevBuf gatherBuf;          // mma_allreduce: the dumps of all the contexts of the group
+  DevBuf defPermA, defPermB, defKeyA, defKeyB, defTmp, defOrd, defMask, defNh, defMax;  // end-of-sample pass over the deferred records (kept: cudaMalloc / cudaFree per sample cost more than the pass)
   DevBuf exportBuf;          // mma_export_table_async: this context's own dump, kept for mma_restore_export (dumpBuf is rewritten by every finish)
 
   int fail(int code, const std::string &msg) {
@@ -505,6 +507,8 @@ void mma_destroy(mma_ctx *ctx) {
   ctx->dumpBuf.release();
   ctx->gatherBuf.release();
   ctx->exportBuf.release();
+  ctx->defPermA.release(); ctx->defPermB.release(); ctx->defKeyA.release(); ctx->defKeyB.release(); ctx->defTmp.release();
+  ctx->defOrd.release(); ctx->defMask.release(); ctx->defNh.release(); ctx->defMax.release();
   for (cudaEvent_t e : ctx->eventPool) cudaEventDestroy(e);
   if (ctx->sc) cudaStreamDestroy(ctx->sc);
   if (ctx->sh) cudaStreamDestroy(ctx->sh);
@@ -1030,9 +1034,8 @@ static int finishDeferred(mma_ctx *ctx, Sample &s, u32 nSlow) {
   TableView table = tableView(s.tableKeys, s.tableVals, ctx->tableCap, s.ctl);
   SlowView slow = slowView(s);
   cudaStream_t st = ctx->sc;
-  // stable sort by ordinal, then by key  ==  ordered by (key, ordinal)
-  DevBuf permA, permB, keyA, keyB, tmp;
-  auto cleanup = [&]() { permA.release(); permB.release(); keyA.release(); keyB.release(); tmp.release(); };
+  DevBuf &permA = ctx->defPermA, &permB = ctx->defPermB, &keyA = ctx->defKeyA, &keyB = ctx->defKeyB, &tmp = ctx->defTmp;
+  auto cleanup = [&]() {};  // (the buffers stay with the context)
 #define CKF(call)                                                                                  \
   do {                                                                                             \
     cudaError_t _e = (call);                                                                       \
@@ -1046,26 +1049,26 @@ static int finishDeferred(mma_ctx *ctx, Sample &s, u32 nSlow) {
   mma_ctx::Timed t(ctx, TC_FINISH);
   const u32 g = gridFor(nSlow, 256);
   if (r.strategy == MMA_STRATEGY_DEFAULT) {
-    // ONE radix sort, by read key: the records of a name become adjacent; each name's few records are then taken in file order
-    // by selection (k_slow_default_byord).  Names with hundreds of records would make that quadratic: then the list is sorted
-    // by (key, ordinal) below like for -y random.
-    DevBuf maxLen;
-    CKF(maxLen.ensure(4));
-    CKF(cudaMemsetAsync(maxLen.p, 0, 4, st));
+    // ONE radix sort, by read key: the records of a name become adjacent (and are gathered into that order); each name's few
+    // records are then taken in file order by selection (k_slow_default_byord).  Names with hundreds of records would make that
+    // quadratic: then the list is sorted by (key, ordinal) below like for -y random.
+    CKF(ctx->defOrd.ensure((size_t)nSlow * 8)); CKF(ctx->defMask.ensure((size_t)nSlow * 8)); CKF(ctx->defNh.ensure((size_t)nSlow * 4)); CKF(ctx->defMax.ensure(4));
+    CKF(cudaMemsetAsync(ctx->defMax.p, 0, 4, st));
     k_iota<<<g, 256, 0, st>>>(permA.as<u32>(), nSlow);
     CKF(cudaMemcpyAsync(keyA.p, slow.key, (size_t)nSlow * 8, cudaMemcpyDeviceToDevice, st));
     CKF(cub::DeviceRadixSort::SortPairs(tmp.p, tmpBytes, keyA.as<u64>(), keyB.as<u64>(), permA.as<u32>(), permB.as<u32>(), (int)nSlow, 0, 64, st));
-    k_slow_maxlen<<<g, 256, 0, st>>>(permB.as<u32>(), nSlow, slow, maxLen.as<u32>());
+    SlowView sorted;
+    sorted.key = keyB.as<u64>(); sorted.ord = ctx->defOrd.as<u64>(); sorted.mask = ctx->defMask.as<u64>(); sorted.nh = ctx->defNh.as<u32>(); sorted.cap = nSlow;
+    k_slow_gather<<<g, 256, 0, st>>>(permB.as<u32>(), nSlow, slow, sorted);
+    k_slow_maxlen<<<g, 256, 0, st>>>(nSlow, sorted, ctx->defMax.as<u32>());
     u32 hMax = 0;
-    CKF(cudaMemcpyAsync(&hMax, maxLen.p, 4, cudaMemcpyDeviceToHost, st));
+    CKF(cudaMemcpyAsync(&hMax, ctx->defMax.p, 4, cudaMemcpyDeviceToHost, st));
     CKF(cudaStreamSynchronize(st));
-    maxLen.release();
-    ctx->launches += 2;
+    ctx->launches += 3;
     if (hMax <= 512) {
-      k_slow_default_byord<<<g, 256, 0, st>>>(permB.as<u32>(), nSlow, slow, r, table, s.ctl);
+      k_slow_default_byord<<<g, 256, 0, st>>>(nSlow, sorted, r, table, s.ctl);
       ctx->launches++;
       CKF(cudaStreamSynchronize(st));
-      cleanup();
       return MMA_OK;
     }
   }
@@ -1331,7 +1334,13 @@ int mma_allreduce(mma_ctx *const *ctxs, uint32_t n_ctx, uint32_t sample) {
   std::vector<ncclComm_t> &comms = g_comms[devices];
   if (comms.empty()) {
     comms.resize(n_ctx);
+    // (NCCL may print its version banner on stdout, where the command line writes the count table: send it to stderr)
+    fflush(stdout);
+    const int savedOut = dup(1);
+    if (savedOut >= 0) dup2(2, 1);
     ncclResult_t r = g_nccl.commInitAll(comms.data(), (int)n_ctx, devices.data());
+    fflush(stdout);
+    if (savedOut >= 0) { dup2(savedOut, 1); close(savedOut); }
     if (r != ncclSuccess) { comms.clear(); g_comms.erase(devices); return ctx->fail(MMA_ERR_CUDA, std::string("ncclCommInitAll: ") + g_nccl.errorString(r)); }
   }
   // 1. end-of-file flush of every shard; its compacted table and counters into the context's dump buffer

@@ -1133,24 +1133,31 @@ __global__ void k_slow_default(const u32 *__restrict__ perm, u32 n, SlowView s, 
 // The same for a list sorted by key ONLY (one radix sort instead of two): the records of a name are taken in ordinal order by
 // repeated selection inside the name's segment (a name has at most a few hundred records; k_slow_maxlen tells the host when that
 // does not hold and the fully sorted route has to be taken).
-__global__ void k_slow_maxlen(const u32 *__restrict__ perm, u32 n, SlowView s, u32 *maxLen) {
+// (`s` holds the list in key order: gathered through the permutation of the sort, so that a name's records are adjacent in memory)
+__global__ void k_slow_gather(const u32 *__restrict__ perm, u32 n, SlowView from, SlowView to) {
   const u32 p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= n) return;
-  const u64 k = s.key[perm[p]];
-  if (p > 0 && s.key[perm[p - 1]] == k) return;
+  const u32 id = perm[p];
+  to.ord[p] = from.ord[id]; to.mask[p] = from.mask[id]; to.nh[p] = from.nh[id];
+}
+__global__ void k_slow_maxlen(u32 n, SlowView s, u32 *maxLen) {
+  const u32 p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n) return;
+  const u64 k = s.key[p];
+  if (p > 0 && s.key[p - 1] == k) return;
   u32 q = p + 1;
-  while (q < n && s.key[perm[q]] == k) ++q;
+  while (q < n && s.key[q] == k) ++q;
   if (q - p > 64) atomicMax(maxLen, q - p);
 }
-__global__ void k_slow_default_byord(const u32 *__restrict__ perm, u32 n, SlowView s, Rules r, TableView table, SampleCtl *ctl) {
+__global__ void k_slow_default_byord(u32 n, SlowView s, Rules r, TableView table, SampleCtl *ctl) {
   const u32 p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= n) return;
-  const u64 k = s.key[perm[p]];
-  if (p > 0 && s.key[perm[p - 1]] == k) return;
+  const u64 k = s.key[p];
+  if (p > 0 && s.key[p - 1] == k) return;
   u32 q = p + 1;
-  u64 lo = s.ord[perm[p]], hi = lo;
+  u64 lo = s.ord[p], hi = lo;
   for (; q < n; ++q) {
-    const u32 id = perm[q];
+    const u32 id = q;
     if (s.key[id] != k) break;
     const u64 o = s.ord[id];
     lo = min(lo, o); hi = max(hi, o);
@@ -1161,10 +1168,10 @@ __global__ void k_slow_default_byord(const u32 *__restrict__ perm, u32 n, SlowVi
   u64 gm = 0, firstOrd = 0, last = 0;
   auto rescued = [&](u64 g, u64 o0, u64 o1) {  // rescue() over the records of the read: ordinals o0..o1 of this name
     u32 cnt = 0;
-    for (u32 z = p; z < q; ++z) { const u32 id = perm[z]; const u64 o = s.ord[id]; if (o >= o0 && o <= o1) cnt += __popcll(s.mask[id]); }
+    for (u32 z = p; z < q; ++z) { const u32 id = z; const u64 o = s.ord[id]; if (o >= o0 && o <= o1) cnt += __popcll(s.mask[id]); }
     return rescueFromCounts(r, g, cnt, [&](u64 bit) {
       u32 c = 0;
-      for (u32 z = p; z < q; ++z) { const u32 id = perm[z]; const u64 o = s.ord[id]; if (o >= o0 && o <= o1 && (s.mask[id] & bit)) ++c; }
+      for (u32 z = p; z < q; ++z) { const u32 id = z; const u64 o = s.ord[id]; if (o >= o0 && o <= o1 && (s.mask[id] & bit)) ++c; }
       return c;
     });
   };
@@ -1173,7 +1180,7 @@ __global__ void k_slow_default_byord(const u32 *__restrict__ perm, u32 n, SlowVi
     u32 best = 0;
     u64 bestOrd = ~0ull;
     for (u32 z = p; z < q; ++z) {
-      const u32 id = perm[z];
+      const u32 id = z;
       const u64 o = s.ord[id];
       if ((step == 0 || o > last) && o < bestOrd) { bestOrd = o; best = id; }
     }
