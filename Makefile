@@ -12,7 +12,7 @@ CXXFLAGS  := -O3 -std=c++17 -fPIC -Wall -Wextra -Iinclude
 NVFLAGS   := $(ARCH) -O3 -std=c++17 -lineinfo -Xcompiler -fPIC -Iinclude
 
 HOST_SRC  := $(wildcard mmannot_b200/csrc/host/*.cpp)
-CLI_SRC   := mmannot_b200/csrc/host/main.cpp mmannot_b200/csrc/host/counter.cpp mmannot_b200/csrc/host/stats_writers.cpp
+CLI_SRC   := mmannot_b200/csrc/host/main.cpp mmannot_b200/csrc/host/counter.cpp mmannot_b200/csrc/host/stats_writers.cpp mmannot_b200/csrc/host/bam_device.cpp
 HOST_LIB_SRC := $(filter-out $(CLI_SRC),$(HOST_SRC))
 HOST_HDR  := $(wildcard mmannot_b200/csrc/host/*.hpp) $(wildcard include/*.h)
 CU_SRC    := $(wildcard mmannot_b200/csrc/*.cu)

@@ -160,6 +160,9 @@ typedef struct mma_timing {
   uint64_t hits;      /* hits submitted since the reset */
   uint64_t batches;   /* k_batch launches since the reset */
   uint64_t fast_miss; /* hits the segment table could not answer (since the sample was reset) */
+  double ms_bam_inflate; /* mma_submit_bam: BGZF inflate ... */
+  double ms_bam_index;   /* ... record walk + prefix sum ... */
+  double ms_bam_parse;   /* ... record parse into hits */
 } mma_timing;
 
 int mma_device_count(void); /* number of CUDA devices visible to the process (0 when there is none) */
@@ -196,6 +199,40 @@ int mma_pack_hits(const mma_hit_batch *wide, uint32_t *packed, uint64_t *run_key
 
 /* mma_submit_hits for a batch in the compact format (same asynchrony and buffer lifetime rules). */
 int mma_submit_hits_packed(mma_ctx *ctx, uint32_t sample, const mma_packed_batch *batch);
+
+/* ---- BAM decode on the device (BamReader, mmannot.cpp:1487-1649): the compressed BGZF members cross PCIe as they lie in the
+ * file and are inflated and parsed into hits on the GPU, which then annotates them like any other batch.
+ *   mma_bam_begin   once per input file, after the caller has read the BAM header (on the host: it is a few KB): the
+ *                   annotation chromosome of every BAM reference (MMA_HIT_CHR_NONE = not in the annotation) and -s.
+ *   mma_submit_bam  a chunk of WHOLE members (host memory, page-locked for speed) with their byte offsets and inflated sizes
+ *                   (the ISIZE field of each member); skip_first = bytes at the start of the chunk's first member that are
+ *                   not alignment records (the end of the BAM header; 0 for later chunks).  Returns with *n_records = records
+ *                   (= hits) of the chunk and *flags = 0 once the chunk's kernels are enqueued.  A non-zero *flags (MMA_BAM_*)
+ *                   means NOTHING of the chunk was counted: the file holds something this route leaves to the host decoder
+ *                   (XA alternative hits, CIGAR operations or aux types the reference warns about, records that straddle
+ *                   members, corrupt data); the caller resets the sample and decodes the file itself (mma_submit_hits*).
+ *   mma_bam_ref_first  out[i] = ordinal (0-based, over the file) of the first record on BAM reference i, ~0 if none yet: for
+ *                   the "chromosome not present in your annotation" warnings (mmannot.cpp:1297), in order of appearance. */
+#define MMA_BAM_BAD_DEFLATE 1u
+#define MMA_BAM_STRADDLE 2u
+#define MMA_BAM_HAS_XA 4u
+#define MMA_BAM_ODD_CIGAR 8u
+#define MMA_BAM_ODD_AUX 16u
+#define MMA_BAM_MALFORMED 32u
+typedef struct mma_bam_chunk {
+  const void *data;              /* whole BGZF members, back to back */
+  uint64_t n_bytes;              /* < 2^32 */
+  const uint32_t *member_offset; /* [n_members + 1] */
+  const uint32_t *member_isize;  /* [n_members]; their sum < 2^32 */
+  uint32_t n_members;
+  uint32_t skip_first;
+} mma_bam_chunk;
+int mma_bam_begin(mma_ctx *ctx, uint32_t sample, const uint32_t *ref_to_chr, uint32_t n_ref, int strandedness /* 0 U, 1 F, 2 R */);
+int mma_submit_bam(mma_ctx *ctx, uint32_t sample, const mma_bam_chunk *chunk, uint64_t *n_records, uint32_t *flags);
+int mma_bam_ref_first(mma_ctx *ctx, uint64_t *out, uint32_t n_ref);
+/* The hits mma_submit_bam decoded from the last chunk, copied to host arrays of n_records entries (tests: the decoder against
+ * the host's XamReader).  Synchronous. */
+int mma_bam_last_hits(mma_ctx *ctx, uint32_t *start, uint32_t *end, uint32_t *meta, uint32_t *nh, uint64_t *read_key);
 
 /* Synchronous: end-of-file flush of the sample (mmannot.cpp:1783-1792) and read-back of its
  * counters and rows.  The arrays belong to the context and stay valid until the next

@@ -73,7 +73,8 @@ int mmh_synth_create(const char *shape, uint64_t seed, double gene_scale, mmh_sy
 void mmh_synth_free(mmh_synth *s);
 uint64_t mmh_synth_n_genes(const mmh_synth *s);
 int mmh_synth_write_annotation(const mmh_synth *s, const char *path);
-/* coordinate_sorted: bit 0 = records sorted by (chromosome, position); bit 1 = no BAM header (a part to be appended to another BGZF file) */
+/* coordinate_sorted: bit 0 = records sorted by (chromosome, position); bit 1 = no BAM header (a part to be appended to another BGZF file);
+ * bit 2 = records may straddle BGZF members (htslib never writes such files; the device BAM decoder hands them to the host decoder) */
 int mmh_synth_write_bam(const mmh_synth *s, const char *path, uint64_t first_read, uint64_t n_reads, const mmh_synth_reads *spec, int coordinate_sorted);
 uint64_t mmh_synth_count_hits(const mmh_synth *s, uint64_t first_read, uint64_t n_reads, const mmh_synth_reads *spec);
 /* packed hits of reads [first_read, first_read + n_reads), identical to decoding the BAM written for them */

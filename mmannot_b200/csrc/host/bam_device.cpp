@@ -1,0 +1,210 @@
+#include "bam_device.hpp"
+
+#include <zlib.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <unordered_map>
+
+namespace mmb {
+
+namespace {
+
+inline uint32_t rd32(const unsigned char *p) { return p[0] | (p[1] << 8) | (p[2] << 16) | (static_cast<uint32_t>(p[3]) << 24); }
+inline uint32_t rd16(const unsigned char *p) { return p[0] | (p[1] << 8); }
+
+// total size of the BGZF member starting at p (0: not a whole BGZF member header in `avail` bytes / not BGZF); *hdr = header length
+size_t bgzfMember(const unsigned char *p, size_t avail, size_t *hdr) {
+  if (avail < 18 || p[0] != 0x1f || p[1] != 0x8b || p[2] != 8 || p[3] != 4) return 0;
+  const size_t xlen = rd16(p + 10);
+  if (avail < 12 + xlen) return 0;
+  for (size_t at = 12; at + 4 <= 12 + xlen;) {
+    const size_t slen = rd16(p + at + 2);
+    if (p[at] == 'B' && p[at + 1] == 'C' && slen == 2 && at + 6 <= 12 + xlen) {
+      *hdr = 12 + xlen;
+      return static_cast<size_t>(rd16(p + at + 4)) + 1;
+    }
+    at += 4 + slen;
+  }
+  return 0;
+}
+
+bool inflateRaw(const unsigned char *src, size_t n, unsigned char *dst, size_t want) {
+  z_stream zs;
+  std::memset(&zs, 0, sizeof(zs));
+  if (inflateInit2(&zs, -15) != Z_OK) return false;
+  zs.next_in = const_cast<unsigned char *>(src); zs.avail_in = static_cast<uInt>(n);
+  zs.next_out = dst; zs.avail_out = static_cast<uInt>(want);
+  const int rc = inflate(&zs, Z_FINISH);
+  const bool ok = (rc == Z_STREAM_END) && zs.total_out == want;
+  inflateEnd(&zs);
+  return ok;
+}
+
+}  // namespace
+
+DeviceBamFeeder::DeviceBamFeeder(mma_ctx *ctx, const FeatureTable &features, Strandedness strandedness)
+    : ctx_(ctx), features_(features), strandedness_(strandedness) {
+  size_t mb = 192;
+  if (const char *e = std::getenv("MMANNOT_B200_BAM_CHUNK_MB")) mb = static_cast<size_t>(std::max(1, std::atoi(e)));
+  cap_ = mb << 20;
+}
+
+DeviceBamFeeder::~DeviceBamFeeder() {
+  mma_free_pinned(buf_[0]);
+  mma_free_pinned(buf_[1]);
+}
+
+DeviceBamFeeder::Result DeviceBamFeeder::run(const std::string &fileName, uint32_t column, uint64_t &nRecords, std::string &warnings,
+                                             std::string &why, std::string &err) {
+  nRecords = 0;
+  FILE *f = std::fopen(fileName.c_str(), "rb");
+  if (!f) { why = "cannot open the file"; return Result::FALLBACK; }
+  struct Closer { FILE *f; ~Closer() { std::fclose(f); } } closer{f};
+  for (int k = 0; k < 2; ++k)
+    if (!buf_[k]) {
+      buf_[k] = static_cast<unsigned char *>(mma_alloc_pinned(cap_));
+      if (!buf_[k]) { why = "no page-locked memory for the file chunks"; return Result::FALLBACK; }
+    }
+  int cur = 0;
+  size_t have = std::fread(buf_[cur], 1, cap_, f);
+  bool eof = have < cap_;
+  // ---- the BAM header, inflated here: magic, text, reference names (mm:1487-1520)
+  std::vector<unsigned char> head;
+  std::vector<uint32_t> headMemberEnd;  // inflated bytes up to the end of each member looked at
+  std::vector<std::string> refNames;
+  size_t headerBytes = 0, scanned = 0;
+  bool headerDone = false;
+  while (!headerDone) {
+    size_t hdr = 0;
+    const size_t total = bgzfMember(buf_[cur] + scanned, have - scanned, &hdr);
+    if (total == 0 || scanned + total > have || total < hdr + 8) { why = "not a BGZF file (or a header larger than a chunk)"; return Result::FALLBACK; }
+    const unsigned char *m = buf_[cur] + scanned;
+    const uint32_t isize = rd32(m + total - 4);
+    const size_t at = head.size();
+    head.resize(at + isize);
+    if (isize && !inflateRaw(m + hdr, total - hdr - 8, head.data() + at, isize)) { why = "corrupt BGZF member in the header"; return Result::FALLBACK; }
+    scanned += total;
+    headMemberEnd.push_back(static_cast<uint32_t>(head.size()));
+    // complete?
+    if (head.size() < 12) continue;
+    if (std::memcmp(head.data(), "BAM\1", 4) != 0) { why = "missing BAM magic"; return Result::FALLBACK; }
+    const size_t lText = rd32(head.data() + 4);
+    size_t p = 8 + lText;
+    if (head.size() < p + 4) continue;
+    const uint32_t nRef = rd32(head.data() + p);
+    p += 4;
+    refNames.clear();
+    bool complete = true;
+    for (uint32_t i = 0; i < nRef; ++i) {
+      if (head.size() < p + 4) { complete = false; break; }
+      const size_t lName = rd32(head.data() + p);
+      if (head.size() < p + 4 + lName + 4) { complete = false; break; }
+      std::string name(reinterpret_cast<const char *>(head.data() + p + 4), lName);
+      refNames.push_back(name.c_str());  // up to the first NUL, like the reference (mm:1510)
+      p += 4 + lName + 4;
+    }
+    if (!complete) continue;
+    headerBytes = p;
+    headerDone = true;
+  }
+  // the member that holds the first record, and how much of it is still header
+  size_t firstMember = 0;
+  while (firstMember < headMemberEnd.size() && headMemberEnd[firstMember] <= headerBytes) ++firstMember;
+  size_t pos = 0;  // byte offset in buf_[cur] of member `firstMember`
+  {
+    size_t off = 0;
+    for (size_t k = 0; k < firstMember; ++k) { size_t hdr; off += bgzfMember(buf_[cur] + off, have - off, &hdr); }
+    pos = off;
+  }
+  uint32_t skipFirst = (firstMember < headMemberEnd.size()) ? static_cast<uint32_t>(headerBytes - (firstMember ? headMemberEnd[firstMember - 1] : 0)) : 0;
+  // reference -> annotation chromosome (only chromosomes that carry features, like XamReader)
+  std::unordered_map<std::string, uint32_t> chrByName;
+  for (size_t i = 0; i < features_.chromosomes.size(); ++i)
+    if (features_.chrHasFeatures[i]) chrByName[features_.chromosomes[i]] = static_cast<uint32_t>(i);
+  std::vector<uint32_t> refToChr(refNames.size(), MMA_HIT_CHR_NONE);
+  for (size_t i = 0; i < refNames.size(); ++i) {
+    auto it = chrByName.find(refNames[i]);
+    if (it != chrByName.end()) refToChr[i] = it->second;
+  }
+  const int strand = strandedness_ == Strandedness::U ? 0 : strandedness_ == Strandedness::F ? 1 : 2;
+  if (mma_bam_begin(ctx_, column, refToChr.data(), static_cast<uint32_t>(refToChr.size()), strand) != MMA_OK) { err = mma_last_error(ctx_); return Result::FAILED; }
+  // ---- chunks of whole members
+  std::vector<uint32_t> memberOff, memberIsize;
+  for (;;) {
+    memberOff.clear(); memberIsize.clear();
+    size_t at = pos;
+    uint64_t inflated = 0;
+    while (at < have) {
+      size_t hdr = 0;
+      const size_t total = bgzfMember(buf_[cur] + at, have - at, &hdr);
+      if (total == 0) {
+        if (have - at >= 18 || eof) { why = "not BGZF all the way (or a truncated file)"; return Result::FALLBACK; }
+        break;  // the member's header is cut by the end of the chunk
+      }
+      if (at + total > have) {
+        if (eof) { why = "truncated BGZF member at the end of the file"; return Result::FALLBACK; }
+        break;
+      }
+      const uint32_t isize = rd32(buf_[cur] + at + total - 4);
+      if (inflated + isize >= 0xF0000000ull) break;  // (a chunk must inflate to less than 4 GB)
+      memberOff.push_back(static_cast<uint32_t>(at - pos));
+      memberIsize.push_back(isize);
+      inflated += isize;
+      at += total;
+    }
+    if (memberOff.empty() && !(eof && at >= have)) { why = "a BGZF member larger than a chunk"; return Result::FALLBACK; }
+    if (!memberOff.empty()) {
+      memberOff.push_back(static_cast<uint32_t>(at - pos));
+      mma_bam_chunk c;
+      c.data = buf_[cur] + pos; c.n_bytes = at - pos;
+      c.member_offset = memberOff.data(); c.member_isize = memberIsize.data();
+      c.n_members = static_cast<uint32_t>(memberIsize.size());
+      c.skip_first = skipFirst;
+      uint64_t n = 0;
+      uint32_t flags = 0;
+      if (mma_submit_bam(ctx_, column, &c, &n, &flags) != MMA_OK) { err = mma_last_error(ctx_); return Result::FAILED; }
+      if (flags) {
+        why = std::string("the file needs the host decoder:") + ((flags & MMA_BAM_HAS_XA) ? " XA tags" : "") + ((flags & MMA_BAM_STRADDLE) ? " records across BGZF members" : "") +
+              ((flags & MMA_BAM_ODD_CIGAR) ? " CIGAR operations with warnings" : "") + ((flags & MMA_BAM_ODD_AUX) ? " unknown aux types" : "") +
+              ((flags & MMA_BAM_BAD_DEFLATE) ? " deflate data this decoder rejects" : "") + ((flags & MMA_BAM_MALFORMED) ? " malformed records" : "");
+        return Result::FALLBACK;
+      }
+      nRecords += n;
+      skipFirst = 0;
+    }
+    if (eof && at >= have) break;
+    // the rest of this buffer (a member cut by its end) moves to the front of the other one, the file continues behind it.
+    // (mma_submit_bam has synchronised on the chunk's copy: this buffer is free; the kernels of the chunk still run.)
+    const size_t rest = have - at;
+    const int nxt = cur ^ 1;
+    std::memcpy(buf_[nxt], buf_[cur] + at, rest);
+    const size_t got = std::fread(buf_[nxt] + rest, 1, cap_ - rest, f);
+    eof = got < cap_ - rest;
+    have = rest + got;
+    cur = nxt;
+    pos = 0;
+    if (have == 0) break;
+  }
+  // ---- the reference's warnings for chromosomes the annotation does not know, in order of first appearance (mm:1297)
+  if (!refNames.empty()) {
+    std::vector<uint64_t> first(refNames.size());
+    if (mma_bam_ref_first(ctx_, first.data(), static_cast<uint32_t>(first.size())) != MMA_OK) { err = mma_last_error(ctx_); return Result::FAILED; }
+    std::vector<std::pair<uint64_t, size_t> > seen;
+    for (size_t i = 0; i < refNames.size(); ++i)
+      if (refToChr[i] == MMA_HIT_CHR_NONE && first[i] != ~0ull && refNames[i] != "*") seen.push_back(std::make_pair(first[i], i));
+    std::sort(seen.begin(), seen.end());
+    std::vector<std::string> said;
+    for (const auto &s : seen) {
+      const std::string &name = refNames[s.second];
+      if (std::find(said.begin(), said.end(), name) != said.end()) continue;
+      said.push_back(name);
+      warnings += "\t\tWarning!  Chromosome '" + name + "' (found in your reads) is not present in your annotation file.\n";
+    }
+  }
+  return Result::DONE;
+}
+
+}  // namespace mmb

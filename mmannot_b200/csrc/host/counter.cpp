@@ -1,5 +1,7 @@
 #include "counter.hpp"
 
+#include "bam_device.hpp"
+
 #include <algorithm>
 #include <cstdio>
 #include <iomanip>
@@ -105,6 +107,26 @@ bool Counter::read(const std::string &fileName, uint32_t column, std::string &er
   XamReader reader(fileName, opt_.format, opt_.strandedness, features_);
   if (!reader.open(err)) return false;
   log << (reader.isBam() ? "Reading BAM file " : "Reading SAM file ") << fileName << std::endl;
+  // BAM on one GPU without per-read statistics: the compressed file goes to the device as it is (inflate + record parse there);
+  // files that route does not take (XA alternative hits, ...) are decoded on the host below, from the start
+  bool onDevice = false;
+  uint64_t deviceRecords = 0;
+  if (reader.isBam() && !writers_ && shards_.empty() && !std::getenv("MMANNOT_B200_HOST_DECODE")) {
+    if (mma_reset_sample(ctx_, column) != MMA_OK) { err = mma_last_error(ctx_); return false; }
+    DeviceBamFeeder feeder(ctx_, features_, opt_.strandedness);
+    std::string w, why;
+    const DeviceBamFeeder::Result r = feeder.run(fileName, column, deviceRecords, w, why, err);
+    if (r == DeviceBamFeeder::Result::FAILED) return false;
+    if (r == DeviceBamFeeder::Result::DONE) {
+      onDevice = true;
+      if (!w.empty()) log << w;
+    } else if (std::getenv("MMANNOT_B200_VERBOSE")) {
+      log << "\t(device BAM decoder not used: " << why << ")" << std::endl;
+    }
+  }
+  if (onDevice) {
+    log << "\t" << withThousands(deviceRecords) << " lines read, done." << std::endl;
+  } else {
   if (!shards_.empty()) {
     if (writers_) { err = "Read / interval statistics need the whole input on one GPU."; return false; }
     if (!readSharded(reader, column, err, log)) return false;
@@ -144,6 +166,7 @@ bool Counter::read(const std::string &fileName, uint32_t column, std::string &er
   }
   }
   log << "\t" << withThousands(reader.recordsRead()) << " lines read, done." << std::endl;
+  }
   if (writers_) writers_->endOfFile();
   mma_sample_result res;
   if (mma_finish_sample(ctx_, column, &res) != MMA_OK) { err = mma_last_error(ctx_); return false; }

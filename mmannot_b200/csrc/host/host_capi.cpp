@@ -121,7 +121,7 @@ void mmh_synth_free(mmh_synth *s) {
 uint64_t mmh_synth_n_genes(const mmh_synth *s) { return s->genome->genes.size(); }
 int mmh_synth_write_annotation(const mmh_synth *s, const char *path) { s->genome->writeAnnotation(path); return 0; }
 int mmh_synth_write_bam(const mmh_synth *s, const char *path, uint64_t first_read, uint64_t n_reads, const mmh_synth_reads *spec, int coordinate_sorted) {
-  if (!s->genome->writeBam(path, first_read, n_reads, toSpec(spec), (coordinate_sorted & 1) != 0, (coordinate_sorted & 2) != 0)) { g_error = std::string("cannot write '") + path + "'"; return -1; }
+  if (!s->genome->writeBam(path, first_read, n_reads, toSpec(spec), (coordinate_sorted & 1) != 0, (coordinate_sorted & 2) != 0, (coordinate_sorted & 4) != 0)) { g_error = std::string("cannot write '") + path + "'"; return -1; }
   return 0;
 }
 uint64_t mmh_synth_count_hits(const mmh_synth *s, uint64_t first_read, uint64_t n_reads, const mmh_synth_reads *spec) {

@@ -47,6 +47,13 @@ class BgzfWriter {
       if (buf_.size() == 0xff00) flush();
     }
   }
+  // htslib never lets an alignment record straddle two members (bgzf_flush_try before every record): the same here, unless
+  // the caller wants a file that does (tests of the decoders' handling of it)
+  void writeRecord(const void *p, size_t n, bool mayStraddle) {
+    if (!mayStraddle && n <= 0xff00 && buf_.size() + n > 0xff00) flush();
+    write(p, n);
+  }
+  void endOfHeader() { flush(); }
   void close() {
     if (!f_) return;
     flush();
@@ -435,7 +442,7 @@ uint64_t SynthGenome::fillHits(const FeatureTable &features, Strandedness s, uin
   return n;
 }
 
-bool SynthGenome::writeBam(const std::string &path, uint64_t first, uint64_t nReads, const SynthReadSpec &spec, bool coordinateSorted, bool headerless) const {
+bool SynthGenome::writeBam(const std::string &path, uint64_t first, uint64_t nReads, const SynthReadSpec &spec, bool coordinateSorted, bool headerless, bool straddle) const {
   BgzfWriter w(path);
   if (!w.ok()) return false;
   std::vector<unsigned char> buf;
@@ -453,6 +460,7 @@ bool SynthGenome::writeBam(const std::string &path, uint64_t first, uint64_t nRe
     put32(buf, static_cast<uint32_t>(chrLen[c]));
   }
   w.write(buf.data(), buf.size());
+  if (!straddle) w.endOfHeader();  // (htslib flushes after the header: the records start a member)
   }
   std::string name;
   std::vector<SynthRecord> recs;
@@ -461,7 +469,7 @@ bool SynthGenome::writeBam(const std::string &path, uint64_t first, uint64_t nRe
       readRecords(r, spec, name, recs);
       for (const SynthRecord &rec : recs) {
         bamRecord(buf, name, rec);
-        w.write(buf.data(), buf.size());
+        w.writeRecord(buf.data(), buf.size(), straddle);
       }
     }
   } else {
@@ -479,7 +487,7 @@ bool SynthGenome::writeBam(const std::string &path, uint64_t first, uint64_t nRe
       char nm[48];
       std::snprintf(nm, sizeof(nm), "sy%llu.%llu", static_cast<unsigned long long>(seed_ % 1000), static_cast<unsigned long long>(it.read));
       bamRecord(buf, nm, it.rec);
-      w.write(buf.data(), buf.size());
+      w.writeRecord(buf.data(), buf.size(), straddle);
     }
   }
   w.close();

@@ -55,7 +55,8 @@ class SynthGenome {
 
   // reads [first, first + nReads): BAM for the reference ...
   // (headerless: records only -- BGZF files can be concatenated, so that a large BAM can be written as parts side by side)
-  bool writeBam(const std::string &path, uint64_t first, uint64_t nReads, const SynthReadSpec &spec, bool coordinateSorted, bool headerless = false) const;
+  bool writeBam(const std::string &path, uint64_t first, uint64_t nReads, const SynthReadSpec &spec, bool coordinateSorted, bool headerless = false,
+                bool straddle = false) const;  // straddle: records may cross BGZF members (htslib never writes that)
   // ... number of hits of the range, and the same hits as packed buffers (chromosome ids of `features`)
   uint64_t countHits(uint64_t first, uint64_t nReads, const SynthReadSpec &spec) const;
   uint64_t fillHits(const FeatureTable &features, Strandedness s, uint64_t first, uint64_t nReads, const SynthReadSpec &spec,

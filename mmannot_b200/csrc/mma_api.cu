@@ -22,6 +22,7 @@
 #include "mma_device.cuh"
 #include "mma_batch_fast.cuh"
 #include "mma_batch_lean.cuh"
+#include "mma_bam.cuh"
 
 using namespace mma;
 
@@ -109,6 +110,8 @@ struct mma_ctx {
   bool timing = false;
   struct Span { int cat; cudaEvent_t a, b; };
   std::vector<Span> spans;
+  struct BamSpan { cudaEvent_t e[4]; };
+  std::vector<BamSpan> bamSpans;
   std::vector<cudaEvent_t> eventPool;
   double ms[TC_N] = {0, 0, 0, 0};
   uint64_t launches = 0, hitsSubmitted = 0, batches = 0;
@@ -126,6 +129,13 @@ struct mma_ctx {
   DevBuf dumpBuf;            // device side of the same
   DevBuf gatherBuf;          // mma_allreduce: the dumps of all the contexts of the group
   DevBuf defPermA, defPermB, defKeyA, defKeyB, defTmp, defOrd, defMask, defNh, defMax;  // end-of-sample pass over the deferred records (kept: cudaMalloc / cudaFree per sample cost more than the pass)
+  // BAM decode on the device (mma_bam.cuh)
+  DevBuf bamComp[2], bamOut, bamMemberOff, bamOutOff, bamCount, bamHitOff, bamRefToChr, bamRefFirst, bamFlags;
+  DevBuf bamStart, bamEnd, bamMeta, bamNh, bamKey;
+  cudaEvent_t bamCopied[2] = {nullptr, nullptr};
+  uint64_t bamChunks = 0, bamOrdinal = 0, bamLastHits = 0;
+  u32 bamNRef = 0, bamStrandedness = 1;
+  double msBam[3] = {0, 0, 0};  // inflate, count + scan, parse
   DevBuf exportBuf;          // mma_export_table_async: this context's own dump, kept for mma_restore_export (dumpBuf is rewritten by every finish)
 
   int fail(int code, const std::string &msg) {
@@ -154,6 +164,14 @@ struct mma_ctx {
       eventPool.push_back(s.a); eventPool.push_back(s.b);
     }
     spans.clear();
+    for (BamSpan &b : bamSpans) {
+      for (int k = 0; k < 3; ++k) {
+        float t = 0;
+        if (cudaEventElapsedTime(&t, b.e[k], b.e[k + 1]) == cudaSuccess) msBam[k] += t;
+      }
+      for (int k = 0; k < 4; ++k) eventPool.push_back(b.e[k]);
+    }
+    bamSpans.clear();
   }
 };
 
@@ -507,6 +525,10 @@ void mma_destroy(mma_ctx *ctx) {
   ctx->dumpBuf.release();
   ctx->gatherBuf.release();
   ctx->exportBuf.release();
+  for (int k = 0; k < 2; ++k) { ctx->bamComp[k].release(); if (ctx->bamCopied[k]) cudaEventDestroy(ctx->bamCopied[k]); }
+  ctx->bamOut.release(); ctx->bamMemberOff.release(); ctx->bamOutOff.release(); ctx->bamCount.release(); ctx->bamHitOff.release();
+  ctx->bamRefToChr.release(); ctx->bamRefFirst.release(); ctx->bamFlags.release();
+  ctx->bamStart.release(); ctx->bamEnd.release(); ctx->bamMeta.release(); ctx->bamNh.release(); ctx->bamKey.release();
   ctx->defPermA.release(); ctx->defPermB.release(); ctx->defKeyA.release(); ctx->defKeyB.release(); ctx->defTmp.release();
   ctx->defOrd.release(); ctx->defMask.release(); ctx->defNh.release(); ctx->defMax.release();
   for (cudaEvent_t e : ctx->eventPool) cudaEventDestroy(e);
@@ -999,6 +1021,138 @@ int mma_annotate_intervals(mma_ctx *ctx, const mma_hit_batch *b, uint64_t *out_m
   return MMA_OK;
 }
 
+int mma_bam_begin(mma_ctx *ctx, uint32_t sample, const uint32_t *ref_to_chr, uint32_t n_ref, int strandedness) {
+  if (!ctx) return MMA_ERR_INVALID;
+  if (sample >= ctx->samples.size()) return ctx->fail(MMA_ERR_INVALID, "sample index out of range");
+  if (n_ref && !ref_to_chr) return ctx->fail(MMA_ERR_INVALID, "null reference table");
+  if (strandedness < 0 || strandedness > 2) return ctx->fail(MMA_ERR_INVALID, "strandedness must be 0 (U), 1 (F) or 2 (R)");
+  CK(cudaSetDevice(ctx->device));
+  CK(ctx->bamRefToChr.ensure((size_t)std::max<u32>(n_ref, 1) * 4)); CK(ctx->bamRefFirst.ensure((size_t)std::max<u32>(n_ref, 1) * 8)); CK(ctx->bamFlags.ensure(4));
+  if (n_ref) CK(cudaMemcpyAsync(ctx->bamRefToChr.p, ref_to_chr, (size_t)n_ref * 4, cudaMemcpyHostToDevice, ctx->sc));
+  CK(cudaMemsetAsync(ctx->bamRefFirst.p, 0xFF, (size_t)std::max<u32>(n_ref, 1) * 8, ctx->sc));
+  CK(cudaStreamSynchronize(ctx->sc));  // (ref_to_chr may be pageable: it must not change under the copy)
+  ctx->bamNRef = n_ref;
+  ctx->bamStrandedness = (u32)strandedness;
+  ctx->bamOrdinal = 0;
+  ctx->bamLastHits = 0;
+  for (int k = 0; k < 2; ++k)
+    if (!ctx->bamCopied[k]) CK(cudaEventCreateWithFlags(&ctx->bamCopied[k], cudaEventDisableTiming));
+  return MMA_OK;
+}
+
+int mma_submit_bam(mma_ctx *ctx, uint32_t sample, const mma_bam_chunk *c, uint64_t *n_records, uint32_t *flags) {
+  if (!ctx) return MMA_ERR_INVALID;
+  if (!c || !n_records || !flags) return ctx->fail(MMA_ERR_INVALID, "null argument");
+  if (!ctx->haveIndex) return ctx->fail(MMA_ERR_STATE, "mma_load_features must be called before hits are submitted");
+  if (sample >= ctx->samples.size()) return ctx->fail(MMA_ERR_INVALID, "sample index out of range");
+  if (!ctx->bamFlags.p) return ctx->fail(MMA_ERR_STATE, "mma_bam_begin must be called first");
+  *n_records = 0; *flags = 0;
+  if (c->n_members == 0) return MMA_OK;
+  if (!c->data || !c->member_offset || !c->member_isize || c->n_bytes >= 0xFFFFFFF0ull || c->member_offset[c->n_members] != c->n_bytes)
+    return ctx->fail(MMA_ERR_INVALID, "malformed BAM chunk");
+  CK(cudaSetDevice(ctx->device));
+  Sample &s = ctx->samples[sample];
+  int rc = initSample(ctx, s);
+  if (rc) return rc;
+  const u32 nM = c->n_members;
+  std::vector<u32> outOff(nM + 1);
+  uint64_t total = 0;
+  for (u32 m = 0; m < nM; ++m) { outOff[m] = (u32)total; total += c->member_isize[m]; if (total >= 0xFFFFFFF0ull) return ctx->fail(MMA_ERR_INVALID, "BAM chunk inflates to 4 GB or more: submit fewer members"); }
+  outOff[nM] = (u32)total;
+  if (c->skip_first > c->member_isize[0]) return ctx->fail(MMA_ERR_INVALID, "skip_first beyond the first member");
+  const int slot = (int)(ctx->bamChunks & 1);
+  // (this slot's previous copy -- two chunks ago -- is long done: its kernels ran before the last chunk's, and that call synchronised)
+  CK(ctx->bamComp[slot].ensure(((size_t)c->n_bytes + 15) & ~(size_t)15));
+  CK(ctx->bamMemberOff.ensure((size_t)(nM + 1) * 4)); CK(ctx->bamOutOff.ensure((size_t)(nM + 1) * 4));
+  CK(ctx->bamCount.ensure((size_t)nM * 4)); CK(ctx->bamHitOff.ensure((size_t)(nM + 1) * 4));
+  CK(cudaMemcpyAsync(ctx->bamComp[slot].p, c->data, (size_t)c->n_bytes, cudaMemcpyHostToDevice, ctx->sh));
+  CK(cudaEventRecord(ctx->bamCopied[slot], ctx->sh));
+  // the output buffer and the tables are shared by consecutive chunks: everything below is ordered on the compute stream
+  CK(cudaStreamWaitEvent(ctx->sc, ctx->bamCopied[slot], 0));
+  CK(ctx->bamOut.ensure(((size_t)total + 64 + 15) & ~(size_t)15));
+  CK(cudaMemcpyAsync(ctx->bamMemberOff.p, c->member_offset, (size_t)(nM + 1) * 4, cudaMemcpyHostToDevice, ctx->sc));
+  CK(cudaMemcpyAsync(ctx->bamOutOff.p, outOff.data(), (size_t)(nM + 1) * 4, cudaMemcpyHostToDevice, ctx->sc));
+  CK(cudaMemsetAsync(ctx->bamFlags.p, 0, 4, ctx->sc));
+  BamView v;
+  v.comp = ctx->bamComp[slot].as<unsigned char>(); v.memberOff = ctx->bamMemberOff.as<u32>(); v.outOff = ctx->bamOutOff.as<u32>();
+  v.out = ctx->bamOut.as<unsigned char>(); v.nMembers = nM; v.skipFirst = c->skip_first;
+  v.refToChr = ctx->bamRefToChr.as<u32>(); v.nRef = ctx->bamNRef; v.strandedness = ctx->bamStrandedness;
+  v.flags = ctx->bamFlags.as<u32>(); v.refFirst = ctx->bamRefFirst.as<unsigned long long>();
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  if (ctx->timing) for (int k = 0; k < 4; ++k) ev[k] = ctx->getEvent();
+  if (ev[0]) cudaEventRecord(ev[0], ctx->sc);
+  {
+    const u32 warps = (nM + MMA_BAM_LANES - 1) / MMA_BAM_LANES;
+    k_bam_inflate<<<gridFor((uint64_t)warps * 32, 128), 128, 0, ctx->sc>>>(v);
+  }
+  if (ev[1]) cudaEventRecord(ev[1], ctx->sc);
+  k_bam_count<<<gridFor(nM, 128), 128, 0, ctx->sc>>>(v, ctx->bamCount.as<u32>());
+  k_bam_scan<<<1, 1024, 0, ctx->sc>>>(ctx->bamCount.as<u32>(), nM, ctx->bamHitOff.as<u32>());
+  if (ev[2]) cudaEventRecord(ev[2], ctx->sc);
+  ctx->launches += 3;
+  u32 hFlags = 0, nHits = 0;
+  CK(cudaMemcpyAsync(&hFlags, ctx->bamFlags.p, 4, cudaMemcpyDeviceToHost, ctx->sc));
+  CK(cudaMemcpyAsync(&nHits, ctx->bamHitOff.as<u32>() + nM, 4, cudaMemcpyDeviceToHost, ctx->sc));
+  CK(cudaStreamSynchronize(ctx->sc));
+  ctx->bamChunks++;
+  if (hFlags) { *flags = hFlags; return MMA_OK; }
+  if (nHits == 0) { ctx->bamLastHits = 0; return MMA_OK; }
+  const size_t cap = ((size_t)nHits + 127) & ~(size_t)127;
+  CK(ctx->bamStart.ensure(cap * 4)); CK(ctx->bamEnd.ensure(cap * 4)); CK(ctx->bamMeta.ensure(cap * 4)); CK(ctx->bamNh.ensure(cap * 4)); CK(ctx->bamKey.ensure(cap * 8));
+  HitOut o;
+  o.start = ctx->bamStart.as<u32>(); o.end = ctx->bamEnd.as<u32>(); o.meta = ctx->bamMeta.as<u32>(); o.nh = ctx->bamNh.as<u32>(); o.key = ctx->bamKey.as<u64>();
+  k_bam_parse<<<gridFor(nM, 64), 64, 0, ctx->sc>>>(v, ctx->bamHitOff.as<u32>(), ctx->bamOrdinal, o);
+  ctx->launches++;
+  if (ev[3]) {
+    cudaEventRecord(ev[3], ctx->sc);
+    ctx->bamSpans.push_back({ev[0], ev[1], ev[2], ev[3]});
+  }
+  // records with the flags only the parse can see (XA, odd CIGAR, odd aux)
+  CK(cudaMemcpyAsync(&hFlags, ctx->bamFlags.p, 4, cudaMemcpyDeviceToHost, ctx->sc));
+  CK(cudaStreamSynchronize(ctx->sc));
+  if (hFlags) { *flags = hFlags; return MMA_OK; }
+  ctx->bamOrdinal += nHits;
+  ctx->bamLastHits = nHits;
+  *n_records = nHits;
+  // the hits are in HBM: annotate them like a device-resident batch, in pieces the per-thread counters can hold
+  for (uint64_t a = 0; a < nHits;) {
+    const uint64_t n = std::min<uint64_t>(nHits - a, 1ull << 27);
+    if ((rc = ensureDeferred(ctx, s, n))) return rc;
+    HitView h;
+    h.n = (u32)n;
+    h.start = o.start + a; h.end = o.end + a; h.meta = o.meta + a; h.nh = o.nh + a; h.key = o.key + a;
+    h.vec = 1u;
+    if (!s.touched) s.deferAll = ctx->preferDefer && ctx->rules.strategy == MMA_STRATEGY_DEFAULT;
+    if ((rc = launchBatch(ctx, s, h))) return rc;
+    if ((rc = afterBatch(ctx, s, n))) return rc;
+    a += n;
+  }
+  return MMA_OK;
+}
+
+int mma_bam_ref_first(mma_ctx *ctx, uint64_t *out, uint32_t n_ref) {
+  if (!ctx) return MMA_ERR_INVALID;
+  if (!out || n_ref != ctx->bamNRef) return ctx->fail(MMA_ERR_INVALID, "reference count differs from mma_bam_begin");
+  if (n_ref == 0) return MMA_OK;
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaMemcpyAsync(out, ctx->bamRefFirst.p, (size_t)n_ref * 8, cudaMemcpyDeviceToHost, ctx->sc));
+  CK(cudaStreamSynchronize(ctx->sc));
+  return MMA_OK;
+}
+
+int mma_bam_last_hits(mma_ctx *ctx, uint32_t *start, uint32_t *end, uint32_t *meta, uint32_t *nh, uint64_t *read_key) {
+  if (!ctx) return MMA_ERR_INVALID;
+  const size_t n = ctx->bamLastHits;
+  if (n == 0) return MMA_OK;
+  if (!start || !end || !meta || !nh || !read_key) return ctx->fail(MMA_ERR_INVALID, "null argument");
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaStreamSynchronize(ctx->sc));
+  CK(cudaMemcpy(start, ctx->bamStart.p, n * 4, cudaMemcpyDeviceToHost)); CK(cudaMemcpy(end, ctx->bamEnd.p, n * 4, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(meta, ctx->bamMeta.p, n * 4, cudaMemcpyDeviceToHost)); CK(cudaMemcpy(nh, ctx->bamNh.p, n * 4, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(read_key, ctx->bamKey.p, n * 8, cudaMemcpyDeviceToHost));
+  return MMA_OK;
+}
+
 int mma_sync(mma_ctx *ctx) {
   if (!ctx) return MMA_ERR_INVALID;
   CK(cudaSetDevice(ctx->device));
@@ -1460,6 +1614,7 @@ int mma_timing_reset(mma_ctx *ctx) {
   CK(cudaStreamSynchronize(ctx->sc));
   ctx->collectTiming();
   for (int i = 0; i < TC_N; ++i) ctx->ms[i] = 0;
+  for (int i = 0; i < 3; ++i) ctx->msBam[i] = 0;
   ctx->launches = 0;
   ctx->hitsSubmitted = 0;
   ctx->batches = 0;
@@ -1478,6 +1633,7 @@ int mma_timing_get(mma_ctx *ctx, mma_timing *out) {
   out->hits = ctx->hitsSubmitted;
   out->batches = ctx->batches;
   out->fast_miss = 0;
+  out->ms_bam_inflate = ctx->msBam[0]; out->ms_bam_index = ctx->msBam[1]; out->ms_bam_parse = ctx->msBam[2];
   for (Sample &sm : ctx->samples)
     if (sm.ctl) {
       u32 fm = 0;

@@ -249,8 +249,8 @@ class Synth:
     def write_annotation(self, path):
         lib().mmh_synth_write_annotation(self._h, os.fsencode(path))
 
-    def write_bam(self, path, first_read, n_reads, coordinate_sorted=False, headerless=False):
-        if lib().mmh_synth_write_bam(self._h, os.fsencode(path), first_read, n_reads, C.byref(self.spec), int(coordinate_sorted) | (2 if headerless else 0)) != 0:
+    def write_bam(self, path, first_read, n_reads, coordinate_sorted=False, headerless=False, straddle=False):
+        if lib().mmh_synth_write_bam(self._h, os.fsencode(path), first_read, n_reads, C.byref(self.spec), int(coordinate_sorted) | (2 if headerless else 0) | (4 if straddle else 0)) != 0:
             raise _err()
 
     def write_bam_parallel(self, path, first_read, n_reads, threads):
