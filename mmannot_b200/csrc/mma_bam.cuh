@@ -54,12 +54,25 @@ struct BamView {
 
 // ---------------------------------------------------------------------------------------------- inflate
 
+// (the inflate and record functions are __host__ __device__: tests/tools/bam_host_check.cu runs them on the CPU against zlib and
+// the host decoder)
+#define MMA_HD __host__ __device__
+MMA_HD inline u32 bitReverse32(u32 x) {
+#ifdef __CUDA_ARCH__
+  return __brev(x);
+#else
+  u32 r = 0;
+  for (int i = 0; i < 32; ++i) r |= ((x >> i) & 1u) << (31 - i);
+  return r;
+#endif
+}
+
 struct BitReader {
   const unsigned char *p, *end;
   u64 buf;
   int cnt;
   bool over;
-  __device__ __forceinline__ void refill() {
+  MMA_HD __forceinline__ void refill() {
     if (cnt <= 32 && p + 4 <= end && ((reinterpret_cast<uintptr_t>(p) & 3) == 0)) {
       buf |= (u64)(*reinterpret_cast<const u32 *>(p)) << cnt;
       p += 4; cnt += 32;
@@ -71,15 +84,15 @@ struct BitReader {
       cnt += 8;
     }
   }
-  __device__ __forceinline__ u32 peek(int n) {  // n <= 24; missing bits read as zero (the caller checks `over` at the end)
+  MMA_HD __forceinline__ u32 peek(int n) {  // n <= 24; missing bits read as zero (the caller checks `over` at the end)
     if (cnt < n) refill();
     return (u32)buf & ((1u << n) - 1u);
   }
-  __device__ __forceinline__ void drop(int n) {
+  MMA_HD __forceinline__ void drop(int n) {
     if (n > cnt) { over = true; buf = 0; cnt = 0; return; }
     buf >>= n; cnt -= n;
   }
-  __device__ __forceinline__ u32 bits(int n) { const u32 v = peek(n); drop(n); return v; }
+  MMA_HD __forceinline__ u32 bits(int n) { const u32 v = peek(n); drop(n); return v; }
 };
 
 // canonical Huffman code: counts per length + symbols in code order (bit-serial decode), and a 9-bit first-level table
@@ -90,7 +103,7 @@ struct Huff {
   unsigned short fast[1 << HUFF_FAST_BITS];  // (length << 9) | symbol for codes of at most 9 bits, 0 = longer / invalid
 };
 
-__device__ __noinline__ bool huffBuild(Huff &h, const unsigned char *length, int n) {
+MMA_HD __noinline__ bool huffBuild(Huff &h, const unsigned char *length, int n) {
   for (int i = 0; i < 16; ++i) h.count[i] = 0;
   for (int i = 0; i < n; ++i) h.count[length[i]]++;
   for (int i = 0; i < (1 << HUFF_FAST_BITS); ++i) h.fast[i] = 0;
@@ -112,7 +125,7 @@ __device__ __noinline__ bool huffBuild(Huff &h, const unsigned char *length, int
   int idx = 0;
   for (int len = 1; len <= HUFF_FAST_BITS; ++len) {
     for (int k = 0; k < h.count[len]; ++k, ++idx, ++code) {
-      const u32 rev = __brev(code) >> (32 - len);
+      const u32 rev = bitReverse32(code) >> (32 - len);
       const unsigned short e = (unsigned short)((len << 9) | h.symbol[idx]);
       for (u32 f = rev; f < (1u << HUFF_FAST_BITS); f += (1u << len)) h.fast[f] = e;
     }
@@ -121,7 +134,7 @@ __device__ __noinline__ bool huffBuild(Huff &h, const unsigned char *length, int
   return true;
 }
 
-__device__ __forceinline__ int huffDecode(const Huff &h, BitReader &br) {
+MMA_HD __forceinline__ int huffDecode(const Huff &h, BitReader &br) {
   const u32 look = br.peek(15);
   const unsigned short e = h.fast[look & ((1u << HUFF_FAST_BITS) - 1u)];
   if (e) { br.drop(e >> 9); return e & 511; }
@@ -137,14 +150,14 @@ __device__ __forceinline__ int huffDecode(const Huff &h, BitReader &br) {
   return -1;
 }
 
-__device__ __constant__ unsigned short kLenBase[29] = {3, 4, 5, 6, 7, 8, 9, 10, 11, 13, 15, 17, 19, 23, 27, 31, 35, 43, 51, 59, 67, 83, 99, 115, 131, 163, 195, 227, 258};
-__device__ __constant__ unsigned char kLenExtra[29] = {0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 4, 5, 5, 5, 5, 0};
-__device__ __constant__ unsigned short kDistBase[30] = {1, 2, 3, 4, 5, 7, 9, 13, 17, 25, 33, 49, 65, 97, 129, 193, 257, 385, 513, 769, 1025, 1537, 2049, 3073, 4097, 6145, 8193, 12289, 16385, 24577};
-__device__ __constant__ unsigned char kDistExtra[30] = {0, 0, 0, 0, 1, 1, 2, 2, 3, 3, 4, 4, 5, 5, 6, 6, 7, 7, 8, 8, 9, 9, 10, 10, 11, 11, 12, 12, 13, 13};
-__device__ __constant__ unsigned char kClOrder[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
+MMA_HD inline u32 kLenBase(int i) { const unsigned short t[29] = {3, 4, 5, 6, 7, 8, 9, 10, 11, 13, 15, 17, 19, 23, 27, 31, 35, 43, 51, 59, 67, 83, 99, 115, 131, 163, 195, 227, 258}; return t[i]; }
+MMA_HD inline u32 kLenExtra(int i) { const unsigned char t[29] = {0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 4, 5, 5, 5, 5, 0}; return t[i]; }
+MMA_HD inline u32 kDistBase(int i) { const unsigned short t[30] = {1, 2, 3, 4, 5, 7, 9, 13, 17, 25, 33, 49, 65, 97, 129, 193, 257, 385, 513, 769, 1025, 1537, 2049, 3073, 4097, 6145, 8193, 12289, 16385, 24577}; return t[i]; }
+MMA_HD inline u32 kDistExtra(int i) { const unsigned char t[30] = {0, 0, 0, 0, 1, 1, 2, 2, 3, 3, 4, 4, 5, 5, 6, 6, 7, 7, 8, 8, 9, 9, 10, 10, 11, 11, 12, 12, 13, 13}; return t[i]; }
+MMA_HD inline u32 kClOrder(int i) { const unsigned char t[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15}; return t[i]; }
 
 // one raw deflate stream (RFC 1951) from [src, src + srcLen) into dst[0 .. dstLen); true when it ends exactly at dstLen
-__device__ __noinline__ bool inflateMember(const unsigned char *src, u32 srcLen, unsigned char *dst, u32 dstLen, Huff &lit, Huff &dist) {
+MMA_HD __noinline__ bool inflateMember(const unsigned char *src, u32 srcLen, unsigned char *dst, u32 dstLen, Huff &lit, Huff &dist) {
   BitReader br{src, src + srcLen, 0ull, 0, false};
   u32 out = 0;
   unsigned char lengths[320];
@@ -169,7 +182,7 @@ __device__ __noinline__ bool inflateMember(const unsigned char *src, u32 srcLen,
         const int nlen = (int)br.bits(5) + 257, ndist = (int)br.bits(5) + 1, ncode = (int)br.bits(4) + 4;
         if (nlen > 286 || ndist > 30) return false;
         for (int i = 0; i < 19; ++i) lengths[i] = 0;
-        for (int i = 0; i < ncode; ++i) lengths[kClOrder[i]] = (unsigned char)br.bits(3);
+        for (int i = 0; i < ncode; ++i) lengths[kClOrder(i)] = (unsigned char)br.bits(3);
         if (!huffBuild(lit, lengths, 19)) return false;  // (the code-length code, built in the literal table for now)
         int idx = 0;
         while (idx < nlen + ndist) {
@@ -201,10 +214,10 @@ __device__ __noinline__ bool inflateMember(const unsigned char *src, u32 srcLen,
         } else {
           const int s = sym - 257;
           if (s >= 29) return false;
-          const u32 len = kLenBase[s] + br.bits(kLenExtra[s]);
+          const u32 len = kLenBase(s) + br.bits((int)kLenExtra(s));
           const int ds = huffDecode(dist, br);
           if (ds < 0 || ds >= 30) return false;
-          const u32 d = kDistBase[ds] + br.bits(kDistExtra[ds]);
+          const u32 d = kDistBase(ds) + br.bits((int)kDistExtra(ds));
           if (d > out || out + len > dstLen) return false;
           const unsigned char *from = dst + out - d;
           for (u32 i = 0; i < len; ++i) dst[out + i] = from[i];  // (byte by byte: the ranges may overlap)
@@ -221,8 +234,8 @@ __device__ __noinline__ bool inflateMember(const unsigned char *src, u32 srcLen,
   return out == dstLen;
 }
 
-__device__ __forceinline__ u32 ld32u(const unsigned char *p) { return (u32)p[0] | ((u32)p[1] << 8) | ((u32)p[2] << 16) | ((u32)p[3] << 24); }
-__device__ __forceinline__ u32 ld16u(const unsigned char *p) { return (u32)p[0] | ((u32)p[1] << 8); }
+MMA_HD __forceinline__ u32 ld32u(const unsigned char *p) { return (u32)p[0] | ((u32)p[1] << 8) | ((u32)p[2] << 16) | ((u32)p[3] << 24); }
+MMA_HD __forceinline__ u32 ld16u(const unsigned char *p) { return (u32)p[0] | ((u32)p[1] << 8); }
 
 // one thread per member, MMA_BAM_LANES members per warp
 __global__ void __launch_bounds__(128) k_bam_inflate(BamView v) {
@@ -252,7 +265,7 @@ __global__ void __launch_bounds__(128) k_bam_inflate(BamView v) {
 // ---------------------------------------------------------------------------------------------- records
 
 // the host's name_key (csrc/host/common.hpp), restated: the read key of every hit must be the one the host decoder would give
-__device__ __forceinline__ u64 nameKey(const unsigned char *p, u32 n) {
+MMA_HD __forceinline__ u64 nameKey(const unsigned char *p, u32 n) {
   u64 h = 0x9E3779B97F4A7C15ull ^ ((u64)n * 0xD6E8FEB86659FD93ull);
   while (n >= 8) {
     const u64 w = (u64)ld32u(p) | ((u64)ld32u(p + 4) << 32);
@@ -298,7 +311,7 @@ struct HitOut {
 };
 
 // one BAM alignment record (the bytes after its block_size field) -> one hit; like XamReader::parseBamRecord without XA
-__device__ __forceinline__ u32 bamRecord(const BamView &v, const unsigned char *p, u32 blockSize, u64 ordinal, const HitOut &o, u32 at) {
+MMA_HD __forceinline__ u32 bamRecord(const BamView &v, const unsigned char *p, u32 blockSize, u64 ordinal, const HitOut &o, u32 at) {
   u32 flags = 0;
   const unsigned char *recEnd = p + blockSize;
   const int refId = (int)ld32u(p), pos = (int)ld32u(p + 4);
@@ -355,7 +368,11 @@ __device__ __forceinline__ u32 bamRecord(const BamView &v, const unsigned char *
   u32 chr = 0x00FFFFFFu;
   if (refId >= 0 && (u32)refId < v.nRef) {
     chr = v.refToChr[refId];
+#ifdef __CUDA_ARCH__
     atomicMin(&v.refFirst[refId], (unsigned long long)ordinal);
+#else
+    if (ordinal < v.refFirst[refId]) v.refFirst[refId] = ordinal;
+#endif
   }
   // XamReader::pushRecordHits emit(): coordinates beyond the 32-bit range cannot touch any feature
   u64 s = start, e = end;

@@ -1,0 +1,96 @@
+// CPU check of the device BAM decoder's inflate and record functions (they are __host__ __device__): every BGZF member of a BAM
+// file inflated by inflateMember must equal zlib's output, and the hits parsed from the records must equal the host decoder's
+// (passed in as a binary dump by tests/test_bam_decoder_host.py).  Usage: bam_host_check file.bam hits.bin strandedness
+#include <zlib.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "mma_bam.cuh"
+
+using namespace mma;
+
+static uint32_t rd32(const unsigned char *p) { return p[0] | (p[1] << 8) | (p[2] << 16) | ((uint32_t)p[3] << 24); }
+static uint32_t rd16(const unsigned char *p) { return p[0] | (p[1] << 8); }
+
+int main(int argc, char **argv) {
+  if (argc < 4) return 2;
+  FILE *f = fopen(argv[1], "rb");
+  if (!f) return 2;
+  std::vector<unsigned char> file;
+  unsigned char tmp[1 << 16];
+  size_t n;
+  while ((n = fread(tmp, 1, sizeof(tmp), f)) > 0) file.insert(file.end(), tmp, tmp + n);
+  fclose(f);
+  // inflate every member twice: zlib and the decoder under test
+  std::vector<unsigned char> all;
+  std::vector<uint32_t> outOff(1, 0);
+  size_t at = 0, members = 0;
+  static Huff lit, dist;
+  while (at + 18 <= file.size()) {
+    const unsigned char *p = &file[at];
+    const size_t xlen = rd16(p + 10), hdr = 12 + xlen, total = rd16(p + 16) + 1u;
+    const uint32_t isize = rd32(p + total - 4);
+    std::vector<unsigned char> a(isize + 1), b(isize + 1);
+    z_stream zs;
+    memset(&zs, 0, sizeof(zs));
+    inflateInit2(&zs, -15);
+    zs.next_in = const_cast<unsigned char *>(p + hdr); zs.avail_in = (uInt)(total - hdr - 8);
+    zs.next_out = a.data(); zs.avail_out = isize;
+    const int rc = inflate(&zs, Z_FINISH);
+    inflateEnd(&zs);
+    if (isize && rc != Z_STREAM_END) { printf("zlib failed on member %zu\n", members); return 1; }
+    if (isize && !inflateMember(p + hdr, (u32)(total - hdr - 8), b.data(), isize, lit, dist)) { printf("inflateMember failed on member %zu (isize %u)\n", members, isize); return 1; }
+    if (memcmp(a.data(), b.data(), isize) != 0) { printf("member %zu differs\n", members); return 1; }
+    all.insert(all.end(), b.begin(), b.begin() + isize);
+    outOff.push_back((uint32_t)all.size());
+    at += total;
+    ++members;
+  }
+  // header
+  const size_t lText = rd32(&all[4]);
+  size_t p = 8 + lText;
+  const uint32_t nRef = rd32(&all[p]);
+  p += 4;
+  for (uint32_t i = 0; i < nRef; ++i) p += 4 + rd32(&all[p]) + 4;
+  // expected hits: n, then start/end/meta/nh (u32 each) and key (u64) arrays
+  FILE *h = fopen(argv[2], "rb");
+  if (!h) return 2;
+  uint64_t nHits = 0;
+  if (fread(&nHits, 8, 1, h) != 1) return 2;
+  std::vector<uint32_t> es(nHits), ee(nHits), em(nHits), en(nHits), refToChr(nRef);
+  std::vector<uint64_t> ek(nHits);
+  if (fread(es.data(), 4, nHits, h) != nHits || fread(ee.data(), 4, nHits, h) != nHits || fread(em.data(), 4, nHits, h) != nHits ||
+      fread(en.data(), 4, nHits, h) != nHits || fread(ek.data(), 8, nHits, h) != nHits || fread(refToChr.data(), 4, nRef, h) != nRef) return 2;
+  fclose(h);
+  std::vector<uint32_t> gs(nHits + 1), ge(nHits + 1), gm(nHits + 1), gn(nHits + 1);
+  std::vector<unsigned long long> gk(nHits + 1);
+  std::vector<unsigned long long> refFirst(nRef + 1, ~0ull);
+  u32 flagsWord = 0;
+  BamView v;
+  memset(&v, 0, sizeof(v));
+  v.out = all.data(); v.refToChr = refToChr.data(); v.nRef = nRef; v.strandedness = (u32)atoi(argv[3]); v.flags = &flagsWord; v.refFirst = refFirst.data();
+  HitOut o{gs.data(), ge.data(), gm.data(), gn.data(), gk.data()};
+  uint64_t k = 0;
+  u32 flags = 0;
+  while (p + 4 <= all.size()) {
+    const uint32_t bs = rd32(&all[p]);
+    if (k >= nHits) { printf("more records than expected hits (%llu)\n", (unsigned long long)nHits); return 1; }
+    flags |= bamRecord(v, &all[p + 4], bs, k, o, (u32)k);
+    p += 4 + bs;
+    ++k;
+  }
+  if (flags) { printf("flags %u\n", flags); return 1; }
+  if (k != nHits) { printf("records %llu != hits %llu\n", (unsigned long long)k, (unsigned long long)nHits); return 1; }
+  for (uint64_t i = 0; i < nHits; ++i)
+    if (gs[i] != es[i] || ge[i] != ee[i] || gm[i] != em[i] || gn[i] != en[i] || gk[i] != ek[i]) {
+      printf("hit %llu differs: start %u/%u end %u/%u meta %x/%x nh %u/%u key %llx/%llx\n", (unsigned long long)i, gs[i], es[i], ge[i], ee[i], gm[i], em[i], gn[i], en[i],
+             (unsigned long long)gk[i], (unsigned long long)ek[i]);
+      return 1;
+    }
+  printf("ok: %zu members, %llu hits\n", members, (unsigned long long)nHits);
+  return 0;
+}
