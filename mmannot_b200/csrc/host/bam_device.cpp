@@ -3,6 +3,7 @@
 #include <zlib.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -68,8 +69,15 @@ DeviceBamFeeder::Result DeviceBamFeeder::run(const std::string &fileName, uint32
       buf_[k] = static_cast<unsigned char *>(mma_alloc_pinned(cap_));
       if (!buf_[k]) { why = "no page-locked memory for the file chunks"; return Result::FALLBACK; }
     }
+  const bool timing = std::getenv("MMANNOT_B200_TIMING") != nullptr;
+  double msRead = 0, msSubmit = 0;
+  auto now = []() { return std::chrono::steady_clock::now(); };
+  auto since = [](std::chrono::steady_clock::time_point t0) { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(); };
+  if (timing) mma_timing_enable(ctx_, 1);
   int cur = 0;
+  auto tr0 = now();
   size_t have = std::fread(buf_[cur], 1, cap_, f);
+  msRead += since(tr0);
   bool eof = have < cap_;
   // ---- the BAM header, inflated here: magic, text, reference names (mm:1487-1520)
   std::vector<unsigned char> head;
@@ -165,7 +173,9 @@ DeviceBamFeeder::Result DeviceBamFeeder::run(const std::string &fileName, uint32
       c.skip_first = skipFirst;
       uint64_t n = 0;
       uint32_t flags = 0;
+      auto ts0 = now();
       if (mma_submit_bam(ctx_, column, &c, &n, &flags) != MMA_OK) { err = mma_last_error(ctx_); return Result::FAILED; }
+      msSubmit += since(ts0);
       if (flags) {
         why = std::string("the file needs the host decoder:") + ((flags & MMA_BAM_HAS_XA) ? " XA tags" : "") + ((flags & MMA_BAM_STRADDLE) ? " records across BGZF members" : "") +
               ((flags & MMA_BAM_ODD_CIGAR) ? " CIGAR operations with warnings" : "") + ((flags & MMA_BAM_ODD_AUX) ? " unknown aux types" : "") +
@@ -181,7 +191,9 @@ DeviceBamFeeder::Result DeviceBamFeeder::run(const std::string &fileName, uint32
     const size_t rest = have - at;
     const int nxt = cur ^ 1;
     std::memcpy(buf_[nxt], buf_[cur] + at, rest);
+    auto tr1 = now();
     const size_t got = std::fread(buf_[nxt] + rest, 1, cap_ - rest, f);
+    msRead += since(tr1);
     eof = got < cap_ - rest;
     have = rest + got;
     cur = nxt;
@@ -203,6 +215,12 @@ DeviceBamFeeder::Result DeviceBamFeeder::run(const std::string &fileName, uint32
       said.push_back(name);
       warnings += "\t\tWarning!  Chromosome '" + name + "' (found in your reads) is not present in your annotation file.\n";
     }
+  }
+  if (timing) {
+    mma_timing t;
+    if (mma_timing_get(ctx_, &t) == MMA_OK)
+      std::fprintf(stderr, "[timing] bam file read %.1f ms, mma_submit_bam %.1f ms (host side), device: inflate %.1f ms, record walk + scan %.1f ms, parse %.1f ms, batch kernels %.1f ms\n",
+                   msRead, msSubmit, t.ms_bam_inflate, t.ms_bam_index, t.ms_bam_parse, t.ms_batch);
   }
   return Result::DONE;
 }

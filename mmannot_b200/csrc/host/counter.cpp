@@ -106,6 +106,7 @@ bool Counter::read(const std::string &fileName, uint32_t column, std::string &er
   if (!pinned_[0].start || !pinned_[1].key) { err = "Cannot allocate page-locked hit buffers."; return false; }
   XamReader reader(fileName, opt_.format, opt_.strandedness, features_);
   if (!reader.open(err)) return false;
+  reader.warnOnlyForUniqueHits(opt_.strategy == MMA_STRATEGY_UNIQUE);
   log << (reader.isBam() ? "Reading BAM file " : "Reading SAM file ") << fileName << std::endl;
   // BAM on one GPU without per-read statistics: the compressed file goes to the device as it is (inflate + record parse there);
   // files that route does not take (XA alternative hits, ...) are decoded on the host below, from the start

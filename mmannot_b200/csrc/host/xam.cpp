@@ -52,9 +52,10 @@ std::string XamReader::takeWarnings() {
   return w;
 }
 
-uint32_t XamReader::chrMetaOf(const std::string &name) {
+uint32_t XamReader::chrMetaOf(const std::string &name, bool quiet) {
   auto it = chrByName_.find(name);
   if (it != chrByName_.end()) return it->second;
+  if (quiet) return HIT_CHR_NONE;  // (a hit the reference never looks at: no warning, and the name stays unreported)
   if (clone_) {  // the owning reader decides, in record order, whether the name is new (decodeBamChunkParallel)
     if (std::find(unknownChr_.begin(), unknownChr_.end(), name) == unknownChr_.end()) {
       warnings_ += '\x01' + name + "\n";
@@ -275,12 +276,6 @@ void XamReader::parseBamRecord(const unsigned char *p, uint32_t blockSize) {
     cigar.push_back(std::make_pair(op < 9 ? CIGAR_OPS[op] : '?', static_cast<int>(v >> 4)));
   }
   q += (lSeq + 1) / 2 + lSeq;
-  uint32_t chrMeta;
-  if (refId < 0 || static_cast<size_t>(refId) >= bamChrMeta_.size()) chrMeta = chrMetaOf("*");
-  else {
-    if (bamChrMeta_[refId] == 0xFFFFFFFFu) bamChrMeta_[refId] = chrMetaOf(bamChrName_[refId]);
-    chrMeta = bamChrMeta_[refId];
-  }
   uint32_t nHits = 1;
   alts_.clear();
   std::string &lastZ = lastZBuf_;
@@ -322,6 +317,14 @@ void XamReader::parseBamRecord(const unsigned char *p, uint32_t blockSize) {
     else if (t0 == 'X' && t1 == 'A') {
       if (lastZ != "0") { parseAlternatives(lastZ); nHits = static_cast<uint32_t>(alts_.size()) + 1; }
     }
+  }
+  uint32_t chrMeta;
+  const bool quiet = uniqueOnly_ && nHits != 1;
+  if (refId < 0 || static_cast<size_t>(refId) >= bamChrMeta_.size()) chrMeta = chrMetaOf("*");
+  else if (bamChrMeta_[refId] != 0xFFFFFFFFu) chrMeta = bamChrMeta_[refId];
+  else {
+    chrMeta = chrMetaOf(bamChrName_[refId], quiet);
+    if (!quiet || chrMeta != HIT_CHR_NONE) bamChrMeta_[refId] = chrMeta;
   }
   uint64_t start = static_cast<uint64_t>(static_cast<int64_t>(pos) + 1);  // ++pos then widened (mm:1536-1537)
   pushRecordHits(name, chrMeta, start, (flag & 0x10) == 0, cigar, false, nHits);
@@ -431,7 +434,7 @@ size_t XamReader::decodeBamChunkParallel() {
 XamReader::XamReader(const XamReader &parent, int)
     : fileName_(parent.fileName_), format_(parent.format_), strandedness_(parent.strandedness_), features_(parent.features_),
       chrByName_(parent.chrByName_), unknownChr_(), bam_(true), bamChrMeta_(parent.bamChrMeta_), bamChrName_(parent.bamChrName_),
-      clone_(true) {}
+      clone_(true), uniqueOnly_(parent.uniqueOnly_) {}
 
 bool XamReader::decodeSamRecord() {
   std::string line;
@@ -467,7 +470,7 @@ bool XamReader::decodeSamRecord() {
       if (value != "0") { parseAlternatives(value); nHits = static_cast<uint32_t>(alts_.size()) + 1; }
     }
   }
-  pushRecordHits(col[0], chrMetaOf(col[2]), start, (flag & 0x10) == 0, cigar, false, nHits);
+  pushRecordHits(col[0], chrMetaOf(col[2], uniqueOnly_ && nHits != 1), start, (flag & 0x10) == 0, cigar, false, nHits);
   return true;
 }
 

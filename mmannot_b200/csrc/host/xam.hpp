@@ -46,6 +46,9 @@ class XamReader {
   // If `names` is given, the name of every hit is appended (for -m).
   size_t nextBatch(const HitBuffers &dst, std::vector<std::string> *names = nullptr);
 
+  // -y unique: the reference only looks at hits with NH = 1 (mm:1773), so a chromosome the annotation does not know is only
+  // reported (mm:1297) when such a hit lies on it
+  void warnOnlyForUniqueHits(bool on) { uniqueOnly_ = on; }
   uint64_t recordsRead() const { return nRecords_; }  // reference's "lines read" (= hits, mm:1772)
   std::string takeWarnings();                         // unknown chromosomes, CIGAR problems, XA problems
 
@@ -62,7 +65,7 @@ class XamReader {
   void pushRecordHits(const std::string &name, uint32_t chrMeta, uint64_t start, bool strand,
                       const std::vector<std::pair<char, int> > &cigar, bool cigarIsStar, uint32_t nHits);
   uint64_t cigarEnd(uint64_t start, uint64_t prevEnd, const std::vector<std::pair<char, int> > &cigar);
-  uint32_t chrMetaOf(const std::string &name);
+  uint32_t chrMetaOf(const std::string &name, bool quiet = false);
   void parseAlternatives(const std::string &xa);
 
   std::string fileName_;
@@ -92,6 +95,7 @@ class XamReader {
   uint64_t nRecords_ = 0;
   unsigned parseThreads_ = 1;   // record parsers working side by side on a chunk (BAM)
   bool clone_ = false;
+  bool uniqueOnly_ = false;
   std::vector<size_t> recOff_;
   std::string warnings_;
 };

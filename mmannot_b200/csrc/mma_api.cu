@@ -1077,6 +1077,7 @@ int mma_submit_bam(mma_ctx *ctx, uint32_t sample, const mma_bam_chunk *c, uint64
   v.comp = ctx->bamComp[slot].as<unsigned char>(); v.memberOff = ctx->bamMemberOff.as<u32>(); v.outOff = ctx->bamOutOff.as<u32>();
   v.out = ctx->bamOut.as<unsigned char>(); v.nMembers = nM; v.skipFirst = c->skip_first;
   v.refToChr = ctx->bamRefToChr.as<u32>(); v.nRef = ctx->bamNRef; v.strandedness = ctx->bamStrandedness;
+  v.uniqueOnly = ctx->rules.strategy == MMA_STRATEGY_UNIQUE ? 1u : 0u;
   v.flags = ctx->bamFlags.as<u32>(); v.refFirst = ctx->bamRefFirst.as<unsigned long long>();
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   if (ctx->timing) for (int k = 0; k < 4; ++k) ev[k] = ctx->getEvent();

@@ -48,6 +48,7 @@ struct BamView {
   const u32 *refToChr;        // [nRef] annotation chromosome of every BAM reference (MMA_HIT_CHR_NONE: not in the annotation)
   u32 nRef;
   u32 strandedness;           // 0 U, 1 F, 2 R (mm:836-844)
+  u32 uniqueOnly;             // -y unique: only hits with NH = 1 are looked at (mm:1773), so only they can reveal an unknown chromosome
   u32 *flags;                 // OR of BamFlag
   unsigned long long *refFirst;  // [nRef] ordinal of the first record seen on each reference (~0: none): for the host's warnings
 };
@@ -368,11 +369,13 @@ MMA_HD __forceinline__ u32 bamRecord(const BamView &v, const unsigned char *p, u
   u32 chr = 0x00FFFFFFu;
   if (refId >= 0 && (u32)refId < v.nRef) {
     chr = v.refToChr[refId];
+    if (!v.uniqueOnly || nHits == 1) {
 #ifdef __CUDA_ARCH__
-    atomicMin(&v.refFirst[refId], (unsigned long long)ordinal);
+      atomicMin(&v.refFirst[refId], (unsigned long long)ordinal);
 #else
-    if (ordinal < v.refFirst[refId]) v.refFirst[refId] = ordinal;
+      if (ordinal < v.refFirst[refId]) v.refFirst[refId] = ordinal;
 #endif
+    }
   }
   // XamReader::pushRecordHits emit(): coordinates beyond the 32-bit range cannot touch any feature
   u64 s = start, e = end;
