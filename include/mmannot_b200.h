@@ -229,6 +229,13 @@ typedef struct mma_bam_chunk {
 } mma_bam_chunk;
 int mma_bam_begin(mma_ctx *ctx, uint32_t sample, const uint32_t *ref_to_chr, uint32_t n_ref, int strandedness /* 0 U, 1 F, 2 R */);
 int mma_submit_bam(mma_ctx *ctx, uint32_t sample, const mma_bam_chunk *chunk, uint64_t *n_records, uint32_t *flags);
+/* Staged upload, so that a large chunk (the inflate kernel wants tens of thousands of members per launch) can be fed from small
+ * page-locked buffers while the file is still being read: mma_bam_stage copies n_bytes to byte `offset` of the chunk under
+ * construction (asynchronously; the host buffer is free again when the NEXT mma_bam_stage / mma_submit_bam call returns, so two
+ * buffers suffice), and mma_submit_bam with chunk->data == NULL takes the staged bytes [0, n_bytes) as its data.
+ * mma_bam_reserve sizes the staging area up front (optional). */
+int mma_bam_reserve(mma_ctx *ctx, uint64_t n_bytes);
+int mma_bam_stage(mma_ctx *ctx, const void *host_bytes, uint64_t n_bytes, uint64_t offset);
 int mma_bam_ref_first(mma_ctx *ctx, uint64_t *out, uint32_t n_ref);
 /* The hits mma_submit_bam decoded from the last chunk, copied to host arrays of n_records entries (tests: the decoder against
  * the host's XamReader).  Synchronous. */

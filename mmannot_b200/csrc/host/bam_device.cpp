@@ -48,7 +48,7 @@ bool inflateRaw(const unsigned char *src, size_t n, unsigned char *dst, size_t w
 
 DeviceBamFeeder::DeviceBamFeeder(mma_ctx *ctx, const FeatureTable &features, Strandedness strandedness)
     : ctx_(ctx), features_(features), strandedness_(strandedness) {
-  size_t mb = 192;
+  size_t mb = 64;
   if (const char *e = std::getenv("MMANNOT_B200_BAM_CHUNK_MB")) mb = static_cast<size_t>(std::max(1, std::atoi(e)));
   cap_ = mb << 20;
 }
@@ -139,55 +139,82 @@ DeviceBamFeeder::Result DeviceBamFeeder::run(const std::string &fileName, uint32
   }
   const int strand = strandedness_ == Strandedness::U ? 0 : strandedness_ == Strandedness::F ? 1 : 2;
   if (mma_bam_begin(ctx_, column, refToChr.data(), static_cast<uint32_t>(refToChr.size()), strand) != MMA_OK) { err = mma_last_error(ctx_); return Result::FAILED; }
-  // ---- chunks of whole members
+  // ---- the file goes to the device in pieces of one page-locked buffer (while the next piece is read); whole members pile up
+  //      in the staging area until there are enough of them for one inflate launch (or the file ends)
+  uint64_t kMaxComp = 1536ull << 20;
+  const uint64_t kMaxOut = 3584ull << 20;
+  if (const char *e = std::getenv("MMANNOT_B200_BAM_LAUNCH_MB")) kMaxComp = static_cast<uint64_t>(std::max(1, std::atoi(e))) << 20;  // (tests: several launches per file)
+  {
+    long here = std::ftell(f);
+    std::fseek(f, 0, SEEK_END);
+    const long size = std::ftell(f);
+    std::fseek(f, here, SEEK_SET);
+    if (size > 0) mma_bam_reserve(ctx_, std::min<uint64_t>(static_cast<uint64_t>(size), kMaxComp) + 65536);
+  }
   std::vector<uint32_t> memberOff, memberIsize;
-  for (;;) {
+  uint64_t staged = 0, inflated = 0;
+  auto submit = [&]() -> int {  // 0 ok, 1 fallback, 2 failed
+    if (memberIsize.empty()) return 0;
+    memberOff.push_back(static_cast<uint32_t>(staged));
+    mma_bam_chunk c;
+    c.data = nullptr; c.n_bytes = staged;
+    c.member_offset = memberOff.data(); c.member_isize = memberIsize.data();
+    c.n_members = static_cast<uint32_t>(memberIsize.size());
+    c.skip_first = skipFirst;
+    uint64_t n = 0;
+    uint32_t flags = 0;
+    auto ts0 = now();
+    if (mma_submit_bam(ctx_, column, &c, &n, &flags) != MMA_OK) { err = mma_last_error(ctx_); return 2; }
+    msSubmit += since(ts0);
+    if (flags) {
+      why = std::string("the file needs the host decoder:") + ((flags & MMA_BAM_HAS_XA) ? " XA tags" : "") + ((flags & MMA_BAM_STRADDLE) ? " records across BGZF members" : "") +
+            ((flags & MMA_BAM_ODD_CIGAR) ? " CIGAR operations with warnings" : "") + ((flags & MMA_BAM_ODD_AUX) ? " unknown aux types" : "") +
+            ((flags & MMA_BAM_BAD_DEFLATE) ? " deflate data this decoder rejects" : "") + ((flags & MMA_BAM_MALFORMED) ? " malformed records" : "");
+      return 1;
+    }
+    nRecords += n;
+    skipFirst = 0;
     memberOff.clear(); memberIsize.clear();
-    size_t at = pos;
-    uint64_t inflated = 0;
+    staged = 0; inflated = 0;
+    return 0;
+  };
+  for (;;) {
+    size_t at = pos, from = pos;  // [from, at) = scanned, not staged yet
+    auto stageScanned = [&]() -> bool {
+      if (at == from) return true;
+      if (mma_bam_stage(ctx_, buf_[cur] + from, at - from, staged - (at - from)) != MMA_OK) { err = mma_last_error(ctx_); return false; }
+      from = at;
+      return true;
+    };
     while (at < have) {
       size_t hdr = 0;
       const size_t total = bgzfMember(buf_[cur] + at, have - at, &hdr);
       if (total == 0) {
         if (have - at >= 18 || eof) { why = "not BGZF all the way (or a truncated file)"; return Result::FALLBACK; }
-        break;  // the member's header is cut by the end of the chunk
+        break;  // the member's header is cut by the end of the buffer
       }
       if (at + total > have) {
         if (eof) { why = "truncated BGZF member at the end of the file"; return Result::FALLBACK; }
         break;
       }
       const uint32_t isize = rd32(buf_[cur] + at + total - 4);
-      if (inflated + isize >= 0xF0000000ull) break;  // (a chunk must inflate to less than 4 GB)
-      memberOff.push_back(static_cast<uint32_t>(at - pos));
+      if (staged + total > kMaxComp || inflated + isize > kMaxOut) {  // enough for one launch
+        if (!stageScanned()) return Result::FAILED;
+        const int rc = submit();
+        if (rc == 1) return Result::FALLBACK;
+        if (rc == 2) return Result::FAILED;
+      }
+      memberOff.push_back(static_cast<uint32_t>(staged));
       memberIsize.push_back(isize);
+      staged += total;
       inflated += isize;
       at += total;
     }
-    if (memberOff.empty() && !(eof && at >= have)) { why = "a BGZF member larger than a chunk"; return Result::FALLBACK; }
-    if (!memberOff.empty()) {
-      memberOff.push_back(static_cast<uint32_t>(at - pos));
-      mma_bam_chunk c;
-      c.data = buf_[cur] + pos; c.n_bytes = at - pos;
-      c.member_offset = memberOff.data(); c.member_isize = memberIsize.data();
-      c.n_members = static_cast<uint32_t>(memberIsize.size());
-      c.skip_first = skipFirst;
-      uint64_t n = 0;
-      uint32_t flags = 0;
-      auto ts0 = now();
-      if (mma_submit_bam(ctx_, column, &c, &n, &flags) != MMA_OK) { err = mma_last_error(ctx_); return Result::FAILED; }
-      msSubmit += since(ts0);
-      if (flags) {
-        why = std::string("the file needs the host decoder:") + ((flags & MMA_BAM_HAS_XA) ? " XA tags" : "") + ((flags & MMA_BAM_STRADDLE) ? " records across BGZF members" : "") +
-              ((flags & MMA_BAM_ODD_CIGAR) ? " CIGAR operations with warnings" : "") + ((flags & MMA_BAM_ODD_AUX) ? " unknown aux types" : "") +
-              ((flags & MMA_BAM_BAD_DEFLATE) ? " deflate data this decoder rejects" : "") + ((flags & MMA_BAM_MALFORMED) ? " malformed records" : "");
-        return Result::FALLBACK;
-      }
-      nRecords += n;
-      skipFirst = 0;
-    }
+    if (!stageScanned()) return Result::FAILED;
+    if (at == pos && !(eof && at >= have)) { why = "a BGZF member larger than a buffer"; return Result::FALLBACK; }
     if (eof && at >= have) break;
-    // the rest of this buffer (a member cut by its end) moves to the front of the other one, the file continues behind it.
-    // (mma_submit_bam has synchronised on the chunk's copy: this buffer is free; the kernels of the chunk still run.)
+    // the rest of this buffer (a member cut by its end) moves to the front of the other one, the file continues behind it;
+    // the copy out of this buffer is waited for by the next mma_bam_stage call, before this buffer is filled again
     const size_t rest = have - at;
     const int nxt = cur ^ 1;
     std::memcpy(buf_[nxt], buf_[cur] + at, rest);
@@ -199,6 +226,11 @@ DeviceBamFeeder::Result DeviceBamFeeder::run(const std::string &fileName, uint32
     cur = nxt;
     pos = 0;
     if (have == 0) break;
+  }
+  {
+    const int rc = submit();
+    if (rc == 1) return Result::FALLBACK;
+    if (rc == 2) return Result::FAILED;
   }
   // ---- the reference's warnings for chromosomes the annotation does not know, in order of first appearance (mm:1297)
   if (!refNames.empty()) {

@@ -105,7 +105,7 @@ bool Counter::read(const std::string &fileName, uint32_t column, std::string &er
   stats_ = mma_sample_stats();
   if (!pinned_[0].start || !pinned_[1].key) { err = "Cannot allocate page-locked hit buffers."; return false; }
   XamReader reader(fileName, opt_.format, opt_.strandedness, features_);
-  if (!reader.open(err)) return false;
+  if (!reader.probe(err)) return false;
   reader.warnOnlyForUniqueHits(opt_.strategy == MMA_STRATEGY_UNIQUE);
   log << (reader.isBam() ? "Reading BAM file " : "Reading SAM file ") << fileName << std::endl;
   // BAM on one GPU without per-read statistics: the compressed file goes to the device as it is (inflate + record parse there);
@@ -128,6 +128,7 @@ bool Counter::read(const std::string &fileName, uint32_t column, std::string &er
   if (onDevice) {
     log << "\t" << withThousands(deviceRecords) << " lines read, done." << std::endl;
   } else {
+  if (!reader.open(err)) return false;
   if (!shards_.empty()) {
     if (writers_) { err = "Read / interval statistics need the whole input on one GPU."; return false; }
     if (!readSharded(reader, column, err, log)) return false;

@@ -72,6 +72,15 @@ uint32_t XamReader::chrMetaOf(const std::string &name, bool quiet) {
 }
 
 bool XamReader::open(std::string &err) {
+  if (!probe(err)) return false;
+  if (!bam_) {
+    sam_.open(fileName_.c_str());
+    return true;
+  }
+  return openBam(err);
+}
+
+bool XamReader::probe(std::string &err) {
   {
     std::ifstream probe(fileName_.c_str());
     if (!probe.good()) {
@@ -90,10 +99,10 @@ bool XamReader::open(std::string &err) {
     }
   }
   bam_ = (f == ReadsFormat::BAM);
-  if (!bam_) {
-    sam_.open(fileName_.c_str());
-    return true;
-  }
+  return true;
+}
+
+bool XamReader::openBam(std::string &err) {
   {
     unsigned threads = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
     if (const char *e = std::getenv("MMANNOT_B200_DECODE_THREADS")) threads = static_cast<unsigned>(std::max(1, std::atoi(e)));

@@ -38,6 +38,8 @@ class XamReader {
 
   // false + message when the file cannot be opened / is not what it claims to be
   bool open(std::string &err);
+  // the checks of open() that need no decoding: the file exists and its format is known (isBam() is valid afterwards)
+  bool probe(std::string &err);
   bool isBam() const { return bam_; }
 
   // Decodes hits into `dst` until it is full or the input ends.  A batch never ends in
@@ -56,6 +58,7 @@ class XamReader {
   struct Hit { uint32_t start, end, meta, nh; uint64_t key; };
   struct Alt { uint32_t chrMeta; bool strand; uint64_t start; std::vector<std::pair<char, int> > cigar; };
 
+  bool openBam(std::string &err);
   bool fillRaw(size_t need);  // make `need` bytes available at rawPos_ (BAM)
   XamReader(const XamReader &parent, int);  // parser clone (decodeBamChunkParallel)
   bool decodeBamRecord();

@@ -133,7 +133,8 @@ struct mma_ctx {
   DevBuf bamComp[2], bamOut, bamMemberOff, bamOutOff, bamCount, bamHitOff, bamRefToChr, bamRefFirst, bamFlags;
   DevBuf bamStart, bamEnd, bamMeta, bamNh, bamKey;
   cudaEvent_t bamCopied[2] = {nullptr, nullptr};
-  uint64_t bamChunks = 0, bamOrdinal = 0, bamLastHits = 0;
+  uint64_t bamChunks = 0, bamOrdinal = 0, bamLastHits = 0, bamStaged = 0;
+  cudaEvent_t bamStageEv = nullptr;
   u32 bamNRef = 0, bamStrandedness = 1;
   double msBam[3] = {0, 0, 0};  // inflate, count + scan, parse
   DevBuf exportBuf;          // mma_export_table_async: this context's own dump, kept for mma_restore_export (dumpBuf is rewritten by every finish)
@@ -526,6 +527,7 @@ void mma_destroy(mma_ctx *ctx) {
   ctx->gatherBuf.release();
   ctx->exportBuf.release();
   for (int k = 0; k < 2; ++k) { ctx->bamComp[k].release(); if (ctx->bamCopied[k]) cudaEventDestroy(ctx->bamCopied[k]); }
+  if (ctx->bamStageEv) cudaEventDestroy(ctx->bamStageEv);
   ctx->bamOut.release(); ctx->bamMemberOff.release(); ctx->bamOutOff.release(); ctx->bamCount.release(); ctx->bamHitOff.release();
   ctx->bamRefToChr.release(); ctx->bamRefFirst.release(); ctx->bamFlags.release();
   ctx->bamStart.release(); ctx->bamEnd.release(); ctx->bamMeta.release(); ctx->bamNh.release(); ctx->bamKey.release();
@@ -1040,6 +1042,41 @@ int mma_bam_begin(mma_ctx *ctx, uint32_t sample, const uint32_t *ref_to_chr, uin
   return MMA_OK;
 }
 
+static int bamGrow(mma_ctx *ctx, DevBuf &b, size_t need, size_t keep) {
+  if (need <= b.bytes) return MMA_OK;
+  DevBuf nb;
+  CK(nb.ensure(std::max(need, b.bytes + b.bytes / 2)));
+  if (keep) {
+    CK(cudaStreamSynchronize(ctx->sh));
+    CK(cudaMemcpy(nb.p, b.p, keep, cudaMemcpyDeviceToDevice));
+  }
+  b.release();
+  b = nb;
+  return MMA_OK;
+}
+
+int mma_bam_reserve(mma_ctx *ctx, uint64_t n_bytes) {
+  if (!ctx) return MMA_ERR_INVALID;
+  CK(cudaSetDevice(ctx->device));
+  return bamGrow(ctx, ctx->bamComp[ctx->bamChunks & 1], (size_t)n_bytes + 16, (size_t)ctx->bamStaged);
+}
+
+int mma_bam_stage(mma_ctx *ctx, const void *host_bytes, uint64_t n_bytes, uint64_t offset) {
+  if (!ctx) return MMA_ERR_INVALID;
+  if (!host_bytes && n_bytes) return ctx->fail(MMA_ERR_INVALID, "null argument");
+  if (offset + n_bytes >= 0xFFFFFFF0ull) return ctx->fail(MMA_ERR_INVALID, "a BAM chunk must stay below 4 GB");
+  CK(cudaSetDevice(ctx->device));
+  if (!ctx->bamStageEv) CK(cudaEventCreateWithFlags(&ctx->bamStageEv, cudaEventDisableTiming));
+  else CK(cudaEventSynchronize(ctx->bamStageEv));  // the previous staged copy has left its host buffer
+  DevBuf &dst = ctx->bamComp[ctx->bamChunks & 1];
+  int rc = bamGrow(ctx, dst, (size_t)(offset + n_bytes) + 16, (size_t)ctx->bamStaged);
+  if (rc) return rc;
+  if (n_bytes) CK(cudaMemcpyAsync(dst.as<char>() + offset, host_bytes, (size_t)n_bytes, cudaMemcpyHostToDevice, ctx->sh));
+  CK(cudaEventRecord(ctx->bamStageEv, ctx->sh));
+  ctx->bamStaged = std::max<uint64_t>(ctx->bamStaged, offset + n_bytes);
+  return MMA_OK;
+}
+
 int mma_submit_bam(mma_ctx *ctx, uint32_t sample, const mma_bam_chunk *c, uint64_t *n_records, uint32_t *flags) {
   if (!ctx) return MMA_ERR_INVALID;
   if (!c || !n_records || !flags) return ctx->fail(MMA_ERR_INVALID, "null argument");
@@ -1048,8 +1085,9 @@ int mma_submit_bam(mma_ctx *ctx, uint32_t sample, const mma_bam_chunk *c, uint64
   if (!ctx->bamFlags.p) return ctx->fail(MMA_ERR_STATE, "mma_bam_begin must be called first");
   *n_records = 0; *flags = 0;
   if (c->n_members == 0) return MMA_OK;
-  if (!c->data || !c->member_offset || !c->member_isize || c->n_bytes >= 0xFFFFFFF0ull || c->member_offset[c->n_members] != c->n_bytes)
+  if (!c->member_offset || !c->member_isize || c->n_bytes >= 0xFFFFFFF0ull || c->member_offset[c->n_members] != c->n_bytes)
     return ctx->fail(MMA_ERR_INVALID, "malformed BAM chunk");
+  if (!c->data && c->n_bytes > ctx->bamStaged) return ctx->fail(MMA_ERR_INVALID, "fewer bytes staged (mma_bam_stage) than the chunk claims");
   CK(cudaSetDevice(ctx->device));
   Sample &s = ctx->samples[sample];
   int rc = initSample(ctx, s);
@@ -1062,11 +1100,12 @@ int mma_submit_bam(mma_ctx *ctx, uint32_t sample, const mma_bam_chunk *c, uint64
   if (c->skip_first > c->member_isize[0]) return ctx->fail(MMA_ERR_INVALID, "skip_first beyond the first member");
   const int slot = (int)(ctx->bamChunks & 1);
   // (this slot's previous copy -- two chunks ago -- is long done: its kernels ran before the last chunk's, and that call synchronised)
-  CK(ctx->bamComp[slot].ensure(((size_t)c->n_bytes + 15) & ~(size_t)15));
+  if (c->data) CK(ctx->bamComp[slot].ensure(((size_t)c->n_bytes + 15) & ~(size_t)15));
   CK(ctx->bamMemberOff.ensure((size_t)(nM + 1) * 4)); CK(ctx->bamOutOff.ensure((size_t)(nM + 1) * 4));
   CK(ctx->bamCount.ensure((size_t)nM * 4)); CK(ctx->bamHitOff.ensure((size_t)(nM + 1) * 4));
-  CK(cudaMemcpyAsync(ctx->bamComp[slot].p, c->data, (size_t)c->n_bytes, cudaMemcpyHostToDevice, ctx->sh));
+  if (c->data) CK(cudaMemcpyAsync(ctx->bamComp[slot].p, c->data, (size_t)c->n_bytes, cudaMemcpyHostToDevice, ctx->sh));
   CK(cudaEventRecord(ctx->bamCopied[slot], ctx->sh));
+  ctx->bamStaged = 0;
   // the output buffer and the tables are shared by consecutive chunks: everything below is ordered on the compute stream
   CK(cudaStreamWaitEvent(ctx->sc, ctx->bamCopied[slot], 0));
   CK(ctx->bamOut.ensure(((size_t)total + 64 + 15) & ~(size_t)15));
@@ -1083,8 +1122,10 @@ int mma_submit_bam(mma_ctx *ctx, uint32_t sample, const mma_bam_chunk *c, uint64
   if (ctx->timing) for (int k = 0; k < 4; ++k) ev[k] = ctx->getEvent();
   if (ev[0]) cudaEventRecord(ev[0], ctx->sc);
   {
-    const u32 warps = (nM + MMA_BAM_LANES - 1) / MMA_BAM_LANES;
-    k_bam_inflate<<<gridFor((uint64_t)warps * 32, 128), 128, 0, ctx->sc>>>(v);
+    u32 lanes = MMA_BAM_LANES;
+    if (const char *e = getenv("MMANNOT_B200_BAM_LANES")) lanes = (u32)std::min(32, std::max(1, atoi(e)));  // (tuning only)
+    const u32 warps = (nM + lanes - 1) / lanes;
+    k_bam_inflate<<<gridFor((uint64_t)warps * 32, 128), 128, 0, ctx->sc>>>(v, lanes);
   }
   if (ev[1]) cudaEventRecord(ev[1], ctx->sc);
   k_bam_count<<<gridFor(nM, 128), 128, 0, ctx->sc>>>(v, ctx->bamCount.as<u32>());

@@ -239,10 +239,10 @@ MMA_HD __forceinline__ u32 ld32u(const unsigned char *p) { return (u32)p[0] | ((
 MMA_HD __forceinline__ u32 ld16u(const unsigned char *p) { return (u32)p[0] | ((u32)p[1] << 8); }
 
 // one thread per member, MMA_BAM_LANES members per warp
-__global__ void __launch_bounds__(128) k_bam_inflate(BamView v) {
+__global__ void __launch_bounds__(128) k_bam_inflate(BamView v, u32 lanes) {
   const u32 warpGlobal = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31u;
-  if (lane >= MMA_BAM_LANES) return;
-  const u32 m = warpGlobal * MMA_BAM_LANES + lane;
+  if (lane >= lanes) return;
+  const u32 m = warpGlobal * lanes + lane;
   if (m >= v.nMembers) return;
   const unsigned char *p = v.comp + v.memberOff[m];
   const u32 total = v.memberOff[m + 1] - v.memberOff[m];
