@@ -117,7 +117,9 @@ typedef struct mma_hit_batch {
  *              bit  31     read strand (MMA_HIT_STRAND_BIT)
  *   run_key[r]             read key of the r-th run of the batch
  *   tile_run_base[t]       number of runs that start before hit t * MMA_PACK_TILE
- *   esc_*                  ascending hit indices with their full end and NH, for hits a field of which did not fit */
+ *   esc_*                  ascending hit indices with their full end and NH, for hits a field of which did not fit
+ * The struct is TRUSTED input, normally the output of mma_pack_hits: tile_run_base, the run-start bits and n_runs must agree and
+ * esc_index must be strictly increasing (the device does not re-check them; inconsistent values read out of bounds). */
 #define MMA_PACK_TILE 1024
 #define MMA_PACKED_CHR_NONE 0x3FFFu
 #define MMA_PACKED_RUN_START 0x40000000u

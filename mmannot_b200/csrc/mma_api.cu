@@ -587,8 +587,8 @@ int mma_load_features(mma_ctx *ctx, const mma_features *f) {
   }
   chrBinBase[nChr] = (u32)entries;
 
-  DevBuf dChr, dStart, dEnd, dType, dStrand, dChrStart, dChrBinBase, dSpanCount, dTotal;
-  auto cleanup = [&]() { dChr.release(); dStart.release(); dEnd.release(); dType.release(); dStrand.release(); dChrStart.release(); dChrBinBase.release(); dSpanCount.release(); dTotal.release(); };
+  DevBuf dChr, dStart, dEnd, dType, dStrand, dChrStart, dChrBinBase, dSpanCount, dSpanOff, dScanTmp, dTotal;
+  auto cleanup = [&]() { dChr.release(); dStart.release(); dEnd.release(); dType.release(); dStrand.release(); dChrStart.release(); dChrBinBase.release(); dSpanCount.release(); dSpanOff.release(); dScanTmp.release(); dTotal.release(); };
 #define CKL(call)                                                                                  \
   do {                                                                                             \
     cudaError_t _e = (call);                                                                       \
@@ -597,7 +597,10 @@ int mma_load_features(mma_ctx *ctx, const mma_features *f) {
   CKL(dChr.ensure((size_t)n * 4)); CKL(dStart.ensure((size_t)n * 4)); CKL(dEnd.ensure((size_t)n * 4));
   CKL(dType.ensure(n)); CKL(dStrand.ensure(n));
   CKL(dChrStart.ensure((size_t)(nChr + 1) * 4)); CKL(dChrBinBase.ensure((size_t)(nChr + 1) * 4));
-  CKL(dSpanCount.ensure((size_t)entries * 4)); CKL(dTotal.ensure(4));
+  CKL(dSpanCount.ensure((size_t)entries * 4)); CKL(dSpanOff.ensure((size_t)entries * 4)); CKL(dTotal.ensure(4));
+  size_t scanBytes = 0;
+  CKL(cub::DeviceScan::ExclusiveSum(nullptr, scanBytes, dSpanCount.as<u32>(), dSpanOff.as<u32>(), (int)entries, ctx->sc));
+  CKL(dScanTmp.ensure(scanBytes ? scanBytes : 1));
   CKL(ctx->feat.ensure((size_t)n * sizeof(uint4)));
   CKL(ctx->chrInfo.ensure((size_t)nChr * sizeof(uint2)));
   CKL(ctx->bins.ensure((size_t)entries * sizeof(uint2)));
@@ -626,7 +629,8 @@ int mma_load_features(mma_ctx *ctx, const mma_features *f) {
     k_pack_features<<<gridFor(n, 256), 256, 0, st>>>(b, ctx->feat.as<uint4>());
     k_prefix_max_end<<<nChr, 256, 0, st>>>(b, ctx->feat.as<uint4>());
     k_build_bins<<<gridFor(entries, 128), 128, 0, st>>>(b, ctx->feat.as<uint4>(), ctx->bins.as<uint2>(), dSpanCount.as<u32>(), nullptr, 0);
-    k_scan_spans<<<1, 1024, 0, st>>>(dSpanCount.as<u32>(), ctx->bins.as<uint2>(), (u32)entries, dTotal.as<u32>());
+    CKL(cub::DeviceScan::ExclusiveSum(dScanTmp.p, scanBytes, dSpanCount.as<u32>(), dSpanOff.as<u32>(), (int)entries, st));
+    k_set_span_offsets<<<gridFor(entries, 256), 256, 0, st>>>(dSpanOff.as<u32>(), dSpanCount.as<u32>(), ctx->bins.as<uint2>(), (u32)entries, dTotal.as<u32>());
     ctx->launches += 4;
   }
   CKL(cudaMemcpyAsync(&total, dTotal.p, 4, cudaMemcpyDeviceToHost, st));

@@ -1391,33 +1391,12 @@ __global__ void k_build_bins(BuildView b, const uint4 *__restrict__ feat, uint2 
   }
 }
 
-// exclusive prefix sum of spanCount into bins[].y (single block, tiles with a running carry)
-__global__ void k_scan_spans(const u32 *__restrict__ spanCount, uint2 *bins, u32 n, u32 *total) {
-  __shared__ u32 warpSum[32];
-  __shared__ u32 carry;
-  if (threadIdx.x == 0) carry = 0;
-  __syncthreads();
-  const u32 lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-  for (u32 base = 0; base < n; base += blockDim.x) {
-    const u32 i = base + threadIdx.x;
-    const u32 x = (i < n) ? spanCount[i] : 0u;
-    u32 v = x;
-    for (int d = 1; d < 32; d <<= 1) { const u32 o = __shfl_up_sync(0xffffffffu, v, d); if (lane >= (u32)d) v += o; }
-    if (lane == 31) warpSum[warp] = v;
-    __syncthreads();
-    if (warp == 0) {
-      u32 w = (lane < (blockDim.x >> 5)) ? warpSum[lane] : 0u;
-      for (int d = 1; d < 32; d <<= 1) { const u32 o = __shfl_up_sync(0xffffffffu, w, d); if (lane >= (u32)d) w += o; }
-      warpSum[lane] = w;
-    }
-    __syncthreads();
-    const u32 incl = v + carry + (warp > 0 ? warpSum[warp - 1] : 0u);
-    if (i < n) bins[i].y = incl - x;
-    __syncthreads();
-    if (threadIdx.x == blockDim.x - 1) carry = incl;
-    __syncthreads();
-  }
-  if (threadIdx.x == 0) *total = carry;
+// offsets of the spanning lists (exclusive prefix sum of spanCount, formed by the library scan the index build uses anyway) into bins[].y
+__global__ void k_set_span_offsets(const u32 *__restrict__ spanOff, const u32 *__restrict__ spanCount, uint2 *bins, u32 n, u32 *total) {
+  const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  bins[i].y = spanOff[i];
+  if (i == n - 1) *total = spanOff[i] + spanCount[i];
 }
 
 // ---- segment answer table

@@ -42,7 +42,7 @@ def test_device_decode_equals_reference_and_host_decode(tmp_path, shape, cfg_key
         base = ["-a", gtf, "-c", cfg_path, "-r", bam] + extra
         ref = run([ref_exe] + base)
         dev = run([CLI] + base, MMANNOT_B200_VERBOSE="1")
-        small = run([CLI] + base, MMANNOT_B200_VERBOSE="1", MMANNOT_B200_BAM_CHUNK_MB="1")
+        small = run([CLI] + base, MMANNOT_B200_VERBOSE="1", MMANNOT_B200_BAM_CHUNK_MB="1", MMANNOT_B200_BAM_LAUNCH_MB="2")
         hst = run([CLI] + base, MMANNOT_B200_HOST_DECODE="1")
         assert dev.returncode == 0, dev.stderr[-800:]
         assert "device BAM decoder not used" not in dev.stderr, dev.stderr[-400:]
