@@ -239,12 +239,8 @@ k_batch_lean(const __grid_constant__ IndexView ix, const __grid_constant__ FastV
     }
   };
 
-  // The run that reaches the end of a tile is never closed there (that would need the first key of the next tile): its state --
-  // first record, union of the element sets (bit 31: irregular), NH and key of its last record -- is carried, and lane 0 closes
-  // it at the top of the next tile when that tile starts another run (after the chunk's last tile: below the loop).
-  bool cValid = false;
+  bool cValid = false, cCont = false;  // cCont: the run open at the end of the tile continues in the next tile
   u32 cStart = 0, cTot = 0, cNh = 0;
-  u64 cKey = KEY_EMPTY;
   // lane 0: does the chunk's first record start a run?  (The state carried into the batch counts as the record before it.)
   bool headFirst = true;
   const Carry *carryIn = nullptr;
@@ -285,7 +281,7 @@ k_batch_lean(const __grid_constant__ IndexView ix, const __grid_constant__ FastV
       }
       const u64 prev = __shfl_up_sync(FULL, key[3], 1);
       // lane 0: the tile's first record starts a run unless the previous tile's last run continues (first tile: see headFirst)
-      const bool head0 = (lane == 0) ? (it == 0 ? headFirst : key[0] != cKey) : (key[0] != prev);
+      const bool head0 = (lane == 0) ? (it == 0 ? headFirst : !cCont) : (key[0] != prev);
       hbits = (head0 ? 1u : 0u) | ((key[1] != key[0]) ? 2u : 0u) | ((key[2] != key[1]) ? 4u : 0u) | ((key[3] != key[2]) ? 8u : 0u);
       F = __ballot_sync(FULL, hbits != 0);
       nextKey = __shfl_sync(FULL, key[3], 31);
@@ -431,7 +427,18 @@ k_batch_lean(const __grid_constant__ IndexView ix, const __grid_constant__ FastV
     u32 nWalk = 0, closeBits = 0;
     u32 inc = 0, lastHeadPos = 0, F2 = 0;
     bool serialTile = false;
+    u32 tileEndsRun = 1;  // the record after the tile's last one starts another run (or the batch ends there)
     if (STRAT == 0 && !DEFER) {
+      // first key of the next tile: from the next stage of the ring, or (last tile of the chunk) from global memory
+      if (t + 1 < t1) {
+        const bool nextFull = (t + 2) * WT_HITS <= h.n;
+        if (nextFull) mbarWait(wbase + LEAN_BAR_OFF + (s ^ 1u) * 8, ((it + 1) >> 1) & 1u);
+        u64 pk = lds64(wbase + (s ^ 1u) * LEAN_STAGE_BYTES + 2048);
+        if (nextFull) pk = normKey(pk);
+        tileEndsRun = (pk != nextKey) ? 1u : 0u;
+      } else if ((size_t)t1 * WT_HITS < h.n) {
+        tileEndsRun = (normKey(__ldg(&h.key[(size_t)t1 * WT_HITS])) != nextKey) ? 1u : 0u;
+      }
       // ---- per-read countdown (mm:1669-1702)
       if (it == 0 && carryIn) {  // lane 0 of the batch's first tile: the read carried into this batch
         if (!(hbits & 1u)) w.walk(0, carryIn->key, carryIn);
@@ -442,15 +449,6 @@ k_batch_lean(const __grid_constant__ IndexView ix, const __grid_constant__ FastV
           ctl->dirty = 1;
         }
       }
-      if (lane == 0 && it != 0 && cValid && (hbits & 1u)) {  // the run carried to the end of the previous tile ended there
-        if (GROUPS) {
-          const u32 rem = (cNh > 1) ? (base - cStart) % cNh : 0u;  // (complete groups were counted by their last records)
-          if (rem) { ++pWalks; w.walk(base - rem, cKey, nullptr); }
-        } else {
-          if ((int)cTot >= 0 && cNh > 1 && cNh == base - cStart) { count((u64)cTot); pOwnClos += 0x10000u; }
-          else if ((int)cTot < 0 || cNh > 1) { ++pWalks; w.walk(cStart, cKey, nullptr); }
-        }
-      }
       const u32 before = F & ((1u << lane) - 1u);
       u32 prevNh = __shfl_up_sync(FULL, nh[3], 1);
       if (lane == 0) prevNh = cNh;
@@ -458,7 +456,7 @@ k_batch_lean(const __grid_constant__ IndexView ix, const __grid_constant__ FastV
       const u32 sPrev = __shfl_sync(FULL, lastHeadPos, before ? (31 - __clz(before)) : 0);
       const u32 nextHead0 = __shfl_down_sync(FULL, hbits & 1u, 1);
       // bit j: the next record starts another run, i.e. this record ends its run (the tile's last record: from the peek)
-      const u32 lastBits = (hbits >> 1) | ((lane < 31u ? nextHead0 : 0u) << 3);  // (the tile's last record: decided by the next tile)
+      const u32 lastBits = (hbits >> 1) | ((lane < 31u ? nextHead0 : tileEndsRun) << 3);
       // a run that starts before this lane's hits: its first record, and whether this warp owns it at all
       const u32 inStart = before ? sPrev : cStart;
       const bool inMine = before || cValid;  // else the run starts in another warp's chunk: that warp finishes it
@@ -660,25 +658,20 @@ k_batch_lean(const __grid_constant__ IndexView ix, const __grid_constant__ FastV
         }
       }
       cNh = __shfl_sync(FULL, nh[3], 31);
-      cKey = nextKey;
+      cCont = tileEndsRun == 0;
     }
   }
-  // ---- the run that reaches the end of the chunk: when it continues in another warp's chunk, its remaining reads (GROUPS: from the
-  //      group that is open there, or starts there) are finished by the serial walk; when it ends with the chunk (or the batch),
-  //      it is closed here like a run carried from tile to tile
-  if (STRAT == 0 && !DEFER && cValid && t1 > t0 && lane == 0) {
-    const u32 next = min(t1 * WT_HITS, h.n);
-    const bool continues = next < h.n && normKey(h.key[next]) == cKey;
-    const u32 rem = (GROUPS && cNh > 1) ? (next - cStart) % cNh : 0u;
+  // ---- a run open at the end of the chunk continues in another warp's chunk: its remaining reads (GROUPS: from the group that is
+  //      open there, or starts there) are finished by the serial walk.  (A run ending exactly at the chunk's last record was
+  //      closed above, like the last run of the batch.)
+  if (STRAT == 0 && !DEFER && cValid && cCont && t1 > t0 && lane == 0) {
+    const u32 next = t1 * WT_HITS;
+    const u64 k = normKey(h.key[next]);
     if (GROUPS) {
-      if (continues || rem) w.walk(next - rem, cKey, nullptr);
-    } else if (continues) {
-      w.walk(cStart, cKey, nullptr);
-    } else if ((int)cTot >= 0 && cNh > 1 && cNh == next - cStart) {
-      count((u64)cTot);
-      pOwnClos += 0x10000u;
-    } else if ((int)cTot < 0 || cNh > 1) {
-      w.walk(cStart, cKey, nullptr);
+      const u32 o = next - cStart;
+      w.walk(next - ((cNh > 1) ? o % cNh : 0u), k, nullptr);
+    } else {
+      w.walk(cStart, k, nullptr);
     }
   }
   const u32 cAsg = pAsgUniq & 0xFFFFu, cClosed = pOwnClos >> 16, cResc = pMissResc >> 16;
