@@ -118,6 +118,9 @@ struct mma_ctx {
   int nSM = 148;
   u32 maxGrid = 0;           // MMANNOT_B200_MAX_GRID=n: cap on k_batch blocks, so that small test inputs still give every warp a multi-tile chunk (testing only)
   size_t randDrawsUsed = 0;  // -y random: rand() draws consumed by the samples finished so far
+  DevBuf rndKeys, rndVals;   // -y random over several input files: what the reference's seen / chosenId / numberSeen keep (mm:1742-1747)
+  u32 rndCap = 0;
+  uint64_t rndNames = 0;     // upper bound of the names held
   int forceGroups = -1;      // MMANNOT_B200_GROUPS=0/1: pin the variant (testing only)
   bool preferDefer = false;  // the last sample / batch left most multi-mapping reads unfinished: start the next sample in DEFER mode
   int forceDefer = -1;       // MMANNOT_B200_DEFER=0/1: pin it (testing only)
@@ -526,6 +529,7 @@ void mma_destroy(mma_ctx *ctx) {
   ctx->dumpBuf.release();
   ctx->gatherBuf.release();
   ctx->exportBuf.release();
+  ctx->rndKeys.release(); ctx->rndVals.release();
   for (int k = 0; k < 2; ++k) { ctx->bamComp[k].release(); if (ctx->bamCopied[k]) cudaEventDestroy(ctx->bamCopied[k]); }
   if (ctx->bamStageEv) cudaEventDestroy(ctx->bamStageEv);
   ctx->bamOut.release(); ctx->bamMemberOff.release(); ctx->bamOutOff.release(); ctx->bamCount.release(); ctx->bamHitOff.release();
@@ -1288,8 +1292,33 @@ static int finishDeferred(mma_ctx *ctx, Sample &s, u32 nSlow) {
     cudaError_t e;
     if ((e = headOrd.ensure((size_t)nSlow * 8)) != cudaSuccess || (e = headSorted.ensure((size_t)nSlow * 8)) != cudaSuccess ||
         (e = nHeadsDev.ensure(4)) != cudaSuccess) { cleanup2(); cleanup(); return ctx->fail(MMA_ERR_CUDA, cudaGetErrorString(e)); }
+    // several input files: the names of this file join the map of the run (worst case: every deferred record another name)
+    RndMap map;
+    map.keys = nullptr; map.vals = nullptr; map.capMask = 0;
+    if (ctx->params.n_samples > 1) {
+      const uint64_t need = 2 * (ctx->rndNames + nSlow) + 1024;
+      if (need > ctx->rndCap) {
+        u32 cap = 1024;
+        while (cap < need && cap < 0x80000000u) cap <<= 1;
+        DevBuf nk, nv;
+        if ((e = nk.ensure((size_t)cap * 8)) != cudaSuccess || (e = nv.ensure((size_t)cap * 8)) != cudaSuccess) { nk.release(); nv.release(); cleanup2(); cleanup(); return ctx->fail(MMA_ERR_CUDA, cudaGetErrorString(e)); }
+        k_fill_u64<<<gridFor(cap, 256), 256, 0, st>>>(nk.as<u64>(), KEY_EMPTY, cap);
+        RndMap to;
+        to.keys = nk.as<u64>(); to.vals = nv.as<u64>(); to.capMask = cap - 1;
+        if (ctx->rndCap) {
+          RndMap from;
+          from.keys = ctx->rndKeys.as<u64>(); from.vals = ctx->rndVals.as<u64>(); from.capMask = ctx->rndCap - 1;
+          k_rnd_rehash<<<gridFor(ctx->rndCap, 256), 256, 0, st>>>(from, to);
+        }
+        cudaStreamSynchronize(st);
+        ctx->rndKeys.release(); ctx->rndVals.release();
+        ctx->rndKeys = nk; ctx->rndVals = nv; ctx->rndCap = cap;
+      }
+      map.keys = ctx->rndKeys.as<u64>(); map.vals = ctx->rndVals.as<u64>(); map.capMask = ctx->rndCap - 1;
+      ctx->rndNames += nSlow;
+    }
     cudaMemsetAsync(nHeadsDev.p, 0, 4, st);
-    k_slow_random_heads<<<g, 256, 0, st>>>(perm, nSlow, slow, headOrd.as<u64>(), nHeadsDev.as<u32>());
+    k_slow_random_heads<<<g, 256, 0, st>>>(perm, nSlow, slow, map, headOrd.as<u64>(), nHeadsDev.as<u32>());
     ctx->launches++;
     u32 nHeads = 0;
     cudaMemcpyAsync(&nHeads, nHeadsDev.p, 4, cudaMemcpyDeviceToHost, st);
@@ -1321,7 +1350,7 @@ static int finishDeferred(mma_ctx *ctx, Sample &s, u32 nSlow) {
     }
     if ((e = randDev.ensure((size_t)std::max<u32>(nHeads, 1) * 4)) != cudaSuccess) { tmp2.release(); cleanup2(); cleanup(); return ctx->fail(MMA_ERR_CUDA, cudaGetErrorString(e)); }
     cudaMemcpyAsync(randDev.p, stream.data(), (size_t)nHeads * 4, cudaMemcpyHostToDevice, st);
-    k_slow_random_pick<<<g, 256, 0, st>>>(perm, nSlow, slow, headSorted.as<u64>(), nHeads, randDev.as<u32>(), r, table);
+    k_slow_random_pick<<<g, 256, 0, st>>>(perm, nSlow, slow, headSorted.as<u64>(), nHeads, randDev.as<u32>(), r, table, map);
     ctx->launches++;
     e = cudaStreamSynchronize(st);
     tmp2.release();

@@ -1208,32 +1208,80 @@ __global__ void k_slow_default_byord(u32 n, SlowView s, Rules r, TableView table
   if (hi - lo + 1 == (u64)len) atomicAdd(&ctl->deferContig, 1u);
 }
 
-// random (mm:1706-1726): segment heads publish the ordinal of the name's first annotated hit ...
-__global__ void k_slow_random_heads(const u32 *__restrict__ perm, u32 n, SlowView s, u64 *headOrd, u32 *nHeads) {
+// random (mm:1706-1726).  A name draws i = rand() % NH at its first annotated hit and its i-th annotated hit (0-based, counted
+// over ALL the input files of the run: Counter::clear keeps seen / chosenId / numberSeen, mm:1742-1747) is the one counted;
+// afterwards the name is "seen" and every further hit of it is ignored.  The state that outlives an input file sits in a device
+// map read key -> RND_SEEN | (chosen index << 32 | annotated hits so far), kept only when the context has several samples.
+#define RND_SEEN 0xFFFFFFFFFFFFFFFFull
+struct RndMap {
+  u64 *keys, *vals;  // open addressing, KEY_EMPTY = free
+  u32 capMask;       // 0 with keys == nullptr: no map (single input file)
+};
+__device__ __forceinline__ bool rndFind(const RndMap &m, u64 key, u64 &val) {
+  if (!m.keys) return false;
+  u32 slot = (u32)mix64(key) & m.capMask;
+  for (u32 probe = 0; probe <= m.capMask; ++probe) {
+    const u64 k = m.keys[slot];
+    if (k == key) { val = m.vals[slot]; return true; }
+    if (k == KEY_EMPTY) return false;
+    slot = (slot + 1) & m.capMask;
+  }
+  return false;
+}
+__device__ __forceinline__ void rndStore(const RndMap &m, u64 key, u64 val) {  // (one thread per key: no two writers of a key)
+  if (!m.keys) return;
+  u32 slot = (u32)mix64(key) & m.capMask;
+  for (u32 probe = 0; probe <= m.capMask; ++probe) {
+    u64 k = m.keys[slot];
+    if (k == KEY_EMPTY) k = atomicCAS(&m.keys[slot], KEY_EMPTY, key), k = (k == KEY_EMPTY) ? key : k;
+    if (k == key) { m.vals[slot] = val; return; }
+    slot = (slot + 1) & m.capMask;
+  }
+}
+__global__ void k_rnd_rehash(RndMap from, RndMap to) {
+  const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i > from.capMask) return;
+  const u64 k = from.keys[i];
+  if (k != KEY_EMPTY) rndStore(to, k, from.vals[i]);
+}
+// ... segment heads of names that have not drawn yet publish the ordinal of the name's first annotated hit ...
+__global__ void k_slow_random_heads(const u32 *__restrict__ perm, u32 n, SlowView s, RndMap map, u64 *headOrd, u32 *nHeads) {
   const u32 p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= n) return;
   const u64 k = s.key[perm[p]];
   if (p > 0 && s.key[perm[p - 1]] == k) return;
+  u64 state;
+  if (rndFind(map, k, state)) return;  // seen, or drew in an earlier file
   headOrd[atomicAdd(nHeads, 1u)] = s.ord[perm[p]];
 }
 // ... and once those ordinals are sorted, the rank of a name's first annotated hit is the index of its
 // rand() draw; the drawn-th annotated hit of the name (if the name has that many) is the one counted.
 __global__ void k_slow_random_pick(const u32 *__restrict__ perm, u32 n, SlowView s, const u64 *__restrict__ sortedHeadOrd, u32 nHeads,
-                                   const u32 *__restrict__ randStream, Rules r, TableView table) {
+                                   const u32 *__restrict__ randStream, Rules r, TableView table, RndMap map) {
   const u32 p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= n) return;
   const u32 id0 = perm[p];
   const u64 k = s.key[id0];
   if (p > 0 && s.key[perm[p - 1]] == k) return;
-  const u64 ord0 = s.ord[id0];
-  u32 lo = 0, hi = nHeads;
-  while (lo < hi) { const u32 mid = (lo + hi) >> 1; if (sortedHeadOrd[mid] < ord0) lo = mid + 1; else hi = mid; }
-  const u32 nh0 = s.nh[id0];
-  const u32 pick = nh0 ? randStream[lo] % nh0 : 0u;
-  const u32 q = p + pick;
-  if (q < n && q >= p) {
-    const u32 id = perm[q];
-    if (s.key[id] == k) tableAdd(table, rescueSingle(r, s.mask[id]), 1);
+  u32 len = 1;  // annotated hits of the name in this file
+  while (p + len < n && s.key[perm[p + len]] == k) ++len;
+  u64 state;
+  u64 chosen, before = 0;  // index of the hit to count; annotated hits of the name in earlier files
+  if (rndFind(map, k, state)) {
+    if (state == RND_SEEN) return;
+    chosen = state >> 32; before = state & 0xFFFFFFFFull;
+  } else {
+    const u64 ord0 = s.ord[id0];
+    u32 lo = 0, hi = nHeads;
+    while (lo < hi) { const u32 mid = (lo + hi) >> 1; if (sortedHeadOrd[mid] < ord0) lo = mid + 1; else hi = mid; }
+    const u32 nh0 = s.nh[id0];
+    chosen = nh0 ? randStream[lo] % nh0 : 0u;
+  }
+  if (chosen >= before && chosen - before < len) {
+    tableAdd(table, rescueSingle(r, s.mask[perm[p + (u32)(chosen - before)]]), 1);
+    rndStore(map, k, RND_SEEN);
+  } else {
+    rndStore(map, k, (chosen << 32) | ((before + len) & 0xFFFFFFFFull));
   }
 }
 

@@ -153,3 +153,26 @@ def test_cli_threads_spread_files_over_contexts(workload):
         assert pr.stdout == ref_out
         pick = lambda txt: [l for l in txt.split("\n") if l.startswith("\t#") or l.startswith("Results for")]
         assert pick(pr.stderr) == pick(ref_err)
+
+
+@pytest.mark.skipif(pyoracle.ref_binary("fixed") is None or not os.path.exists(CLI), reason="needs oracle/_ref and the CLI binary")
+def test_random_remembers_read_names_across_input_files(workload):
+    """-y random keeps seen / chosenId / numberSeen over the input files of a run (Counter::clear does not touch them,
+    mmannot.cpp:1742-1747): a name that was counted in one file is ignored in the next, a name whose drawn hit lies beyond its
+    hits in one file goes on counting in the next.  Three files with overlapping read ranges (so that names repeat), also
+    decoded on the host."""
+    w = workload
+    bams = []
+    for i, (first, n) in enumerate(((0, 12000), (6000, 12000), (0, 20000))):
+        b = str(w["tmp"] / ("overlap%d.bam" % i))
+        if not os.path.exists(b):
+            w["synth"].write_bam(b, first, n)
+        bams.append(b)
+    common_args = ["-a", w["gtf"], "-c", w["cfg_path"], "-r"] + bams + ["-s", "F", "-y", "random"]
+    rc, ref_out, ref_err = pyoracle.run_reference(common_args, kind="fixed")
+    assert rc == 0, ref_err
+    for env in ({}, {"MMANNOT_B200_HOST_DECODE": "1"}):
+        pr = subprocess.run([CLI] + common_args, capture_output=True, text=True, timeout=300, env=dict(os.environ, **env))
+        assert pr.returncode == 0, pr.stderr
+        assert pr.stdout == ref_out
+        assert pyoracle.parse_stats(pr.stderr) == pyoracle.parse_stats(ref_err)
