@@ -1130,10 +1130,8 @@ int mma_submit_bam(mma_ctx *ctx, uint32_t sample, const mma_bam_chunk *c, uint64
   if (ctx->timing) for (int k = 0; k < 4; ++k) ev[k] = ctx->getEvent();
   if (ev[0]) cudaEventRecord(ev[0], ctx->sc);
   {
-    u32 lanes = MMA_BAM_LANES;
-    if (const char *e = getenv("MMANNOT_B200_BAM_LANES")) lanes = (u32)std::min(32, std::max(1, atoi(e)));  // (tuning only)
-    const u32 warps = (nM + lanes - 1) / lanes;
-    k_bam_inflate<<<gridFor((uint64_t)warps * 32, 128), 128, 0, ctx->sc>>>(v, lanes);
+    const u32 warps = (nM + MMA_BAM_LANES - 1) / MMA_BAM_LANES;
+    k_bam_inflate<<<gridFor((uint64_t)warps * 32, BAM_INFLATE_THREADS), BAM_INFLATE_THREADS, 0, ctx->sc>>>(v);
   }
   if (ev[1]) cudaEventRecord(ev[1], ctx->sc);
   k_bam_count<<<gridFor(nM, 128), 128, 0, ctx->sc>>>(v, ctx->bamCount.as<u32>());

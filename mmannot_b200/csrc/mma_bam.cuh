@@ -98,13 +98,17 @@ struct BitReader {
 
 // canonical Huffman code: counts per length + symbols in code order (bit-serial decode), and a 9-bit first-level table
 #define HUFF_FAST_BITS 9
-struct Huff {
+template <int NSYM>
+struct HuffT {
   unsigned short count[16];
-  unsigned short symbol[288];
+  unsigned short symbol[NSYM];
   unsigned short fast[1 << HUFF_FAST_BITS];  // (length << 9) | symbol for codes of at most 9 bits, 0 = longer / invalid
 };
+typedef HuffT<288> Huff;      // literal / length code (and the code-length code while a dynamic block's header is read)
+typedef HuffT<32> HuffDist;   // distance code
 
-MMA_HD __noinline__ bool huffBuild(Huff &h, const unsigned char *length, int n) {
+template <int NSYM>
+MMA_HD __noinline__ bool huffBuild(HuffT<NSYM> &h, const unsigned char *length, int n) {
   for (int i = 0; i < 16; ++i) h.count[i] = 0;
   for (int i = 0; i < n; ++i) h.count[length[i]]++;
   for (int i = 0; i < (1 << HUFF_FAST_BITS); ++i) h.fast[i] = 0;
@@ -135,7 +139,8 @@ MMA_HD __noinline__ bool huffBuild(Huff &h, const unsigned char *length, int n) 
   return true;
 }
 
-MMA_HD __forceinline__ int huffDecode(const Huff &h, BitReader &br) {
+template <int NSYM>
+MMA_HD __forceinline__ int huffDecode(const HuffT<NSYM> &h, BitReader &br) {
   const u32 look = br.peek(15);
   const unsigned short e = h.fast[look & ((1u << HUFF_FAST_BITS) - 1u)];
   if (e) { br.drop(e >> 9); return e & 511; }
@@ -151,14 +156,28 @@ MMA_HD __forceinline__ int huffDecode(const Huff &h, BitReader &br) {
   return -1;
 }
 
-MMA_HD inline u32 kLenBase(int i) { const unsigned short t[29] = {3, 4, 5, 6, 7, 8, 9, 10, 11, 13, 15, 17, 19, 23, 27, 31, 35, 43, 51, 59, 67, 83, 99, 115, 131, 163, 195, 227, 258}; return t[i]; }
-MMA_HD inline u32 kLenExtra(int i) { const unsigned char t[29] = {0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 4, 5, 5, 5, 5, 0}; return t[i]; }
-MMA_HD inline u32 kDistBase(int i) { const unsigned short t[30] = {1, 2, 3, 4, 5, 7, 9, 13, 17, 25, 33, 49, 65, 97, 129, 193, 257, 385, 513, 769, 1025, 1537, 2049, 3073, 4097, 6145, 8193, 12289, 16385, 24577}; return t[i]; }
-MMA_HD inline u32 kDistExtra(int i) { const unsigned char t[30] = {0, 0, 0, 0, 1, 1, 2, 2, 3, 3, 4, 4, 5, 5, 6, 6, 7, 7, 8, 8, 9, 9, 10, 10, 11, 11, 12, 12, 13, 13}; return t[i]; }
-MMA_HD inline u32 kClOrder(int i) { const unsigned char t[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15}; return t[i]; }
+// length / distance code tables of RFC 1951 (constant memory on the device, plain arrays for the CPU check)
+#define MMA_DEFLATE_TABLES(Q)                                                                                                                  \
+  Q unsigned short kLenBaseT[29] = {3, 4, 5, 6, 7, 8, 9, 10, 11, 13, 15, 17, 19, 23, 27, 31, 35, 43, 51, 59, 67, 83, 99, 115, 131, 163, 195, 227, 258}; \
+  Q unsigned char kLenExtraT[29] = {0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 4, 5, 5, 5, 5, 0};                          \
+  Q unsigned short kDistBaseT[30] = {1, 2, 3, 4, 5, 7, 9, 13, 17, 25, 33, 49, 65, 97, 129, 193, 257, 385, 513, 769, 1025, 1537, 2049, 3073, 4097, 6145, 8193, 12289, 16385, 24577}; \
+  Q unsigned char kDistExtraT[30] = {0, 0, 0, 0, 1, 1, 2, 2, 3, 3, 4, 4, 5, 5, 6, 6, 7, 7, 8, 8, 9, 9, 10, 10, 11, 11, 12, 12, 13, 13};              \
+  Q unsigned char kClOrderT[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
+namespace devtab { MMA_DEFLATE_TABLES(__device__ __constant__) }
+namespace hosttab { MMA_DEFLATE_TABLES(static const) }
+#ifdef __CUDA_ARCH__
+#define MMA_TAB(name) devtab::name
+#else
+#define MMA_TAB(name) hosttab::name
+#endif
+MMA_HD inline u32 kLenBase(int i) { return MMA_TAB(kLenBaseT)[i]; }
+MMA_HD inline u32 kLenExtra(int i) { return MMA_TAB(kLenExtraT)[i]; }
+MMA_HD inline u32 kDistBase(int i) { return MMA_TAB(kDistBaseT)[i]; }
+MMA_HD inline u32 kDistExtra(int i) { return MMA_TAB(kDistExtraT)[i]; }
+MMA_HD inline u32 kClOrder(int i) { return MMA_TAB(kClOrderT)[i]; }
 
 // one raw deflate stream (RFC 1951) from [src, src + srcLen) into dst[0 .. dstLen); true when it ends exactly at dstLen
-MMA_HD __noinline__ bool inflateMember(const unsigned char *src, u32 srcLen, unsigned char *dst, u32 dstLen, Huff &lit, Huff &dist) {
+MMA_HD __noinline__ bool inflateMember(const unsigned char *src, u32 srcLen, unsigned char *dst, u32 dstLen, Huff &lit, HuffDist &dist) {
   BitReader br{src, src + srcLen, 0ull, 0, false};
   u32 out = 0;
   unsigned char lengths[320];
@@ -220,8 +239,20 @@ MMA_HD __noinline__ bool inflateMember(const unsigned char *src, u32 srcLen, uns
           if (ds < 0 || ds >= 30) return false;
           const u32 d = kDistBase(ds) + br.bits((int)kDistExtra(ds));
           if (d > out || out + len > dstLen) return false;
+          // the source lies d bytes behind the destination: up to min(d, 8) bytes can be read before any of them is rewritten, so
+          // the loads of a chunk do not wait for one another (a run-length match, d < 8, repeats its d bytes)
           const unsigned char *from = dst + out - d;
-          for (u32 i = 0; i < len; ++i) dst[out + i] = from[i];  // (byte by byte: the ranges may overlap)
+          u32 i = 0;
+          if (d >= 8) {
+            for (; i + 8 <= len; i += 8) {
+              unsigned char b[8];
+#pragma unroll
+              for (int k = 0; k < 8; ++k) b[k] = from[i + k];
+#pragma unroll
+              for (int k = 0; k < 8; ++k) dst[out + i + k] = b[k];
+            }
+          }
+          for (; i < len; ++i) dst[out + i] = from[i];
           out += len;
         }
         if (br.over) return false;
@@ -239,10 +270,15 @@ MMA_HD __forceinline__ u32 ld32u(const unsigned char *p) { return (u32)p[0] | ((
 MMA_HD __forceinline__ u32 ld16u(const unsigned char *p) { return (u32)p[0] | ((u32)p[1] << 8); }
 
 // one thread per member, MMA_BAM_LANES members per warp
-__global__ void __launch_bounds__(128) k_bam_inflate(BamView v, u32 lanes) {
+#define BAM_INFLATE_THREADS 128
+__global__ void __launch_bounds__(BAM_INFLATE_THREADS) k_bam_inflate(BamView v) {
+  // the Huffman tables of the members in flight live in shared memory (44 KB per block: every symbol is a table lookup, and
+  // local memory behind L1 missed 6 % of them)
+  __shared__ Huff litTab[BAM_INFLATE_THREADS / 32][MMA_BAM_LANES];
+  __shared__ HuffDist distTab[BAM_INFLATE_THREADS / 32][MMA_BAM_LANES];
   const u32 warpGlobal = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31u;
-  if (lane >= lanes) return;
-  const u32 m = warpGlobal * lanes + lane;
+  if (lane >= MMA_BAM_LANES) return;
+  const u32 m = warpGlobal * MMA_BAM_LANES + lane;
   if (m >= v.nMembers) return;
   const unsigned char *p = v.comp + v.memberOff[m];
   const u32 total = v.memberOff[m + 1] - v.memberOff[m];
@@ -256,10 +292,7 @@ __global__ void __launch_bounds__(128) k_bam_inflate(BamView v, u32 lanes) {
     if (hdr + 8 > total) ok = false;
   }
   if (ok && ld32u(p + total - 4) != want) ok = false;
-  if (ok && want) {
-    Huff lit, dist;
-    ok = inflateMember(p + hdr, total - hdr - 8, v.out + v.outOff[m], want, lit, dist);
-  }
+  if (ok && want) ok = inflateMember(p + hdr, total - hdr - 8, v.out + v.outOff[m], want, litTab[threadIdx.x >> 5][lane], distTab[threadIdx.x >> 5][lane]);
   if (!ok) atomicOr(v.flags, (u32)BAM_BAD_DEFLATE);
 }
 

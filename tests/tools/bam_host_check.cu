@@ -29,7 +29,8 @@ int main(int argc, char **argv) {
   std::vector<unsigned char> all;
   std::vector<uint32_t> outOff(1, 0);
   size_t at = 0, members = 0;
-  static Huff lit, dist;
+  static Huff lit;
+  static HuffDist dist;
   while (at + 18 <= file.size()) {
     const unsigned char *p = &file[at];
     const size_t xlen = rd16(p + 10), hdr = 12 + xlen, total = rd16(p + 16) + 1u;
