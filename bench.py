@@ -233,7 +233,7 @@ def run_reference_arm(args):
         line = {"impl": "reference", "metric": "alignment_records_per_sec", "value": v, "unit": "records/s", "n_gpus": args.gpus,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * records / v, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
-                "config": bench_config(wl, args, extra={"sample_reads_per_file": args.ref_reads, "files": n_files}),
+                "config": bench_config(wl, args, max(1, args.gpus)), "config_detail": {"sample_reads_per_file": args.ref_reads, "files": n_files},
                 "cpu_baseline": {"value": v, "unit": "records/s", "cores": used, "kind": "reference", "sample": desc},
                 "e2e": {"value": v, "unit": "records/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0, "host_cores": cores}
@@ -602,12 +602,9 @@ def run_product_arm(args):
             line = {"metric": "alignment_records_per_sec", "value": main["value"], "unit": "records/s", "n_gpus": world, "steps": args.steps,
                     "warmup": args.warmup, "ms_per_step": main["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                     "dtype": "u32", "data": "synthetic",
-                    "config": bench_config(wl, args, reads=reads, hits=n_hits, extra={
-                        "features": int(wl.annotation.n), "elements": int(wl.config.n_elements), "batch_hits": dev_batch, "batch_hits_e2e": batch,
-                        "index_bytes": index_bytes, "segments": segments,
-                        "sharding": main["multi_gpu"],
-                        "l2": "inputs (%.2f GB per pass) larger than L2; no explicit flush" % (24e-9 * n_hits),
-                        "order": "name-grouped (mapper order)"}),
+                    "config": bench_config(wl, args, world),
+                    "config_detail": {"hits_per_gpu": n_hits, "features": int(wl.annotation.n), "elements": int(wl.config.n_elements), "batch_hits": dev_batch,
+                                      "batch_hits_e2e": batch, "index_bytes": index_bytes, "segments": segments, "gb_per_pass": 24e-9 * n_hits},
                     "e2e": {"value": e2e_value, "unit": "records/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                             "ms_per_step": wall_e2e / args.steps, "timer": "host wall clock around synchronize",
                             "format": "compact transfer format as the host decoder emits it (mma_submit_hits_packed: 8 B/hit + 8 B/run, expanded on the device); "
@@ -628,14 +625,13 @@ def run_product_arm(args):
     return 0
 
 
-def bench_config(wl, args, reads=None, hits=None, extra=None):
-    """The `config` object both arms print (same keys, so that the driver can compare them)."""
-    c = {"workload": wl.w["describe"], "name": wl.name, "shape": wl.w["shape"], "strategy": wl.w["strategy"], "strand": wl.w["strand"],
-         "overlap": wl.w["overlap"], "reads_per_gpu": reads if reads is not None else (args.reads or wl.w["reads"])}
-    if hits is not None:
-        c["hits_per_gpu"] = hits
-    c.update(extra or {})
-    return c
+def bench_config(wl, args, world):
+    """The `config` object, IDENTICAL in both arms (the driver compares them); what only one arm knows goes to `config_detail`."""
+    reads = args.reads or wl.w["reads"]
+    return {"workload": wl.w["describe"], "name": wl.name, "shape": wl.w["shape"], "strategy": wl.w["strategy"], "strand": wl.w["strand"],
+            "overlap": wl.w["overlap"], "reads_per_gpu": reads, "order": "name-grouped (mapper order)",
+            "l2": "inputs (24 B per hit, ~2.1 hits per read: GBs per pass) larger than L2; no explicit flush",
+            "sharding": "read-name ranges, index replicated, tables merged on the GPUs around one NCCL all-gather" if world > 1 else "single GPU"}
 
 
 def time_cli_file(wl, n_reads, threads):

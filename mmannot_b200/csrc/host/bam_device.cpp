@@ -7,6 +7,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <future>
 #include <unordered_map>
 
 namespace mmb {
@@ -143,6 +144,9 @@ DeviceBamFeeder::Result DeviceBamFeeder::run(const std::string &fileName, uint32
   //      in the staging area until there are enough of them for one inflate launch (or the file ends)
   uint64_t kMaxComp = 1536ull << 20;
   const uint64_t kMaxOut = 3584ull << 20;
+  // a launch as soon as this much is staged (checked between buffers): the device inflates while the file is still being read
+  uint64_t kLaunch = 256ull << 20;
+  if (kLaunch > kMaxComp) kLaunch = kMaxComp;
   if (const char *e = std::getenv("MMANNOT_B200_BAM_LAUNCH_MB")) kMaxComp = static_cast<uint64_t>(std::max(1, std::atoi(e))) << 20;  // (tests: several launches per file)
   {
     long here = std::ftell(f);
@@ -213,14 +217,20 @@ DeviceBamFeeder::Result DeviceBamFeeder::run(const std::string &fileName, uint32
     if (!stageScanned()) return Result::FAILED;
     if (at == pos && !(eof && at >= have)) { why = "a BGZF member larger than a buffer"; return Result::FALLBACK; }
     if (eof && at >= have) break;
-    // the rest of this buffer (a member cut by its end) moves to the front of the other one, the file continues behind it;
-    // the copy out of this buffer is waited for by the next mma_bam_stage call, before this buffer is filled again
+    // the rest of this buffer (a member cut by its end) moves to the front of the other one, the file continues behind it (read
+    // by a helper thread while this one may be waiting for a launch); the copy out of this buffer is waited for by the next
+    // mma_bam_stage call, before this buffer is filled again
     const size_t rest = have - at;
     const int nxt = cur ^ 1;
     std::memcpy(buf_[nxt], buf_[cur] + at, rest);
     auto tr1 = now();
-    const size_t got = std::fread(buf_[nxt] + rest, 1, cap_ - rest, f);
+    std::future<size_t> reading = std::async(std::launch::async, [&, nxt, rest]() { return std::fread(buf_[nxt] + rest, 1, cap_ - rest, f); });
+    int rc = 0;
+    if (staged >= kLaunch) rc = submit();
+    const size_t got = reading.get();
     msRead += since(tr1);
+    if (rc == 1) return Result::FALLBACK;
+    if (rc == 2) return Result::FAILED;
     eof = got < cap_ - rest;
     have = rest + got;
     cur = nxt;
