@@ -140,6 +140,7 @@ struct mma_ctx {
   cudaEvent_t bamStageEv = nullptr;
   u32 bamNRef = 0, bamStrandedness = 1;
   double msBam[3] = {0, 0, 0};  // inflate, count + scan, parse
+  DevBuf walkMap;            // k_batch_lean -> k_batch_walk: one bit per hit of a launch (zero between launches: the walk clears what it reads)
   DevBuf exportBuf;          // mma_export_table_async: this context's own dump, kept for mma_restore_export (dumpBuf is rewritten by every finish)
 
   int fail(int code, const std::string &msg) {
@@ -342,8 +343,17 @@ void launchBatchKernels(mma_ctx *ctx, Sample &s, const HitView &hAll) {
         if (ctx->carveout >= 0) pct = ctx->carveout;
         cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
       }
-      mma_ctx::Timed t(ctx, TC_BATCH);
-      kernel<<<grid, LEAN_THREADS, smem, ctx->sc>>>(ctx->index, ctx->fast, h, r, table, s.ctl, slow, open);
+      u32 *walkMap = ctx->walkMap.as<u32>();  // (sized by launchBatch)
+      {
+        mma_ctx::Timed t(ctx, TC_BATCH);
+        kernel<<<grid, LEAN_THREADS, smem, ctx->sc>>>(ctx->index, ctx->fast, h, r, table, s.ctl, slow, walkMap);
+      }
+      if (STRAT == 0) {  // the runs the scan left: one thread per marked run (usually none), and the read carried into the batch
+        mma_ctx::Timed t(ctx, TC_CLOSE);
+        const u32 gridW = defer ? 1u : std::max<u32>(1u, std::min<u32>(gridFor((h.n + 127) / 128, 256), (u32)ctx->nSM * 8u));  // a lane reads 128 bits per round
+        k_batch_walk<MODE><<<gridW, 256, 0, ctx->sc>>>(ctx->index, ctx->fast, h, r, table, s.ctl, slow, open, walkMap, defer ? 1 : 0);
+        ctx->launches += 1;
+      }
     } else if (ctx->fast.bm) {
       launched = true;
       u32 grid = std::max<u32>(1u, std::min<u32>((nWT + FAST_WARPS - 1) / FAST_WARPS, (u32)ctx->nSM * MMA_FAST_BLOCKS_PER_SM));
@@ -387,6 +397,14 @@ void launchBatchMode(mma_ctx *ctx, Sample &s, const HitView &h) {
 }
 
 int launchBatch(mma_ctx *ctx, Sample &s, const HitView &h) {
+  if (ctx->rules.strategy == MMA_STRATEGY_DEFAULT && ctx->fast.ent) {  // k_batch_lean marks the runs it leaves to k_batch_walk: a bit per hit
+    const size_t need = ((size_t)h.n + 127) / 128 * 16 + 16;
+    if (need > ctx->walkMap.bytes) {
+      const size_t want = std::max<size_t>(need, ((size_t)ctx->params.max_batch_hits + 127) / 128 * 16 + 16);
+      if (ctx->walkMap.ensure(want) != cudaSuccess) return ctx->fail(MMA_ERR_CUDA, "out of device memory (walk map)");
+      CK(cudaMemsetAsync(ctx->walkMap.p, 0, ctx->walkMap.bytes, ctx->sc));
+    }
+  }
   if (ctx->rules.mode == 0) launchBatchMode<0>(ctx, s, h);
   else if (ctx->rules.mode == 1) launchBatchMode<1>(ctx, s, h);
   else launchBatchMode<2>(ctx, s, h);
@@ -529,6 +547,7 @@ void mma_destroy(mma_ctx *ctx) {
   ctx->dumpBuf.release();
   ctx->gatherBuf.release();
   ctx->exportBuf.release();
+  ctx->walkMap.release();
   ctx->rndKeys.release(); ctx->rndVals.release();
   for (int k = 0; k < 2; ++k) { ctx->bamComp[k].release(); if (ctx->bamCopied[k]) cudaEventDestroy(ctx->bamCopied[k]); }
   if (ctx->bamStageEv) cudaEventDestroy(ctx->bamStageEv);

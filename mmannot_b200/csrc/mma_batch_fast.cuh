@@ -363,8 +363,10 @@ k_batch_fast(const __grid_constant__ IndexView ix, const __grid_constant__ FastV
         if (lane == 0) prevNh = cNh;
         const u32 badBits = ((!(hbits & 1u) && nh[0] != prevNh) ? 1u : 0u) | ((!(hbits & 2u) && nh[1] != nh[0]) ? 2u : 0u) |
                             ((!(hbits & 4u) && nh[2] != nh[1]) ? 4u : 0u) | ((!(hbits & 8u) && nh[3] != nh[2]) ? 8u : 0u);
-        serialTile = forceWalk || __any_sync(FULL, (badBits & validBits) != 0);
         const u32 before = F & ((1u << lane) - 1u);
+        // (only in runs this warp owns: the run reaching into the chunk's first tile is the previous chunk's, NH carried or not)
+        const u32 ownBits = (before || cValid) ? 0xFu : (hbits & 1u) ? 0xEu : (hbits & 2u) ? 0xCu : (hbits & 4u) ? 0x8u : 0u;
+        serialTile = forceWalk || __any_sync(FULL, (badBits & validBits & ownBits) != 0);
         lastHeadPos = base + (31 - __clz(hbits | 1u));
         const u32 sPrev = __shfl_sync(FULL, lastHeadPos, before ? (31 - __clz(before)) : 0);
         // a run that starts before this lane's hits: its first record, and whether this warp owns it at all

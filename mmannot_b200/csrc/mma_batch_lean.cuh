@@ -17,18 +17,20 @@
 //             rescued reads are counted from the histogram columns at the end instead of per record.
 //
 // Everything that is not the regular shape (-m rescue, unfinished read names, runs whose NH disagrees with their length, runs cut
-// by a chunk border) takes the serial RunWalker of mma_device.cuh exactly as in k_batch: results are identical by construction
-// and checked against the oracle by the same tests.
+// by a chunk border, the read carried into the batch) takes the serial RunWalker of mma_device.cuh exactly as in k_batch -- but
+// not here: the lane that finds such a run sets the bit of its first record in a bitmap, and k_batch_walk (below, launched behind
+// this kernel) walks the marked runs, one thread per run.  The tile loop holds no call, which is what lets it live in its
+// register budget, and the walks of a messy batch spread over the whole GPU instead of serialising inside a warp.
 #pragma once
 #include "mma_batch_fast.cuh"
 
 namespace mma {
 
 #ifndef MMA_LEAN_THREADS
-#define MMA_LEAN_THREADS 512
+#define MMA_LEAN_THREADS 640
 #endif
 #ifndef MMA_LEAN_MAXREG
-#define MMA_LEAN_MAXREG 128  // 16 warps per SM (registers are handed out per SM quarter: warps per block in fours)
+#define MMA_LEAN_MAXREG 96  // 20 warps per SM (registers are handed out per SM quarter: 5 warps x 32 lanes x 96 <= 16384; warps per block in fours)
 #endif
 #ifndef MMA_LEAN_BLOCKS_PER_SM
 #define MMA_LEAN_BLOCKS_PER_SM 1  // one block per SM: the block-wide tables exist once, the shared memory they do not take stays L1
@@ -104,23 +106,6 @@ inline size_t leanSmemBytes(u32 nDict, u32 nChr, u32 nElements) {
   return offsetof(LeanSmem<HIST>, var) + 8ull * nDict + 8ull * (nChr + 1) + (HIST ? 2ull * (nElements + 1) * LEAN_THREADS : 0ull) + 16;
 }
 
-template <bool HIST>
-struct LeanCount {  // one read counted for an element set, from divergent code (the serial walker)
-  LeanSmem<HIST> &sm;
-  unsigned short *hist;  // this thread's column
-  const TableView &table;
-  __device__ __forceinline__ void operator()(u64 ckey) const {
-    if (HIST) {
-      const u32 c = (u32)ckey;
-      if (c == 0) return;
-      if (c & (c - 1)) sm.bt.add(ckey, 1, table);
-      else hist[(__ffs(c) - 1) * LEAN_THREADS] += 1;
-    } else if (ckey) {
-      sm.bt.add(ckey, 1, table);
-    }
-  }
-};
-
 // A hit the bin entry could not answer: the record of its segment (index = rank of the bin + boundaries up to the read start),
 // then like fastAnnotate (which this replaces on the hot path: no chromosome check, no stepping).
 template <int MODE>
@@ -159,7 +144,7 @@ __device__ __forceinline__ u32 recordAnnotate(const FastView &fx, const IndexVie
 template <int MODE, int STRAT, int RUNS>
 __global__ void __maxnreg__(MMA_LEAN_MAXREG)
 k_batch_lean(const __grid_constant__ IndexView ix, const __grid_constant__ FastView fx, const __grid_constant__ HitView h, const __grid_constant__ Rules r,
-             const __grid_constant__ TableView table, SampleCtl *ctl, const __grid_constant__ SlowView slow, const __grid_constant__ KeySetView open) {
+             const __grid_constant__ TableView table, SampleCtl *ctl, const __grid_constant__ SlowView slow, u32 *walkMap) {
   constexpr bool HIST = (STRAT != 3);
   constexpr bool GROUPS = RUNS == 1, DEFER = (RUNS == 2) && STRAT == 0;
   constexpr u32 FULL = 0xffffffffu;
@@ -186,7 +171,6 @@ k_batch_lean(const __grid_constant__ IndexView ix, const __grid_constant__ FastV
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
-  const Annotator<MODE, true> annot{ix, fx, r.overlap};
   const u32 seq = ctl->batchSeq;
   // every run takes the serial walker when rescue() needs multiplicities or some read name is known as unfinished
   const bool forceWalk = (STRAT == 0) && (r.rescue || __shfl_sync(FULL, ctl->openCount, 0) != 0);
@@ -198,8 +182,10 @@ k_batch_lean(const __grid_constant__ IndexView ix, const __grid_constant__ FastV
   u32 pMissResc = 0;  // segment-table misses | (rescue() active only) closed reads resolved to one element << 16
   u32 pWalks = 0, cVis = 0;
 
-  LeanCount<HIST> count{sm, myHist, table};
-  RunWalker<MODE, true, LeanCount<HIST>> w{h, r, annot, ctl, slow, open, count, seq, 0u, 0u};
+  // a run the scan cannot close is left to k_batch_walk (launched behind this kernel): bit i of walkMap = "walk the run from record i"
+  auto queueWalk = [&](u32 i0) {
+    if (i0 < h.n) atomicOr(&walkMap[i0 >> 5], 1u << (i0 & 31u));  // (a run of padding slots has nothing to walk)
+  };
 
   const u32 nWT = (h.n + WT_HITS - 1) / WT_HITS;
   const u32 nWarps = gridDim.x * LEAN_WARPS;
@@ -242,15 +228,13 @@ k_batch_lean(const __grid_constant__ IndexView ix, const __grid_constant__ FastV
   bool cValid = false, cCont = false;  // cCont: the run open at the end of the tile continues in the next tile
   u32 cStart = 0, cTot = 0, cNh = 0;
   // lane 0: does the chunk's first record start a run?  (The state carried into the batch counts as the record before it.)
+  // The read carried into the batch itself is k_batch_walk's.
   bool headFirst = true;
-  const Carry *carryIn = nullptr;
-  if (DEFER) {
-    if (lane == 0 && t0 == 0 && t0 < t1 && ctl->carry[seq & 1].valid) carryIn = &ctl->carry[seq & 1];
-  } else if (STRAT == 0 && lane == 0 && t0 < t1) {
+  if (STRAT == 0 && !DEFER && lane == 0 && t0 < t1) {
     const u64 first = normKey(__ldg(&h.key[(size_t)t0 * WT_HITS]));
     if (t0 == 0) {
       const Carry &c = ctl->carry[seq & 1];
-      if (c.valid) { carryIn = &c; headFirst = c.key != first; }
+      if (c.valid) headFirst = c.key != first;
     } else {
       headFirst = normKey(__ldg(&h.key[(size_t)t0 * WT_HITS - 1])) != first;
     }
@@ -369,10 +353,6 @@ k_batch_lean(const __grid_constant__ IndexView ix, const __grid_constant__ FastV
     }
     if (DEFER) {
       // every record with NH > 1 to the deferred list: {key, ordinal, element set, NH}
-      if (it == 0 && carryIn) {  // (a read carried out of a batch that still ran the countdown: it joins the list like its later records)
-        --w.nReads;
-        slowAppend(slow, ctl, carryIn->key, carryIn->ord, carryIn->gm, carryIn->remaining + 1);
-      }
       const u32 mb = (nh[0] > 1 ? 1u : 0u) | (nh[1] > 1 ? 2u : 0u) | (nh[2] > 1 ? 4u : 0u) | (nh[3] > 1 ? 8u : 0u);
       u32 mine4 = __popc(mb), incl = mine4;
 #pragma unroll
@@ -440,15 +420,6 @@ k_batch_lean(const __grid_constant__ IndexView ix, const __grid_constant__ FastV
         tileEndsRun = (normKey(__ldg(&h.key[(size_t)t1 * WT_HITS])) != nextKey) ? 1u : 0u;
       }
       // ---- per-read countdown (mm:1669-1702)
-      if (it == 0 && carryIn) {  // lane 0 of the batch's first tile: the read carried into this batch
-        if (!(hbits & 1u)) w.walk(0, carryIn->key, carryIn);
-        else {  // its name does not continue: unfinished
-          --w.nReads;
-          slowAppend(slow, ctl, carryIn->key, carryIn->ord, carryIn->gm, carryIn->remaining + 1);
-          keySetInsert(open, carryIn->key, seq, ctl);
-          ctl->dirty = 1;
-        }
-      }
       const u32 before = F & ((1u << lane) - 1u);
       u32 prevNh = __shfl_up_sync(FULL, nh[3], 1);
       if (lane == 0) prevNh = cNh;
@@ -471,8 +442,10 @@ k_batch_lean(const __grid_constant__ IndexView ix, const __grid_constant__ FastV
         // record of a group counts the read.  A run that ends inside a group leaves an unfinished read: serial walk
         // (RunWalker) from the start of that group.  A tile in which NH changes inside a run -- or any tile while rescue() needs
         // multiplicities or some read name is known as unfinished -- is resolved serially: one walk per run (serialTile).
-        const u32 badBits = ((!(hbits & 1u) && nh[0] != prevNh) ? 1u : 0u) | ((!(hbits & 2u) && nh[1] != nh[0]) ? 2u : 0u) |
-                            ((!(hbits & 4u) && nh[2] != nh[1]) ? 4u : 0u) | ((!(hbits & 8u) && nh[3] != nh[2]) ? 8u : 0u);
+        u32 badBits = ((!(hbits & 1u) && nh[0] != prevNh) ? 1u : 0u) | ((!(hbits & 2u) && nh[1] != nh[0]) ? 2u : 0u) |
+                      ((!(hbits & 4u) && nh[2] != nh[1]) ? 4u : 0u) | ((!(hbits & 8u) && nh[3] != nh[2]) ? 8u : 0u);
+        // (only in runs this warp owns: the run reaching into the chunk's first tile is the previous chunk's, NH carried or not)
+        if (!inMine) badBits &= (hbits & 1u) ? 0xEu : (hbits & 2u) ? 0xCu : (hbits & 4u) ? 0x8u : 0u;
         serialTile = forceWalk || __any_sync(FULL, badBits != 0);
         if (!serialTile) {
           u32 hb2 = hbits, endBits = 0;
@@ -528,23 +501,23 @@ k_batch_lean(const __grid_constant__ IndexView ix, const __grid_constant__ FastV
           if (walkBits) {  // rare
 #pragma unroll
             for (int j = 0; j < 4; ++j)
-              if ((walkBits >> j) & 1u) mine.scratch[lane * 4 + nWalk++] = base + j - off[j];
+              if ((walkBits >> j) & 1u) { queueWalk(base + j - off[j]); ++nWalk; }
           }
         } else {
           // serial tile: the run carried into the tile (from the start of its open group) and every run that starts in it
           if (lane == 0 && cValid && !(hbits & 1u)) {
             const u32 o = base - cStart;
-            mine.scratch[lane * 4 + nWalk++] = base - ((cNh > 1) ? o % cNh : 0u);
+            queueWalk(base - ((cNh > 1) ? o % cNh : 0u)); ++nWalk;
           }
 #pragma unroll
           for (int j = 0; j < 4; ++j)
-            if ((hbits >> j) & 1u) mine.scratch[lane * 4 + nWalk++] = base + j;
+            if ((hbits >> j) & 1u) { queueWalk(base + j); ++nWalk; }
         }
       } else {
         // A run of n records that all carry NH = n (> 1) is one read; its element set is the union over the run: a
         // segmented OR scan over the 128 hits of the warp tile (bit 31 of the scanned word = "irregular": NH changes inside
         // the run, or every run has to be walked), seeded with the state carried from the previous tile.  The lane owning
-        // the run's LAST record closes it; irregular runs take the serial walk (RunWalker), started by the same lane.
+        // the run's LAST record closes it; irregular runs are marked for the serial walk (k_batch_walk) by the same lane.
         u32 pre[4], acc = 0;
         const u32 force = forceWalk ? 0x80000000u : 0u;
 #pragma unroll
@@ -574,18 +547,21 @@ k_batch_lean(const __grid_constant__ IndexView ix, const __grid_constant__ FastV
           if (isHead) { carryTot = 0; own = true; }
           runLen = isHead ? 1u : runLen + 1u;
           const u32 tot = carryTot | pre[j];  // union of the run's element sets up to this record, wherever the run starts
-          if (((lastBits >> j) & 1u) && own) {
-            // a run of reads that are their own group (NH <= 1 throughout) has nothing to close
-            if ((int)tot >= 0 && nh[j] > 1 && nh[j] == runLen) { ev[j] = tot; closeBits |= 1u << j; }
-            else if ((int)tot < 0 || nh[j] > 1) walkBits |= 1u << j;
-          }
+          // the run's last record, in a run this warp owns: closed here when it is regular, else walked (a run of reads that are
+          // their own group, NH <= 1 throughout, has nothing to close).  Branch-free: the lanes disagree on almost every tile.
+          const bool last = ((lastBits >> j) & 1u) && own;
+          const bool regular = (int)tot >= 0 && nh[j] > 1 && nh[j] == runLen;
+          const bool irregular = !regular && ((int)tot < 0 || nh[j] > 1);
+          ev[j] = (last && regular) ? tot : ev[j];
+          closeBits |= (last && regular) ? (1u << j) : 0u;
+          walkBits |= (last && irregular) ? (1u << j) : 0u;
         }
         if (walkBits) {  // rare
 #pragma unroll
           for (int j = 0; j < 4; ++j)
             if ((walkBits >> j) & 1u) {
               const u32 hbLe = hbits & ((2u << j) - 1u);
-              mine.scratch[lane * 4 + nWalk++] = hbLe ? base + (31 - __clz(hbLe)) : inStart;
+              queueWalk(hbLe ? base + (31 - __clz(hbLe)) : inStart); ++nWalk;
             }
         }
       }
@@ -628,11 +604,6 @@ k_batch_lean(const __grid_constant__ IndexView ix, const __grid_constant__ FastV
     }
     if (STRAT == 0 && !DEFER) {
       pWalks += nWalk;
-#pragma unroll 1
-      for (u32 q = 0; q < nWalk; ++q) {
-        const u32 i0 = mine.scratch[lane * 4 + q];
-        if (i0 < h.n) w.walk(i0, normKey(h.key[i0]), nullptr);  // (a run of padding slots has nothing to walk)
-      }
       const u32 incLast = __shfl_sync(FULL, inc, 31);
       if (GROUPS) {
         // the run (and, inside it, the group) still open at the end of the tile
@@ -661,17 +632,84 @@ k_batch_lean(const __grid_constant__ IndexView ix, const __grid_constant__ FastV
       cCont = tileEndsRun == 0;
     }
   }
-  // ---- a run open at the end of the chunk continues in another warp's chunk: its remaining reads (GROUPS: from the group that is
-  //      open there, or starts there) are finished by the serial walk.  (A run ending exactly at the chunk's last record was
-  //      closed above, like the last run of the batch.)
-  if (STRAT == 0 && !DEFER && cValid && cCont && t1 > t0 && lane == 0) {
+  // ---- a run open at the end of the chunk continues in another warp's chunk (which leaves it alone: it does not own its start).
+  //      This warp finishes it: the records of the run in the NEXT tile are annotated, 4 per lane, and lane 0 takes the countdown
+  //      through them (GROUPS: from the group open at the border through every later group of the run).  No per-hit counter moves:
+  //      the hits belong to the other chunk.  A run that is irregular, that reaches beyond that tile or (GROUPS) that ends inside
+  //      a group is marked for k_batch_walk from the run's (the open group's) first record.  (A run ending exactly at the chunk's
+  //      last record was closed above, like the last run of the batch.)
+  if (STRAT == 0 && !DEFER && cValid && cCont && t1 > t0) {
     const u32 next = t1 * WT_HITS;
-    const u64 k = normKey(h.key[next]);
-    if (GROUPS) {
-      const u32 o = next - cStart;
-      w.walk(next - ((cNh > 1) ? o % cNh : 0u), k, nullptr);
-    } else {
-      w.walk(cStart, k, nullptr);
+    const u32 o = next - cStart;                                              // records of the run inside this chunk
+    const u32 inGroup = (GROUPS && cNh > 1) ? o % cNh : 0u;                   // GROUPS: ... of which in the group open at the border
+    const u32 walkFrom = GROUPS ? next - inGroup : cStart;
+    const u64 k = normKey(lds64(wbase + ((t1 - t0 - 1u) & 1u) * LEAN_STAGE_BYTES + 2048 + 127 * 8));  // the chunk's last record
+    u32 tn[4], tm[4], eq = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const size_t i = (size_t)next + lane * 4 + j;
+      const bool v = i < h.n;
+      const u64 kk = v ? normKey(__ldg(&h.key[i])) : ~k;
+      const u32 qs = v ? __ldg(&h.start[i]) : 0u, qe = v ? __ldg(&h.end[i]) : 0u, qm = v ? __ldg(&h.meta[i]) : 0x00FFFFFFu;
+      tn[j] = v ? __ldg(&h.nh[i]) : 0u;
+      tm[j] = 0;
+      if (kk == k) {
+        eq |= 1u << j;
+        const u32 chr = qm & 0x00FFFFFFu;
+        bool pass = true;
+        if (MODE != 0 && qe >= qs) {  // (as in the loop: no feature can overlap the read by more than end - start)
+          const u32 ol = qe - qs;
+          if (MODE == 1) pass = (ol != 0) && (__fmul_rn((float)(ol + 1u), r.overlap) <= (float)ol);
+          else pass = (ol != 0) && ((float)ol >= r.overlap);
+        }
+        if (chr < fx.nChr && pass) tm[j] = recordAnnotate<MODE>(fx, ix, smChr[chr], qs, qe, qm, r.overlap) & ~FAST_MISS;
+      }
+    }
+    const u32 lead = (eq == 0xFu) ? 4u : (u32)__ffs(~eq) - 1u;  // this lane's records that continue the run, if every lane before is all run
+    const u32 fullLanes = __ballot_sync(FULL, eq == 0xFu);
+    const u32 fp = (fullLanes == FULL) ? 32u : (u32)__ffs(~fullLanes) - 1u;  // first lane that is not all run
+    const u32 mineN = (lane < fp) ? 4u : (lane == fp) ? lead : 0u;
+    const u32 tailLen = __reduce_add_sync(FULL, mineN);
+    u32 prevNh = __shfl_up_sync(FULL, tn[3], 1);
+    if (lane == 0) prevNh = cNh;
+    bool bad = false;
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if ((u32)j < mineN) {
+        bad |= tn[j] != (j ? tn[j > 0 ? j - 1 : 0] : prevNh);
+        mine.scratch[lane * 4 + j] = tm[j];
+      }
+    const bool anyBad = __any_sync(FULL, bad) || forceWalk || (int)cTot < 0 || fp == 32u;
+    __syncwarp();
+    if (lane == 0) {
+      if (anyBad) {
+        queueWalk(walkFrom);
+      } else if (cNh > 1) {  // (a run of reads that are their own group has nothing to close)
+        // one read closed by the countdown, counted like the closes of the loop
+        auto closeRead = [&](u32 c) {
+          pOwnClos += 1u << 16;
+          if (c == 0) return;
+          if (HIST && (c & (c - 1)) == 0) myHist[(31 - __clz(c)) * LEAN_THREADS] += 1;
+          else sm.bt.add((u64)c, 1, table);
+        };
+        if (!GROUPS) {
+          if (o + tailLen == cNh) {
+            u32 acc = cTot;
+            for (u32 q = 0; q < tailLen; ++q) acc |= mine.scratch[q];
+            closeRead(acc);
+          } else {
+            queueWalk(walkFrom);
+          }
+        } else if ((o + tailLen) % cNh != 0) {  // the run ends inside a group
+          queueWalk(walkFrom);
+        } else {
+          u32 acc = inGroup ? cTot : 0u, pos = inGroup;
+          for (u32 q = 0; q < tailLen; ++q) {
+            acc |= mine.scratch[q];
+            if (++pos == cNh) { closeRead(acc); acc = 0; pos = 0; }
+          }
+        }
+      }
     }
   }
   const u32 cAsg = pAsgUniq & 0xFFFFu, cClosed = pOwnClos >> 16, cResc = pMissResc >> 16;
@@ -687,7 +725,7 @@ k_batch_lean(const __grid_constant__ IndexView ix, const __grid_constant__ FastV
     }
   }
   u32 cUnassigned = cHits - cAsg;
-  u32 cReads = cHits - cMulti + cClosed + w.nReads, cRescued = cResc + (r.rescue ? w.nRescued : 0u);
+  u32 cReads = cHits - cMulti + cClosed, cRescued = cResc;  // (the reads k_batch_walk opens and closes are added there)
 
   // ---- block epilogue: counters, the private histogram columns and the private table
   cHits = __reduce_add_sync(FULL, cHits); cUnassigned = __reduce_add_sync(FULL, cUnassigned);
@@ -726,6 +764,167 @@ k_batch_lean(const __grid_constant__ IndexView ix, const __grid_constant__ FastV
     if (sv) atomicAdd(&ctl->stats[tid], (u64)(long long)sv);
   }
   if (tid == 7 && sm.stat[7]) atomicAdd(&ctl->fastMiss, sm.stat[7]);
+}
+
+// RunWalker::walk (mma_device.cuh) for a whole warp: the same sequence of decisions, taken by all 32 lanes on identical state, with
+// the records of the run fetched and annotated 32 at a time (lane l holds record base + l) -- the serial walk is a chain of dependent
+// loads per record, and the runs left to k_batch_walk (one per chunk border on clean input) would otherwise be a tail of tens of
+// microseconds behind every batch.  Side effects (counts, deferred records, the carry, the open-name set) are lane 0's.
+template <int MODE>
+struct WarpWalker {
+  const HitView &h;
+  const Rules &r;
+  const Annotator<MODE, true> &annot;
+  SampleCtl *ctl;
+  const SlowView &slow;
+  const KeySetView &open;
+  const TableView &table;
+  u32 seq, lane;
+  int nReads, nRescued;  // (identical on all lanes)
+
+  __device__ __forceinline__ u64 maskAt(u32 j) const { return annot(h.start[j], h.end[j], h.meta[j]); }
+
+  __device__ u64 rescueGroup(u32 first, u32 end, u64 gm) const {  // as RunWalker::rescueGroup (every lane computes the same)
+    u32 total = 0;
+    for (u32 j = first; j < end; ++j)
+      if (h.nh[j] > 1) total += __popcll(maskAt(j));
+    return rescueFromCounts(r, gm, total, [&](u64 bit) {
+      u32 c = 0;
+      for (u32 j = first; j < end; ++j)
+        if (h.nh[j] > 1 && (maskAt(j) & bit)) ++c;
+      return c;
+    });
+  }
+
+  // i = first record of the run inside this batch, k = its key; `cin` = state carried into the batch (or null); all lanes alike
+  __device__ __forceinline__ void walk(u32 i, u64 k, const Carry *cin) {  // (inlined: the walker then lives in registers)
+    constexpr u32 FULL = 0xffffffffu;
+    u32 routedL = 0;
+    if (lane == 0) routedL = ((ctl->openCount != 0) && keySetLookup(open, k, seq) == 1) ? 1u : 0u;
+    const bool routed = __shfl_sync(FULL, routedL, 0) != 0;
+    bool isOpen = false, fromCarry = false;
+    u32 remaining = 0, first = i;
+    u64 gm = 0;
+    if (cin) { isOpen = true; fromCarry = true; remaining = cin->remaining; gm = cin->gm; }
+    u32 wb = 0;  // the window: records wb .. wb + 31
+    bool inRun = false;
+    u32 wNh = 0;
+    u64 wMask = 0;
+    u32 j = i;
+    for (; j < h.n; ++j) {
+      if (j == i || j - wb >= 32u) {
+        wb = j;
+        const u32 q = j + lane;
+        inRun = q < h.n && (q == i || normKey(h.key[q]) == k);
+        wNh = inRun ? h.nh[q] : 0u;
+        wMask = (inRun && wNh > 1) ? maskAt(q) : 0ull;
+      }
+      const u32 src = j - wb;
+      if (!__shfl_sync(FULL, inRun ? 1u : 0u, src)) break;  // end of the run
+      const u32 nhj = __shfl_sync(FULL, wNh, src);
+      if (!(nhj > 1)) continue;
+      const u64 mj = __shfl_sync(FULL, wMask, src);
+      if (routed) {
+        if (lane == 0) slowAppend(slow, ctl, k, ctl->ordBase + j, mj, nhj);
+        continue;
+      }
+      if (!isOpen) { isOpen = true; fromCarry = false; remaining = nhj - 1; gm = mj; first = j; ++nReads; }
+      else { --remaining; gm |= mj; }
+      if (remaining == 0) {
+        if (gm != 0) {
+          if (r.rescue) gm = rescueGroup(first, j + 1, gm);  // never a carried read: rescue mode does not carry
+          if (lane == 0) tableAdd(table, gm, 1);
+          if (__popcll(gm) == 1) ++nRescued;
+        }
+        isOpen = false;
+      }
+    }
+    if (!isOpen) return;
+    if (routed) return;  // (a carried read is never routed: its name would have been deferred instead of carried)
+    if (j >= h.n && !r.rescue) {  // the run reaches the end of the batch: carry the open read over
+      if (lane == 0) {
+        Carry &c = ctl->carry[(seq + 1) & 1];
+        c.key = k; c.gm = gm; c.remaining = remaining;
+        c.ord = fromCarry ? cin->ord : ctl->ordBase + first;
+        __threadfence();
+        c.valid = 1;
+      }
+      return;
+    }
+    // unfinished read: the deferred path opens it again
+    --nReads;
+    if (lane == 0) {
+      if (fromCarry) slowAppend(slow, ctl, k, cin->ord, cin->gm, cin->remaining + 1);  // stands for the records of earlier batches
+      for (u32 q = fromCarry ? i : first; q < j; ++q) {
+        const u32 nhq = h.nh[q];
+        if (nhq > 1) slowAppend(slow, ctl, k, ctl->ordBase + q, maskAt(q), nhq);
+      }
+      keySetInsert(open, k, seq, ctl);
+      ctl->dirty = 1;
+    }
+  }
+};
+
+// The runs k_batch_lean marked (walkMap: bit i = "the run whose first record to look at is i"), one WARP per run, and the read
+// carried into the batch (warp 0).  Counts go straight to the device table; the words of the bitmap are cleared as they are read
+// (four per lane and round; the map is allocated with the padding for that).
+template <int MODE>
+__global__ void __launch_bounds__(256)
+k_batch_walk(const __grid_constant__ IndexView ix, const __grid_constant__ FastView fx, const __grid_constant__ HitView h, const __grid_constant__ Rules r,
+             const __grid_constant__ TableView table, SampleCtl *ctl, const __grid_constant__ SlowView slow, const __grid_constant__ KeySetView open,
+             u32 *walkMap, int defer) {  // (__grid_constant__: the walker holds references to the views -- no per-thread copies on the stack)
+  constexpr u32 FULL = 0xffffffffu;
+  const Annotator<MODE, true> annot{ix, fx, r.overlap};
+  const u32 seq = ctl->batchSeq;
+  const u32 lane = threadIdx.x & 31u;
+  WarpWalker<MODE> w{h, r, annot, ctl, slow, open, table, seq, lane, 0, 0};
+  const u32 gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nWarps = (gridDim.x * blockDim.x) >> 5;
+  if (gwarp == 0 && h.n) {
+    const Carry &c = ctl->carry[seq & 1];
+    if (c.valid) {
+      if (defer) {  // a read carried out of a batch that still ran the countdown: it joins the deferred list like its later records
+        --w.nReads;
+        if (lane == 0) slowAppend(slow, ctl, c.key, c.ord, c.gm, c.remaining + 1);
+      } else if (c.key == normKey(h.key[0])) {
+        w.walk(0, c.key, &c);
+      } else {  // its name does not continue: unfinished
+        --w.nReads;
+        if (lane == 0) {
+          slowAppend(slow, ctl, c.key, c.ord, c.gm, c.remaining + 1);
+          keySetInsert(open, c.key, seq, ctl);
+          ctl->dirty = 1;
+        }
+      }
+    }
+  }
+  const u32 nQuads = defer ? 0u : ((h.n + 31u) / 32u + 3u) / 4u;  // (the DEFER variant marks nothing)
+  uint4 *const map4 = reinterpret_cast<uint4 *>(walkMap);
+  for (u32 q0 = gwarp * 32u; q0 < nQuads; q0 += nWarps * 32u) {
+    const u32 q = q0 + lane;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (q < nQuads) v = map4[q];
+    const bool any = (v.x | v.y | v.z | v.w) != 0;
+    if (any) map4[q] = make_uint4(0, 0, 0, 0);
+    u32 lanes = __ballot_sync(FULL, any);
+    while (lanes) {
+      const int src = __ffs(lanes) - 1;
+      lanes &= lanes - 1;
+      const u32 word0 = (q0 + (u32)src) * 4u;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        u32 bits = __shfl_sync(FULL, c == 0 ? v.x : c == 1 ? v.y : c == 2 ? v.z : v.w, src);
+        while (bits) {
+          const u32 i0 = (word0 + c) * 32u + (u32)(__ffs(bits) - 1);
+          bits &= bits - 1;
+          w.walk(i0, normKey(h.key[i0]), nullptr);
+        }
+      }
+    }
+  }
+  if (lane == 0) {
+    if (w.nReads) atomicAdd(&ctl->stats[ST_READS], (u64)(long long)w.nReads);
+    if (w.nRescued) atomicAdd(&ctl->stats[ST_RESCUED], (u64)(long long)w.nRescued);
+  }
 }
 
 }  // namespace mma
