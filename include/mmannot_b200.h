@@ -213,8 +213,9 @@ int mma_submit_hits_packed(mma_ctx *ctx, uint32_t sample, const mma_packed_batch
  *                   means NOTHING of the chunk was counted: the file holds something this route leaves to the host decoder
  *                   (XA alternative hits, CIGAR operations or aux types the reference warns about, records that straddle
  *                   members, corrupt data); the caller resets the sample and decodes the file itself (mma_submit_hits*).
- *   mma_bam_ref_first  out[i] = ordinal (0-based, over the file) of the first record on BAM reference i, ~0 if none yet: for
- *                   the "chromosome not present in your annotation" warnings (mmannot.cpp:1297), in order of appearance. */
+ *   mma_bam_ref_first  out[i] = ordinal (0-based, over the file) of the first record on BAM reference i, ~0 if none yet --
+ *                   kept only for references mapped to MMA_HIT_CHR_NONE (others stay ~0): for the "chromosome not present in
+ *                   your annotation" warnings (mmannot.cpp:1297), in order of appearance. */
 #define MMA_BAM_BAD_DEFLATE 1u
 #define MMA_BAM_STRADDLE 2u
 #define MMA_BAM_HAS_XA 4u
@@ -231,6 +232,12 @@ typedef struct mma_bam_chunk {
 } mma_bam_chunk;
 int mma_bam_begin(mma_ctx *ctx, uint32_t sample, const uint32_t *ref_to_chr, uint32_t n_ref, int strandedness /* 0 U, 1 F, 2 R */);
 int mma_submit_bam(mma_ctx *ctx, uint32_t sample, const mma_bam_chunk *chunk, uint64_t *n_records, uint32_t *flags);
+/* The same in two halves, so that the caller can read and stage the NEXT chunk while this one is inflated: _start enqueues the
+ * inflate and the record walk and returns at once (the chunk's arrays may be released when it returns); _finish waits for them
+ * and runs the record parse and the batch kernels, with the outputs of mma_submit_bam.  One chunk in flight at a time;
+ * mma_bam_stage calls made between the two build the next chunk. */
+int mma_submit_bam_start(mma_ctx *ctx, uint32_t sample, const mma_bam_chunk *chunk);
+int mma_submit_bam_finish(mma_ctx *ctx, uint64_t *n_records, uint32_t *flags);
 /* Staged upload, so that a large chunk (the inflate kernel wants tens of thousands of members per launch) can be fed from small
  * page-locked buffers while the file is still being read: mma_bam_stage copies n_bytes to byte `offset` of the chunk under
  * construction (asynchronously; the host buffer is free again when the NEXT mma_bam_stage / mma_submit_bam call returns, so two

@@ -8,7 +8,13 @@
 #include <cstdlib>
 #include <cstring>
 #include <future>
+#include <thread>
 #include <unordered_map>
+#include <vector>
+
+#include <fcntl.h>
+#include <sys/stat.h>
+#include <unistd.h>
 
 namespace mmb {
 
@@ -45,11 +51,47 @@ bool inflateRaw(const unsigned char *src, size_t n, unsigned char *dst, size_t w
   return ok;
 }
 
+// `want` bytes of the file from `offset` into dst, by several threads (one thread copies out of the page cache at 2-4 GB/s on the
+// hosts this runs on: less than the link to the device takes).  Returns the bytes read (less than `want` only at the end of the file).
+size_t readAt(int fd, uint64_t fileSize, uint64_t offset, unsigned char *dst, size_t want) {
+  if (offset >= fileSize) return 0;
+  const size_t n = static_cast<size_t>(std::min<uint64_t>(want, fileSize - offset));
+  const size_t slice = 8u << 20;
+  unsigned nThreads = static_cast<unsigned>(std::min<size_t>((n + slice - 1) / slice, 8));
+  const unsigned hw = std::thread::hardware_concurrency();
+  if (hw && nThreads > std::max(1u, hw / 2)) nThreads = std::max(1u, hw / 2);
+  std::vector<size_t> got(std::max(1u, nThreads), 0);
+  auto work = [&](unsigned t) {
+    const size_t per = (n + nThreads - 1) / nThreads;
+    const size_t a = std::min(n, per * t), b = std::min(n, a + per);
+    size_t done = a;
+    while (done < b) {
+      const ssize_t r = ::pread(fd, dst + done, b - done, static_cast<off_t>(offset + done));
+      if (r <= 0) break;
+      done += static_cast<size_t>(r);
+    }
+    got[t] = done - a;
+  };
+  if (nThreads <= 1) { nThreads = 1; work(0); return got[0]; }
+  std::vector<std::thread> th;
+  for (unsigned t = 1; t < nThreads; ++t) th.emplace_back(work, t);
+  work(0);
+  for (auto &x : th) x.join();
+  // (a short slice in the middle would leave a hole: report only the contiguous part)
+  size_t total = 0;
+  const size_t per = (n + nThreads - 1) / nThreads;
+  for (unsigned t = 0; t < nThreads; ++t) {
+    total += got[t];
+    if (got[t] < std::min(n, per * (t + 1)) - std::min(n, per * t)) break;
+  }
+  return total;
+}
+
 }  // namespace
 
 DeviceBamFeeder::DeviceBamFeeder(mma_ctx *ctx, const FeatureTable &features, Strandedness strandedness)
     : ctx_(ctx), features_(features), strandedness_(strandedness) {
-  size_t mb = 64;
+  size_t mb = 32;  // (page-locking costs ~0.45 ms per MB on the hosts this runs on: two small buffers, refilled by several threads)
   if (const char *e = std::getenv("MMANNOT_B200_BAM_CHUNK_MB")) mb = static_cast<size_t>(std::max(1, std::atoi(e)));
   cap_ = mb << 20;
 }
@@ -62,22 +104,29 @@ DeviceBamFeeder::~DeviceBamFeeder() {
 DeviceBamFeeder::Result DeviceBamFeeder::run(const std::string &fileName, uint32_t column, uint64_t &nRecords, std::string &warnings,
                                              std::string &why, std::string &err) {
   nRecords = 0;
-  FILE *f = std::fopen(fileName.c_str(), "rb");
-  if (!f) { why = "cannot open the file"; return Result::FALLBACK; }
-  struct Closer { FILE *f; ~Closer() { std::fclose(f); } } closer{f};
+  const int fd = ::open(fileName.c_str(), O_RDONLY);
+  if (fd < 0) { why = "cannot open the file"; return Result::FALLBACK; }
+  struct Closer { int fd; ~Closer() { ::close(fd); } } closer{fd};
+  struct stat stt;
+  if (::fstat(fd, &stt) != 0 || !S_ISREG(stt.st_mode)) { why = "not a regular file"; return Result::FALLBACK; }
+  const uint64_t fileSize = static_cast<uint64_t>(stt.st_size);
+  uint64_t filePos = 0;
+  const auto tRun0 = std::chrono::steady_clock::now();
   for (int k = 0; k < 2; ++k)
     if (!buf_[k]) {
       buf_[k] = static_cast<unsigned char *>(mma_alloc_pinned(cap_));
       if (!buf_[k]) { why = "no page-locked memory for the file chunks"; return Result::FALLBACK; }
     }
   const bool timing = std::getenv("MMANNOT_B200_TIMING") != nullptr;
-  double msRead = 0, msSubmit = 0;
+  const double msPinned = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tRun0).count();
+  double msRead = 0, msSubmit = 0, msStage = 0, msReserve = 0;
   auto now = []() { return std::chrono::steady_clock::now(); };
   auto since = [](std::chrono::steady_clock::time_point t0) { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(); };
   if (timing) mma_timing_enable(ctx_, 1);
   int cur = 0;
   auto tr0 = now();
-  size_t have = std::fread(buf_[cur], 1, cap_, f);
+  size_t have = readAt(fd, fileSize, filePos, buf_[cur], cap_);
+  filePos += have;
   msRead += since(tr0);
   bool eof = have < cap_;
   // ---- the BAM header, inflated here: magic, text, reference names (mm:1487-1520)
@@ -149,26 +198,22 @@ DeviceBamFeeder::Result DeviceBamFeeder::run(const std::string &fileName, uint32
   if (kLaunch > kMaxComp) kLaunch = kMaxComp;
   if (const char *e = std::getenv("MMANNOT_B200_BAM_LAUNCH_MB")) kMaxComp = static_cast<uint64_t>(std::max(1, std::atoi(e))) << 20;  // (tests: several launches per file)
   {
-    long here = std::ftell(f);
-    std::fseek(f, 0, SEEK_END);
-    const long size = std::ftell(f);
-    std::fseek(f, here, SEEK_SET);
-    if (size > 0) mma_bam_reserve(ctx_, std::min<uint64_t>(static_cast<uint64_t>(size), kMaxComp) + 65536);
+    auto tv0 = now();
+    if (fileSize > 0) mma_bam_reserve(ctx_, std::min<uint64_t>(fileSize, kMaxComp) + 65536);
+    msReserve = since(tv0);
   }
   std::vector<uint32_t> memberOff, memberIsize;
   uint64_t staged = 0, inflated = 0;
-  auto submit = [&]() -> int {  // 0 ok, 1 fallback, 2 failed
-    if (memberIsize.empty()) return 0;
-    memberOff.push_back(static_cast<uint32_t>(staged));
-    mma_bam_chunk c;
-    c.data = nullptr; c.n_bytes = staged;
-    c.member_offset = memberOff.data(); c.member_isize = memberIsize.data();
-    c.n_members = static_cast<uint32_t>(memberIsize.size());
-    c.skip_first = skipFirst;
+  // A launch is started for what is staged and finished only before the next one starts (or at the end of the file): the device
+  // inflates chunk k while chunk k + 1 is read and staged.
+  bool pending = false;
+  auto finishPending = [&]() -> int {  // 0 ok, 1 fallback, 2 failed
+    if (!pending) return 0;
+    pending = false;
     uint64_t n = 0;
     uint32_t flags = 0;
     auto ts0 = now();
-    if (mma_submit_bam(ctx_, column, &c, &n, &flags) != MMA_OK) { err = mma_last_error(ctx_); return 2; }
+    if (mma_submit_bam_finish(ctx_, &n, &flags) != MMA_OK) { err = mma_last_error(ctx_); return 2; }
     msSubmit += since(ts0);
     if (flags) {
       why = std::string("the file needs the host decoder:") + ((flags & MMA_BAM_HAS_XA) ? " XA tags" : "") + ((flags & MMA_BAM_STRADDLE) ? " records across BGZF members" : "") +
@@ -177,6 +222,22 @@ DeviceBamFeeder::Result DeviceBamFeeder::run(const std::string &fileName, uint32
       return 1;
     }
     nRecords += n;
+    return 0;
+  };
+  auto submit = [&]() -> int {
+    if (memberIsize.empty()) return 0;
+    const int rcp = finishPending();
+    if (rcp) return rcp;
+    memberOff.push_back(static_cast<uint32_t>(staged));
+    mma_bam_chunk c;
+    c.data = nullptr; c.n_bytes = staged;
+    c.member_offset = memberOff.data(); c.member_isize = memberIsize.data();
+    c.n_members = static_cast<uint32_t>(memberIsize.size());
+    c.skip_first = skipFirst;
+    auto ts0 = now();
+    if (mma_submit_bam_start(ctx_, column, &c) != MMA_OK) { err = mma_last_error(ctx_); return 2; }
+    msSubmit += since(ts0);
+    pending = true;
     skipFirst = 0;
     memberOff.clear(); memberIsize.clear();
     staged = 0; inflated = 0;
@@ -186,7 +247,9 @@ DeviceBamFeeder::Result DeviceBamFeeder::run(const std::string &fileName, uint32
     size_t at = pos, from = pos;  // [from, at) = scanned, not staged yet
     auto stageScanned = [&]() -> bool {
       if (at == from) return true;
+      auto tg0 = now();
       if (mma_bam_stage(ctx_, buf_[cur] + from, at - from, staged - (at - from)) != MMA_OK) { err = mma_last_error(ctx_); return false; }
+      msStage += since(tg0);
       from = at;
       return true;
     };
@@ -224,10 +287,12 @@ DeviceBamFeeder::Result DeviceBamFeeder::run(const std::string &fileName, uint32
     const int nxt = cur ^ 1;
     std::memcpy(buf_[nxt], buf_[cur] + at, rest);
     auto tr1 = now();
-    std::future<size_t> reading = std::async(std::launch::async, [&, nxt, rest]() { return std::fread(buf_[nxt] + rest, 1, cap_ - rest, f); });
+    const uint64_t readFrom = filePos;
+    std::future<size_t> reading = std::async(std::launch::async, [&, nxt, rest, readFrom]() { return readAt(fd, fileSize, readFrom, buf_[nxt] + rest, cap_ - rest); });
     int rc = 0;
     if (staged >= kLaunch) rc = submit();
     const size_t got = reading.get();
+    filePos += got;
     msRead += since(tr1);
     if (rc == 1) return Result::FALLBACK;
     if (rc == 2) return Result::FAILED;
@@ -238,7 +303,8 @@ DeviceBamFeeder::Result DeviceBamFeeder::run(const std::string &fileName, uint32
     if (have == 0) break;
   }
   {
-    const int rc = submit();
+    int rc = submit();
+    if (rc == 0) rc = finishPending();
     if (rc == 1) return Result::FALLBACK;
     if (rc == 2) return Result::FAILED;
   }
@@ -261,8 +327,9 @@ DeviceBamFeeder::Result DeviceBamFeeder::run(const std::string &fileName, uint32
   if (timing) {
     mma_timing t;
     if (mma_timing_get(ctx_, &t) == MMA_OK)
-      std::fprintf(stderr, "[timing] bam file read %.1f ms, mma_submit_bam %.1f ms (host side), device: inflate %.1f ms, record walk + scan %.1f ms, parse %.1f ms, batch kernels %.1f ms\n",
-                   msRead, msSubmit, t.ms_bam_inflate, t.ms_bam_index, t.ms_bam_parse, t.ms_batch);
+      std::fprintf(stderr, "[timing] bam file read %.1f ms, mma_submit_bam %.1f ms (host side), device: inflate %.1f ms, record walk + scan %.1f ms, parse %.1f ms, batch kernels %.1f ms; "
+                           "host: page-locked buffers %.1f ms, reserve %.1f ms, staging calls %.1f ms, feeder total %.1f ms\n",
+                   msRead, msSubmit, t.ms_bam_inflate, t.ms_bam_index, t.ms_bam_parse, t.ms_batch, msPinned, msReserve, msStage, since(tRun0));
   }
   return Result::DONE;
 }

@@ -140,6 +140,14 @@ struct mma_ctx {
   cudaEvent_t bamStageEv = nullptr;
   u32 bamNRef = 0, bamStrandedness = 1;
   double msBam[3] = {0, 0, 0};  // inflate, count + scan, parse
+  struct BamPending {        // the chunk between mma_submit_bam_start and mma_submit_bam_finish
+    bool active = false, empty = false;
+    u32 sample = 0;
+    BamView v{};
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  } bamPend;
+  u32 *bamPendHost = nullptr;  // page-locked: {flags, hits} of the chunk in flight
+  cudaEvent_t bamPendEv = nullptr;
   DevBuf walkMap;            // k_batch_lean -> k_batch_walk: one bit per hit of a launch (zero between launches: the walk clears what it reads)
   DevBuf exportBuf;          // mma_export_table_async: this context's own dump, kept for mma_restore_export (dumpBuf is rewritten by every finish)
 
@@ -551,6 +559,8 @@ void mma_destroy(mma_ctx *ctx) {
   ctx->rndKeys.release(); ctx->rndVals.release();
   for (int k = 0; k < 2; ++k) { ctx->bamComp[k].release(); if (ctx->bamCopied[k]) cudaEventDestroy(ctx->bamCopied[k]); }
   if (ctx->bamStageEv) cudaEventDestroy(ctx->bamStageEv);
+  if (ctx->bamPendEv) cudaEventDestroy(ctx->bamPendEv);
+  if (ctx->bamPendHost) cudaFreeHost(ctx->bamPendHost);
   ctx->bamOut.release(); ctx->bamMemberOff.release(); ctx->bamOutOff.release(); ctx->bamCount.release(); ctx->bamHitOff.release();
   ctx->bamRefToChr.release(); ctx->bamRefFirst.release(); ctx->bamFlags.release();
   ctx->bamStart.release(); ctx->bamEnd.release(); ctx->bamMeta.release(); ctx->bamNh.release(); ctx->bamKey.release();
@@ -710,7 +720,9 @@ int mma_load_features(mma_ctx *ctx, const mma_features *f) {
     uint32_t fshift = ctx->params.fast_bin_shift;
     uint64_t totalExtent = 0;
     for (uint32_t c = 0; c < nChr; ++c) totalExtent += extent[c];
-    const bool useEnt = fshift == 0 && (totalExtent >> 6) + 3ull * nChr <= MMA_MAX_BIN_ENTRIES && !getenv("MMANNOT_B200_NO_BINS");
+    uint64_t maxBins = MMA_MAX_BIN_ENTRIES;
+    if (const char *mb = getenv("MMANNOT_B200_MAX_BINS")) maxBins = strtoull(mb, nullptr, 10);  // tuning: bin entries for larger annotations
+    const bool useEnt = fshift == 0 && (totalExtent >> 6) + 3ull * nChr <= maxBins && !getenv("MMANNOT_B200_NO_BINS");
     if (useEnt) fshift = 6;
     if (fshift == 0) {
       fshift = 5;
@@ -1064,6 +1076,11 @@ int mma_bam_begin(mma_ctx *ctx, uint32_t sample, const uint32_t *ref_to_chr, uin
   ctx->bamStrandedness = (u32)strandedness;
   ctx->bamOrdinal = 0;
   ctx->bamLastHits = 0;
+  if (ctx->bamPend.active) {  // (a file given up half-way: its last chunk is dropped)
+    CK(cudaStreamSynchronize(ctx->sc));
+    for (int k = 0; k < 4; ++k) if (ctx->bamPend.ev[k]) ctx->eventPool.push_back(ctx->bamPend.ev[k]);
+    ctx->bamPend = mma_ctx::BamPending();
+  }
   for (int k = 0; k < 2; ++k)
     if (!ctx->bamCopied[k]) CK(cudaEventCreateWithFlags(&ctx->bamCopied[k], cudaEventDisableTiming));
   return MMA_OK;
@@ -1085,7 +1102,10 @@ static int bamGrow(mma_ctx *ctx, DevBuf &b, size_t need, size_t keep) {
 int mma_bam_reserve(mma_ctx *ctx, uint64_t n_bytes) {
   if (!ctx) return MMA_ERR_INVALID;
   CK(cudaSetDevice(ctx->device));
-  return bamGrow(ctx, ctx->bamComp[ctx->bamChunks & 1], (size_t)n_bytes + 16, (size_t)ctx->bamStaged);
+  // both staging slots: the one being filled, and the one the next chunk is staged into while this one is inflated
+  int rc = bamGrow(ctx, ctx->bamComp[ctx->bamChunks & 1], (size_t)n_bytes + 16, (size_t)ctx->bamStaged);
+  if (rc) return rc;
+  return bamGrow(ctx, ctx->bamComp[(ctx->bamChunks & 1) ^ 1], (size_t)n_bytes + 16, 0);
 }
 
 int mma_bam_stage(mma_ctx *ctx, const void *host_bytes, uint64_t n_bytes, uint64_t offset) {
@@ -1104,14 +1124,20 @@ int mma_bam_stage(mma_ctx *ctx, const void *host_bytes, uint64_t n_bytes, uint64
   return MMA_OK;
 }
 
-int mma_submit_bam(mma_ctx *ctx, uint32_t sample, const mma_bam_chunk *c, uint64_t *n_records, uint32_t *flags) {
+// mma_submit_bam in two halves, so that the caller can read and stage the NEXT chunk while this one is inflated:
+//   start   enqueues inflate -> record walk -> scan for the chunk (staged bytes or c->data) and returns at once
+//   finish  waits for them, then parse -> batch kernels (the record count sizes the hit arrays and the launches)
+// One chunk in flight at a time; mma_bam_stage calls between the two go to the other staging slot.
+int mma_submit_bam_start(mma_ctx *ctx, uint32_t sample, const mma_bam_chunk *c) {
   if (!ctx) return MMA_ERR_INVALID;
-  if (!c || !n_records || !flags) return ctx->fail(MMA_ERR_INVALID, "null argument");
+  if (!c) return ctx->fail(MMA_ERR_INVALID, "null argument");
   if (!ctx->haveIndex) return ctx->fail(MMA_ERR_STATE, "mma_load_features must be called before hits are submitted");
   if (sample >= ctx->samples.size()) return ctx->fail(MMA_ERR_INVALID, "sample index out of range");
   if (!ctx->bamFlags.p) return ctx->fail(MMA_ERR_STATE, "mma_bam_begin must be called first");
-  *n_records = 0; *flags = 0;
-  if (c->n_members == 0) return MMA_OK;
+  if (ctx->bamPend.active) return ctx->fail(MMA_ERR_STATE, "a BAM chunk is already in flight (mma_submit_bam_finish)");
+  ctx->bamPend = mma_ctx::BamPending();
+  ctx->bamPend.sample = sample;
+  if (c->n_members == 0) { ctx->bamPend.active = true; ctx->bamPend.empty = true; return MMA_OK; }
   if (!c->member_offset || !c->member_isize || c->n_bytes >= 0xFFFFFFF0ull || c->member_offset[c->n_members] != c->n_bytes)
     return ctx->fail(MMA_ERR_INVALID, "malformed BAM chunk");
   if (!c->data && c->n_bytes > ctx->bamStaged) return ctx->fail(MMA_ERR_INVALID, "fewer bytes staged (mma_bam_stage) than the chunk claims");
@@ -1125,6 +1151,8 @@ int mma_submit_bam(mma_ctx *ctx, uint32_t sample, const mma_bam_chunk *c, uint64
   for (u32 m = 0; m < nM; ++m) { outOff[m] = (u32)total; total += c->member_isize[m]; if (total >= 0xFFFFFFF0ull) return ctx->fail(MMA_ERR_INVALID, "BAM chunk inflates to 4 GB or more: submit fewer members"); }
   outOff[nM] = (u32)total;
   if (c->skip_first > c->member_isize[0]) return ctx->fail(MMA_ERR_INVALID, "skip_first beyond the first member");
+  if (!ctx->bamPendHost) CK(cudaHostAlloc(&ctx->bamPendHost, 4 * sizeof(u32), cudaHostAllocDefault));
+  if (!ctx->bamPendEv) CK(cudaEventCreateWithFlags(&ctx->bamPendEv, cudaEventDisableTiming));
   const int slot = (int)(ctx->bamChunks & 1);
   // (this slot's previous copy -- two chunks ago -- is long done: its kernels ran before the last chunk's, and that call synchronised)
   if (c->data) CK(ctx->bamComp[slot].ensure(((size_t)c->n_bytes + 15) & ~(size_t)15));
@@ -1133,19 +1161,20 @@ int mma_submit_bam(mma_ctx *ctx, uint32_t sample, const mma_bam_chunk *c, uint64
   if (c->data) CK(cudaMemcpyAsync(ctx->bamComp[slot].p, c->data, (size_t)c->n_bytes, cudaMemcpyHostToDevice, ctx->sh));
   CK(cudaEventRecord(ctx->bamCopied[slot], ctx->sh));
   ctx->bamStaged = 0;
-  // the output buffer and the tables are shared by consecutive chunks: everything below is ordered on the compute stream
-  CK(cudaStreamWaitEvent(ctx->sc, ctx->bamCopied[slot], 0));
+  // the output buffer and the tables are shared by consecutive chunks: everything below is ordered on the compute stream (the
+  // small tables first: a copy from pageable memory waits for the stream, which must not mean waiting for the staged bytes)
   CK(ctx->bamOut.ensure(((size_t)total + 64 + 15) & ~(size_t)15));
   CK(cudaMemcpyAsync(ctx->bamMemberOff.p, c->member_offset, (size_t)(nM + 1) * 4, cudaMemcpyHostToDevice, ctx->sc));
   CK(cudaMemcpyAsync(ctx->bamOutOff.p, outOff.data(), (size_t)(nM + 1) * 4, cudaMemcpyHostToDevice, ctx->sc));
   CK(cudaMemsetAsync(ctx->bamFlags.p, 0, 4, ctx->sc));
-  BamView v;
+  CK(cudaStreamWaitEvent(ctx->sc, ctx->bamCopied[slot], 0));
+  BamView &v = ctx->bamPend.v;
   v.comp = ctx->bamComp[slot].as<unsigned char>(); v.memberOff = ctx->bamMemberOff.as<u32>(); v.outOff = ctx->bamOutOff.as<u32>();
   v.out = ctx->bamOut.as<unsigned char>(); v.nMembers = nM; v.skipFirst = c->skip_first;
   v.refToChr = ctx->bamRefToChr.as<u32>(); v.nRef = ctx->bamNRef; v.strandedness = ctx->bamStrandedness;
   v.uniqueOnly = ctx->rules.strategy == MMA_STRATEGY_UNIQUE ? 1u : 0u;
   v.flags = ctx->bamFlags.as<u32>(); v.refFirst = ctx->bamRefFirst.as<unsigned long long>();
-  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t *ev = ctx->bamPend.ev;
   if (ctx->timing) for (int k = 0; k < 4; ++k) ev[k] = ctx->getEvent();
   if (ev[0]) cudaEventRecord(ev[0], ctx->sc);
   {
@@ -1157,13 +1186,32 @@ int mma_submit_bam(mma_ctx *ctx, uint32_t sample, const mma_bam_chunk *c, uint64
   k_bam_scan<<<1, 1024, 0, ctx->sc>>>(ctx->bamCount.as<u32>(), nM, ctx->bamHitOff.as<u32>());
   if (ev[2]) cudaEventRecord(ev[2], ctx->sc);
   ctx->launches += 3;
-  u32 hFlags = 0, nHits = 0;
-  CK(cudaMemcpyAsync(&hFlags, ctx->bamFlags.p, 4, cudaMemcpyDeviceToHost, ctx->sc));
-  CK(cudaMemcpyAsync(&nHits, ctx->bamHitOff.as<u32>() + nM, 4, cudaMemcpyDeviceToHost, ctx->sc));
-  CK(cudaStreamSynchronize(ctx->sc));
+  CK(cudaMemcpyAsync(&ctx->bamPendHost[0], ctx->bamFlags.p, 4, cudaMemcpyDeviceToHost, ctx->sc));
+  CK(cudaMemcpyAsync(&ctx->bamPendHost[1], ctx->bamHitOff.as<u32>() + nM, 4, cudaMemcpyDeviceToHost, ctx->sc));
+  CK(cudaEventRecord(ctx->bamPendEv, ctx->sc));
   ctx->bamChunks++;
-  if (hFlags) { *flags = hFlags; return MMA_OK; }
-  if (nHits == 0) { ctx->bamLastHits = 0; return MMA_OK; }
+  ctx->bamPend.active = true;
+  return MMA_OK;
+}
+
+int mma_submit_bam_finish(mma_ctx *ctx, uint64_t *n_records, uint32_t *flags) {
+  if (!ctx) return MMA_ERR_INVALID;
+  if (!n_records || !flags) return ctx->fail(MMA_ERR_INVALID, "null argument");
+  if (!ctx->bamPend.active) return ctx->fail(MMA_ERR_STATE, "no BAM chunk in flight (mma_submit_bam_start)");
+  *n_records = 0; *flags = 0;
+  ctx->bamPend.active = false;
+  if (ctx->bamPend.empty) return MMA_OK;
+  CK(cudaSetDevice(ctx->device));
+  Sample &s = ctx->samples[ctx->bamPend.sample];
+  const BamView &v = ctx->bamPend.v;
+  const u32 nM = v.nMembers;
+  cudaEvent_t *ev = ctx->bamPend.ev;
+  auto dropEvents = [&]() { for (int k = 0; k < 4; ++k) if (ev[k]) { ctx->eventPool.push_back(ev[k]); ev[k] = nullptr; } };
+  CK(cudaEventSynchronize(ctx->bamPendEv));
+  u32 hFlags = ctx->bamPendHost[0];
+  const u32 nHits = ctx->bamPendHost[1];
+  if (hFlags) { dropEvents(); *flags = hFlags; return MMA_OK; }
+  if (nHits == 0) { dropEvents(); ctx->bamLastHits = 0; return MMA_OK; }
   const size_t cap = ((size_t)nHits + 127) & ~(size_t)127;
   CK(ctx->bamStart.ensure(cap * 4)); CK(ctx->bamEnd.ensure(cap * 4)); CK(ctx->bamMeta.ensure(cap * 4)); CK(ctx->bamNh.ensure(cap * 4)); CK(ctx->bamKey.ensure(cap * 8));
   HitOut o;
@@ -1173,15 +1221,18 @@ int mma_submit_bam(mma_ctx *ctx, uint32_t sample, const mma_bam_chunk *c, uint64
   if (ev[3]) {
     cudaEventRecord(ev[3], ctx->sc);
     ctx->bamSpans.push_back({ev[0], ev[1], ev[2], ev[3]});
+    for (int k = 0; k < 4; ++k) ev[k] = nullptr;
   }
   // records with the flags only the parse can see (XA, odd CIGAR, odd aux)
-  CK(cudaMemcpyAsync(&hFlags, ctx->bamFlags.p, 4, cudaMemcpyDeviceToHost, ctx->sc));
+  CK(cudaMemcpyAsync(&ctx->bamPendHost[0], ctx->bamFlags.p, 4, cudaMemcpyDeviceToHost, ctx->sc));
   CK(cudaStreamSynchronize(ctx->sc));
+  hFlags = ctx->bamPendHost[0];
   if (hFlags) { *flags = hFlags; return MMA_OK; }
   ctx->bamOrdinal += nHits;
   ctx->bamLastHits = nHits;
   *n_records = nHits;
   // the hits are in HBM: annotate them like a device-resident batch, in pieces the per-thread counters can hold
+  int rc;
   for (uint64_t a = 0; a < nHits;) {
     const uint64_t n = std::min<uint64_t>(nHits - a, 1ull << 27);
     if ((rc = ensureDeferred(ctx, s, n))) return rc;
@@ -1195,6 +1246,15 @@ int mma_submit_bam(mma_ctx *ctx, uint32_t sample, const mma_bam_chunk *c, uint64
     a += n;
   }
   return MMA_OK;
+}
+
+int mma_submit_bam(mma_ctx *ctx, uint32_t sample, const mma_bam_chunk *c, uint64_t *n_records, uint32_t *flags) {
+  if (!ctx) return MMA_ERR_INVALID;
+  if (!c || !n_records || !flags) return ctx->fail(MMA_ERR_INVALID, "null argument");
+  *n_records = 0; *flags = 0;
+  const int rc = mma_submit_bam_start(ctx, sample, c);
+  if (rc) return rc;
+  return mma_submit_bam_finish(ctx, n_records, flags);
 }
 
 int mma_bam_ref_first(mma_ctx *ctx, uint64_t *out, uint32_t n_ref) {

@@ -402,9 +402,11 @@ MMA_HD __forceinline__ u32 bamRecord(const BamView &v, const unsigned char *p, u
   u32 chr = 0x00FFFFFFu;
   if (refId >= 0 && (u32)refId < v.nRef) {
     chr = v.refToChr[refId];
-    if (!v.uniqueOnly || nHits == 1) {
+    // (only the warnings about chromosomes the annotation does not know use this; an atomic per record on a handful of addresses
+    // tripled the time of this kernel)
+    if ((chr & 0x00FFFFFFu) == 0x00FFFFFFu && (!v.uniqueOnly || nHits == 1)) {
 #ifdef __CUDA_ARCH__
-      atomicMin(&v.refFirst[refId], (unsigned long long)ordinal);
+      if (ordinal < *(volatile const unsigned long long *)&v.refFirst[refId]) atomicMin(&v.refFirst[refId], (unsigned long long)ordinal);
 #else
       if (ordinal < v.refFirst[refId]) v.refFirst[refId] = ordinal;
 #endif

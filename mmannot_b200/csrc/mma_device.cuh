@@ -1149,63 +1149,98 @@ __global__ void k_slow_maxlen(u32 n, SlowView s, u32 *maxLen) {
   while (q < n && s.key[q] == k) ++q;
   if (q - p > 64) atomicMax(maxLen, q - p);
 }
-__global__ void k_slow_default_byord(u32 n, SlowView s, Rules r, TableView table, SampleCtl *ctl) {
+// One thread per read name (the thread of its first record in key order).  Counts go through a block-private table and the
+// counters through shared memory: with one global atomic per name on a handful of addresses this pass was bound by same-address
+// atomics (8 ms per 16 M records).
+__global__ void __launch_bounds__(256) k_slow_default_byord(u32 n, SlowView s, Rules r, TableView table, SampleCtl *ctl) {
+  __shared__ BlockTable<1024> bt;
+  __shared__ u32 shStat[4];  // reads, rescued, names, names whose records were adjacent in the file
+  bt.init();
+  if (threadIdx.x < 4) shStat[threadIdx.x] = 0;
+  __syncthreads();
   const u32 p = blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= n) return;
-  const u64 k = s.key[p];
-  if (p > 0 && s.key[p - 1] == k) return;
-  u32 q = p + 1;
-  u64 lo = s.ord[p], hi = lo;
-  for (; q < n; ++q) {
-    const u32 id = q;
-    if (s.key[id] != k) break;
-    const u64 o = s.ord[id];
-    lo = min(lo, o); hi = max(hi, o);
-  }
-  const u32 len = q - p;
-  bool isOpen = false;
-  u32 remaining = 0, nReads = 0, nRescued = 0;
-  u64 gm = 0, firstOrd = 0, last = 0;
-  auto rescued = [&](u64 g, u64 o0, u64 o1) {  // rescue() over the records of the read: ordinals o0..o1 of this name
-    u32 cnt = 0;
-    for (u32 z = p; z < q; ++z) { const u32 id = z; const u64 o = s.ord[id]; if (o >= o0 && o <= o1) cnt += __popcll(s.mask[id]); }
-    return rescueFromCounts(r, g, cnt, [&](u64 bit) {
-      u32 c = 0;
-      for (u32 z = p; z < q; ++z) { const u32 id = z; const u64 o = s.ord[id]; if (o >= o0 && o <= o1 && (s.mask[id] & bit)) ++c; }
-      return c;
-    });
-  };
-  for (u32 step = 0; step < len; ++step) {
-    // the record with the smallest ordinal not taken yet (ordinals are distinct)
-    u32 best = 0;
-    u64 bestOrd = ~0ull;
-    for (u32 z = p; z < q; ++z) {
-      const u32 id = z;
+  u32 nReads = 0, nRescued = 0, nSegs = 0, nContig = 0;
+  if (p < n && (p == 0 || s.key[p - 1] != s.key[p])) {
+    const u64 k = s.key[p];
+    u32 q = p + 1;
+    u64 lo = s.ord[p], hi = lo;
+    const u32 nh0 = s.nh[p];
+    u64 orAll = s.mask[p];
+    bool sameNh = true;
+    for (; q < n; ++q) {
+      const u32 id = q;
+      if (s.key[id] != k) break;
       const u64 o = s.ord[id];
-      if ((step == 0 || o > last) && o < bestOrd) { bestOrd = o; best = id; }
+      lo = min(lo, o); hi = max(hi, o);
+      orAll |= s.mask[id];
+      sameNh &= s.nh[id] == nh0;
     }
-    last = bestOrd;
-    const u64 mq = s.mask[best];
-    if (!isOpen) { isOpen = true; remaining = s.nh[best] - 1; gm = mq; firstOrd = bestOrd; ++nReads; }
-    else { --remaining; gm |= mq; }
-    if (remaining == 0) {
-      if (gm != 0) {
-        if (r.rescue) gm = rescued(gm, firstOrd, bestOrd);
-        tableAdd(table, gm, 1);
+    const u32 len = q - p;
+    nSegs = 1;
+    nContig = (hi - lo + 1 == (u64)len) ? 1u : 0u;
+    if (sameNh && nh0 == len && !r.rescue) {
+      // the usual shape -- NH records, all carrying that NH: one read whatever the order of its records (the countdown opens at
+      // the first and closes at the last of them), its element set the union over all of them
+      nReads = 1;
+      if (orAll != 0) {
+        bt.add(orAll, 1, table);
+        if (__popcll(orAll) == 1) nRescued = 1;
+      }
+    } else {
+      bool isOpen = false;
+      u32 remaining = 0;
+      u64 gm = 0, firstOrd = 0, last = 0;
+      auto rescued = [&](u64 g, u64 o0, u64 o1) {  // rescue() over the records of the read: ordinals o0..o1 of this name
+        u32 cnt = 0;
+        for (u32 z = p; z < q; ++z) { const u64 o = s.ord[z]; if (o >= o0 && o <= o1) cnt += __popcll(s.mask[z]); }
+        return rescueFromCounts(r, g, cnt, [&](u64 bit) {
+          u32 c = 0;
+          for (u32 z = p; z < q; ++z) { const u64 o = s.ord[z]; if (o >= o0 && o <= o1 && (s.mask[z] & bit)) ++c; }
+          return c;
+        });
+      };
+      for (u32 step = 0; step < len; ++step) {
+        // the record with the smallest ordinal not taken yet (ordinals are distinct)
+        u32 best = 0;
+        u64 bestOrd = ~0ull;
+        for (u32 z = p; z < q; ++z) {
+          const u64 o = s.ord[z];
+          if ((step == 0 || o > last) && o < bestOrd) { bestOrd = o; best = z; }
+        }
+        last = bestOrd;
+        const u64 mq = s.mask[best];
+        if (!isOpen) { isOpen = true; remaining = s.nh[best] - 1; gm = mq; firstOrd = bestOrd; ++nReads; }
+        else { --remaining; gm |= mq; }
+        if (remaining == 0) {
+          if (gm != 0) {
+            if (r.rescue) gm = rescued(gm, firstOrd, bestOrd);
+            bt.add(gm, 1, table);
+            if (__popcll(gm) == 1) ++nRescued;
+          }
+          isOpen = false;
+        }
+      }
+      if (isOpen && gm != 0) {  // flush at end of file
+        if (r.rescue) gm = rescued(gm, firstOrd, last);
+        bt.add(gm, 1, table);
         if (__popcll(gm) == 1) ++nRescued;
       }
-      isOpen = false;
     }
   }
-  if (isOpen && gm != 0) {  // flush at end of file
-    if (r.rescue) gm = rescued(gm, firstOrd, last);
-    tableAdd(table, gm, 1);
-    if (__popcll(gm) == 1) ++nRescued;
+  nReads = __reduce_add_sync(0xffffffffu, nReads); nRescued = __reduce_add_sync(0xffffffffu, nRescued);
+  nSegs = __reduce_add_sync(0xffffffffu, nSegs); nContig = __reduce_add_sync(0xffffffffu, nContig);
+  if ((threadIdx.x & 31u) == 0) {
+    if (nReads) atomicAdd(&shStat[0], nReads);
+    if (nRescued) atomicAdd(&shStat[1], nRescued);
+    if (nSegs) atomicAdd(&shStat[2], nSegs);
+    if (nContig) atomicAdd(&shStat[3], nContig);
   }
-  if (nReads) atomicAdd(&ctl->stats[ST_READS], (u64)nReads);
-  if (nRescued) atomicAdd(&ctl->stats[ST_RESCUED], (u64)nRescued);
-  atomicAdd(&ctl->deferSegs, 1u);
-  if (hi - lo + 1 == (u64)len) atomicAdd(&ctl->deferContig, 1u);
+  __syncthreads();
+  bt.flush(table);
+  if (threadIdx.x == 0 && shStat[0]) atomicAdd(&ctl->stats[ST_READS], (u64)shStat[0]);
+  if (threadIdx.x == 1 && shStat[1]) atomicAdd(&ctl->stats[ST_RESCUED], (u64)shStat[1]);
+  if (threadIdx.x == 2 && shStat[2]) atomicAdd(&ctl->deferSegs, shStat[2]);
+  if (threadIdx.x == 3 && shStat[3]) atomicAdd(&ctl->deferContig, shStat[3]);
 }
 
 // random (mm:1706-1726).  A name draws i = rand() % NH at its first annotated hit and its i-th annotated hit (0-based, counted

@@ -22,7 +22,7 @@ EXPORTS = [
     "mma_submit_hits", "mma_submit_hits_device", "mma_finish_sample", "mma_reset_sample", "mma_dense_counts",
     "mma_sync", "mma_stream", "mma_timing_enable", "mma_timing_reset", "mma_timing_get", "mma_index_bytes", "mma_version", "mma_readback_bytes", "mma_dominant_kernel", "mma_index_segments", "mma_annotate_hits", "mma_annotate_intervals", "mma_pack_hits", "mma_submit_hits_packed", "mma_device_count", "mma_warmup", "mma_export_bytes", "mma_export_table", "mma_import_tables",
     "mma_export_rows", "mma_export_head_bytes", "mma_import_tables_strided", "mma_allreduce", "mma_batch_kernel", "mma_export_table_async", "mma_restore_export",
-    "mma_bam_begin", "mma_submit_bam", "mma_bam_ref_first", "mma_bam_last_hits", "mma_bam_reserve", "mma_bam_stage",
+    "mma_bam_begin", "mma_submit_bam", "mma_submit_bam_start", "mma_submit_bam_finish", "mma_bam_ref_first", "mma_bam_last_hits", "mma_bam_reserve", "mma_bam_stage",
 ]
 
 
