@@ -219,11 +219,24 @@ def time_reference(wl, n_files, reads_per_file, first_read=0, reps=1, warmup=0):
     return out, records, n_files, desc
 
 
+def scratch_root():
+    """Where the synthetic GFF / BAM files of BOTH arms go: a RAM-backed tmpfs when the box has one with room (the files were
+    written a moment ago, so either way they are read from memory -- but on a disk-backed /tmp the write-back of a freshly written
+    0.8 GB BAM runs while it is read, and file -> table time then measures the box's disk: 260 ms on one box, 1600 ms on another)."""
+    try:
+        st = os.statvfs("/dev/shm")
+        if st.f_bavail * st.f_frsize >= (12 << 30) and os.access("/dev/shm", os.W_OK):
+            return "/dev/shm"
+    except OSError:
+        pass
+    return None
+
+
 def run_reference_arm(args):
     rank, _, world = dist_env()
     if rank != 0:
         return 0
-    tmp = tempfile.mkdtemp(prefix="mmannot_bench_")
+    tmp = tempfile.mkdtemp(prefix="mmannot_bench_", dir=scratch_root())
     try:
         wl = Workload(args.workload, tmp)
         cores = os.cpu_count() or 1
@@ -471,7 +484,7 @@ def run_product_arm(args):
             rank, wl.name, wl.annotation.n, reads, n_hits, time.time() - t0, threads))
         return hs
 
-    tmp = tempfile.mkdtemp(prefix="mmannot_bench_%d_" % rank)
+    tmp = tempfile.mkdtemp(prefix="mmannot_bench_%d_" % rank, dir=scratch_root())
     try:
         wl = Workload(args.workload, tmp)
         w = wl.w
@@ -557,7 +570,7 @@ def run_product_arm(args):
             for name in ("flybase6_paired", "hs38_multi"):
                 if name == args.workload:
                     continue
-                tmp2 = tempfile.mkdtemp(prefix="mmannot_bench_%d_%s_" % (rank, name))
+                tmp2 = tempfile.mkdtemp(prefix="mmannot_bench_%d_%s_" % (rank, name), dir=scratch_root())
                 try:
                     wl2 = Workload(name, tmp2)
                     hs2 = make_hitset(wl2, args.secondary_reads or wl2.w["reads"])
@@ -667,7 +680,7 @@ def time_cli_file(wl, n_reads, threads):
         raise RuntimeError("no timing line from the command line")
     size = None
     return {"value": records / (best[0] * 1e-3), "unit": "records/s", "records": records, "reads": n_reads, "read_ms": best[0],
-            "process_wall_s": best[1], "bam_write_s": t_write,
+            "process_wall_s": best[1], "bam_write_s": t_write, "bam_dir": os.path.dirname(bam) + (" (tmpfs)" if bam.startswith("/dev/shm") else ""),
             "breakdown": best[2],
             "what": "one BAM -> count table through mmannot_b200/bin/mmannot_b200, timed inside the process around Counter::read: the compressed "
                     "file over PCIe, BGZF inflate + BAM record parse + batch kernels on the device (mma_submit_bam), table read-back; "

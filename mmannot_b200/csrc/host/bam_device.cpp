@@ -207,6 +207,7 @@ DeviceBamFeeder::Result DeviceBamFeeder::run(const std::string &fileName, uint32
   // A launch is started for what is staged and finished only before the next one starts (or at the end of the file): the device
   // inflates chunk k while chunk k + 1 is read and staged.
   bool pending = false;
+  unsigned nLaunches = 0;
   auto finishPending = [&]() -> int {  // 0 ok, 1 fallback, 2 failed
     if (!pending) return 0;
     pending = false;
@@ -238,6 +239,7 @@ DeviceBamFeeder::Result DeviceBamFeeder::run(const std::string &fileName, uint32
     if (mma_submit_bam_start(ctx_, column, &c) != MMA_OK) { err = mma_last_error(ctx_); return 2; }
     msSubmit += since(ts0);
     pending = true;
+    ++nLaunches;
     skipFirst = 0;
     memberOff.clear(); memberIsize.clear();
     staged = 0; inflated = 0;
@@ -290,7 +292,7 @@ DeviceBamFeeder::Result DeviceBamFeeder::run(const std::string &fileName, uint32
     const uint64_t readFrom = filePos;
     std::future<size_t> reading = std::async(std::launch::async, [&, nxt, rest, readFrom]() { return readAt(fd, fileSize, readFrom, buf_[nxt] + rest, cap_ - rest); });
     int rc = 0;
-    if (staged >= kLaunch) rc = submit();
+    if (staged >= (nLaunches == 0 ? std::min<uint64_t>(kLaunch, 64ull << 20) : kLaunch)) rc = submit();  // (a small first launch: the device starts early)
     const size_t got = reading.get();
     filePos += got;
     msRead += since(tr1);

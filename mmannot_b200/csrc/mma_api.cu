@@ -110,7 +110,7 @@ struct mma_ctx {
   bool timing = false;
   struct Span { int cat; cudaEvent_t a, b; };
   std::vector<Span> spans;
-  struct BamSpan { cudaEvent_t e[4]; };
+  struct BamSpan { cudaEvent_t e[5]; };  // inflate e0..e1, record walk + scan e1..e2, (host: the next chunk is read) parse e3..e4
   std::vector<BamSpan> bamSpans;
   std::vector<cudaEvent_t> eventPool;
   double ms[TC_N] = {0, 0, 0, 0};
@@ -144,8 +144,9 @@ struct mma_ctx {
     bool active = false, empty = false;
     u32 sample = 0;
     BamView v{};
-    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
   } bamPend;
+  u32 bamInflateBlocks = 0;
   u32 *bamPendHost = nullptr;  // page-locked: {flags, hits} of the chunk in flight
   cudaEvent_t bamPendEv = nullptr;
   DevBuf walkMap;            // k_batch_lean -> k_batch_walk: one bit per hit of a launch (zero between launches: the walk clears what it reads)
@@ -180,9 +181,9 @@ struct mma_ctx {
     for (BamSpan &b : bamSpans) {
       for (int k = 0; k < 3; ++k) {
         float t = 0;
-        if (cudaEventElapsedTime(&t, b.e[k], b.e[k + 1]) == cudaSuccess) msBam[k] += t;
+        if (cudaEventElapsedTime(&t, b.e[k == 2 ? 3 : k], b.e[k == 2 ? 4 : k + 1]) == cudaSuccess) msBam[k] += t;
       }
-      for (int k = 0; k < 4; ++k) eventPool.push_back(b.e[k]);
+      for (int k = 0; k < 5; ++k) eventPool.push_back(b.e[k]);
     }
     bamSpans.clear();
   }
@@ -1068,7 +1069,7 @@ int mma_bam_begin(mma_ctx *ctx, uint32_t sample, const uint32_t *ref_to_chr, uin
   if (n_ref && !ref_to_chr) return ctx->fail(MMA_ERR_INVALID, "null reference table");
   if (strandedness < 0 || strandedness > 2) return ctx->fail(MMA_ERR_INVALID, "strandedness must be 0 (U), 1 (F) or 2 (R)");
   CK(cudaSetDevice(ctx->device));
-  CK(ctx->bamRefToChr.ensure((size_t)std::max<u32>(n_ref, 1) * 4)); CK(ctx->bamRefFirst.ensure((size_t)std::max<u32>(n_ref, 1) * 8)); CK(ctx->bamFlags.ensure(4));
+  CK(ctx->bamRefToChr.ensure((size_t)std::max<u32>(n_ref, 1) * 4)); CK(ctx->bamRefFirst.ensure((size_t)std::max<u32>(n_ref, 1) * 8)); CK(ctx->bamFlags.ensure(8));
   if (n_ref) CK(cudaMemcpyAsync(ctx->bamRefToChr.p, ref_to_chr, (size_t)n_ref * 4, cudaMemcpyHostToDevice, ctx->sc));
   CK(cudaMemsetAsync(ctx->bamRefFirst.p, 0xFF, (size_t)std::max<u32>(n_ref, 1) * 8, ctx->sc));
   CK(cudaStreamSynchronize(ctx->sc));  // (ref_to_chr may be pageable: it must not change under the copy)
@@ -1078,7 +1079,7 @@ int mma_bam_begin(mma_ctx *ctx, uint32_t sample, const uint32_t *ref_to_chr, uin
   ctx->bamLastHits = 0;
   if (ctx->bamPend.active) {  // (a file given up half-way: its last chunk is dropped)
     CK(cudaStreamSynchronize(ctx->sc));
-    for (int k = 0; k < 4; ++k) if (ctx->bamPend.ev[k]) ctx->eventPool.push_back(ctx->bamPend.ev[k]);
+    for (int k = 0; k < 5; ++k) if (ctx->bamPend.ev[k]) ctx->eventPool.push_back(ctx->bamPend.ev[k]);
     ctx->bamPend = mma_ctx::BamPending();
   }
   for (int k = 0; k < 2; ++k)
@@ -1166,7 +1167,7 @@ int mma_submit_bam_start(mma_ctx *ctx, uint32_t sample, const mma_bam_chunk *c) 
   CK(ctx->bamOut.ensure(((size_t)total + 64 + 15) & ~(size_t)15));
   CK(cudaMemcpyAsync(ctx->bamMemberOff.p, c->member_offset, (size_t)(nM + 1) * 4, cudaMemcpyHostToDevice, ctx->sc));
   CK(cudaMemcpyAsync(ctx->bamOutOff.p, outOff.data(), (size_t)(nM + 1) * 4, cudaMemcpyHostToDevice, ctx->sc));
-  CK(cudaMemsetAsync(ctx->bamFlags.p, 0, 4, ctx->sc));
+  CK(cudaMemsetAsync(ctx->bamFlags.p, 0, 8, ctx->sc));  // (the flags word and the member counter of k_bam_inflate)
   CK(cudaStreamWaitEvent(ctx->sc, ctx->bamCopied[slot], 0));
   BamView &v = ctx->bamPend.v;
   v.comp = ctx->bamComp[slot].as<unsigned char>(); v.memberOff = ctx->bamMemberOff.as<u32>(); v.outOff = ctx->bamOutOff.as<u32>();
@@ -1175,11 +1176,18 @@ int mma_submit_bam_start(mma_ctx *ctx, uint32_t sample, const mma_bam_chunk *c) 
   v.uniqueOnly = ctx->rules.strategy == MMA_STRATEGY_UNIQUE ? 1u : 0u;
   v.flags = ctx->bamFlags.as<u32>(); v.refFirst = ctx->bamRefFirst.as<unsigned long long>();
   cudaEvent_t *ev = ctx->bamPend.ev;
-  if (ctx->timing) for (int k = 0; k < 4; ++k) ev[k] = ctx->getEvent();
+  if (ctx->timing) for (int k = 0; k < 5; ++k) ev[k] = ctx->getEvent();
   if (ev[0]) cudaEventRecord(ev[0], ctx->sc);
   {
+    if (!ctx->bamInflateBlocks) {  // blocks the GPU holds at once
+      int perSM = 0;
+      CK(cudaFuncSetAttribute(k_bam_inflate, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));  // (its tables are its working set)
+      CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_bam_inflate, BAM_INFLATE_THREADS, 0));
+      ctx->bamInflateBlocks = (u32)std::max(1, perSM) * (u32)ctx->nSM;
+    }
     const u32 warps = (nM + MMA_BAM_LANES - 1) / MMA_BAM_LANES;
-    k_bam_inflate<<<gridFor((uint64_t)warps * 32, BAM_INFLATE_THREADS), BAM_INFLATE_THREADS, 0, ctx->sc>>>(v);
+    const u32 grid = std::min<u32>(gridFor((uint64_t)warps * 32, BAM_INFLATE_THREADS), ctx->bamInflateBlocks);
+    k_bam_inflate<<<grid, BAM_INFLATE_THREADS, 0, ctx->sc>>>(v, ctx->bamFlags.as<u32>() + 1);
   }
   if (ev[1]) cudaEventRecord(ev[1], ctx->sc);
   k_bam_count<<<gridFor(nM, 128), 128, 0, ctx->sc>>>(v, ctx->bamCount.as<u32>());
@@ -1206,7 +1214,7 @@ int mma_submit_bam_finish(mma_ctx *ctx, uint64_t *n_records, uint32_t *flags) {
   const BamView &v = ctx->bamPend.v;
   const u32 nM = v.nMembers;
   cudaEvent_t *ev = ctx->bamPend.ev;
-  auto dropEvents = [&]() { for (int k = 0; k < 4; ++k) if (ev[k]) { ctx->eventPool.push_back(ev[k]); ev[k] = nullptr; } };
+  auto dropEvents = [&]() { for (int k = 0; k < 5; ++k) if (ev[k]) { ctx->eventPool.push_back(ev[k]); ev[k] = nullptr; } };
   CK(cudaEventSynchronize(ctx->bamPendEv));
   u32 hFlags = ctx->bamPendHost[0];
   const u32 nHits = ctx->bamPendHost[1];
@@ -1216,12 +1224,13 @@ int mma_submit_bam_finish(mma_ctx *ctx, uint64_t *n_records, uint32_t *flags) {
   CK(ctx->bamStart.ensure(cap * 4)); CK(ctx->bamEnd.ensure(cap * 4)); CK(ctx->bamMeta.ensure(cap * 4)); CK(ctx->bamNh.ensure(cap * 4)); CK(ctx->bamKey.ensure(cap * 8));
   HitOut o;
   o.start = ctx->bamStart.as<u32>(); o.end = ctx->bamEnd.as<u32>(); o.meta = ctx->bamMeta.as<u32>(); o.nh = ctx->bamNh.as<u32>(); o.key = ctx->bamKey.as<u64>();
+  if (ev[3]) cudaEventRecord(ev[3], ctx->sc);
   k_bam_parse<<<gridFor(nM, 64), 64, 0, ctx->sc>>>(v, ctx->bamHitOff.as<u32>(), ctx->bamOrdinal, o);
   ctx->launches++;
-  if (ev[3]) {
-    cudaEventRecord(ev[3], ctx->sc);
-    ctx->bamSpans.push_back({ev[0], ev[1], ev[2], ev[3]});
-    for (int k = 0; k < 4; ++k) ev[k] = nullptr;
+  if (ev[4]) {
+    cudaEventRecord(ev[4], ctx->sc);
+    ctx->bamSpans.push_back({ev[0], ev[1], ev[2], ev[3], ev[4]});
+    for (int k = 0; k < 5; ++k) ev[k] = nullptr;
   }
   // records with the flags only the parse can see (XA, odd CIGAR, odd aux)
   CK(cudaMemcpyAsync(&ctx->bamPendHost[0], ctx->bamFlags.p, 4, cudaMemcpyDeviceToHost, ctx->sc));

@@ -96,22 +96,23 @@ struct BitReader {
   MMA_HD __forceinline__ u32 bits(int n) { const u32 v = peek(n); drop(n); return v; }
 };
 
-// canonical Huffman code: counts per length + symbols in code order (bit-serial decode), and a 9-bit first-level table
-#define HUFF_FAST_BITS 9
-template <int NSYM>
+// canonical Huffman code: counts per length + symbols in code order (bit-serial decode), and a first-level table of FB bits
+// (9 for the literal / length code; 6 for the 30 distance symbols: the tables of the members in flight share the SM's shared
+// memory, and what the distance table gives up lets 7 blocks run per SM instead of 5)
+template <int NSYM, int FB>
 struct HuffT {
   unsigned short count[16];
   unsigned short symbol[NSYM];
-  unsigned short fast[1 << HUFF_FAST_BITS];  // (length << 9) | symbol for codes of at most 9 bits, 0 = longer / invalid
+  unsigned short fast[1 << FB];  // (length << 9) | symbol for codes of at most FB bits, 0 = longer / invalid
 };
-typedef HuffT<288> Huff;      // literal / length code (and the code-length code while a dynamic block's header is read)
-typedef HuffT<32> HuffDist;   // distance code
+typedef HuffT<288, 9> Huff;      // literal / length code (and the code-length code while a dynamic block's header is read)
+typedef HuffT<32, 6> HuffDist;   // distance code
 
-template <int NSYM>
-MMA_HD __noinline__ bool huffBuild(HuffT<NSYM> &h, const unsigned char *length, int n) {
+template <int NSYM, int FB>
+MMA_HD __noinline__ bool huffBuild(HuffT<NSYM, FB> &h, const unsigned char *length, int n) {
   for (int i = 0; i < 16; ++i) h.count[i] = 0;
   for (int i = 0; i < n; ++i) h.count[length[i]]++;
-  for (int i = 0; i < (1 << HUFF_FAST_BITS); ++i) h.fast[i] = 0;
+  for (int i = 0; i < (1 << FB); ++i) h.fast[i] = 0;
   if (h.count[0] == n) return true;  // no codes: legal for an unused distance code
   int left = 1;
   for (int len = 1; len < 16; ++len) {
@@ -128,23 +129,23 @@ MMA_HD __noinline__ bool huffBuild(HuffT<NSYM> &h, const unsigned char *length, 
   // the bit reader delivers the first bit in bit 0, so the index is the code reversed
   u32 code = 0;
   int idx = 0;
-  for (int len = 1; len <= HUFF_FAST_BITS; ++len) {
+  for (int len = 1; len <= FB; ++len) {
     for (int k = 0; k < h.count[len]; ++k, ++idx, ++code) {
       const u32 rev = bitReverse32(code) >> (32 - len);
       const unsigned short e = (unsigned short)((len << 9) | h.symbol[idx]);
-      for (u32 f = rev; f < (1u << HUFF_FAST_BITS); f += (1u << len)) h.fast[f] = e;
+      for (u32 f = rev; f < (1u << FB); f += (1u << len)) h.fast[f] = e;
     }
     code <<= 1;
   }
   return true;
 }
 
-template <int NSYM>
-MMA_HD __forceinline__ int huffDecode(const HuffT<NSYM> &h, BitReader &br) {
+template <int NSYM, int FB>
+MMA_HD __forceinline__ int huffDecode(const HuffT<NSYM, FB> &h, BitReader &br) {
   const u32 look = br.peek(15);
-  const unsigned short e = h.fast[look & ((1u << HUFF_FAST_BITS) - 1u)];
+  const unsigned short e = h.fast[look & ((1u << FB) - 1u)];
   if (e) { br.drop(e >> 9); return e & 511; }
-  // bit-serial tail (codes longer than 9 bits)
+  // bit-serial tail (codes longer than FB bits)
   int code = 0, first = 0, index = 0;
   for (int len = 1; len < 16; ++len) {
     code |= (int)((look >> (len - 1)) & 1u);
@@ -239,20 +240,37 @@ MMA_HD __noinline__ bool inflateMember(const unsigned char *src, u32 srcLen, uns
           if (ds < 0 || ds >= 30) return false;
           const u32 d = kDistBase(ds) + br.bits((int)kDistExtra(ds));
           if (d > out || out + len > dstLen) return false;
-          // the source lies d bytes behind the destination: up to min(d, 8) bytes can be read before any of them is rewritten, so
-          // the loads of a chunk do not wait for one another (a run-length match, d < 8, repeats its d bytes)
-          const unsigned char *from = dst + out - d;
+          // The source lies d bytes behind the destination.  With d >= 8 the copy goes by aligned 32-bit words: destination word k
+          // is cut out of two aligned source words by a funnel shift, and the second of them -- reused as the first of word
+          // k + 1 -- ends at most 6 bytes behind the source position, i.e. before anything this copy has yet to write (the
+          // byte-wise copy was 35 % of the kernel's issue slots: the decoder runs one lane per instruction).  A run-length
+          // match (d < 8) repeats its d bytes one by one.
+          unsigned char *to = dst + out;
+          const unsigned char *from = to - d;
           u32 i = 0;
-          if (d >= 8) {
-            for (; i + 8 <= len; i += 8) {
-              unsigned char b[8];
-#pragma unroll
-              for (int k = 0; k < 8; ++k) b[k] = from[i + k];
-#pragma unroll
-              for (int k = 0; k < 8; ++k) dst[out + i + k] = b[k];
+          if (d >= 8 && len >= 8) {
+            const u32 head = (4u - (u32)((size_t)to & 3u)) & 3u;
+            for (; i < head; ++i) to[i] = from[i];
+            const size_t sa = (size_t)(from + i);
+            const u32 sh = (u32)(sa & 3u) * 8u;
+            const u32 *sw = reinterpret_cast<const u32 *>(sa & ~(size_t)3);
+            u32 *dw = reinterpret_cast<u32 *>(to + i);
+            if (sh == 0) {
+              for (; i + 4 <= len; i += 4) *dw++ = *sw++;
+            } else {
+              u32 lo = *sw++;
+              for (; i + 4 <= len; i += 4) {
+                const u32 hi = *sw++;
+#ifdef __CUDA_ARCH__
+                *dw++ = __funnelshift_r(lo, hi, sh);
+#else
+                *dw++ = (lo >> sh) | (hi << (32u - sh));
+#endif
+                lo = hi;
+              }
             }
           }
-          for (; i < len; ++i) dst[out + i] = from[i];
+          for (; i < len; ++i) to[i] = from[i];
           out += len;
         }
         if (br.over) return false;
@@ -269,31 +287,34 @@ MMA_HD __noinline__ bool inflateMember(const unsigned char *src, u32 srcLen, uns
 MMA_HD __forceinline__ u32 ld32u(const unsigned char *p) { return (u32)p[0] | ((u32)p[1] << 8) | ((u32)p[2] << 16) | ((u32)p[3] << 24); }
 MMA_HD __forceinline__ u32 ld16u(const unsigned char *p) { return (u32)p[0] | ((u32)p[1] << 8); }
 
-// one thread per member, MMA_BAM_LANES members per warp
+// one thread per member, MMA_BAM_LANES members per warp.  The grid is what the GPU holds at once (the Huffman tables in shared
+// memory bound it at ~80 members per SM) and every lane takes the next member from a counter when it is done with one, so the
+// size of a launch does not matter.  (The kernel is bound by issue slots, not by its tail: 1.02 threads per warp instruction at
+// 57 % issue utilisation -- profiles/r02b_inflate.txt.)
 #define BAM_INFLATE_THREADS 128
-__global__ void __launch_bounds__(BAM_INFLATE_THREADS) k_bam_inflate(BamView v) {
-  // the Huffman tables of the members in flight live in shared memory (44 KB per block: every symbol is a table lookup, and
+__global__ void __launch_bounds__(BAM_INFLATE_THREADS) k_bam_inflate(BamView v, u32 *next) {
+  // the Huffman tables of the members in flight live in shared memory (30 KB per block: every symbol is a table lookup, and
   // local memory behind L1 missed 6 % of them)
   __shared__ Huff litTab[BAM_INFLATE_THREADS / 32][MMA_BAM_LANES];
   __shared__ HuffDist distTab[BAM_INFLATE_THREADS / 32][MMA_BAM_LANES];
-  const u32 warpGlobal = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31u;
+  const u32 lane = threadIdx.x & 31u;
   if (lane >= MMA_BAM_LANES) return;
-  const u32 m = warpGlobal * MMA_BAM_LANES + lane;
-  if (m >= v.nMembers) return;
-  const unsigned char *p = v.comp + v.memberOff[m];
-  const u32 total = v.memberOff[m + 1] - v.memberOff[m];
-  const u32 want = v.outOff[m + 1] - v.outOff[m];
-  // gzip member: 10 fixed bytes, XLEN + extra field (FLG.FEXTRA is set in BGZF), deflate data, CRC32, ISIZE
-  bool ok = total >= 28 && p[0] == 0x1f && p[1] == 0x8b && p[2] == 8 && (p[3] & 4);
-  u32 hdr = 0;
-  if (ok) {
-    hdr = 12 + ld16u(p + 10);
-    if (p[3] & ~4u) ok = false;  // (name / comment / header CRC fields: not BGZF)
-    if (hdr + 8 > total) ok = false;
+  for (u32 m = atomicAdd(next, 1u); m < v.nMembers; m = atomicAdd(next, 1u)) {
+    const unsigned char *p = v.comp + v.memberOff[m];
+    const u32 total = v.memberOff[m + 1] - v.memberOff[m];
+    const u32 want = v.outOff[m + 1] - v.outOff[m];
+    // gzip member: 10 fixed bytes, XLEN + extra field (FLG.FEXTRA is set in BGZF), deflate data, CRC32, ISIZE
+    bool ok = total >= 28 && p[0] == 0x1f && p[1] == 0x8b && p[2] == 8 && (p[3] & 4);
+    u32 hdr = 0;
+    if (ok) {
+      hdr = 12 + ld16u(p + 10);
+      if (p[3] & ~4u) ok = false;  // (name / comment / header CRC fields: not BGZF)
+      if (hdr + 8 > total) ok = false;
+    }
+    if (ok && ld32u(p + total - 4) != want) ok = false;
+    if (ok && want) ok = inflateMember(p + hdr, total - hdr - 8, v.out + v.outOff[m], want, litTab[threadIdx.x >> 5][lane], distTab[threadIdx.x >> 5][lane]);
+    if (!ok) atomicOr(v.flags, (u32)BAM_BAD_DEFLATE);
   }
-  if (ok && ld32u(p + total - 4) != want) ok = false;
-  if (ok && want) ok = inflateMember(p + hdr, total - hdr - 8, v.out + v.outOff[m], want, litTab[threadIdx.x >> 5][lane], distTab[threadIdx.x >> 5][lane]);
-  if (!ok) atomicOr(v.flags, (u32)BAM_BAD_DEFLATE);
 }
 
 // ---------------------------------------------------------------------------------------------- records
