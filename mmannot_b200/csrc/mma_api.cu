@@ -367,9 +367,18 @@ void launchBatchKernels(mma_ctx *ctx, Sample &s, const HitView &hAll) {
       launched = true;
       u32 grid = std::max<u32>(1u, std::min<u32>((nWT + FAST_WARPS - 1) / FAST_WARPS, (u32)ctx->nSM * MMA_FAST_BLOCKS_PER_SM));
       if (ctx->maxGrid) grid = std::min(grid, ctx->maxGrid);
-      mma_ctx::Timed t(ctx, TC_BATCH);
-      if (groups) k_batch_fast<MODE, STRAT, (STRAT == 0)><<<grid, FAST_THREADS, 0, ctx->sc>>>(ctx->index, ctx->fast, h, r, table, s.ctl, slow, open);
-      else k_batch_fast<MODE, STRAT, false><<<grid, FAST_THREADS, 0, ctx->sc>>>(ctx->index, ctx->fast, h, r, table, s.ctl, slow, open);
+      u32 *walkMap = ctx->walkMap.as<u32>();  // (sized by launchBatch)
+      {
+        mma_ctx::Timed t(ctx, TC_BATCH);
+        if (groups) k_batch_fast<MODE, STRAT, (STRAT == 0)><<<grid, FAST_THREADS, 0, ctx->sc>>>(ctx->index, ctx->fast, h, r, table, s.ctl, slow, walkMap);
+        else k_batch_fast<MODE, STRAT, false><<<grid, FAST_THREADS, 0, ctx->sc>>>(ctx->index, ctx->fast, h, r, table, s.ctl, slow, walkMap);
+      }
+      if (STRAT == 0) {
+        mma_ctx::Timed t(ctx, TC_CLOSE);
+        const u32 gridW = std::max<u32>(1u, std::min<u32>(gridFor((h.n + 127) / 128, 256), (u32)ctx->nSM * 8u));
+        k_batch_walk<MODE><<<gridW, 256, 0, ctx->sc>>>(ctx->index, ctx->fast, h, r, table, s.ctl, slow, open, walkMap, 0);
+        ctx->launches += 1;
+      }
     }
   }
   if (!launched) {
@@ -406,7 +415,7 @@ void launchBatchMode(mma_ctx *ctx, Sample &s, const HitView &h) {
 }
 
 int launchBatch(mma_ctx *ctx, Sample &s, const HitView &h) {
-  if (ctx->rules.strategy == MMA_STRATEGY_DEFAULT && ctx->fast.ent) {  // k_batch_lean marks the runs it leaves to k_batch_walk: a bit per hit
+  if (ctx->rules.strategy == MMA_STRATEGY_DEFAULT && ctx->fast.enabled) {  // k_batch_lean / k_batch_fast mark the runs they leave to k_batch_walk: a bit per hit
     const size_t need = ((size_t)h.n + 127) / 128 * 16 + 16;
     if (need > ctx->walkMap.bytes) {
       const size_t want = std::max<size_t>(need, ((size_t)ctx->params.max_batch_hits + 127) / 128 * 16 + 16);

@@ -120,7 +120,7 @@ struct FastCount {  // one read counted for an element set, from divergent code 
 template <int MODE, int STRAT, bool GROUPS>
 __global__ void __launch_bounds__(FAST_THREADS, MMA_FAST_BLOCKS_PER_SM)
 k_batch_fast(const __grid_constant__ IndexView ix, const __grid_constant__ FastView fx, const __grid_constant__ HitView h, const __grid_constant__ Rules r,
-             const __grid_constant__ TableView table, SampleCtl *ctl, const __grid_constant__ SlowView slow, const __grid_constant__ KeySetView open) {
+             const __grid_constant__ TableView table, SampleCtl *ctl, const __grid_constant__ SlowView slow, u32 *walkMap) {
   constexpr bool HIST = (STRAT != 3);
   constexpr int SLOTS = (STRAT == 3) ? 1024 : 2048;
   constexpr u32 FULL = 0xffffffffu;
@@ -134,7 +134,6 @@ k_batch_fast(const __grid_constant__ IndexView ix, const __grid_constant__ FastV
   if (tid < ST_N) sm.stat[tid] = 0;
   for (u32 c = tid; c < fx.nChr; c += FAST_THREADS) sm.chrInfo[c] = fx.chrInfo[c];  // launched only when nChr <= CHR_SMEM
   __syncthreads();
-  const Annotator<MODE, true> annot{ix, fx, r.overlap};
   const u32 seq = ctl->batchSeq;
   // every run takes the serial walker when rescue() needs multiplicities or some read name is known as unfinished
   const bool forceWalk = (STRAT == 0) && (r.rescue || __shfl_sync(FULL, ctl->openCount, 0) != 0);
@@ -145,8 +144,11 @@ k_batch_fast(const __grid_constant__ IndexView ix, const __grid_constant__ FastV
   u32 pClosResc = 0;  // multi-mapping reads closed by the parallel countdown | of which rescued << 16
   u32 pWalks = 0;     // serial walks started (feeds the host's choice between the two variants of this kernel)
 
-  FastCount<HIST, SLOTS> count{sm, table, tid};
-  RunWalker<MODE, true, FastCount<HIST, SLOTS>> w{h, r, annot, ctl, slow, open, count, seq, 0u, 0u};
+  // a run the scan cannot close, a run cut by the chunk border and the read carried into the batch are k_batch_walk's (launched
+  // behind this kernel, see mma_batch_lean.cuh): bit i of walkMap = "walk the run from record i".  No call in the tile loop.
+  auto queueWalk = [&](u32 i0) {
+    if (i0 < h.n) atomicOr(&walkMap[i0 >> 5], 1u << (i0 & 31u));
+  };
 
   const u32 nWT = (h.n + WT_HITS - 1) / WT_HITS;
   const u32 nWarps = gridDim.x * FAST_WARPS;
@@ -202,7 +204,6 @@ k_batch_fast(const __grid_constant__ IndexView ix, const __grid_constant__ FastV
     }
     // ---- run starts
     u32 hbits = 0, F = 0;
-    const Carry *carryIn = nullptr;
     u64 nextKey = KEY_EMPTY;
     u32 tileEndsRun = 1;  // lane 31: the record after the tile's last one starts another run (or the batch ends there)
     if (STRAT == 0) {
@@ -216,7 +217,7 @@ k_batch_fast(const __grid_constant__ IndexView ix, const __grid_constant__ FastV
         else if (base == 0) {
           const Carry &c = ctl->carry[seq & 1];
           prev = KEY_EMPTY;
-          if (c.valid) { carryIn = &c; prev = c.key; }
+          if (c.valid) prev = c.key;  // (the read carried into the batch is k_batch_walk's; here only: does its name continue?)
         } else prev = normKey(h.key[base - 1]);
       }
       hbits = ((key[0] != prev) ? 1u : 0u) | ((key[1] != key[0]) ? 2u : 0u) | ((key[2] != key[1]) ? 4u : 0u) | ((key[3] != key[2]) ? 8u : 0u);
@@ -342,15 +343,6 @@ k_batch_fast(const __grid_constant__ IndexView ix, const __grid_constant__ FastV
     if (GROUPS) {
       if (STRAT == 0) {
         // ---- per-read countdown (mm:1669-1702)
-        if (carryIn) {  // lane 0 of the batch's first tile: the read carried into this batch
-          if (!(hbits & 1u)) w.walk(0, carryIn->key, carryIn);
-          else {  // its name does not continue: unfinished
-            --w.nReads;
-            slowAppend(slow, ctl, carryIn->key, carryIn->ord, carryIn->gm, carryIn->remaining + 1);
-            keySetInsert(open, carryIn->key, seq, ctl);
-            ctl->dirty = 1;
-          }
-        }
         // A read opens at a record with NH = n > 1 and takes the n - 1 records of its name that follow, so a run of records
         // sharing a read key and carrying the same NH = n is a sequence of GROUPS of n records, one read each (one group for
         // single-end data, two -- the two mates -- for paired-end data, mm:1673-1681).  The element set of a read is the
@@ -441,15 +433,6 @@ k_batch_fast(const __grid_constant__ IndexView ix, const __grid_constant__ FastV
     } else {
       if (STRAT == 0) {
         // ---- per-read countdown (mm:1669-1702)
-        if (carryIn) {  // lane 0 of the batch's first tile: the read carried into this batch
-          if (!(hbits & 1u)) w.walk(0, carryIn->key, carryIn);
-          else {  // its name does not continue: unfinished
-            --w.nReads;
-            slowAppend(slow, ctl, carryIn->key, carryIn->ord, carryIn->gm, carryIn->remaining + 1);
-            keySetInsert(open, carryIn->key, seq, ctl);
-            ctl->dirty = 1;
-          }
-        }
         // A run of n records that all carry NH = n (> 1) is one read; its element set is the union over the run: a
         // segmented OR scan over the 128 hits of the warp tile (bit 31 of the scanned word = "irregular": NH changes inside
         // the run, or every run has to be walked), seeded with the state carried from the previous tile.  The lane owning
@@ -538,7 +521,7 @@ k_batch_fast(const __grid_constant__ IndexView ix, const __grid_constant__ FastV
     if (STRAT == 0) {
       pWalks += nWalk;
 #pragma unroll 1
-      for (u32 q = 0; q < nWalk; ++q) { const u32 i0 = sm.walkQ[q][tid]; w.walk(i0, normKey(h.key[i0]), nullptr); }
+      for (u32 q = 0; q < nWalk; ++q) queueWalk(sm.walkQ[q][tid]);
       if (GROUPS) {
         // the run (and, inside it, the group) still open at the end of the tile
         if (!serialTile) {
@@ -575,16 +558,16 @@ k_batch_fast(const __grid_constant__ IndexView ix, const __grid_constant__ FastV
     //      was closed above, like the last run of the batch.)
     if (STRAT == 0 && cValid && cCont && t1 > t0 && lane == 0) {
       const u32 next = t1 * WT_HITS, o = next - cStart;
-      w.walk(next - ((cNh > 1) ? o % cNh : 0u), cKey, nullptr);
+      queueWalk(next - ((cNh > 1) ? o % cNh : 0u));
     }
   } else {
     // ---- a read open at the end of the chunk that continues in another warp's chunk: finished by the serial walk.  (A run
     //      ending exactly at the chunk's last record was closed above, like the last run of the batch.)
-    if (STRAT == 0 && cValid && cCont && t1 > t0 && lane == 0) w.walk(cStart, cKey, nullptr);
+    if (STRAT == 0 && cValid && cCont && t1 > t0 && lane == 0) queueWalk(cStart);
   }
   u32 cHits = pHitsMiss & 0xFFFFu, cMiss = pHitsMiss >> 16, cUnassigned = cHits - (pAsgUniq & 0xFFFFu), cAmbiguous = pMultAmbi >> 16;
   u32 cUnique = pAsgUniq >> 16, cMultiple = pMultAmbi & 0xFFFFu;
-  u32 cReads = cHits - cMultiple + (pClosResc & 0xFFFFu) + w.nReads, cRescued = (pClosResc >> 16) + w.nRescued;
+  u32 cReads = cHits - cMultiple + (pClosResc & 0xFFFFu), cRescued = pClosResc >> 16;  // (what k_batch_walk opens and closes is added there)
 
   // ---- block epilogue: counters, the private histogram columns and the private table
   cHits = __reduce_add_sync(FULL, cHits); cUnassigned = __reduce_add_sync(FULL, cUnassigned);
