@@ -16,7 +16,9 @@
 // Two variants of the per-read step (template flag GROUPS): the plain one closes a run of n records carrying NH = n as one
 // read; the GROUPS one cuts a run of k x n records into k reads inside the scan (paired-end data) and resolves a tile in
 // which NH changes inside a run serially.  Whatever does not fit (-m rescue, batches following one that left unfinished read
-// names, runs ending inside a group) takes the serial RunWalker of mma_device.cuh, exactly as in k_batch.
+// names, runs ending inside a group, runs cut by a chunk border, the read carried into the batch) takes the serial walk of
+// RunWalker (mma_device.cuh) as in k_batch -- but in k_batch_walk (mma_batch_lean.cuh), launched behind this kernel: a lane
+// only marks the run's first record in a bitmap.
 #pragma once
 #include "mma_device.cuh"
 
@@ -99,7 +101,7 @@ struct FastSmem {
 };
 
 template <bool HIST, int SLOTS>
-struct FastCount {  // one read counted for an element set, from divergent code (the serial walker)
+struct FastCount {  // one read counted for an element set, from divergent code (unused since the serial walker left the kernel)
   FastSmem<HIST, SLOTS> &sm;
   const TableView &table;
   u32 tid;
@@ -436,7 +438,7 @@ k_batch_fast(const __grid_constant__ IndexView ix, const __grid_constant__ FastV
         // A run of n records that all carry NH = n (> 1) is one read; its element set is the union over the run: a
         // segmented OR scan over the 128 hits of the warp tile (bit 31 of the scanned word = "irregular": NH changes inside
         // the run, or every run has to be walked), seeded with the state carried from the previous tile.  The lane owning
-        // the run's LAST record closes it; irregular runs take the serial walk (RunWalker), started by the same lane.
+        // the run's LAST record closes it; irregular runs are marked for the serial walk (k_batch_walk) by the same lane.
         u32 prevNh = __shfl_up_sync(FULL, nh[3], 1);
         if (lane == 0) prevNh = cNh;
         u32 pre[4], acc = 0;
