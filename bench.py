@@ -599,7 +599,7 @@ def run_product_arm(args):
             except Exception:  # noqa: BLE001
                 pass
             cpu = None
-            if not args.no_cpu_baseline:
+            if not args.no_cpu_baseline and world == 1:  # (the contract: rank 0 at N = 1 only)
                 try:
                     n_files = args.ref_threads or 1
                     vals, records, used, desc = time_reference(wl, n_files, args.cpu_reads, reps=1)
@@ -607,7 +607,7 @@ def run_product_arm(args):
                 except Exception as e:  # noqa: BLE001
                     cpu = {"value": None, "unit": "records/s", "cores": 0, "kind": "reference", "sample": "unavailable: %s" % e}
             e2e_file = None
-            if not args.no_file:
+            if not args.no_file and world == 1:  # (one file through one GPU: nothing to add at N > 1)
                 try:
                     e2e_file = time_cli_file(wl, args.file_reads, threads)
                 except Exception as e:  # noqa: BLE001
