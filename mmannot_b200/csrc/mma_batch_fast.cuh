@@ -554,18 +554,78 @@ k_batch_fast(const __grid_constant__ IndexView ix, const __grid_constant__ FastV
       cCont = __shfl_sync(FULL, tileEndsRun, 31) == 0;
     }
   }
-  if (GROUPS) {
-    // ---- a run open at the end of the chunk continues in another warp's chunk: its remaining reads, from the group that is
-    //      open there (or starts there), are finished by the serial walk.  (A run ending exactly at the chunk's last record
-    //      was closed above, like the last run of the batch.)
-    if (STRAT == 0 && cValid && cCont && t1 > t0 && lane == 0) {
-      const u32 next = t1 * WT_HITS, o = next - cStart;
-      queueWalk(next - ((cNh > 1) ? o % cNh : 0u));
+  // ---- a run open at the end of the chunk continues in another warp's chunk (which leaves it alone: it does not own its start).
+  //      This warp finishes it, as k_batch_lean does: the records of the run in the NEXT tile are annotated, 4 per lane, and lane 0
+  //      takes the countdown through them (GROUPS: from the group open at the border through every later group of the run).  No
+  //      per-hit counter moves: the hits belong to the other chunk.  A run that is irregular, that reaches beyond that tile or
+  //      (GROUPS) that ends inside a group is marked for k_batch_walk.  (A run ending exactly at the chunk's last record was closed
+  //      above, like the last run of the batch.)
+  if (STRAT == 0 && cValid && cCont && t1 > t0) {
+    const u32 next = t1 * WT_HITS;
+    const u32 o = next - cStart;                               // records of the run inside this chunk
+    const u32 inGroup = (GROUPS && cNh > 1) ? o % cNh : 0u;    // GROUPS: ... of which in the group open at the border
+    const u32 walkFrom = GROUPS ? next - inGroup : cStart;
+    const Annotator<MODE, true> annot{ix, fx, r.overlap};
+    u32 tn[4], eq = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const size_t i = (size_t)next + lane * 4 + j;
+      const bool v = i < h.n;
+      const u64 kk = v ? normKey(__ldg(&h.key[i])) : ~cKey;
+      tn[j] = v ? __ldg(&h.nh[i]) : 0u;
+      if (kk == cKey) {
+        eq |= 1u << j;
+        sm.slowRes[warp][lane * 4 + j] = (u32)annot(__ldg(&h.start[i]), __ldg(&h.end[i]), __ldg(&h.meta[i]));
+      }
     }
-  } else {
-    // ---- a read open at the end of the chunk that continues in another warp's chunk: finished by the serial walk.  (A run
-    //      ending exactly at the chunk's last record was closed above, like the last run of the batch.)
-    if (STRAT == 0 && cValid && cCont && t1 > t0 && lane == 0) queueWalk(cStart);
+    const u32 lead = (eq == 0xFu) ? 4u : (u32)__ffs(~eq) - 1u;  // this lane's records that continue the run, if every lane before is all run
+    const u32 fullLanes = __ballot_sync(FULL, eq == 0xFu);
+    const u32 fp = (fullLanes == FULL) ? 32u : (u32)__ffs(~fullLanes) - 1u;  // first lane that is not all run
+    const u32 mineN = (lane < fp) ? 4u : (lane == fp) ? lead : 0u;
+    const u32 tailLen = __reduce_add_sync(FULL, mineN);
+    u32 prevNh = __shfl_up_sync(FULL, tn[3], 1);
+    if (lane == 0) prevNh = cNh;
+    bool bad = false;
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if ((u32)j < mineN) bad |= tn[j] != (j ? tn[j > 0 ? j - 1 : 0] : prevNh);
+    const bool anyBad = __any_sync(FULL, bad) || forceWalk || (int)cTot < 0 || fp == 32u;
+    __syncwarp();
+    if (lane == 0) {
+      if (anyBad) {
+        queueWalk(walkFrom);
+      } else if (cNh > 1) {  // (a run of reads that are their own group has nothing to close)
+        // one read closed by the countdown, counted like the closes of the loop
+        auto closeRead = [&](u32 c) {
+          pClosResc += 1u;
+          if (c == 0) return;
+          if ((c & (c - 1)) == 0) {
+            pClosResc += 1u << 16;  // a multi-mapping read resolved to one element (mm:1691)
+            if (HIST) sm.hist[__ffs(c) - 1][tid] += 1;
+            else sm.bt.add((u64)c, 1, table);
+          } else {
+            sm.bt.add((u64)c, 1, table);
+          }
+        };
+        if (!GROUPS) {
+          if (o + tailLen == cNh) {
+            u32 acc = cTot;
+            for (u32 q = 0; q < tailLen; ++q) acc |= sm.slowRes[warp][q];
+            closeRead(acc);
+          } else {
+            queueWalk(walkFrom);
+          }
+        } else if ((o + tailLen) % cNh != 0) {  // the run ends inside a group
+          queueWalk(walkFrom);
+        } else {
+          u32 acc = inGroup ? cTot : 0u, pos = inGroup;
+          for (u32 q = 0; q < tailLen; ++q) {
+            acc |= sm.slowRes[warp][q];
+            if (++pos == cNh) { closeRead(acc); acc = 0; pos = 0; }
+          }
+        }
+      }
+    }
   }
   u32 cHits = pHitsMiss & 0xFFFFu, cMiss = pHitsMiss >> 16, cUnassigned = cHits - (pAsgUniq & 0xFFFFu), cAmbiguous = pMultAmbi >> 16;
   u32 cUnique = pAsgUniq >> 16, cMultiple = pMultAmbi & 0xFFFFu;
