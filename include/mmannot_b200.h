@@ -212,7 +212,8 @@ int mma_submit_hits_packed(mma_ctx *ctx, uint32_t sample, const mma_packed_batch
  *                   (= hits) of the chunk and *flags = 0 once the chunk's kernels are enqueued.  A non-zero *flags (MMA_BAM_*)
  *                   means NOTHING of the chunk was counted: the file holds something this route leaves to the host decoder
  *                   (XA alternative hits, CIGAR operations or aux types the reference warns about, records that straddle
- *                   members, corrupt data); the caller resets the sample and decodes the file itself (mma_submit_hits*).
+ *                   members, corrupt data, two neighbouring records whose names differ but hash to one read key); the caller
+ *                   resets the sample and decodes the file itself (mma_submit_hits*).
  *   mma_bam_ref_first  out[i] = ordinal (0-based, over the file) of the first record on BAM reference i, ~0 if none yet --
  *                   kept only for references mapped to MMA_HIT_CHR_NONE (others stay ~0): for the "chromosome not present in
  *                   your annotation" warnings (mmannot.cpp:1297), in order of appearance. */
@@ -222,6 +223,7 @@ int mma_submit_hits_packed(mma_ctx *ctx, uint32_t sample, const mma_packed_batch
 #define MMA_BAM_ODD_CIGAR 8u
 #define MMA_BAM_ODD_AUX 16u
 #define MMA_BAM_MALFORMED 32u
+#define MMA_BAM_KEY_COLLISION 64u /* neighbouring records with one 64-bit read key and different names (mmannot.cpp:1656-1662 keys by the name) */
 typedef struct mma_bam_chunk {
   const void *data;              /* whole BGZF members, back to back */
   uint64_t n_bytes;              /* < 2^32 */

@@ -55,6 +55,9 @@ void mmh_reader_close(mmh_reader *r);
 uint64_t mmh_reader_next(mmh_reader *r, uint64_t cap, uint32_t *start, uint32_t *end, uint32_t *meta, uint32_t *nh, uint64_t *read_key);
 uint64_t mmh_reader_records(const mmh_reader *r);
 size_t mmh_reader_warnings(mmh_reader *r, char *buf, size_t cap);
+/* Read-key verification (the reference keys reads by the name string, mmannot.cpp:1656-1662; the device by mmh_name_key of it):
+ * "" while every pair of neighbouring records with one key had one name, else the first pair of different names sharing a key. */
+size_t mmh_reader_key_collision(mmh_reader *r, char *buf, size_t cap);
 
 uint64_t mmh_name_key(const char *name, size_t len);
 

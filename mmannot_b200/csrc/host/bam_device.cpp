@@ -219,7 +219,8 @@ DeviceBamFeeder::Result DeviceBamFeeder::run(const std::string &fileName, uint32
     if (flags) {
       why = std::string("the file needs the host decoder:") + ((flags & MMA_BAM_HAS_XA) ? " XA tags" : "") + ((flags & MMA_BAM_STRADDLE) ? " records across BGZF members" : "") +
             ((flags & MMA_BAM_ODD_CIGAR) ? " CIGAR operations with warnings" : "") + ((flags & MMA_BAM_ODD_AUX) ? " unknown aux types" : "") +
-            ((flags & MMA_BAM_BAD_DEFLATE) ? " deflate data this decoder rejects" : "") + ((flags & MMA_BAM_MALFORMED) ? " malformed records" : "");
+            ((flags & MMA_BAM_BAD_DEFLATE) ? " deflate data this decoder rejects" : "") + ((flags & MMA_BAM_MALFORMED) ? " malformed records" : "") +
+            ((flags & MMA_BAM_KEY_COLLISION) ? " read names sharing a 64-bit key" : "");
       return 1;
     }
     nRecords += n;

@@ -168,6 +168,11 @@ bool Counter::read(const std::string &fileName, uint32_t column, std::string &er
   }
   }
   log << "\t" << withThousands(reader.recordsRead()) << " lines read, done." << std::endl;
+  // the strategies that group records by read (mm:1669-1702, mm:1706-1726) rely on the 64-bit key standing for the name
+  if ((opt_.strategy == MMA_STRATEGY_DEFAULT || opt_.strategy == MMA_STRATEGY_RANDOM) && !reader.keyCollision().empty()) {
+    err = "Read names " + reader.keyCollision() + " of '" + fileName + "' share one 64-bit read key: their hits would be counted as one read.";
+    return false;
+  }
   }
   if (writers_) writers_->endOfFile();
   mma_sample_result res;

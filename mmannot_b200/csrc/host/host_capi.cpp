@@ -96,6 +96,7 @@ uint64_t mmh_reader_next(mmh_reader *r, uint64_t cap, uint32_t *start, uint32_t 
 }
 uint64_t mmh_reader_records(const mmh_reader *r) { return r->reader->recordsRead(); }
 size_t mmh_reader_warnings(mmh_reader *r, char *buf, size_t cap) { return copyOut(r->reader->takeWarnings(), buf, cap); }
+size_t mmh_reader_key_collision(mmh_reader *r, char *buf, size_t cap) { return copyOut(r->reader->keyCollision(), buf, cap); }
 
 uint64_t mmh_name_key(const char *name, size_t len) { return name_key(name, len); }
 

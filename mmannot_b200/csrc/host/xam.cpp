@@ -40,6 +40,20 @@ XamReader::XamReader(const std::string &fileName, ReadsFormat format, Strandedne
     : fileName_(fileName), format_(format), strandedness_(strandedness), features_(features) {
   for (size_t i = 0; i < features.chromosomes.size(); ++i)
     if (features.chrHasFeatures[i]) chrByName_[features.chromosomes[i]] = static_cast<uint32_t>(i);
+  if (const char *m = std::getenv("MMANNOT_B200_KEY_MASK")) keyMask_ = std::strtoull(m, nullptr, 0);
+}
+
+// Neighbouring records with one key must carry one name (see keyCollision() in the header).
+void XamReader::checkKey(const std::string &name, uint64_t key) {
+  if (!havePrev_) {
+    havePrev_ = true;
+    firstName_ = name; firstKey_ = key;
+    prevName_ = name; prevKey_ = key;
+  } else if (key != prevKey_) {
+    prevName_ = name; prevKey_ = key;
+  } else if (name != prevName_ && keyCollision_.empty()) {
+    keyCollision_ = "'" + prevName_ + "' and '" + name + "'";
+  }
 }
 
 XamReader::~XamReader() {
@@ -220,7 +234,8 @@ void XamReader::parseAlternatives(const std::string &xa) {
 
 void XamReader::pushRecordHits(const std::string &name, uint32_t chrMeta, uint64_t start, bool strand,
                                const std::vector<std::pair<char, int> > &cigar, bool, uint32_t nHits) {
-  const uint64_t key = name_key(name.data(), name.size());
+  const uint64_t key = name_key(name.data(), name.size()) & keyMask_;
+  checkKey(name, key);
   uint64_t end = start;  // Read::reset, mm:878-879
   auto emit = [&](uint32_t cm, uint64_t s, uint64_t e, bool fwd) {
     Hit h;
@@ -422,6 +437,15 @@ size_t XamReader::decodeBamChunkParallel() {
     XamReader &c = *clones[t];
     pending_.insert(pending_.end(), c.pending_.begin(), c.pending_.end());
     nRecords_ += c.nRecords_;
+    // read-key verification across the border of two ranges, then the clone's own finding
+    if (c.havePrev_) {
+      if (havePrev_ && c.firstKey_ == prevKey_ && c.firstName_ != prevName_ && keyCollision_.empty())
+        keyCollision_ = "'" + prevName_ + "' and '" + c.firstName_ + "'";
+      if (keyCollision_.empty()) keyCollision_ = c.keyCollision_;
+      if (!havePrev_) { firstName_ = c.firstName_; firstKey_ = c.firstKey_; }
+      havePrev_ = true;
+      prevName_ = c.prevName_; prevKey_ = c.prevKey_;
+    }
     // warnings: lines starting with \x01 announce a chromosome the clone did not know
     size_t a = 0;
     while (a < c.warnings_.size()) {
@@ -443,7 +467,7 @@ size_t XamReader::decodeBamChunkParallel() {
 XamReader::XamReader(const XamReader &parent, int)
     : fileName_(parent.fileName_), format_(parent.format_), strandedness_(parent.strandedness_), features_(parent.features_),
       chrByName_(parent.chrByName_), unknownChr_(), bam_(true), bamChrMeta_(parent.bamChrMeta_), bamChrName_(parent.bamChrName_),
-      clone_(true), uniqueOnly_(parent.uniqueOnly_) {}
+      clone_(true), uniqueOnly_(parent.uniqueOnly_), keyMask_(parent.keyMask_) {}
 
 bool XamReader::decodeSamRecord() {
   std::string line;

@@ -53,6 +53,12 @@ class XamReader {
   void warnOnlyForUniqueHits(bool on) { uniqueOnly_ = on; }
   uint64_t recordsRead() const { return nRecords_; }  // reference's "lines read" (= hits, mm:1772)
   std::string takeWarnings();                         // unknown chromosomes, CIGAR problems, XA problems
+  // Read-key verification.  The device tells reads apart by the 64-bit key of the name, the reference by the name string
+  // (mm:1656-1662, mm:1671): whenever two neighbouring records carry the same key their names are compared here.  Empty = every
+  // such pair had equal names; else the first pair of DIFFERENT names sharing a key ("'a' and 'b'"), which the device would count
+  // as one read.  (Name-grouped input: every pair that could be merged is a neighbouring pair.  Coordinate-sorted input: the
+  // pairs that are not neighbours are not seen; DESIGN.md section 7 gives their probability.)
+  const std::string &keyCollision() const { return keyCollision_; }
 
  private:
   struct Hit { uint32_t start, end, meta, nh; uint64_t key; };
@@ -69,6 +75,7 @@ class XamReader {
                       const std::vector<std::pair<char, int> > &cigar, bool cigarIsStar, uint32_t nHits);
   uint64_t cigarEnd(uint64_t start, uint64_t prevEnd, const std::vector<std::pair<char, int> > &cigar);
   uint32_t chrMetaOf(const std::string &name, bool quiet = false);
+  void checkKey(const std::string &name, uint64_t key);
   void parseAlternatives(const std::string &xa);
 
   std::string fileName_;
@@ -101,6 +108,11 @@ class XamReader {
   bool uniqueOnly_ = false;
   std::vector<size_t> recOff_;
   std::string warnings_;
+  // read-key verification (keyCollision): the last name seen with its key; a clone also keeps the first of its range
+  std::string prevName_, firstName_, keyCollision_;
+  uint64_t prevKey_ = 0, firstKey_ = 0;
+  bool havePrev_ = false;
+  uint64_t keyMask_ = ~0ull;  // test knob MMANNOT_B200_KEY_MASK: keys cut down to a few bits so that collisions can be staged
 };
 
 }  // namespace mmb

@@ -15,7 +15,10 @@
 //                   pos + 1, end = start + sum(M, D, =, X) - 1 (Read::parseCigar, mm:852-875), chromosome through the refID table
 //                   the host resolved against the annotation, strand by -s (mm:836-844), NH from the record's NH tag with the
 //                   reference's type rule (only unsigned types carry a value, mm:1596-1618), read key = the host's 64-bit name
-//                   hash (common.hpp name_key) restated here.
+//                   hash (common.hpp name_key) restated here.  The key stands for the name string the reference keys by
+//                   (mm:1656-1662): whenever two neighbouring records carry the same key their names are compared byte by byte
+//                   (inside a member, and the member's last record against the first record of the next member of the chunk);
+//                   a pair that differs raises BAM_KEY_COLLISION.
 //
 // What this route does not do is flagged and left to the host decoder, for the whole file: XA tags (alternative hits need the
 // text parser and the NM carried from record to record, mm:1360-1399), CIGAR operations the reference warns about ('N' and
@@ -36,6 +39,7 @@ enum BamFlag : u32 {
   BAM_ODD_CIGAR = 8u,      // 'N' or an unknown CIGAR operation: the reference prints a warning per occurrence
   BAM_ODD_AUX = 16u,       // unknown aux type / malformed aux area
   BAM_MALFORMED = 32u,     // record shorter than its fixed part / fields beyond the record
+  BAM_KEY_COLLISION = 64u, // two neighbouring records share a read key but not the name (the host decoder names them and refuses the file)
 };
 
 struct BamView {
@@ -338,16 +342,16 @@ MMA_HD __forceinline__ u64 nameKey(const unsigned char *p, u32 n) {
 }
 
 // records of member m: [begin, end) inside v.out
-__device__ __forceinline__ void memberRange(const BamView &v, u32 m, u32 &begin, u32 &end) {
+MMA_HD __forceinline__ void memberRange(const BamView &v, u32 m, u32 &begin, u32 &end) {
   begin = v.outOff[m] + (m == 0 ? v.skipFirst : 0u);
   end = v.outOff[m + 1];
 }
 
-__global__ void k_bam_count(BamView v, u32 *count) {
-  const u32 m = blockIdx.x * blockDim.x + threadIdx.x;
-  if (m >= v.nMembers) return;
-  u32 pos, end, n = 0;
+// number of records of member m; false when the member does not start at a record and end at one
+MMA_HD __forceinline__ bool bamCountMember(const BamView &v, u32 m, u32 &n) {
+  u32 pos, end;
   memberRange(v, m, pos, end);
+  n = 0;
   bool bad = pos > end;
   while (!bad && pos < end) {
     if (pos + 4 > end) { bad = true; break; }
@@ -356,8 +360,16 @@ __global__ void k_bam_count(BamView v, u32 *count) {
     pos += 4 + bs;
     ++n;
   }
-  if (bad) atomicOr(v.flags, (u32)BAM_STRADDLE);
-  count[m] = bad ? 0u : n;
+  if (bad) n = 0;
+  return !bad;
+}
+
+__global__ void k_bam_count(BamView v, u32 *count) {
+  const u32 m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= v.nMembers) return;
+  u32 n;
+  if (!bamCountMember(v, m, n)) atomicOr(v.flags, (u32)BAM_STRADDLE);
+  count[m] = n;
 }
 
 struct HitOut {
@@ -365,9 +377,26 @@ struct HitOut {
   u64 *key;
 };
 
+// read name of a record as the key was formed from it (bytes up to the first NUL, mm:1545); p = nullptr: no record
+struct RecName {
+  const unsigned char *p;
+  u32 len;
+  u64 key;
+};
+MMA_HD __forceinline__ bool sameName(const RecName &a, const RecName &b) {
+  if (a.len != b.len) return false;
+  for (u32 i = 0; i < a.len; ++i)
+    if (a.p[i] != b.p[i]) return false;
+  return true;
+}
+#ifndef MMA_NAME_KEY_MASK
+#define MMA_NAME_KEY_MASK (~0ull)  // (tests/tools/bam_host_check.cu cuts the keys down to a few bits to stage collisions)
+#endif
+
 // one BAM alignment record (the bytes after its block_size field) -> one hit; like XamReader::parseBamRecord without XA
-MMA_HD __forceinline__ u32 bamRecord(const BamView &v, const unsigned char *p, u32 blockSize, u64 ordinal, const HitOut &o, u32 at) {
+MMA_HD __forceinline__ u32 bamRecord(const BamView &v, const unsigned char *p, u32 blockSize, u64 ordinal, const HitOut &o, u32 at, RecName &name) {
   u32 flags = 0;
+  name.p = nullptr; name.len = 0; name.key = 0;
   const unsigned char *recEnd = p + blockSize;
   const int refId = (int)ld32u(p), pos = (int)ld32u(p + 4);
   const u32 lReadName = p[8];
@@ -379,7 +408,8 @@ MMA_HD __forceinline__ u32 bamRecord(const BamView &v, const unsigned char *p, u
   }
   u32 nameLen = 0;
   while (nameLen < lReadName && q[nameLen]) ++nameLen;  // up to the first NUL (mm:1545)
-  const u64 key = nameKey(q, nameLen);
+  const u64 key = nameKey(q, nameLen) & MMA_NAME_KEY_MASK;
+  name.p = q; name.len = nameLen; name.key = key;
   q += lReadName;
   const u64 start = (u64)((long long)pos + 1);  // ++pos then widened (mm:1536-1537)
   u64 end = start;
@@ -444,19 +474,51 @@ MMA_HD __forceinline__ u32 bamRecord(const BamView &v, const unsigned char *p, u
   return flags;
 }
 
-__global__ void k_bam_parse(BamView v, const u32 *__restrict__ hitOff, u64 ordBase, HitOut o) {
-  const u32 m = blockIdx.x * blockDim.x + threadIdx.x;
-  if (m >= v.nMembers) return;
+// the records of member m -> hits [at, stop); returns the OR of the records' flags.  Read-key verification on the way: a record
+// with its predecessor's key must have its predecessor's name, and so must the first record of the next member that holds one
+// (members without records lie between the parts of a concatenated file and before the end of every BGZF file).
+MMA_HD __forceinline__ u32 bamParseMember(const BamView &v, u32 m, u32 at, u32 stop, u64 ordBase, const HitOut &o) {
   u32 pos, end;
   memberRange(v, m, pos, end);
-  u32 at = hitOff[m], flags = 0;
-  const u32 stop = hitOff[m + 1];
+  u32 flags = 0;
+  RecName prev{nullptr, 0, 0};
   while (pos + 4 <= end && at < stop) {
     const u32 bs = ld32u(v.out + pos);
-    flags |= bamRecord(v, v.out + pos + 4, bs, ordBase + at, o, at);
+    RecName cur;
+    flags |= bamRecord(v, v.out + pos + 4, bs, ordBase + at, o, at, cur);
+    if (cur.p) {
+      if (prev.p && cur.key == prev.key && !sameName(prev, cur)) flags |= BAM_KEY_COLLISION;
+      prev = cur;
+    }
     pos += 4 + bs;
     ++at;
   }
+  if (prev.p) {
+    for (u32 nx = m + 1; nx < v.nMembers; ++nx) {
+      u32 nb, ne;
+      memberRange(v, nx, nb, ne);
+      if (nb >= ne) continue;  // no record in this member
+      // (a member that does not start with a whole record was flagged by k_bam_count: only what is read here must lie inside it)
+      if ((u64)nb + 36 <= ne) {
+        const unsigned char *q = v.out + nb + 36;
+        const u32 lReadName = v.out[nb + 12];
+        if ((u64)nb + 36 + lReadName <= ne) {
+          RecName first{q, 0, 0};
+          while (first.len < lReadName && q[first.len]) ++first.len;
+          first.key = nameKey(q, first.len) & MMA_NAME_KEY_MASK;
+          if (first.key == prev.key && !sameName(prev, first)) flags |= BAM_KEY_COLLISION;
+        }
+      }
+      break;
+    }
+  }
+  return flags;
+}
+
+__global__ void k_bam_parse(BamView v, const u32 *__restrict__ hitOff, u64 ordBase, HitOut o) {
+  const u32 m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= v.nMembers) return;
+  const u32 flags = bamParseMember(v, m, hitOff[m], hitOff[m + 1], ordBase, o);
   if (flags) atomicOr(v.flags, flags);
 }
 

@@ -51,6 +51,8 @@ def lib():
         L.mmh_reader_records.restype = C.c_uint64
         L.mmh_reader_warnings.argtypes = [C.c_void_p, C.c_char_p, C.c_size_t]
         L.mmh_reader_warnings.restype = C.c_size_t
+        L.mmh_reader_key_collision.argtypes = [C.c_void_p, C.c_char_p, C.c_size_t]
+        L.mmh_reader_key_collision.restype = C.c_size_t
         L.mmh_name_key.argtypes = [C.c_char_p, C.c_size_t]
         L.mmh_name_key.restype = C.c_uint64
         _lib = L
@@ -161,8 +163,9 @@ class Hits:
         return Hits(*[np.concatenate([getattr(p, k) for p in parts]) for k in Hits.__slots__])
 
 
-def read_hits(annotation, path, strandedness="F", fmt=0, batch=1 << 20):
-    """Decode a whole SAM/BAM file into one Hits object (plus the decoder's warnings)."""
+def read_hits(annotation, path, strandedness="F", fmt=0, batch=1 << 20, collision=None):
+    """Decode a whole SAM/BAM file into one Hits object (plus the decoder's warnings).  `collision`: a list that receives the
+    decoder's read-key verification result ("" or the first two different names sharing a key)."""
     L = lib()
     h = C.c_void_p()
     if L.mmh_reader_open(annotation._h, os.fsencode(path), fmt, strandedness.encode()[0:1], C.byref(h)) != 0:
@@ -178,6 +181,9 @@ def read_hits(annotation, path, strandedness="F", fmt=0, batch=1 << 20):
         buf = C.create_string_buffer(1 << 20)
         L.mmh_reader_warnings(h, buf, 1 << 20)
         warnings = buf.value.decode("utf-8", "replace")
+        if collision is not None:
+            L.mmh_reader_key_collision(h, buf, 1 << 20)
+            collision.append(buf.value.decode("utf-8", "replace"))
     finally:
         L.mmh_reader_close(h)
     if not parts:

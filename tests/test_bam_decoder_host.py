@@ -18,17 +18,20 @@ CFGS = json.load(open(os.path.join(common.GOLDEN, "configs.json")))
 TOOL_SRC = os.path.join(common.ROOT, "tests", "tools", "bam_host_check.cu")
 
 
-@pytest.fixture(scope="module")
-def tool(tmp_path_factory):
-    common.ensure_built(("host",))
-    exe = str(tmp_path_factory.mktemp("tool") / "bam_host_check")
+def build_tool(exe, defines=()):
     nvcc = "/usr/local/cuda/bin/nvcc"
     if not os.path.exists(nvcc):
         pytest.skip("nvcc not available")
     # (the device side of the headers is compiled too, for the product's architecture; only the host side runs here)
     subprocess.check_call([nvcc, "-O2", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-I" + os.path.join(common.ROOT, "include"),
-                           "-I" + os.path.join(common.ROOT, "mmannot_b200", "csrc"), "-o", exe, TOOL_SRC, "-lz"])
+                           "-I" + os.path.join(common.ROOT, "mmannot_b200", "csrc")] + list(defines) + ["-o", exe, TOOL_SRC, "-lz"])
     return exe
+
+
+@pytest.fixture(scope="module")
+def tool(tmp_path_factory):
+    common.ensure_built(("host",))
+    return build_tool(str(tmp_path_factory.mktemp("tool") / "bam_host_check"))
 
 
 def recompress(src, dst, level):
@@ -90,3 +93,23 @@ def test_inflate_and_records_on_the_cpu(tool, tmp_path, shape, cfg_key, spec):
                 continue
             pr = subprocess.run([tool, path, dump, str(code)], capture_output=True, text=True)
             assert pr.returncode == 0, (name, strand, pr.stdout[-300:])
+
+
+@pytest.mark.parametrize("mask", ["0xFull", "0xFFFull"])
+def test_read_key_verification_on_the_cpu(tmp_path, mask):
+    """bamParseMember (the body of k_bam_parse) with the read keys cut down to 4 / 12 bits: exactly the members that hold a pair
+    of neighbouring records with one key and two names -- inside the member or across the border to the next member with a
+    record -- must raise BAM_KEY_COLLISION (the tool finds the expected members with one plain walk over all records).  The
+    uncut keys raise nothing: that is the `flags` check of the test above."""
+    common.ensure_built(("host",))
+    exe = build_tool(str(tmp_path / "bam_host_check_keys"), ["-DMMA_NAME_KEY_MASK=" + mask, "-DEXPECT_COLLISIONS"])
+    synth = host.Synth("tair10", 32, gene_scale=0.05, max_nh=4)
+    bam = str(tmp_path / "r.bam")
+    synth.write_bam_parallel(bam, 0, 120000, 3)  # (three parts: members without records lie between them)
+    pr = subprocess.run([exe, bam, "-", "1"], capture_output=True, text=True)  # (no expected hits in this mode)
+    assert pr.returncode == 0, pr.stdout[-300:]
+    words = pr.stdout.split()
+    pairs, flagged, border = int(words[3]), int(words[6]), int(words[9])
+    assert pairs > 0 and flagged > 0
+    if mask == "0xFull":
+        assert border > 0, "no colliding pair across a member border in this input: the border check did not run"
