@@ -118,8 +118,10 @@ typedef struct mma_hit_batch {
  *   run_key[r]             read key of the r-th run of the batch
  *   tile_run_base[t]       number of runs that start before hit t * MMA_PACK_TILE
  *   esc_*                  ascending hit indices with their full end and NH, for hits a field of which did not fit
- * The struct is TRUSTED input, normally the output of mma_pack_hits: tile_run_base, the run-start bits and n_runs must agree and
- * esc_index must be strictly increasing (the device does not re-check them; inconsistent values read out of bounds). */
+ * Normally the output of mma_pack_hits.  mma_submit_hits_packed checks what costs O(tiles + escapes) (mma_check_packed, deep = 0:
+ * tile_run_base monotone and within n_runs, esc_index strictly increasing and below n) and the device never reads outside the
+ * arrays; run-start bits that disagree with tile_run_base / n_runs, or an escaped hit missing from esc_index, give wrong read
+ * keys / saturated fields without an error -- callers that build the struct themselves can run mma_check_packed(.., 1) on it. */
 #define MMA_PACK_TILE 1024
 #define MMA_PACKED_CHR_NONE 0x3FFFu
 #define MMA_PACKED_RUN_START 0x40000000u
@@ -198,6 +200,10 @@ int mma_submit_hits_device(mma_ctx *ctx, uint32_t sample, const mma_hit_batch *d
  * esc_capacity, or a chromosome id >= MMA_PACKED_CHR_NONE): submit it in the wide format instead. */
 int mma_pack_hits(const mma_hit_batch *wide, uint32_t *packed, uint64_t *run_key, uint32_t *tile_run_base, uint32_t *esc_index,
                   uint32_t *esc_end, uint32_t *esc_nh, uint64_t esc_capacity, mma_packed_batch *out);
+
+/* Host-side consistency check of a packed batch (no device work, no context): MMA_OK or MMA_ERR_INVALID.  deep = 0: pointers,
+ * counts, tile_run_base and esc_index, O(tiles + escapes); deep != 0: also the run-start bits of every tile and the escaped hits, O(n). */
+int mma_check_packed(const mma_packed_batch *batch, int deep);
 
 /* mma_submit_hits for a batch in the compact format (same asynchrony and buffer lifetime rules). */
 int mma_submit_hits_packed(mma_ctx *ctx, uint32_t sample, const mma_packed_batch *batch);

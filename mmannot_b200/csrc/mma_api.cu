@@ -907,6 +907,47 @@ int mma_pack_hits(const mma_hit_batch *w, uint32_t *packed, uint64_t *run_key, u
   return MMA_OK;
 }
 
+// Consistency of a batch in the compact format (no device work).  deep = 0: the pointers, the counts, tile_run_base (starts at 0,
+// never falls, grows by at most a tile's hits per tile, stays within n_runs) and esc_index (strictly increasing, below n) --
+// O(tiles + escapes), what mma_submit_hits_packed checks on every call.  deep != 0: also the run-start bits of every tile against
+// tile_run_base / n_runs and every escaped hit against esc_index -- O(n), for callers that build the struct themselves.
+int mma_check_packed(const mma_packed_batch *pb, int deep) {
+  if (!pb) return MMA_ERR_INVALID;
+  const uint64_t n = pb->n;
+  if (n == 0) return MMA_OK;
+  if (n > 0xFFFFFFF0ull) return MMA_ERR_INVALID;
+  if (!pb->start || !pb->packed || !pb->run_key || !pb->tile_run_base || pb->n_runs == 0 || pb->n_runs > n) return MMA_ERR_INVALID;
+  if (!(pb->packed[0] & MMA_PACKED_RUN_START)) return MMA_ERR_INVALID;
+  if (pb->n_escapes > n || (pb->n_escapes && (!pb->esc_index || !pb->esc_end || !pb->esc_nh))) return MMA_ERR_INVALID;
+  const uint64_t nTiles = (n + MMA_PACK_TILE - 1) / MMA_PACK_TILE;
+  if (pb->tile_run_base[0] != 0) return MMA_ERR_INVALID;
+  for (uint64_t t = 1; t < nTiles; ++t) {
+    const uint64_t a = pb->tile_run_base[t - 1], b = pb->tile_run_base[t];
+    if (b < a || b - a > MMA_PACK_TILE || b == 0 || b > pb->n_runs) return MMA_ERR_INVALID;
+  }
+  if (pb->n_runs - pb->tile_run_base[nTiles - 1] > n - (nTiles - 1) * MMA_PACK_TILE) return MMA_ERR_INVALID;
+  for (uint64_t e = 0; e < pb->n_escapes; ++e)
+    if (pb->esc_index[e] >= n || (e && pb->esc_index[e] <= pb->esc_index[e - 1])) return MMA_ERR_INVALID;
+  if (deep) {
+    uint64_t e = 0;
+    for (uint64_t t = 0; t < nTiles; ++t) {
+      const uint64_t lo = t * MMA_PACK_TILE, hi = std::min<uint64_t>(n, lo + MMA_PACK_TILE);
+      uint64_t starts = 0;
+      for (uint64_t i = lo; i < hi; ++i) {
+        const uint32_t pk = pb->packed[i];
+        starts += (pk >> 30) & 1u;
+        if ((pk & 255u) == 255u || ((pk >> 8) & 255u) == 255u) {  // an escaped hit must be listed
+          while (e < pb->n_escapes && pb->esc_index[e] < i) ++e;
+          if (e >= pb->n_escapes || pb->esc_index[e] != i) return MMA_ERR_INVALID;
+        }
+      }
+      const uint64_t next = (t + 1 < nTiles) ? pb->tile_run_base[t + 1] : pb->n_runs;
+      if (starts != next - pb->tile_run_base[t]) return MMA_ERR_INVALID;
+    }
+  }
+  return MMA_OK;
+}
+
 int mma_submit_hits_packed(mma_ctx *ctx, uint32_t sample, const mma_packed_batch *pb) {
   if (!ctx) return MMA_ERR_INVALID;
   if (!pb) return ctx->fail(MMA_ERR_INVALID, "null batch");
@@ -914,9 +955,7 @@ int mma_submit_hits_packed(mma_ctx *ctx, uint32_t sample, const mma_packed_batch
   if (sample >= ctx->samples.size()) return ctx->fail(MMA_ERR_INVALID, "sample index out of range");
   if (pb->n > ctx->params.max_batch_hits) return ctx->fail(MMA_ERR_INVALID, "batch larger than max_batch_hits");
   const uint64_t n = pb->n;
-  if (n && (!pb->start || !pb->packed || !pb->run_key || !pb->tile_run_base || pb->n_runs == 0 || pb->n_runs > n ||
-            !(pb->packed[0] & MMA_PACKED_RUN_START) || (pb->n_escapes && (!pb->esc_index || !pb->esc_end || !pb->esc_nh))))
-    return ctx->fail(MMA_ERR_INVALID, "malformed packed batch");
+  if (mma_check_packed(pb, 0) != MMA_OK) return ctx->fail(MMA_ERR_INVALID, "malformed packed batch");
   CK(cudaSetDevice(ctx->device));
   Sample &s = ctx->samples[sample];
   int rc = initSample(ctx, s);
@@ -946,7 +985,7 @@ int mma_submit_hits_packed(mma_ctx *ctx, uint32_t sample, const mma_packed_batch
   PackedView pv;
   pv.start = g.start.as<u32>(); pv.packed = g.packed.as<u32>(); pv.tileRunBase = g.tileBase.as<u32>();
   pv.escIndex = g.escIndex.as<u32>(); pv.escEnd = g.escEnd.as<u32>(); pv.escNh = g.escNh.as<u32>();
-  pv.runKey = g.runKey.as<u64>(); pv.n = (u32)n; pv.nEsc = (u32)pb->n_escapes;
+  pv.runKey = g.runKey.as<u64>(); pv.n = (u32)n; pv.nEsc = (u32)pb->n_escapes; pv.nRuns = (u32)pb->n_runs;
   {
     mma_ctx::Timed t(ctx, TC_CLOSE);
     k_expand_packed<<<(u32)nTiles, PACK_TILE / 4, 0, ctx->sc>>>(pv, g.end.as<u32>(), g.meta.as<u32>(), g.nh.as<u32>(), g.key.as<u64>());

@@ -938,7 +938,7 @@ __global__ void k_widen_counts(const u32 *__restrict__ in, u64 *__restrict__ out
 struct PackedView {
   const u32 *start, *packed, *tileRunBase, *escIndex, *escEnd, *escNh;
   const u64 *runKey;
-  u32 n, nEsc;
+  u32 n, nEsc, nRuns;
 };
 __global__ void __launch_bounds__(PACK_TILE / 4)
 k_expand_packed(PackedView pv, u32 *__restrict__ end, u32 *__restrict__ meta, u32 *__restrict__ nh, u64 *__restrict__ key) {
@@ -976,7 +976,9 @@ k_expand_packed(PackedView pv, u32 *__restrict__ end, u32 *__restrict__ meta, u3
     end[i] = e;
     nh[i] = n;
     meta[i] = (chr == 0x3FFFu ? 0x00FFFFFFu : chr) | (p[j] & 0x80000000u);
-    key[i] = pv.runKey[before - 1u];
+    // (the struct is the host's word: run-start bits that disagree with tileRunBase / nRuns give wrong keys, never a read
+    // outside runKey -- `before` = 0 wraps and is clamped as well)
+    key[i] = pv.runKey[min(before - 1u, pv.nRuns - 1u)];
   }
 }
 

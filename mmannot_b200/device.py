@@ -20,7 +20,7 @@ FAST_OFF = 0xFFFFFFFF  # fast_bin_shift=None: no segment answer table
 EXPORTS = [
     "mma_create", "mma_destroy", "mma_last_error", "mma_load_features", "mma_alloc_pinned", "mma_free_pinned",
     "mma_submit_hits", "mma_submit_hits_device", "mma_finish_sample", "mma_reset_sample", "mma_dense_counts",
-    "mma_sync", "mma_stream", "mma_timing_enable", "mma_timing_reset", "mma_timing_get", "mma_index_bytes", "mma_version", "mma_readback_bytes", "mma_dominant_kernel", "mma_index_segments", "mma_annotate_hits", "mma_annotate_intervals", "mma_pack_hits", "mma_submit_hits_packed", "mma_device_count", "mma_warmup", "mma_export_bytes", "mma_export_table", "mma_import_tables",
+    "mma_sync", "mma_stream", "mma_timing_enable", "mma_timing_reset", "mma_timing_get", "mma_index_bytes", "mma_version", "mma_readback_bytes", "mma_dominant_kernel", "mma_index_segments", "mma_annotate_hits", "mma_annotate_intervals", "mma_pack_hits", "mma_check_packed", "mma_submit_hits_packed", "mma_device_count", "mma_warmup", "mma_export_bytes", "mma_export_table", "mma_import_tables",
     "mma_export_rows", "mma_export_head_bytes", "mma_import_tables_strided", "mma_allreduce", "mma_batch_kernel", "mma_export_table_async", "mma_restore_export",
     "mma_bam_begin", "mma_submit_bam", "mma_submit_bam_start", "mma_submit_bam_finish", "mma_bam_ref_first", "mma_bam_last_hits", "mma_bam_reserve", "mma_bam_stage",
 ]
@@ -119,6 +119,7 @@ def lib():
         L.mma_alloc_pinned.restype = C.c_void_p
         L.mma_free_pinned.argtypes = [C.c_void_p]
         L.mma_pack_hits.argtypes = [C.POINTER(HitBatch)] + [C.c_void_p] * 6 + [C.c_uint64, C.POINTER(PackedBatch)]
+        L.mma_check_packed.argtypes = [C.POINTER(PackedBatch), C.c_int]
         L.mma_submit_hits_packed.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(PackedBatch)]
         L.mma_export_bytes.argtypes = [C.c_void_p]
         L.mma_export_bytes.restype = C.c_uint64
