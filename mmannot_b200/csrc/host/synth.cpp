@@ -248,7 +248,7 @@ void SynthGenome::writeAnnotation(const std::string &path) const {
   std::stable_sort(order.begin(), order.end(), [this](uint32_t a, uint32_t b) {
     return genes[a].chr != genes[b].chr ? genes[a].chr < genes[b].chr : genes[a].start < genes[b].start;
   });
-  char gid[64], tid[64];
+  char gid[64], tid[80];
   for (uint32_t gi : order) {
     const SynthGene &g = genes[gi];
     const GeneClass &gc = classes_[g.cls];
