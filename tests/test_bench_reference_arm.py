@@ -37,3 +37,26 @@ def test_reference_arm_prints_the_contract_line():
     import argparse
     wl = argparse.Namespace(w=bench.WORKLOADS["tair10_srna"], name="tair10_srna")
     assert d["config"] == bench.bench_config(wl, argparse.Namespace(reads=0), 1)
+
+
+def test_reference_arm_under_torchrun_prints_one_line_from_rank_0():
+    """N > 1 (the driver launches both arms through torch.distributed.run): rank 0 alone times the reference and prints the line,
+    the other ranks leave with exit code 0 and print nothing."""
+    from oracle import pyoracle
+    if not os.path.exists(pyoracle.ref_binary("fixed")):
+        pytest.skip("oracle/_ref not built")
+    common.ensure_built(("host",))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29533", os.path.join(common.ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1",
+           "--warmup", "1", "--ref-reads", "5000", "--ref-threads", "2"]
+    pr = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=common.ROOT)
+    assert pr.returncode == 0, pr.stderr[-500:]
+    lines = [ln for ln in pr.stdout.splitlines() if ln.strip().startswith("{")]
+    assert len(lines) == 1, "exactly one JSON line on stdout"
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["n_gpus"] == 2 and d["value"] > 0
+    sys.path.insert(0, common.ROOT)
+    import bench
+    import argparse
+    wl = argparse.Namespace(w=bench.WORKLOADS["tair10_srna"], name="tair10_srna")
+    assert d["config"] == bench.bench_config(wl, argparse.Namespace(reads=0), 2)
