@@ -66,3 +66,31 @@ def test_oracle_equals_reference(workload, args, ann_opt):
     assert table == {k: v[0] for k, v in ref_rows.items()}
     for k, v in ref_stats.items():
         assert res["stats"][k] == v, k
+
+
+@pytest.mark.parametrize("args", [["-s", "F", "-y", "ratio"], ["-s", "U", "-y", "ratio", "-l", "0.5"]], ids=["F", "U -l 0.5"])
+def test_ratio_table_from_integer_counts_equals_reference(workload, args):
+    """-y ratio: the device keeps INTEGER counts per (element set, NH) and the host forms each cell as the sum over NH, in
+    ascending NH, of count * (1.0 / NH) (Counter::read, csrc/host/counter.cpp), where the reference adds 1.0 / NH hit by hit in
+    file order (mm:1730) and prints (unsigned) round(value) (mm:1868).  The two double sums may differ in the last bits; the
+    printed tables must not.  Here the integer counts come from the oracle's per-hit element sets."""
+    w = workload
+    rc, out, err = pyoracle.run_reference(["-a", w["gtf"], "-r", w["bam"], "-c", w["cfg_path"]] + args, kind="fixed")
+    assert rc == 0, err
+    _, ref_rows = pyoracle.parse_table(out)
+    o = common.case_options(args)
+    hits, _ = host.read_hits(w["ann"], w["bam"], o["strand"])
+    res = pyoracle.run(w["cfg"].elem_line, w["cfg"].elem_strand, w["cfg"].elem_vicinity, w["ann"], hits, strategy="ratio",
+                       overlap=o["overlap"], want_hit_masks=True)
+    masks, nh = res["hit_mask"], hits.nh
+    counts = {}
+    for m, n in zip(masks[masks != 0].tolist(), nh[masks != 0].tolist()):
+        counts[(m, n)] = counts.get((m, n), 0) + 1
+    cells = {}
+    for (m, n) in sorted(counts):  # ascending (set, NH), like the sort of the rows in Counter::read
+        cells[m] = cells.get(m, 0.0) + float(counts[(m, n)]) * (1.0 / n if n else 1.0)
+    table = {w["cfg"].row_name(m): round_half_away(v) for m, v in cells.items()}
+    assert table == {k: v[0] for k, v in ref_rows.items()}
+    # and the doubles themselves agree with the hit-by-hit sums within the stated tolerance
+    for m, v in res["rows"].items():
+        assert abs(cells[m] - v) <= 1e-9 * max(1.0, abs(v))
