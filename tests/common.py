@@ -44,7 +44,7 @@ def case_options(args):
         if a == "-s": o["strand"] = args[i + 1]
         elif a == "-y": o["strategy"] = args[i + 1]
         elif a == "-l": o["overlap"] = float(np.float32(float(args[i + 1])))
-        elif a == "-e": o["rescue_threshold"] = float(np.float32(np.float32(float(args[i + 1])) / np.float32(100.0)))
+        elif a == "-e": o["rescue_threshold"] = float(np.float32(float(np.float32(float(args[i + 1]))) / 100.0))  # (float)(stof(arg) / 100.0), mm:2024
         elif a == "-m": o["read_stats"] = True
         elif a in ("-d", "-D"): o["variant"] = "chrY_d5000_D200"
         i += 2

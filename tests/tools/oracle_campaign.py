@@ -19,7 +19,8 @@ SHAPES = [("tair10", "configTAIR10", dict(max_nh=20)), ("hs38", "configHS38", di
           ("flybase6", "configFlybase6", dict(max_nh=8, paired=True, rna_seq=True))]
 OPTS = [["-s", "F"], ["-s", "R", "-l", "1"], ["-s", "U", "-l", "0.5"], ["-s", "F", "-l", "15"], ["-s", "R", "-l", "0.9"],
         ["-s", "F", "-y", "unique"], ["-s", "U", "-y", "ratio"], ["-s", "F", "-y", "random"], ["-s", "U", "-d", "300", "-D", "2500"],
-        ["-s", "F", "-l", "0.99", "-y", "ratio"]]
+        ["-s", "F", "-l", "0.99", "-y", "ratio"], ["-s", "F", "-m", "@", "-e", "50"], ["-s", "U", "-m", "@", "-e", "33"], ["-s", "R", "-m", "@", "-e", "80", "-y", "ratio"],
+        ["-s", "F", "-m", "@", "-e", "67", "-y", "random"]]  # ("@" = a scratch file: the rescue test only runs with -m, mm:491)
 
 
 def main():
@@ -44,16 +45,16 @@ def main():
             o = common.case_options(args)
             up, down = (300, 2500) if "-d" in args else (None, None)
             ann = host.Annotation(cfg, gtf, up, down) if up else host.Annotation(cfg, gtf)
-            rc, out, err = pyoracle.run_reference(["-a", gtf, "-r", bam, "-c", cfg_path] + args, kind="fixed")
+            rc, out, err = pyoracle.run_reference(["-a", gtf, "-r", bam, "-c", cfg_path] + [os.path.join(tmp, "m.txt") if a == "@" else a for a in args], kind="fixed")
             assert rc == 0, err
             _, ref_rows = pyoracle.parse_table(out)
             ref_stats = pyoracle.parse_stats(err)[0]
             hits, _ = host.read_hits(ann, bam, o["strand"])
             res = pyoracle.run(cfg.elem_line, cfg.elem_strand, cfg.elem_vicinity, ann, hits, strategy=o["strategy"], overlap=o["overlap"],
-                               want_hit_masks=(o["strategy"] == "ratio"))
+                               rescue_threshold=o["rescue_threshold"], read_stats=o["read_stats"], want_hit_masks=(o["strategy"] == "ratio"))
             table = {cfg.row_name(m): round_half_away(v) for m, v in res["rows"].items()}
             ok = table == {k: v[0] for k, v in ref_rows.items()} and all(res["stats"][k] == v for k, v in ref_stats.items())
-            if o["strategy"] == "ratio":  # the cells as Counter::read forms them from the device's integer counts per (set, NH)
+            if o["strategy"] == "ratio" and not o["read_stats"]:  # the cells as Counter::read forms them from the device's integer counts per (set, NH)
                 masks, counts, cells = res["hit_mask"], {}, {}
                 for m, n in zip(masks[masks != 0].tolist(), hits.nh[masks != 0].tolist()):
                     counts[(m, n)] = counts.get((m, n), 0) + 1
