@@ -64,3 +64,10 @@ def test_version_string():
     from mmannot_b200 import device
     assert b"sm_100a" in device.lib().mma_version()
     assert device.lib().mma_dominant_kernel() in (b"k_batch_lean", b"k_batch_fast")
+
+
+def test_every_exported_symbol_is_documented():
+    """INTEGRATION.md section 5 lists every symbol of the device ABI with the reference interface it replaces."""
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    missing = [n for n in declared("mmannot_b200.h") if "`" + n + "`" not in doc]
+    assert not missing, missing
